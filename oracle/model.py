@@ -1,0 +1,388 @@
+"""Python side of the CPU ORACLE (TEST INFRASTRUCTURE, NOT PRODUCT CODE).
+
+PARITY UNPINNED -- see oracle/vsr_oracle.h.  This module restates, for the oracle only, the integer /
+naming work that surrounds the hot path:
+
+* ``java_random``      java.util.Random (LCG + polar nextGaussian), used by 2dhmsr terrain builders
+* ``build_shape``      2dhmsr RobotUtils.buildShape(String)             [U]  (call site Starter.java:405)
+* ``create_terrain``   2dhmsr Locomotion.createTerrain(String)          [U]  (call site Starter.java:87,91)
+* ``sensor_config``    2dhmsr RobotUtils.buildSensorizingFunction       [U]  (call site Starter.java:404)
+* ``inner_neurons``    /root/reference/.../builder/function/MLP.java:28-42   [V]
+* ``count_weights``    2dhmsr MultiLayerPerceptron.countWeights         [U]
+* ``episode_steps``    the ``while (t < finalT) t += dt`` loop of Locomotion.apply and
+                       Outcome.subOutcome's key selection, emulated in IEEE double [U]
+
+and binds ``liboracle`` through ctypes.  Nothing under ``vsrevolution_b200/`` imports this file.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+import subprocess
+from dataclasses import dataclass, field
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libvsr_oracle.so")
+
+
+# --------------------------------------------------------------------------------------------------
+# java.util.Random
+# --------------------------------------------------------------------------------------------------
+class JavaRandom:
+    """Bit-exact java.util.Random (nextInt/nextDouble/nextGaussian)."""
+
+    _M = (1 << 48) - 1
+
+    def __init__(self, seed: int):
+        self.seed = (seed ^ 0x5DEECE66D) & self._M
+        self._have = False
+        self._next_g = 0.0
+
+    def _next(self, bits: int) -> int:
+        self.seed = (self.seed * 0x5DEECE66D + 0xB) & self._M
+        v = self.seed >> (48 - bits)
+        if v >= 1 << (bits - 1) and bits == 32:
+            v -= 1 << 32
+        return v
+
+    def next_int(self, bound: int | None = None) -> int:
+        if bound is None:
+            return self._next(32)
+        r = self._next(31)
+        m = bound - 1
+        if (bound & m) == 0:
+            return (bound * r) >> 31
+        u = r
+        while True:
+            r = u % bound
+            if u - r + m < (1 << 31):
+                return r
+            u = self._next(31)
+
+    def next_double(self) -> float:
+        return ((self._next(26) << 27) + self._next(27)) * (1.0 / (1 << 53))
+
+    def next_gaussian(self) -> float:
+        if self._have:
+            self._have = False
+            return self._next_g
+        while True:
+            v1 = 2 * self.next_double() - 1
+            v2 = 2 * self.next_double() - 1
+            s = v1 * v1 + v2 * v2
+            if 0 < s < 1:
+                break
+        mul = math.sqrt(-2 * math.log(s) / s)
+        self._next_g = v2 * mul
+        self._have = True
+        return v1 * mul
+
+
+# --------------------------------------------------------------------------------------------------
+# shapes / terrains / sensors / MLP sizing
+# --------------------------------------------------------------------------------------------------
+def build_shape(name: str) -> np.ndarray:
+    """name -> uint8 mask [h][w], row y=0 is the BOTTOM row (voxel (x,y) sits at (x*L, y*L))."""
+    kind, dims = name.split("-")
+    w, h = (int(v) for v in dims.split("x"))
+    m = np.zeros((h, w), dtype=np.uint8)
+    for y in range(h):
+        for x in range(w):
+            if kind in ("box", "worm"):
+                v = True
+            elif kind == "biped":
+                v = not (y < h // 2 and x >= w // 4 and x < w * 3 // 4)
+            elif kind == "tripod":
+                v = not (y < h // 2 and x != 0 and x != w - 1 and x != w // 2)
+            elif kind == "comb":
+                v = y >= h // 2 or x % 2 == 0
+            else:
+                raise ValueError(f"unknown shape {name}")
+            m[y, x] = 1 if v else 0
+    return m
+
+
+TERRAIN_BORDER_HEIGHT = 100.0
+TERRAIN_LENGTH = 2000.0
+TERRAIN_BORDER_WIDTH = 10.0
+
+
+def create_terrain(name: str) -> tuple[np.ndarray, np.ndarray]:
+    p = name.split("-")
+    if name == "flat":
+        xs = [0.0, TERRAIN_BORDER_WIDTH, TERRAIN_LENGTH - TERRAIN_BORDER_WIDTH, TERRAIN_LENGTH]
+        ys = [TERRAIN_BORDER_HEIGHT, 5.0, 5.0, TERRAIN_BORDER_HEIGHT]
+    elif p[0] in ("hilly", "steppy"):
+        h, w, seed = float(p[1]), float(p[2]), int(p[3])
+        rnd = JavaRandom(seed)
+        xs = [0.0, TERRAIN_BORDER_WIDTH]
+        ys = [TERRAIN_BORDER_HEIGHT, 0.0]
+        while xs[-1] < TERRAIN_LENGTH - TERRAIN_BORDER_WIDTH:
+            xs.append(xs[-1] + max(1.0, (rnd.next_gaussian() * 0.25 + 1) * w))
+            if p[0] == "hilly":
+                ys.append(ys[-1] + rnd.next_gaussian() * h)
+            else:
+                xs.append(xs[-1] + 0.5)
+                ys.append(ys[-1])
+                ys.append(ys[-1] + rnd.next_gaussian() * h)
+        xs.append(xs[-1] + TERRAIN_BORDER_WIDTH)
+        ys.append(TERRAIN_BORDER_HEIGHT)
+    elif p[0] in ("downhill", "uphill"):
+        angle = float(p[1])
+        dy = (TERRAIN_LENGTH - 2 * TERRAIN_BORDER_WIDTH) * math.sin(angle / 180 * math.pi)
+        xs = [0.0, TERRAIN_BORDER_WIDTH, TERRAIN_LENGTH - TERRAIN_BORDER_WIDTH, TERRAIN_LENGTH]
+        if p[0] == "downhill":
+            ys = [TERRAIN_BORDER_HEIGHT + dy, 5 + dy, 5.0, TERRAIN_BORDER_HEIGHT]
+        else:
+            ys = [TERRAIN_BORDER_HEIGHT, 5.0, 5 + dy, TERRAIN_BORDER_HEIGHT + dy]
+    else:
+        raise ValueError(f"unknown terrain {name}")
+    return np.asarray(xs, dtype=np.float64), np.asarray(ys, dtype=np.float64)
+
+
+SENSOR_AREA_RATIO, SENSOR_TOUCH, SENSOR_VELOCITY, SENSOR_ANGLE = 0, 1, 2, 3
+
+
+class VoSensor(C.Structure):
+    _fields_ = [("kind", C.c_int), ("axes", C.c_int), ("rotated", C.c_int), ("soft_norm", C.c_int),
+                ("dom_min", C.c_double), ("dom_max", C.c_double), ("avg_window", C.c_double),
+                ("noise_sigma", C.c_double)]
+
+
+def _sensor(kind, axes=0, rotated=0, soft_norm=0, dom=(0.0, 1.0), avg=0.0, noise=0.0):
+    return VoSensor(kind, axes, rotated, soft_norm, dom[0], dom[1], avg, noise)
+
+
+def sensor_config(name: str) -> list[VoSensor]:
+    """'uniform-a+t+vxy-0.01' -> per-voxel sensor list (PREDEFINED_SENSORS of RobotUtils [U])."""
+    kind, names, sigma = name.split("-")
+    if kind != "uniform":
+        raise ValueError(f"unsupported sensor config {name}")
+    sigma = float(sigma)
+    out = []
+    for s in names.split("+"):
+        if s == "a":
+            out.append(_sensor(SENSOR_AREA_RATIO, soft_norm=1, dom=(0.5, 1.5), noise=sigma))
+        elif s == "t":
+            out.append(_sensor(SENSOR_TOUCH, avg=0.25, noise=sigma))
+        elif s == "r":
+            out.append(_sensor(SENSOR_ANGLE, soft_norm=1, dom=(-math.pi, math.pi), noise=sigma))
+        elif s in ("vx", "vy", "vxy"):
+            axes = {"vx": 1, "vy": 2, "vxy": 3}[s]
+            out.append(_sensor(SENSOR_VELOCITY, axes=axes, rotated=1, soft_norm=1, dom=(-8.0, 8.0), avg=0.5, noise=sigma))
+        else:
+            raise ValueError(f"unsupported sensor {s}")
+    return out
+
+
+def sensor_dim(s: VoSensor) -> int:
+    return bin(s.axes & 3).count("1") if s.kind == SENSOR_VELOCITY else 1
+
+
+def java_round(x: float) -> int:
+    """Java Math.round(double): floor(x + 0.5)."""
+    return int(math.floor(x + 0.5))
+
+
+def inner_neurons(n_in: int, n_out: int, ratio: float, n_layers: int) -> list[int]:
+    """builder/function/MLP.java:28-42 (Java int division truncates toward zero)."""
+    def idiv(a, b):
+        q = abs(a) // abs(b)
+        return q if (a >= 0) == (b >= 0) else -q
+    inner = [0] * n_layers
+    center = int(max(2, java_round(n_in * ratio)))
+    if n_layers > 1:
+        for i in range(n_layers // 2):
+            inner[i] = n_in + idiv(center - n_in, n_layers // 2 + 1) * (i + 1)
+        for i in range(n_layers // 2, n_layers):
+            inner[i] = center + idiv(n_out - center, n_layers // 2 + 1) * (i - n_layers // 2)
+    elif n_layers > 0:
+        inner[0] = center
+    return inner
+
+
+def count_weights(neurons: list[int]) -> int:
+    return sum(neurons[i + 1] * (neurons[i] + 1) for i in range(len(neurons) - 1))
+
+
+def episode_steps(final_t: float, transient_t: float, dt: float = 1.0 / 60.0) -> tuple[int, int, int]:
+    """(n_steps, k_first, k_last): emulates t accumulation in double; kept keys are transient<=t<final."""
+    t, k, k_first, k_last = 0.0, 0, 0, 0
+    while t < final_t:
+        t += dt
+        k += 1
+        if transient_t <= t < final_t:
+            if not k_first:
+                k_first = k
+            k_last = k
+    return k, k_first, k_last
+
+
+# --------------------------------------------------------------------------------------------------
+# ctypes binding
+# --------------------------------------------------------------------------------------------------
+class VoParams(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("dt",)] + [("vel_iters", C.c_int), ("pos_iters", C.c_int)] + \
+        [(n, C.c_double) for n in ("gravity_y", "baumgarte", "linear_tol", "angular_tol", "max_linear_corr",
+                                   "max_translation", "max_rotation", "restitution_velocity", "side_length",
+                                   "mass_side_ratio", "spring_f", "spring_d", "lin_damping", "ang_damping",
+                                   "voxel_mass", "area_ratio_max_delta", "voxel_friction", "voxel_restitution")] + \
+        [("limit_contraction", C.c_int), ("scaffolding_mask", C.c_int)] + \
+        [(n, C.c_double) for n in ("ground_friction", "ground_restitution", "ground_thickness", "place_x_gap",
+                                   "place_y_gap", "final_t", "transient_t")]
+
+
+class VoCtrl(C.Structure):
+    _fields_ = [("kind", C.c_int), ("freq", C.c_double), ("amp", C.c_double), ("n_layers", C.c_int),
+                ("layers", C.c_int * 8), ("signals", C.c_int), ("input_activation", C.c_int)]
+
+
+class VoResult(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("velocity", "distance", "time", "first_x", "last_x")] + \
+        [("n_steps", C.c_int), ("k_first", C.c_int), ("k_last", C.c_int)] + \
+        [(n, C.c_int64) for n in ("n_spring_vel", "n_rope_vel", "n_weld_vel", "n_contact_pt_vel", "n_block_vel",
+                                  "n_rope_pos", "n_weld_pos", "n_contact_pt_pos", "n_detect_pairs", "n_pos_iters",
+                                  "n_manifolds")]
+
+
+CTRL_PHASE_SIN, CTRL_MLP_CENTRALIZED, CTRL_MLP_DISTRIBUTED_HOMO = 0, 1, 2
+
+_lib = None
+
+
+def build_lib(force: bool = False) -> str:
+    src = os.path.join(_HERE, "vsr_oracle.c")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-B" if force else "-s"], stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build_lib()
+        _lib = C.CDLL(_LIB_PATH)
+        _lib.vo_default_params.argtypes = [C.POINTER(VoParams)]
+        _lib.vo_genome_len.restype = C.c_int
+        _lib.vo_run.restype = C.c_int
+        _lib.vo_eval_batch.restype = C.c_int
+    return _lib
+
+
+def default_params(final_t: float = 30.0, transient_t: float = 1.0) -> VoParams:
+    p = VoParams()
+    lib().vo_default_params(C.byref(p))
+    p.final_t = final_t
+    p.transient_t = transient_t
+    return p
+
+
+@dataclass
+class Model:
+    """Everything the oracle needs for one (shape, sensors, controller, terrain) problem."""
+    shape: str
+    terrain: str
+    sensors_name: str
+    ctrl_kind: int
+    params: VoParams
+    freq: float = 1.0
+    amp: float = 1.0
+    ratio: float = 0.65
+    n_inner: int = 1
+    signals: int = 1
+    input_activation: int = 1
+    mask: np.ndarray = field(init=False)
+    tx: np.ndarray = field(init=False)
+    ty: np.ndarray = field(init=False)
+    sensors: list = field(init=False)
+    ctrl: VoCtrl = field(init=False)
+
+    def __post_init__(self):
+        self.mask = np.ascontiguousarray(build_shape(self.shape))
+        self.tx, self.ty = create_terrain(self.terrain)
+        self.sensors = sensor_config(self.sensors_name) if self.sensors_name else []
+        nv = int(self.mask.sum())
+        dim = sum(sensor_dim(s) for s in self.sensors)
+        c = VoCtrl()
+        c.kind = self.ctrl_kind
+        c.freq, c.amp = self.freq, self.amp
+        c.signals = self.signals
+        c.input_activation = self.input_activation
+        if self.ctrl_kind == CTRL_MLP_CENTRALIZED:
+            n_in, n_out = nv * dim, nv
+        elif self.ctrl_kind == CTRL_MLP_DISTRIBUTED_HOMO:
+            n_in, n_out = dim + 4 * self.signals, 1 + 4 * self.signals
+        else:
+            n_in = n_out = 0
+        if self.ctrl_kind != CTRL_PHASE_SIN:
+            neurons = [n_in] + inner_neurons(n_in, n_out, self.ratio, self.n_inner) + [n_out]
+            c.n_layers = len(neurons)
+            for i, n in enumerate(neurons):
+                c.layers[i] = n
+        self.ctrl = c
+
+    @property
+    def n_voxels(self) -> int:
+        return int(self.mask.sum())
+
+    @property
+    def h(self) -> int:
+        return self.mask.shape[0]
+
+    @property
+    def w(self) -> int:
+        return self.mask.shape[1]
+
+    def _sensor_array(self):
+        arr = (VoSensor * max(1, len(self.sensors)))()
+        for i, s in enumerate(self.sensors):
+            arr[i] = s
+        return arr
+
+    def genome_len(self) -> int:
+        return lib().vo_genome_len(self.w, self.h, self.mask.ctypes.data_as(C.c_void_p), self._sensor_array(),
+                                   len(self.sensors), C.byref(self.ctrl))
+
+    def run(self, genome: np.ndarray, trace_steps: int = 0):
+        g = np.ascontiguousarray(genome, dtype=np.float64)
+        nv = self.n_voxels
+        tv = np.zeros((trace_steps, nv, 4, 2)) if trace_steps else None
+        tb = np.zeros((trace_steps, nv * 4, 6)) if trace_steps else None
+        tc = np.zeros((trace_steps, nv)) if trace_steps else None
+        res = VoResult()
+        ptr = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
+        rc = lib().vo_run(C.byref(self.params), self.w, self.h, ptr(self.mask), self._sensor_array(), len(self.sensors),
+                          C.byref(self.ctrl), ptr(self.tx), ptr(self.ty), len(self.tx), ptr(g), len(g),
+                          trace_steps, ptr(tv), ptr(tb), ptr(tc), C.byref(res))
+        if rc:
+            raise RuntimeError(f"vo_run failed: {rc}")
+        return res, tv, tb, tc
+
+    def eval_batch(self, genomes: np.ndarray, n_threads: int = 1, want_results: bool = False):
+        g = np.ascontiguousarray(genomes, dtype=np.float64)
+        n = g.shape[0]
+        fit = np.zeros(n)
+        results = (VoResult * n)() if want_results else None
+        ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+        rc = lib().vo_eval_batch(C.byref(self.params), self.w, self.h, ptr(self.mask), self._sensor_array(),
+                                 len(self.sensors), C.byref(self.ctrl), ptr(self.tx), ptr(self.ty), len(self.tx),
+                                 ptr(g), g.shape[1], n, n_threads, ptr(fit), results)
+        if rc:
+            raise RuntimeError(f"vo_eval_batch failed: {rc}")
+        return (fit, results) if want_results else fit
+
+
+def config_model(i: int, final_t: float | None = None) -> Model:
+    """The BASELINE.json configs."""
+    if i in (1, 2, 5):
+        return Model("biped-4x3", "flat", "uniform-a-0", CTRL_MLP_CENTRALIZED, default_params(final_t or 30.0))
+    if i == 3:
+        return Model("worm-8x2", "hilly-1-10-0", "", CTRL_PHASE_SIN, default_params(final_t or 60.0), freq=1.0)
+    if i == 4:
+        return Model("comb-7x2", "steppy-0.25-1-0", "uniform-t+vxy+a-0", CTRL_MLP_DISTRIBUTED_HOMO,
+                     default_params(final_t or 30.0), signals=1)
+    raise ValueError(i)

@@ -1,0 +1,142 @@
+/*
+ * vsr_oracle.h -- CPU ORACLE (TEST INFRASTRUCTURE, NOT PRODUCT CODE).
+ *
+ * Double-precision, single-robot, strictly sequential restatement of the path
+ *   Locomotion.apply(robot) -> Outcome            (2dhmsr 1.12.1, un-vendored)
+ *   World.step(1)                                 (dyn4j 3.4.x, un-vendored)
+ * as called from /root/reference/src/main/java/it/units/erallab/locomotion/Starter.java:83-94,427-435.
+ *
+ * PARITY UNPINNED: neither dependency's source, nor a JVM, nor any golden vector exists in
+ * /root/reference.  Every constant and formula here is restated from the
+ * published algorithm of those libraries and is tagged [U] in docs/PHYSICS_SPEC.md.  The oracle is
+ * pinned only by closed-form known-answer tests (tests/test_oracle_known_answers.py).
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load
+ * this library.  The product (libvsr_eval.so) never links or calls it.
+ */
+#ifndef VSR_ORACLE_H
+#define VSR_ORACLE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Physics + task parameters.  Defaults (vo_default_params) restate dyn4j Settings() and
+ * 2dhmsr Voxel/Ground/Locomotion constants; see docs/PHYSICS_SPEC.md for the provenance of each. */
+typedef struct {
+  /* dyn4j Settings */
+  double dt;                   /* step frequency, 1/60 s                                   */
+  int    vel_iters;            /* velocity constraint solver iterations, 10                */
+  int    pos_iters;            /* position constraint solver iterations, 10                */
+  double gravity_y;            /* World.EARTH_GRAVITY = (0,-9.8)                            */
+  double baumgarte;            /* 0.2                                                      */
+  double linear_tol;           /* 0.005                                                    */
+  double angular_tol;          /* 2 degrees                                                */
+  double max_linear_corr;      /* 0.2                                                      */
+  double max_translation;      /* 2.0 per step                                             */
+  double max_rotation;         /* pi/2 per step                                            */
+  double restitution_velocity; /* 1.0                                                      */
+  /* 2dhmsr Voxel */
+  double side_length;          /* 3                                                        */
+  double mass_side_ratio;      /* 0.3                                                      */
+  double spring_f;             /* 8 Hz                                                     */
+  double spring_d;             /* 0.3                                                      */
+  double lin_damping;          /* 1                                                        */
+  double ang_damping;          /* 1                                                        */
+  double voxel_mass;           /* 1 (0.25 per corner mass)                                 */
+  double area_ratio_max_delta; /* 0.225                                                    */
+  double voxel_friction;       /* 100                                                      */
+  double voxel_restitution;    /* 0.1                                                      */
+  int    limit_contraction;    /* 1: four lower-limit rope joints per voxel                */
+  int    scaffolding_mask;     /* bit0 SIDE_INTERNAL bit1 SIDE_EXTERNAL bit2 SIDE_CROSS bit3 CENTRAL_CROSS */
+  /* 2dhmsr Ground */
+  double ground_friction;      /* dyn4j fixture default 0.2                                */
+  double ground_restitution;   /* dyn4j fixture default 0.0                                */
+  double ground_thickness;     /* 50 below min(ys)                                         */
+  /* 2dhmsr Locomotion */
+  double place_x_gap;          /* 1                                                        */
+  double place_y_gap;          /* 1                                                        */
+  double final_t;              /* episode time                                             */
+  double transient_t;          /* Starter.java:143 episodeTransientTime                    */
+} vo_params;
+
+enum { VO_SENSOR_AREA_RATIO = 0, VO_SENSOR_TOUCH = 1, VO_SENSOR_VELOCITY = 2, VO_SENSOR_ANGLE = 3 };
+
+/* One sensor of the uniform per-voxel sensor list: Noisy(SoftNormalization(Average(base))) with each
+ * wrapper optional. */
+typedef struct {
+  int    kind;
+  int    axes;        /* VELOCITY: bit0 = X, bit1 = Y (readings emitted in that order) */
+  int    rotated;     /* VELOCITY: express in the voxel frame */
+  int    soft_norm;   /* wrap in SoftNormalization */
+  double dom_min, dom_max;
+  double avg_window;  /* >0: wrap in Average(window seconds) */
+  double noise_sigma; /* >0: Noisy -- NOT implemented by the oracle (returns error) */
+} vo_sensor;
+
+enum { VO_CTRL_PHASE_SIN = 0, VO_CTRL_MLP_CENTRALIZED = 1, VO_CTRL_MLP_DISTRIBUTED_HOMO = 2 };
+
+typedef struct {
+  int    kind;
+  double freq, amp;        /* PHASE_SIN */
+  int    n_layers;         /* MLP: number of entries of layers[] (input, hidden..., output) */
+  int    layers[8];
+  int    signals;          /* DISTRIBUTED: signals per side */
+  int    input_activation; /* MLP: apply tanh to the input layer (2dhmsr quirk, [U]) */
+} vo_ctrl;
+
+/* Per-episode result (what Outcome getters used by the host need). */
+typedef struct {
+  double velocity;     /* Outcome.getVelocity() over [transient_t, final_t]      */
+  double distance;     /* Outcome.getDistance()                                  */
+  double time;         /* Outcome.getTime()                                      */
+  double first_x, last_x;
+  int    n_steps;      /* steps simulated                                        */
+  int    k_first, k_last; /* 1-based step indices of first/last kept observation  */
+  /* operation tallies (totals over the whole episode) for the roofline's algorithmic work */
+  int64_t n_spring_vel, n_rope_vel, n_weld_vel, n_contact_pt_vel, n_block_vel;
+  int64_t n_rope_pos, n_weld_pos, n_contact_pt_pos;
+  int64_t n_detect_pairs, n_pos_iters, n_manifolds;
+} vo_result;
+
+void vo_default_params(vo_params* p);
+
+/* counts: voxels, springs, ropes, welds for a mask (w*h, row-major y*w+x, y=0 bottom) */
+int vo_counts(const vo_params* p, int w, int h, const uint8_t* mask, int* n_vox, int* n_springs, int* n_ropes, int* n_welds);
+
+/* Genome length for the given body/sensors/controller (or <0 on error). */
+int vo_genome_len(int w, int h, const uint8_t* mask, const vo_sensor* sensors, int n_sensors, const vo_ctrl* ctrl);
+
+/*
+ * Run one episode.
+ *  trace_steps : number of leading steps for which to record traces (0 = none)
+ *  trace_vertices : [trace_steps][n_vox][4][2] outer voxel-poly vertices after each step (may be NULL)
+ *  trace_bodies   : [trace_steps][n_vox*4][6] (x,y,angle,vx,vy,w) of every corner mass (may be NULL)
+ *  trace_ctrl     : [trace_steps][n_vox] applied control value f (may be NULL)
+ * returns 0 on success, negative on error.
+ */
+int vo_run(const vo_params* p, int w, int h, const uint8_t* mask,
+           const vo_sensor* sensors, int n_sensors, const vo_ctrl* ctrl,
+           const double* terrain_x, const double* terrain_y, int n_terrain,
+           const double* genome, int genome_len,
+           int trace_steps, double* trace_vertices, double* trace_bodies, double* trace_ctrl,
+           vo_result* out);
+
+/* Evaluate n genomes ([n][genome_len] row-major) on n_threads host threads; velocity -> fitness_out[n]. */
+int vo_eval_batch(const vo_params* p, int w, int h, const uint8_t* mask,
+                  const vo_sensor* sensors, int n_sensors, const vo_ctrl* ctrl,
+                  const double* terrain_x, const double* terrain_y, int n_terrain,
+                  const double* genomes, int genome_len, int n, int n_threads,
+                  double* fitness_out, vo_result* results_out);
+
+/* Low-level test hooks for known-answer tests (single bodies / single joints, no robot). */
+int vo_test_free_fall(const vo_params* p, int n_steps, double* y_out, double* vy_out);
+int vo_test_spring_pair(const vo_params* p, double rest, double initial_len, int n_steps, double* len_out);
+int vo_test_box_drop(const vo_params* p, double angle0, double height, double vx0, int n_steps, double* state_out /*[n][6]*/);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
