@@ -1,0 +1,169 @@
+/*
+ * vsr_eval.h -- C ABI of libvsr_eval.so: the B200 batched evaluator that replaces, for a whole
+ * population at once, the per-individual fitness evaluation of VSREvolution
+ *
+ *     qualityFunction = transformation . Locomotion.apply . subOutcome(transientT, T)
+ *     (reference: src/main/java/it/units/erallab/locomotion/Starter.java:83-94 buildLocomotionTask,
+ *      :427-435 Problem.qualityFunction, :174 fitness = Outcome::getVelocity)
+ *
+ * Plain C types only: pointers, sizes, PODs.  No C++ exception crosses this boundary; every call
+ * returns 0 (VSR_OK) or a negative vsr_status and vsr_last_error() gives the message.  The caller
+ * owns every buffer it passes; the library keeps no pointer after a call returns.  A vsr_ctx is not
+ * re-entrant (one vsr_eval in flight per context); create one context per host thread or serialise.
+ *
+ * There is NO CPU fallback: if no CUDA device is usable, vsr_ctx_create fails with VSR_ECUDA.
+ *
+ * INTEGRATION.md shows the JNI/Panama stub that binds these entry points from the Java host.
+ */
+#ifndef VSR_EVAL_H
+#define VSR_EVAL_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  VSR_OK = 0,
+  VSR_EINVAL = -1,   /* bad argument (-> IllegalArgumentException in the Java shim)              */
+  VSR_ECUDA = -2,    /* CUDA runtime failure or no device                                        */
+  VSR_ENOMEM = -3,   /* host or device allocation failed                                         */
+  VSR_EDIM = -4,     /* dimension mismatch (genome length, MLP I/O size; mirrors the mappers'    */
+                     /* IllegalArgumentException, e.g. builder/function/MLP.java:56-62)          */
+  VSR_EUNSUPPORTED = -5, /* valid in the reference but outside this build (e.g. >32 voxels)      */
+  VSR_ESTATE = -6    /* call order (body/controller not set)                                     */
+} vsr_status;
+
+/* ---- environment: replaces `new Locomotion(finalT, groundProfile, new Settings())`,
+ *      Starter.java:67,87 -------------------------------------------------------------------- */
+typedef struct {
+  /* dyn4j Settings() (Starter.java:67 PHYSICS_SETTINGS) */
+  double dt;
+  int32_t vel_iters, pos_iters;
+  double gravity_y, baumgarte, linear_tol, angular_tol, max_linear_corr, max_translation, max_rotation,
+      restitution_velocity;
+  /* 2dhmsr Voxel defaults */
+  double side_length, mass_side_ratio, spring_f, spring_d, lin_damping, ang_damping, voxel_mass,
+      area_ratio_max_delta, voxel_friction, voxel_restitution;
+  int32_t limit_contraction, scaffolding_mask;
+  /* 2dhmsr Ground */
+  double ground_friction, ground_restitution, ground_thickness;
+  /* 2dhmsr Locomotion */
+  double place_x_gap, place_y_gap;
+  double final_t;      /* Starter.java:142 episodeTime */
+  double transient_t;  /* Starter.java:143 episodeTransientTime (subOutcome lower bound) */
+  /* terrain polyline == Locomotion.createTerrain(name) (Starter.java:87); copied at create */
+  const double* terrain_x;
+  const double* terrain_y;
+  int32_t n_terrain;
+  /* execution */
+  int32_t precision;   /* 32 (default, FP32 state) or 64 (FP64 kernel build, for parity studies) */
+  int32_t n_devices;   /* 0 = current device only; else devices[0..n_devices) shard the batch by index */
+  int32_t devices[8];
+} vsr_env_desc;
+
+/* ---- sensors: one entry of the uniform per-voxel list built by
+ *      RobotUtils.buildSensorizingFunction("uniform-<s1+s2..>-<sigma>") (Starter.java:404-405) - */
+enum { VSR_SENSOR_AREA_RATIO = 0, VSR_SENSOR_TOUCH = 1, VSR_SENSOR_VELOCITY = 2, VSR_SENSOR_ANGLE = 3 };
+typedef struct {
+  int32_t kind;
+  int32_t axes;       /* VELOCITY: bit0 X, bit1 Y */
+  int32_t rotated;    /* VELOCITY: voxel frame */
+  int32_t soft_norm;  /* SoftNormalization wrapper */
+  double dom_min, dom_max;
+  double avg_window;  /* Average wrapper window [s], 0 = none */
+  double noise_sigma; /* Noisy wrapper; must be 0 in this build (VSR_EUNSUPPORTED otherwise) */
+} vsr_sensor_desc;
+
+/* ---- controllers: CentralizedSensing (builder/robot/BrainCentralized.java:42-45), PhaseSin
+ *      (builder/robot/BrainPhaseValues.java:47-50), homogeneous DistributedSensing
+ *      (builder/robot/BrainHomoDistributed.java:76-87) ----------------------------------------- */
+typedef enum { VSR_CTRL_PHASE_SIN = 0, VSR_CTRL_MLP_CENTRALIZED = 1, VSR_CTRL_MLP_DISTRIBUTED_HOMO = 2 } vsr_ctrl_kind;
+
+/* ---- per-robot result: the Outcome getters the host reads (locomotion/NamedFunctions.java:68-70) */
+typedef struct {
+  double velocity;   /* Outcome.getVelocity()  == the fitness (Starter.java:174)                   */
+  double distance;   /* Outcome.getDistance()                                                       */
+  double time;       /* Outcome.getTime()                                                           */
+  double first_x, last_x;
+  int32_t n_steps, k_first, k_last;
+  int32_t contact_overflow; /* >0: the per-warp contact pool overflowed (results unreliable)        */
+} vsr_result;
+
+typedef struct vsr_ctx vsr_ctx;
+
+/* defaults = `new Settings()` + 2dhmsr constants; terrain NULL, final_t 30, transient_t 1 */
+int vsr_env_default(vsr_env_desc* env);
+
+int vsr_ctx_create(const vsr_env_desc* env, vsr_ctx** out);
+void vsr_ctx_destroy(vsr_ctx* ctx);
+const char* vsr_last_error(const vsr_ctx* ctx); /* ctx may be NULL: error of the last failed create */
+
+/* body grid: mask[y*w+x] != 0 where a voxel exists, y = 0 is the bottom row; same sensors on every voxel.
+ * Replaces RobotUtils.buildSensorizingFunction(cfg).apply(RobotUtils.buildShape(shape)) (Starter.java:402-406). */
+int vsr_body_set(vsr_ctx* ctx, int32_t w, int32_t h, const uint8_t* mask, const vsr_sensor_desc* sensors, int32_t n_sensors);
+
+/* controller: layers[] = MLP neurons per layer incl. input and output (ignored for PHASE_SIN) */
+int vsr_controller_set(vsr_ctx* ctx, vsr_ctrl_kind kind, const int32_t* layers, int32_t n_layers, int32_t signals,
+                       double freq, double amp, int32_t mlp_input_activation);
+
+int vsr_genome_len(const vsr_ctx* ctx); /* >=0, or negative status */
+int vsr_n_voxels(const vsr_ctx* ctx);
+
+/*
+ * Evaluate n robots.  genomes: [n][G] row-major doubles in HOST memory (G = vsr_genome_len).
+ * fitness_out: [n] doubles (velocity).  results_out: [n] or NULL.
+ * Includes the H2D upload of the genomes and the D2H read of the results.
+ */
+int vsr_eval(vsr_ctx* ctx, const double* genomes, int32_t n, double* fitness_out, vsr_result* results_out);
+
+/*
+ * Device-resident variant on the context's first device: d_genomes / d_fitness / d_results are DEVICE
+ * pointers (d_results may be NULL).  Enqueues on `stream` (a cudaStream_t, NULL = default stream) and
+ * does not synchronise.
+ */
+int vsr_eval_device(vsr_ctx* ctx, const double* d_genomes, int32_t n, double* d_fitness, vsr_result* d_results, void* stream);
+
+/*
+ * Parity trace of ONE robot for the first n_steps steps (all outputs optional, HOST memory):
+ *  vertices_out [n_steps][n_voxels][4][2], bodies_out [n_steps][n_voxels*4][6] (x,y,angle,vx,vy,w),
+ *  ctrl_out [n_steps][n_voxels].
+ */
+int vsr_trace(vsr_ctx* ctx, const double* genome, int32_t n_steps, double* vertices_out, double* bodies_out,
+              double* ctrl_out, vsr_result* result_out);
+
+/* timing / accounting of the most recent vsr_eval / vsr_eval_device on device 0 of the context */
+double vsr_last_kernel_ms(vsr_ctx* ctx);    /* CUDA-event duration of the episode kernel; syncs the stream */
+int64_t vsr_kernel_launches(const vsr_ctx* ctx); /* total episode-kernel launches so far */
+int vsr_kernel_info(const vsr_ctx* ctx, int32_t* regs_per_thread, int32_t* smem_bytes, int32_t* threads_per_cta,
+                    int32_t* robots_per_warp, int32_t* ctas_per_sm);
+
+/* ---- integer / naming layer (bit-exact parity surface) -------------------------- */
+/* RobotUtils.buildShape(name): writes w*h bytes, returns 0 and sets *w,*h; cap = capacity of mask */
+int vsr_shape_mask(const char* name, int32_t* w, int32_t* h, uint8_t* mask, int32_t cap);
+/* Locomotion.createTerrain(name): returns number of points (or negative); writes up to cap */
+int vsr_terrain(const char* name, double* xs, double* ys, int32_t cap);
+/* RobotUtils.buildSensorizingFunction("uniform-a+t-0"): returns number of sensors per voxel */
+int vsr_sensor_config(const char* name, vsr_sensor_desc* out, int32_t cap);
+/* builder/function/MLP.java:28-42 innerNeurons */
+int vsr_mlp_inner_neurons(int32_t n_in, int32_t n_out, double ratio, int32_t n_inner, int32_t* out);
+/* MultiLayerPerceptron.countWeights(neurons) */
+int vsr_mlp_count_weights(const int32_t* neurons, int32_t n_layers);
+/* flat genome index of weight (layer l, to-neuron j, from k; k = 0 is the bias) */
+int vsr_mlp_weight_index(const int32_t* neurons, int32_t n_layers, int32_t l, int32_t j, int32_t k);
+/* Locomotion.apply's `while (t < finalT) t += dt` and subOutcome's kept key range, in IEEE double */
+int vsr_episode_steps(double final_t, double transient_t, double dt, int32_t* n_steps, int32_t* k_first, int32_t* k_last);
+/* CentralizedSensing input order: for input i -> cell index (y*w+x), sensor index, reading index */
+int vsr_input_map(const vsr_ctx* ctx, int32_t* cell, int32_t* sensor, int32_t* reading, int32_t cap);
+/* voxel order used for controller outputs / PhaseSin genome: voxel c -> cell index */
+int vsr_voxel_cells(const vsr_ctx* ctx, int32_t* cell, int32_t cap);
+/* joint counts of the body */
+int vsr_counts(const vsr_ctx* ctx, int32_t* n_voxels, int32_t* n_springs, int32_t* n_ropes, int32_t* n_welds);
+/* java.util.Random replay (terrain builders): fills out[n] with nextGaussian() of Random(seed) */
+int vsr_java_random_gaussians(int64_t seed, double* out, int32_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

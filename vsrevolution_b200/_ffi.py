@@ -1,0 +1,276 @@
+"""ctypes binding of libvsr_eval.so (include/vsr_eval.h).  No fallback: importing the evaluator without the
+built CUDA library raises, and creating a context without a CUDA device raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvsr_eval.so")
+
+VSR_OK, VSR_EINVAL, VSR_ECUDA, VSR_ENOMEM, VSR_EDIM, VSR_EUNSUPPORTED, VSR_ESTATE = 0, -1, -2, -3, -4, -5, -6
+CTRL_PHASE_SIN, CTRL_MLP_CENTRALIZED, CTRL_MLP_DISTRIBUTED_HOMO = 0, 1, 2
+SENSOR_AREA_RATIO, SENSOR_TOUCH, SENSOR_VELOCITY, SENSOR_ANGLE = 0, 1, 2, 3
+
+
+class EnvDesc(C.Structure):
+    _fields_ = (
+        [("dt", C.c_double), ("vel_iters", C.c_int32), ("pos_iters", C.c_int32)]
+        + [(n, C.c_double) for n in ("gravity_y", "baumgarte", "linear_tol", "angular_tol", "max_linear_corr",
+                                     "max_translation", "max_rotation", "restitution_velocity", "side_length",
+                                     "mass_side_ratio", "spring_f", "spring_d", "lin_damping", "ang_damping",
+                                     "voxel_mass", "area_ratio_max_delta", "voxel_friction", "voxel_restitution")]
+        + [("limit_contraction", C.c_int32), ("scaffolding_mask", C.c_int32)]
+        + [(n, C.c_double) for n in ("ground_friction", "ground_restitution", "ground_thickness", "place_x_gap",
+                                     "place_y_gap", "final_t", "transient_t")]
+        + [("terrain_x", C.POINTER(C.c_double)), ("terrain_y", C.POINTER(C.c_double)), ("n_terrain", C.c_int32),
+           ("precision", C.c_int32), ("n_devices", C.c_int32), ("devices", C.c_int32 * 8)]
+    )
+
+
+class SensorDesc(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("axes", C.c_int32), ("rotated", C.c_int32), ("soft_norm", C.c_int32),
+                ("dom_min", C.c_double), ("dom_max", C.c_double), ("avg_window", C.c_double),
+                ("noise_sigma", C.c_double)]
+
+
+class Result(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("velocity", "distance", "time", "first_x", "last_x")] + \
+        [(n, C.c_int32) for n in ("n_steps", "k_first", "k_last", "contact_overflow")]
+
+
+RESULT_DTYPE = np.dtype([("velocity", "f8"), ("distance", "f8"), ("time", "f8"), ("first_x", "f8"), ("last_x", "f8"),
+                         ("n_steps", "i4"), ("k_first", "i4"), ("k_last", "i4"), ("contact_overflow", "i4")])
+assert RESULT_DTYPE.itemsize == C.sizeof(Result)
+
+
+class VsrError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"libvsr_eval error {code}: {message}")
+        self.code = code
+
+
+class VsrIllegalArgument(VsrError, ValueError):
+    """Maps VSR_EINVAL / VSR_EDIM, like the IllegalArgumentException the reference mappers throw."""
+
+
+_lib = None
+
+_SIGS = {
+    "vsr_env_default": (C.c_int, [C.POINTER(EnvDesc)]),
+    "vsr_ctx_create": (C.c_int, [C.POINTER(EnvDesc), C.POINTER(C.c_void_p)]),
+    "vsr_ctx_destroy": (None, [C.c_void_p]),
+    "vsr_last_error": (C.c_char_p, [C.c_void_p]),
+    "vsr_body_set": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(SensorDesc), C.c_int32]),
+    "vsr_controller_set": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_double,
+                                     C.c_double, C.c_int32]),
+    "vsr_genome_len": (C.c_int, [C.c_void_p]),
+    "vsr_n_voxels": (C.c_int, [C.c_void_p]),
+    "vsr_eval": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "vsr_eval_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vsr_trace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vsr_last_kernel_ms": (C.c_double, [C.c_void_p]),
+    "vsr_kernel_launches": (C.c_int64, [C.c_void_p]),
+    "vsr_kernel_info": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_int32)] * 5),
+    "vsr_shape_mask": (C.c_int, [C.c_char_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_void_p, C.c_int32]),
+    "vsr_terrain": (C.c_int, [C.c_char_p, C.c_void_p, C.c_void_p, C.c_int32]),
+    "vsr_sensor_config": (C.c_int, [C.c_char_p, C.POINTER(SensorDesc), C.c_int32]),
+    "vsr_mlp_inner_neurons": (C.c_int, [C.c_int32, C.c_int32, C.c_double, C.c_int32, C.POINTER(C.c_int32)]),
+    "vsr_mlp_count_weights": (C.c_int, [C.POINTER(C.c_int32), C.c_int32]),
+    "vsr_mlp_weight_index": (C.c_int, [C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "vsr_episode_steps": (C.c_int, [C.c_double, C.c_double, C.c_double] + [C.POINTER(C.c_int32)] * 3),
+    "vsr_input_map": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
+    "vsr_voxel_cells": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
+    "vsr_counts": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_int32)] * 4),
+    "vsr_java_random_gaussians": (C.c_int, [C.c_int64, C.c_void_p, C.c_int32]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGS)
+
+
+def lib():
+    """Load libvsr_eval.so.  Raises (never falls back) when the CUDA extension has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc: int, ctx=None):
+    if rc >= 0:
+        return rc
+    msg = lib().vsr_last_error(ctx)
+    msg = msg.decode() if msg else ""
+    if rc in (VSR_EINVAL, VSR_EDIM):
+        raise VsrIllegalArgument(rc, msg)
+    raise VsrError(rc, msg)
+
+
+def env_default() -> EnvDesc:
+    e = EnvDesc()
+    check(lib().vsr_env_default(C.byref(e)))
+    return e
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """Thin RAII wrapper of vsr_ctx."""
+
+    def __init__(self, env: EnvDesc, terrain_x: np.ndarray, terrain_y: np.ndarray):
+        self._h = C.c_void_p()
+        tx = np.ascontiguousarray(terrain_x, dtype=np.float64)
+        ty = np.ascontiguousarray(terrain_y, dtype=np.float64)
+        env.terrain_x = tx.ctypes.data_as(C.POINTER(C.c_double))
+        env.terrain_y = ty.ctypes.data_as(C.POINTER(C.c_double))
+        env.n_terrain = len(tx)
+        check(lib().vsr_ctx_create(C.byref(env), C.byref(self._h)))
+        self.env = env
+
+    def close(self):
+        if self._h:
+            lib().vsr_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def body_set(self, mask: np.ndarray, sensors: list[SensorDesc]):
+        m = np.ascontiguousarray(mask, dtype=np.uint8)
+        arr = (SensorDesc * max(1, len(sensors)))(*sensors)
+        check(lib().vsr_body_set(self._h, m.shape[1], m.shape[0], _ptr(m), arr, len(sensors)), self._h)
+
+    def controller_set(self, kind: int, layers=(), signals=0, freq=1.0, amp=1.0, input_activation=1):
+        arr = (C.c_int32 * max(1, len(layers)))(*layers)
+        check(lib().vsr_controller_set(self._h, kind, arr, len(layers), signals, freq, amp, input_activation), self._h)
+
+    @property
+    def genome_len(self) -> int:
+        return check(lib().vsr_genome_len(self._h), self._h)
+
+    @property
+    def n_voxels(self) -> int:
+        return check(lib().vsr_n_voxels(self._h), self._h)
+
+    def eval(self, genomes: np.ndarray, want_results: bool = False):
+        g = np.ascontiguousarray(genomes, dtype=np.float64)
+        if g.ndim != 2 or g.shape[1] != self.genome_len:
+            raise VsrIllegalArgument(VSR_EDIM, f"Wrong number of values: {self.genome_len} expected, {g.shape[-1]} found")
+        fit = np.empty(g.shape[0], dtype=np.float64)
+        res = np.empty(g.shape[0], dtype=RESULT_DTYPE) if want_results else None
+        check(lib().vsr_eval(self._h, _ptr(g), g.shape[0], _ptr(fit), _ptr(res)), self._h)
+        return (fit, res) if want_results else fit
+
+    def eval_into(self, genomes: np.ndarray, fitness_out: np.ndarray):
+        """Zero-allocation variant for timing loops: genomes [n][G] float64 C-contiguous, fitness_out [n]."""
+        check(lib().vsr_eval(self._h, _ptr(genomes), genomes.shape[0], _ptr(fitness_out), None), self._h)
+
+    def eval_device(self, d_genomes: int, n: int, d_fitness: int, d_results: int = 0, stream: int = 0):
+        check(lib().vsr_eval_device(self._h, C.c_void_p(d_genomes), n, C.c_void_p(d_fitness),
+                                    C.c_void_p(d_results) if d_results else None,
+                                    C.c_void_p(stream) if stream else None), self._h)
+
+    def trace(self, genome: np.ndarray, n_steps: int):
+        g = np.ascontiguousarray(genome, dtype=np.float64)
+        nv = self.n_voxels
+        tv = np.zeros((n_steps, nv, 4, 2))
+        tb = np.zeros((n_steps, nv * 4, 6))
+        tc = np.zeros((n_steps, nv))
+        res = np.zeros(1, dtype=RESULT_DTYPE)
+        check(lib().vsr_trace(self._h, _ptr(g), n_steps, _ptr(tv), _ptr(tb), _ptr(tc), _ptr(res)), self._h)
+        return res[0], tv, tb, tc
+
+    def last_kernel_ms(self) -> float:
+        return lib().vsr_last_kernel_ms(self._h)
+
+    def kernel_launches(self) -> int:
+        return lib().vsr_kernel_launches(self._h)
+
+    def kernel_info(self) -> dict:
+        v = [C.c_int32() for _ in range(5)]
+        check(lib().vsr_kernel_info(self._h, *[C.byref(x) for x in v]), self._h)
+        return dict(zip(("regs_per_thread", "smem_bytes", "threads_per_cta", "robots_per_warp", "ctas_per_sm"),
+                        [x.value for x in v]))
+
+    def counts(self) -> tuple[int, int, int, int]:
+        v = [C.c_int32() for _ in range(4)]
+        check(lib().vsr_counts(self._h, *[C.byref(x) for x in v]), self._h)
+        return tuple(x.value for x in v)
+
+    def input_map(self):
+        n = check(lib().vsr_input_map(self._h, None, None, None, 0), self._h)
+        a, b, c = (np.zeros(n, dtype=np.int32) for _ in range(3))
+        check(lib().vsr_input_map(self._h, _ptr(a), _ptr(b), _ptr(c), n), self._h)
+        return a, b, c
+
+    def voxel_cells(self):
+        n = check(lib().vsr_voxel_cells(self._h, None, 0), self._h)
+        a = np.zeros(n, dtype=np.int32)
+        check(lib().vsr_voxel_cells(self._h, _ptr(a), n), self._h)
+        return a
+
+
+# ---- naming / integer layer ------------------------------------------------------------------------
+def shape_mask(name: str) -> np.ndarray:
+    w, h = C.c_int32(), C.c_int32()
+    check(lib().vsr_shape_mask(name.encode(), C.byref(w), C.byref(h), None, 0))
+    m = np.zeros((h.value, w.value), dtype=np.uint8)
+    check(lib().vsr_shape_mask(name.encode(), C.byref(w), C.byref(h), _ptr(m), m.size))
+    return m
+
+
+def terrain(name: str):
+    n = check(lib().vsr_terrain(name.encode(), None, None, 0))
+    xs, ys = np.zeros(n), np.zeros(n)
+    check(lib().vsr_terrain(name.encode(), _ptr(xs), _ptr(ys), n))
+    return xs, ys
+
+
+def sensor_config(name: str) -> list[SensorDesc]:
+    n = check(lib().vsr_sensor_config(name.encode(), None, 0))
+    arr = (SensorDesc * max(1, n))()
+    check(lib().vsr_sensor_config(name.encode(), arr, n))
+    return [arr[i] for i in range(n)]
+
+
+def mlp_inner_neurons(n_in: int, n_out: int, ratio: float, n_inner: int) -> list[int]:
+    arr = (C.c_int32 * max(1, n_inner))()
+    check(lib().vsr_mlp_inner_neurons(n_in, n_out, ratio, n_inner, arr))
+    return [arr[i] for i in range(n_inner)]
+
+
+def mlp_count_weights(neurons) -> int:
+    arr = (C.c_int32 * len(neurons))(*neurons)
+    return check(lib().vsr_mlp_count_weights(arr, len(neurons)))
+
+
+def mlp_weight_index(neurons, l: int, j: int, k: int) -> int:
+    arr = (C.c_int32 * len(neurons))(*neurons)
+    return check(lib().vsr_mlp_weight_index(arr, len(neurons), l, j, k))
+
+
+def episode_steps(final_t: float, transient_t: float, dt: float = 1.0 / 60.0):
+    v = [C.c_int32() for _ in range(3)]
+    check(lib().vsr_episode_steps(final_t, transient_t, dt, *[C.byref(x) for x in v]))
+    return tuple(x.value for x in v)
+
+
+def java_random_gaussians(seed: int, n: int) -> np.ndarray:
+    out = np.zeros(n)
+    check(lib().vsr_java_random_gaussians(seed, _ptr(out), n))
+    return out

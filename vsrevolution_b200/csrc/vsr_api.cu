@@ -1,0 +1,610 @@
+// vsr_api.cu -- C ABI of libvsr_eval.so: contexts, model assembly, device buffers, kernel launches.
+// Boundary documented in include/vsr_eval.h; replaces Starter.buildLocomotionTask (Starter.java:83-94).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "vsr_kernel.cuh"
+
+namespace {
+
+constexpr int kWarps = 4;
+
+thread_local std::string g_create_error;
+
+struct DeviceState {
+  int dev = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  double *d_tx = nullptr, *d_ty = nullptr;
+  uint8_t* d_win = nullptr;
+  void* d_hist = nullptr;
+  size_t hist_bytes = 0;
+  double* d_genomes = nullptr;
+  double* d_fitness = nullptr;
+  vsr_result* d_results = nullptr;
+  double* h_genomes = nullptr; // pinned staging
+  double* h_fitness = nullptr;
+  vsr_result* h_results = nullptr;
+  size_t cap = 0; // robots the buffers hold
+  bool timed = false;
+};
+
+} // namespace
+
+struct vsr_ctx {
+  vsr_env_desc env;
+  std::vector<double> tx, ty;
+  // body
+  bool has_body = false, has_ctrl = false;
+  int w = 0, h = 0, n_vox = 0;
+  std::vector<uint8_t> mask;
+  std::vector<int> cell_of_vox, vox_of_cell;
+  std::vector<vsr_sensor_desc> sensors;
+  // controller
+  vsr_ctrl_kind kind = VSR_CTRL_PHASE_SIN;
+  std::vector<int> layers;
+  int signals = 0, in_act = 1;
+  double freq = 1, amp = 1;
+  // derived
+  bool ready = false;
+  vsr::KParams kp;
+  std::vector<uint8_t> win_tab;
+  size_t smem_bytes = 0;
+  std::vector<DeviceState> devs;
+  std::string err;
+  int64_t launches = 0;
+};
+
+namespace {
+
+int fail(vsr_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg;
+  else g_create_error = msg;
+  return code;
+}
+
+#define CK(call)                                                                                     \
+  do {                                                                                               \
+    cudaError_t e_ = (call);                                                                         \
+    if (e_ != cudaSuccess)                                                                           \
+      return fail(ctx, VSR_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));               \
+  } while (0)
+
+double ground_y_at(const std::vector<double>& tx, const std::vector<double>& ty, double x) {
+  for (size_t i = 1; i < tx.size(); i++)
+    if (x >= tx[i - 1] && x <= tx[i]) {
+      double u = (x - tx[i - 1]) / (tx[i] - tx[i - 1]);
+      return ty[i - 1] + u * (ty[i] - ty[i - 1]);
+    }
+  return -INFINITY;
+}
+
+int sensor_dim(const vsr_sensor_desc& s) {
+  if (s.kind == VSR_SENSOR_VELOCITY) return ((s.axes & 1) ? 1 : 0) + ((s.axes & 2) ? 1 : 0);
+  return 1;
+}
+
+int genome_len_of(const vsr_ctx* c) {
+  if (!c->has_body || !c->has_ctrl) return VSR_ESTATE;
+  int dim = 0;
+  for (auto& s : c->sensors) dim += sensor_dim(s);
+  if (c->kind == VSR_CTRL_PHASE_SIN) return c->n_vox;
+  int n_in = c->layers.front(), n_out = c->layers.back();
+  if (c->kind == VSR_CTRL_MLP_CENTRALIZED) {
+    if (n_in != c->n_vox * dim || n_out != c->n_vox) return VSR_EDIM;
+  } else {
+    if (n_in != dim + 4 * c->signals || n_out != 1 + 4 * c->signals) return VSR_EDIM;
+  }
+  return vsr_mlp_count_weights(c->layers.data(), (int)c->layers.size());
+}
+
+size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
+
+template <class R>
+void launch_kernel(const vsr::KParams& kp, int grid, size_t smem, cudaStream_t st) {
+  vsr::vsr_episode_kernel<R, kWarps><<<grid, kWarps * 32, smem, st>>>(kp);
+}
+
+const void* kernel_ptr(int precision) {
+  return precision == 64 ? (const void*)vsr::vsr_episode_kernel<double, kWarps> : (const void*)vsr::vsr_episode_kernel<float, kWarps>;
+}
+
+// (re)derive everything that depends on env + body + controller
+int finalize(vsr_ctx* ctx) {
+  ctx->ready = false;
+  if (!ctx->has_body || !ctx->has_ctrl) return VSR_OK;
+  const vsr_env_desc& e = ctx->env;
+  int glen = genome_len_of(ctx);
+  if (glen < 0) return fail(ctx, glen, "controller I/O dimensions do not match the body/sensors (VSR_EDIM)");
+  vsr::KParams& k = ctx->kp;
+  std::memset(&k, 0, sizeof(k));
+  k.dt = e.dt; k.g = e.gravity_y; k.baumgarte = e.baumgarte; k.lin_tol = e.linear_tol; k.ang_tol = e.angular_tol;
+  k.max_lin_corr = e.max_linear_corr; k.max_trans = e.max_translation; k.max_rot = e.max_rotation;
+  k.rest_vel = e.restitution_velocity; k.vel_iters = e.vel_iters; k.pos_iters = e.pos_iters;
+  const double L = e.side_length, m = L * e.mass_side_ratio;
+  k.side_len = L;
+  k.half = m / 2;
+  const double density = (e.voxel_mass / 4) / (m * m), mass = density * m * m, inertia = mass * (m * m + m * m) / 12.0;
+  k.inv_m = 1.0 / mass; k.inv_i = 1.0 / inertia;
+  k.mu = std::sqrt(e.voxel_friction * e.ground_friction);
+  k.rest_e = std::fmax(e.voxel_restitution, e.ground_restitution);
+  k.lin_f = std::fmin(std::fmax(1.0 - e.dt * e.lin_damping, 0.0), 1.0);
+  k.ang_f = std::fmin(std::fmax(1.0 - e.dt * e.ang_damping, 0.0), 1.0);
+  const double min_side = std::sqrt(L * L * (1.0 - e.area_ratio_max_delta)), max_side = std::sqrt(L * L * (1.0 + e.area_ratio_max_delta));
+  k.range_min[0] = min_side - 2 * m; k.range_rest[0] = L - 2 * m; k.range_max[0] = max_side - 2 * m;
+  k.range_min[1] = std::sqrt(m * m + k.range_min[0] * k.range_min[0]);
+  k.range_rest[1] = std::sqrt(m * m + k.range_rest[0] * k.range_rest[0]);
+  k.range_max[1] = std::sqrt(m * m + k.range_max[0] * k.range_max[0]);
+  k.range_min[2] = (min_side - m) * std::sqrt(2.0); k.range_rest[2] = (L - m) * std::sqrt(2.0); k.range_max[2] = (max_side - m) * std::sqrt(2.0);
+  k.rope_lower = min_side - m;
+  {
+    const double w = 2.0 * M_PI * e.spring_f, c = e.dt * (2.0 * e.spring_d * w + e.dt * w * w);
+    k.sp_sigma = 1.0 / (c + 1.0);
+    k.sp_cfrac = c / (c + 1.0);
+    k.sp_beta = e.dt * w * w / c;
+  }
+  k.weld_anchor = m;
+  k.scaff_mask = e.scaffolding_mask; k.limit_contraction = e.limit_contraction;
+  // body
+  k.n_vox = ctx->n_vox;
+  k.lanes_per_robot = ctx->n_vox;
+  k.robots_per_warp = 32 / ctx->n_vox;
+  for (int v = 0; v < ctx->n_vox; v++) {
+    int cell = ctx->cell_of_vox[v], x = cell % ctx->w, y = cell / ctx->w;
+    auto nb = [&](int ax, int ay) -> int8_t {
+      if (ax < 0 || ax >= ctx->w || ay < 0 || ay >= ctx->h) return -1;
+      return (int8_t)ctx->vox_of_cell[ay * ctx->w + ax];
+    };
+    k.nb_l[v] = nb(x - 1, y); k.nb_r[v] = nb(x + 1, y); k.nb_d[v] = nb(x, y - 1); k.nb_u[v] = nb(x, y + 1);
+  }
+  // Locomotion.apply initial placement
+  {
+    double minx = INFINITY;
+    for (int v = 0; v < ctx->n_vox; v++) minx = std::fmin(minx, (ctx->cell_of_vox[v] % ctx->w) * L - L / 2);
+    const double dx = (ctx->tx[1] + e.place_x_gap) - minx;
+    double min_gap = INFINITY;
+    for (int v = 0; v < ctx->n_vox; v++) {
+      int cell = ctx->cell_of_vox[v], x = cell % ctx->w, y = cell / ctx->w;
+      double cx = x * L + dx, miny = y * L - L / 2;
+      min_gap = std::fmin(min_gap, miny - ground_y_at(ctx->tx, ctx->ty, cx));
+    }
+    const double dy = e.place_y_gap - min_gap;
+    if (!std::isfinite(dy)) return fail(ctx, VSR_EINVAL, "robot is placed outside the terrain");
+    for (int v = 0; v < ctx->n_vox; v++) {
+      int cell = ctx->cell_of_vox[v];
+      k.vox_x0[v] = (cell % ctx->w) * L + dx;
+      k.vox_y0[v] = (cell / ctx->w) * L + dy;
+    }
+  }
+  k.n_t = (int)ctx->tx.size();
+  k.base_y = *std::min_element(ctx->ty.begin(), ctx->ty.end()) - e.ground_thickness;
+  // episode
+  int ns, kf, kl;
+  int rc = vsr_episode_steps(e.final_t, e.transient_t, e.dt, &ns, &kf, &kl);
+  if (rc) return fail(ctx, rc, "bad episode times");
+  if (!kf) return fail(ctx, VSR_EINVAL, "no observation falls inside [transient_t, final_t)");
+  k.n_steps = ns; k.k_first = kf; k.k_last = kl;
+  // sensors
+  k.n_sensors = (int)ctx->sensors.size();
+  int off = 0, navg = 0;
+  std::vector<double> windows;
+  for (int i = 0; i < k.n_sensors; i++) {
+    const vsr_sensor_desc& s = ctx->sensors[i];
+    vsr::SensorK& sk = k.sensors[i];
+    sk.kind = s.kind; sk.axes = s.axes; sk.rotated = s.rotated; sk.soft_norm = s.soft_norm;
+    sk.dom_min = s.dom_min; sk.dom_max = s.dom_max;
+    sk.off = off; sk.dim = sensor_dim(s);
+    sk.avg = -1;
+    if (s.avg_window > 0) {
+      sk.avg = navg;
+      for (int d = 0; d < sk.dim; d++) windows.push_back(s.avg_window);
+      navg += sk.dim;
+    }
+    off += sk.dim;
+  }
+  if (off > 8 || navg > vsr::kMaxAvg) return fail(ctx, VSR_EUNSUPPORTED, "more than 8 readings / 6 averaged readings per voxel");
+  k.sens_dim = off; k.n_avg = navg;
+  // Average windows: count of stored readings with t_j >= t_k - window, emulated in double
+  ctx->win_tab.assign((size_t)std::max(navg, 1) * (ns + 1), 1);
+  int max_win = 1;
+  if (navg) {
+    std::vector<double> ts(ns + 1, 0.0);
+    volatile double t = 0.0;
+    for (int s = 1; s <= ns; s++) { t = t + e.dt; ts[s] = t; }
+    for (int a = 0; a < navg; a++)
+      for (int s = 1; s <= ns; s++) {
+        int cnt = 0;
+        for (int j = s; j >= 1 && ts[j] >= ts[s] - windows[a]; j--) cnt++;
+        if (cnt > 250) return fail(ctx, VSR_EUNSUPPORTED, "Average window longer than 250 steps");
+        ctx->win_tab[(size_t)a * (ns + 1) + s] = (uint8_t)cnt;
+        max_win = std::max(max_win, cnt);
+      }
+  }
+  k.hist_cap = max_win + 2;
+  // controller
+  k.ctrl_kind = ctx->kind; k.signals = ctx->signals; k.in_act = ctx->in_act; k.freq = ctx->freq; k.amp = ctx->amp;
+  k.genome_len = glen;
+  k.n_layers = (int)ctx->layers.size();
+  k.max_neurons = 1;
+  for (int i = 0; i < k.n_layers; i++) { k.layers[i] = ctx->layers[i]; k.max_neurons = std::max(k.max_neurons, ctx->layers[i]); }
+  // shared memory layout (per warp)
+  const size_t rs = e.precision == 64 ? 8 : 4;
+  int S = 64;
+  if (const char* ev = std::getenv("VSR_POOL_SLOTS")) S = std::max(8, std::min(255, std::atoi(ev)));
+  k.pool_slots = S;
+  size_t o = 0;
+  k.off_pool_p = (int)o; o = align16(o + 2 * vsr::kPoolPersist * S * rs);
+  k.off_pool_s = (int)o; o = align16(o + vsr::kPoolSolve * S * rs);
+  k.off_pool_m = (int)o; o = align16(o + 2 * S * 4);
+  k.off_pool_cnt = (int)o; o = align16(o + 4);
+  k.off_w = (int)o;
+  if (ctx->kind != VSR_CTRL_PHASE_SIN) o = align16(o + (size_t)k.robots_per_warp * glen * rs);
+  k.off_act = (int)o;
+  if (ctx->kind == VSR_CTRL_MLP_CENTRALIZED) o = align16(o + (size_t)k.robots_per_warp * 2 * k.max_neurons * rs);
+  if (ctx->kind == VSR_CTRL_MLP_DISTRIBUTED_HOMO) o = align16(o + (size_t)2 * k.max_neurons * 32 * rs);
+  k.off_sig = (int)o;
+  if (ctx->kind == VSR_CTRL_MLP_DISTRIBUTED_HOMO) o = align16(o + (size_t)2 * 32 * 4 * std::max(1, k.signals) * rs);
+  k.smem_warp_stride = (int)o;
+  ctx->smem_bytes = o * kWarps;
+  if (ctx->smem_bytes > 227 * 1024) return fail(ctx, VSR_EUNSUPPORTED, "controller too large for shared memory");
+  // per-device uploads
+  for (auto& d : ctx->devs) {
+    CK(cudaSetDevice(d.dev));
+    CK(cudaFuncSetAttribute(kernel_ptr(e.precision), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_bytes));
+    if (d.d_win) { cudaFree(d.d_win); d.d_win = nullptr; }
+    CK(cudaMalloc(&d.d_win, ctx->win_tab.size()));
+    CK(cudaMemcpy(d.d_win, ctx->win_tab.data(), ctx->win_tab.size(), cudaMemcpyHostToDevice));
+  }
+  ctx->ready = true;
+  return VSR_OK;
+}
+
+int ensure_capacity(vsr_ctx* ctx, DeviceState& d, size_t n) {
+  CK(cudaSetDevice(d.dev));
+  const vsr::KParams& k = ctx->kp;
+  if (n > d.cap) {
+    size_t cap = std::max(n, d.cap * 2);
+    if (d.d_genomes) { cudaFree(d.d_genomes); cudaFree(d.d_fitness); cudaFree(d.d_results); cudaFreeHost(d.h_genomes); cudaFreeHost(d.h_fitness); cudaFreeHost(d.h_results); }
+    d.cap = 0;
+    CK(cudaMalloc(&d.d_genomes, cap * k.genome_len * sizeof(double)));
+    CK(cudaMalloc(&d.d_fitness, cap * sizeof(double)));
+    CK(cudaMalloc(&d.d_results, cap * sizeof(vsr_result)));
+    CK(cudaMallocHost(&d.h_genomes, cap * k.genome_len * sizeof(double)));
+    CK(cudaMallocHost(&d.h_fitness, cap * sizeof(double)));
+    CK(cudaMallocHost(&d.h_results, cap * sizeof(vsr_result)));
+    d.cap = cap;
+  }
+  return VSR_OK;
+}
+
+int grid_for(const vsr::KParams& k, size_t n) {
+  const size_t per_cta = (size_t)kWarps * k.robots_per_warp;
+  return (int)((n + per_cta - 1) / per_cta);
+}
+
+int ensure_hist(vsr_ctx* ctx, DeviceState& d, int grid) {
+  const vsr::KParams& k = ctx->kp;
+  if (!k.n_avg) return VSR_OK;
+  const size_t rs = ctx->env.precision == 64 ? 8 : 4;
+  size_t bytes = (size_t)k.hist_cap * k.n_avg * grid * kWarps * 32 * rs;
+  if (bytes > d.hist_bytes) {
+    if (d.d_hist) cudaFree(d.d_hist);
+    d.hist_bytes = 0;
+    CK(cudaMalloc(&d.d_hist, bytes));
+    d.hist_bytes = bytes;
+  }
+  return VSR_OK;
+}
+
+// enqueue the episode kernel for n robots whose genomes are at d_genomes (device)
+int enqueue(vsr_ctx* ctx, DeviceState& d, const double* d_genomes, size_t n, double* d_fitness, vsr_result* d_results,
+            cudaStream_t st, double* trv, double* trb, double* trc, int trace_steps, bool time_it) {
+  if (n == 0) return VSR_OK;
+  vsr::KParams k = ctx->kp;
+  const int grid = grid_for(k, n);
+  int rc = ensure_hist(ctx, d, grid);
+  if (rc) return rc;
+  k.tx = d.d_tx; k.ty = d.d_ty; k.win_tab = d.d_win; k.hist = d.d_hist;
+  k.genomes = d_genomes; k.fitness = d_fitness; k.results = d_results; k.n_robots = (int)n;
+  k.tr_vertices = trv; k.tr_bodies = trb; k.tr_ctrl = trc; k.trace_steps = trace_steps;
+  if (time_it) CK(cudaEventRecord(d.ev0, st));
+  if (ctx->env.precision == 64) launch_kernel<double>(k, grid, ctx->smem_bytes, st);
+  else launch_kernel<float>(k, grid, ctx->smem_bytes, st);
+  CK(cudaGetLastError());
+  if (time_it) { CK(cudaEventRecord(d.ev1, st)); d.timed = true; }
+  ctx->launches++;
+  return VSR_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int vsr_env_default(vsr_env_desc* e) {
+  if (!e) return VSR_EINVAL;
+  std::memset(e, 0, sizeof(*e));
+  e->dt = 1.0 / 60.0; e->vel_iters = 10; e->pos_iters = 10; e->gravity_y = -9.8; e->baumgarte = 0.2;
+  e->linear_tol = 0.005; e->angular_tol = 2.0 * M_PI / 180.0; e->max_linear_corr = 0.2; e->max_translation = 2.0;
+  e->max_rotation = 0.5 * M_PI; e->restitution_velocity = 1.0;
+  e->side_length = 3.0; e->mass_side_ratio = 0.3; e->spring_f = 8.0; e->spring_d = 0.3; e->lin_damping = 1.0;
+  e->ang_damping = 1.0; e->voxel_mass = 1.0; e->area_ratio_max_delta = 0.225; e->voxel_friction = 100.0;
+  e->voxel_restitution = 0.1; e->limit_contraction = 1; e->scaffolding_mask = 0xF;
+  e->ground_friction = 0.2; e->ground_restitution = 0.0; e->ground_thickness = 50.0;
+  e->place_x_gap = 1.0; e->place_y_gap = 1.0; e->final_t = 30.0; e->transient_t = 1.0;
+  e->precision = 32;
+  return VSR_OK;
+}
+
+int vsr_ctx_create(const vsr_env_desc* env, vsr_ctx** out) {
+  vsr_ctx* ctx = nullptr; // for CK/fail before the context exists
+  if (!env || !out) return fail(nullptr, VSR_EINVAL, "null argument");
+  *out = nullptr;
+  if (!env->terrain_x || !env->terrain_y || env->n_terrain < 2) return fail(nullptr, VSR_EINVAL, "terrain polyline missing");
+  for (int i = 1; i < env->n_terrain; i++)
+    if (!(env->terrain_x[i] > env->terrain_x[i - 1])) return fail(nullptr, VSR_EINVAL, "terrain xs must be strictly increasing");
+  if (env->precision != 32 && env->precision != 64) return fail(nullptr, VSR_EINVAL, "precision must be 32 or 64");
+  if (!(env->dt > 0) || env->vel_iters < 0 || env->pos_iters < 0 || !(env->final_t > 0)) return fail(nullptr, VSR_EINVAL, "bad settings");
+  if (env->n_devices < 0 || env->n_devices > 8) return fail(nullptr, VSR_EINVAL, "n_devices out of range");
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0)
+    return fail(nullptr, VSR_ECUDA, std::string("no CUDA device: ") + (ce != cudaSuccess ? cudaGetErrorString(ce) : "device count is 0") +
+                                        " (this library has no CPU fallback)");
+  vsr_ctx* c = new (std::nothrow) vsr_ctx();
+  if (!c) return fail(nullptr, VSR_ENOMEM, "out of host memory");
+  c->env = *env;
+  c->tx.assign(env->terrain_x, env->terrain_x + env->n_terrain);
+  c->ty.assign(env->terrain_y, env->terrain_y + env->n_terrain);
+  c->env.terrain_x = nullptr; c->env.terrain_y = nullptr;
+  std::vector<int> ids;
+  if (env->n_devices == 0) {
+    int cur = 0;
+    cudaGetDevice(&cur);
+    ids.push_back(cur);
+  } else {
+    for (int i = 0; i < env->n_devices; i++) ids.push_back(env->devices[i]);
+  }
+  ctx = c;
+  for (int id : ids) {
+    if (id < 0 || id >= ndev) { int rc = fail(nullptr, VSR_EINVAL, "device id out of range"); vsr_ctx_destroy(c); return rc; }
+    DeviceState d;
+    d.dev = id;
+    c->devs.push_back(d);
+  }
+  for (auto& d : c->devs) {
+    auto ck = [&](cudaError_t e_, const char* what) -> bool {
+      if (e_ == cudaSuccess) return true;
+      g_create_error = std::string(what) + ": " + cudaGetErrorString(e_);
+      return false;
+    };
+    bool ok = ck(cudaSetDevice(d.dev), "cudaSetDevice") && ck(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking), "cudaStreamCreate") &&
+              ck(cudaEventCreate(&d.ev0), "cudaEventCreate") && ck(cudaEventCreate(&d.ev1), "cudaEventCreate") &&
+              ck(cudaMalloc(&d.d_tx, sizeof(double) * c->tx.size()), "cudaMalloc") && ck(cudaMalloc(&d.d_ty, sizeof(double) * c->ty.size()), "cudaMalloc") &&
+              ck(cudaMemcpy(d.d_tx, c->tx.data(), sizeof(double) * c->tx.size(), cudaMemcpyHostToDevice), "cudaMemcpy") &&
+              ck(cudaMemcpy(d.d_ty, c->ty.data(), sizeof(double) * c->ty.size(), cudaMemcpyHostToDevice), "cudaMemcpy");
+    if (!ok) { vsr_ctx_destroy(c); return VSR_ECUDA; }
+  }
+  *out = c;
+  return VSR_OK;
+}
+
+void vsr_ctx_destroy(vsr_ctx* c) {
+  if (!c) return;
+  for (auto& d : c->devs) {
+    cudaSetDevice(d.dev);
+    if (d.stream) cudaStreamSynchronize(d.stream);
+    cudaFree(d.d_tx); cudaFree(d.d_ty); cudaFree(d.d_win); cudaFree(d.d_hist);
+    cudaFree(d.d_genomes); cudaFree(d.d_fitness); cudaFree(d.d_results);
+    cudaFreeHost(d.h_genomes); cudaFreeHost(d.h_fitness); cudaFreeHost(d.h_results);
+    if (d.ev0) cudaEventDestroy(d.ev0);
+    if (d.ev1) cudaEventDestroy(d.ev1);
+    if (d.stream) cudaStreamDestroy(d.stream);
+  }
+  delete c;
+}
+
+const char* vsr_last_error(const vsr_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int vsr_body_set(vsr_ctx* ctx, int32_t w, int32_t h, const uint8_t* mask, const vsr_sensor_desc* sensors, int32_t n_sensors) {
+  if (!ctx) return VSR_EINVAL;
+  if (w <= 0 || h <= 0 || !mask || n_sensors < 0 || (n_sensors > 0 && !sensors)) return fail(ctx, VSR_EINVAL, "bad body arguments");
+  if (n_sensors > vsr::kMaxSensors) return fail(ctx, VSR_EUNSUPPORTED, "too many sensors per voxel");
+  int nv = 0;
+  for (int i = 0; i < w * h; i++) nv += mask[i] ? 1 : 0;
+  if (nv == 0) return fail(ctx, VSR_EINVAL, "Target robot has no voxels");
+  if (nv > vsr::kMaxVox) return fail(ctx, VSR_EUNSUPPORTED, "bodies with more than 32 voxels are not supported by this build");
+  for (int i = 0; i < n_sensors; i++) {
+    if (sensors[i].noise_sigma != 0) return fail(ctx, VSR_EUNSUPPORTED, "Noisy sensors (sigma > 0) are not supported by this build");
+    if (sensors[i].kind < 0 || sensors[i].kind > VSR_SENSOR_ANGLE) return fail(ctx, VSR_EINVAL, "unknown sensor kind");
+    if (sensors[i].kind == VSR_SENSOR_VELOCITY && !(sensors[i].axes & 3)) return fail(ctx, VSR_EINVAL, "velocity sensor without axes");
+    if (sensors[i].soft_norm && !(sensors[i].dom_max > sensors[i].dom_min)) return fail(ctx, VSR_EINVAL, "empty sensor domain");
+  }
+  ctx->w = w; ctx->h = h; ctx->n_vox = nv;
+  ctx->mask.assign(mask, mask + w * h);
+  ctx->vox_of_cell.assign(w * h, -1);
+  ctx->cell_of_vox.clear();
+  for (int i = 0; i < w * h; i++)
+    if (mask[i]) { ctx->vox_of_cell[i] = (int)ctx->cell_of_vox.size(); ctx->cell_of_vox.push_back(i); }
+  ctx->sensors.assign(sensors, sensors + n_sensors);
+  ctx->has_body = true;
+  return finalize(ctx);
+}
+
+int vsr_controller_set(vsr_ctx* ctx, vsr_ctrl_kind kind, const int32_t* layers, int32_t n_layers, int32_t signals, double freq,
+                       double amp, int32_t in_act) {
+  if (!ctx) return VSR_EINVAL;
+  if (kind != VSR_CTRL_PHASE_SIN) {
+    if (!layers || n_layers < 2 || n_layers > vsr::kMaxLayers) return fail(ctx, VSR_EINVAL, "MLP needs 2..8 layers");
+    for (int i = 0; i < n_layers; i++)
+      if (layers[i] <= 0 || layers[i] > 255) return fail(ctx, VSR_EUNSUPPORTED, "layer size must be in 1..255");
+    if (kind == VSR_CTRL_MLP_DISTRIBUTED_HOMO && (signals < 0 || signals > 4)) return fail(ctx, VSR_EUNSUPPORTED, "signals must be in 0..4");
+  }
+  ctx->kind = kind;
+  ctx->layers.clear();
+  if (kind != VSR_CTRL_PHASE_SIN) ctx->layers.assign(layers, layers + n_layers);
+  ctx->signals = kind == VSR_CTRL_MLP_DISTRIBUTED_HOMO ? signals : 0;
+  ctx->freq = freq; ctx->amp = amp; ctx->in_act = in_act ? 1 : 0;
+  ctx->has_ctrl = true;
+  return finalize(ctx);
+}
+
+int vsr_genome_len(const vsr_ctx* ctx) { return ctx ? genome_len_of(ctx) : VSR_EINVAL; }
+int vsr_n_voxels(const vsr_ctx* ctx) { return ctx && ctx->has_body ? ctx->n_vox : VSR_ESTATE; }
+
+int vsr_eval(vsr_ctx* ctx, const double* genomes, int32_t n, double* fitness_out, vsr_result* results_out) {
+  if (!ctx) return VSR_EINVAL;
+  if (!ctx->ready) return fail(ctx, VSR_ESTATE, "body and controller must be set before vsr_eval");
+  if (n < 0 || (n > 0 && (!genomes || !fitness_out))) return fail(ctx, VSR_EINVAL, "bad vsr_eval arguments");
+  if (n == 0) return VSR_OK;
+  const int G = ctx->kp.genome_len;
+  const size_t nd = ctx->devs.size(), per = ((size_t)n + nd - 1) / nd;
+  // shard by contiguous index ranges; one stream per device; no inter-device traffic
+  for (size_t i = 0; i < nd; i++) {
+    DeviceState& d = ctx->devs[i];
+    size_t lo = std::min((size_t)n, i * per), hi = std::min((size_t)n, lo + per), cnt = hi - lo;
+    if (!cnt) continue;
+    int rc = ensure_capacity(ctx, d, cnt);
+    if (rc) return rc;
+    std::memcpy(d.h_genomes, genomes + lo * G, cnt * G * sizeof(double));
+    CK(cudaMemcpyAsync(d.d_genomes, d.h_genomes, cnt * G * sizeof(double), cudaMemcpyHostToDevice, d.stream));
+    rc = enqueue(ctx, d, d.d_genomes, cnt, d.d_fitness, results_out ? d.d_results : nullptr, d.stream, nullptr, nullptr, nullptr, 0, i == 0);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(d.h_fitness, d.d_fitness, cnt * sizeof(double), cudaMemcpyDeviceToHost, d.stream));
+    if (results_out) CK(cudaMemcpyAsync(d.h_results, d.d_results, cnt * sizeof(vsr_result), cudaMemcpyDeviceToHost, d.stream));
+  }
+  for (size_t i = 0; i < nd; i++) {
+    DeviceState& d = ctx->devs[i];
+    size_t lo = std::min((size_t)n, i * per), hi = std::min((size_t)n, lo + per), cnt = hi - lo;
+    if (!cnt) continue;
+    CK(cudaSetDevice(d.dev));
+    CK(cudaStreamSynchronize(d.stream));
+    std::memcpy(fitness_out + lo, d.h_fitness, cnt * sizeof(double));
+    if (results_out) std::memcpy(results_out + lo, d.h_results, cnt * sizeof(vsr_result));
+  }
+  return VSR_OK;
+}
+
+int vsr_eval_device(vsr_ctx* ctx, const double* d_genomes, int32_t n, double* d_fitness, vsr_result* d_results, void* stream) {
+  if (!ctx) return VSR_EINVAL;
+  if (!ctx->ready) return fail(ctx, VSR_ESTATE, "body and controller must be set before vsr_eval_device");
+  if (n < 0 || (n > 0 && (!d_genomes || !d_fitness))) return fail(ctx, VSR_EINVAL, "bad vsr_eval_device arguments");
+  DeviceState& d = ctx->devs[0];
+  CK(cudaSetDevice(d.dev));
+  return enqueue(ctx, d, d_genomes, (size_t)n, d_fitness, d_results, (cudaStream_t)stream, nullptr, nullptr, nullptr, 0, true);
+}
+
+int vsr_trace(vsr_ctx* ctx, const double* genome, int32_t n_steps, double* vertices_out, double* bodies_out, double* ctrl_out,
+              vsr_result* result_out) {
+  if (!ctx) return VSR_EINVAL;
+  if (!ctx->ready) return fail(ctx, VSR_ESTATE, "body and controller must be set before vsr_trace");
+  if (!genome || n_steps < 0) return fail(ctx, VSR_EINVAL, "bad vsr_trace arguments");
+  DeviceState& d = ctx->devs[0];
+  int rc = ensure_capacity(ctx, d, 1);
+  if (rc) return rc;
+  const int G = ctx->kp.genome_len, nv = ctx->n_vox;
+  n_steps = std::min(n_steps, ctx->kp.n_steps);
+  double *dv = nullptr, *db = nullptr, *dc = nullptr;
+  const size_t bv = (size_t)n_steps * nv * 8 * sizeof(double), bb = (size_t)n_steps * nv * 24 * sizeof(double), bc = (size_t)n_steps * nv * sizeof(double);
+  if (vertices_out && n_steps) CK(cudaMalloc(&dv, bv));
+  if (bodies_out && n_steps) CK(cudaMalloc(&db, bb));
+  if (ctrl_out && n_steps) CK(cudaMalloc(&dc, bc));
+  CK(cudaMemcpyAsync(d.d_genomes, genome, G * sizeof(double), cudaMemcpyHostToDevice, d.stream));
+  rc = enqueue(ctx, d, d.d_genomes, 1, d.d_fitness, d.d_results, d.stream, dv, db, dc, n_steps, false);
+  if (rc == VSR_OK) {
+    cudaError_t e_ = cudaStreamSynchronize(d.stream);
+    if (e_ != cudaSuccess) rc = fail(ctx, VSR_ECUDA, std::string("trace kernel: ") + cudaGetErrorString(e_));
+  }
+  if (rc == VSR_OK) {
+    if (dv) cudaMemcpy(vertices_out, dv, bv, cudaMemcpyDeviceToHost);
+    if (db) cudaMemcpy(bodies_out, db, bb, cudaMemcpyDeviceToHost);
+    if (dc) cudaMemcpy(ctrl_out, dc, bc, cudaMemcpyDeviceToHost);
+    if (result_out) cudaMemcpy(result_out, d.d_results, sizeof(vsr_result), cudaMemcpyDeviceToHost);
+  }
+  cudaFree(dv); cudaFree(db); cudaFree(dc);
+  return rc;
+}
+
+double vsr_last_kernel_ms(vsr_ctx* ctx) {
+  if (!ctx || ctx->devs.empty() || !ctx->devs[0].timed) return -1.0;
+  DeviceState& d = ctx->devs[0];
+  cudaSetDevice(d.dev);
+  if (cudaEventSynchronize(d.ev1) != cudaSuccess) return -1.0;
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, d.ev0, d.ev1) != cudaSuccess) return -1.0;
+  return ms;
+}
+
+int64_t vsr_kernel_launches(const vsr_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int vsr_kernel_info(const vsr_ctx* ctx_c, int32_t* regs, int32_t* smem, int32_t* threads, int32_t* rpw, int32_t* ctas_per_sm) {
+  vsr_ctx* ctx = const_cast<vsr_ctx*>(ctx_c);
+  if (!ctx) return VSR_EINVAL;
+  if (!ctx->ready) return fail(ctx, VSR_ESTATE, "body and controller must be set first");
+  CK(cudaSetDevice(ctx->devs[0].dev));
+  cudaFuncAttributes a;
+  CK(cudaFuncGetAttributes(&a, kernel_ptr(ctx->env.precision)));
+  int nb = 0;
+  if (ctx->env.precision == 64)
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, vsr::vsr_episode_kernel<double, kWarps>, kWarps * 32, ctx->smem_bytes));
+  else
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, vsr::vsr_episode_kernel<float, kWarps>, kWarps * 32, ctx->smem_bytes));
+  if (regs) *regs = a.numRegs;
+  if (smem) *smem = (int)ctx->smem_bytes;
+  if (threads) *threads = kWarps * 32;
+  if (rpw) *rpw = ctx->kp.robots_per_warp;
+  if (ctas_per_sm) *ctas_per_sm = nb;
+  return VSR_OK;
+}
+
+int vsr_input_map(const vsr_ctx* ctx, int32_t* cell, int32_t* sensor, int32_t* reading, int32_t cap) {
+  if (!ctx || !ctx->has_body) return VSR_ESTATE;
+  int n = 0;
+  // CentralizedSensing: voxels in Grid.values() order (row-major y*w+x, nulls skipped), sensors in list order
+  for (int v = 0; v < ctx->n_vox; v++)
+    for (size_t s = 0; s < ctx->sensors.size(); s++)
+      for (int r = 0; r < sensor_dim(ctx->sensors[s]); r++) {
+        if (n < cap) {
+          if (cell) cell[n] = ctx->cell_of_vox[v];
+          if (sensor) sensor[n] = (int)s;
+          if (reading) reading[n] = r;
+        }
+        n++;
+      }
+  return n;
+}
+
+int vsr_voxel_cells(const vsr_ctx* ctx, int32_t* cell, int32_t cap) {
+  if (!ctx || !ctx->has_body) return VSR_ESTATE;
+  for (int v = 0; v < ctx->n_vox && v < cap; v++)
+    if (cell) cell[v] = ctx->cell_of_vox[v];
+  return ctx->n_vox;
+}
+
+int vsr_counts(const vsr_ctx* ctx, int32_t* n_voxels, int32_t* n_springs, int32_t* n_ropes, int32_t* n_welds) {
+  if (!ctx || !ctx->has_body) return VSR_ESTATE;
+  int per = 0, sm = ctx->env.scaffolding_mask;
+  if (sm & 1) per += 4;
+  if (sm & 2) per += 4;
+  if (sm & 4) per += 8;
+  if (sm & 8) per += 2;
+  int nw = 0;
+  for (int v = 0; v < ctx->n_vox; v++) {
+    int cell = ctx->cell_of_vox[v], x = cell % ctx->w, y = cell / ctx->w;
+    if (x > 0 && ctx->mask[cell - 1]) nw += 2;
+    if (y > 0 && ctx->mask[cell - ctx->w]) nw += 2;
+  }
+  if (n_voxels) *n_voxels = ctx->n_vox;
+  if (n_springs) *n_springs = ctx->n_vox * per;
+  if (n_ropes) *n_ropes = ctx->env.limit_contraction ? ctx->n_vox * 4 : 0;
+  if (n_welds) *n_welds = nw;
+  return VSR_OK;
+}
+
+} // extern "C"
