@@ -1,0 +1,277 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hot path (BASELINE.json: voxel-steps/s and 30 s-episode evals/s).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--robots R] [--workload 2|3|4]
+
+One "step" = one pass of the hot path over one population batch: R robots (default 4096 per GPU, BASELINE
+config 2: biped-4x3, CentralizedSensing 10-7-10 MLP, flat terrain, 30 s at dt=1/60 -> 1801 physics steps each).
+N>1: one process per GPU (torchrun), robots sharded by index, no data-path collective ("weak" scaling: every
+GPU gets its own R robots); timing is max over ranks.
+
+`value`  : device-resident throughput (genomes already in HBM), CUDA events on the launch stream.
+`e2e`    : same metric through PopulationEvaluator.evaluate() with HOST buffers (H2D + kernel + D2H).
+`roofline`: FP32-issue roofline of the episode kernel: algorithmic flops from the ORACLE's
+           operation tallies, live CUDA-event kernel time.
+`cpu_baseline`: the CPU oracle (C port of the reference algorithm, "port") on the host cores, bounded sample.
+`--impl reference`: times that CPU port alone (the Java reference cannot run here: no JVM, deps un-vendored).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# ---- algorithmic flop constants (counted on the ORACLE's source) -----------------
+FLOPS = dict(spring_vel=38, spring_init=71, rope_vel=40, rope_init=30, weld_vel=78, weld_init=54, weld_pos=115,
+             contact_pt_vel=47, contact_pt_pos=33, contact_init=43, detect_pair=280, body_step=48, voxel_act=140)
+
+WORKLOADS = {
+    2: dict(name="config2: biped-4x3, brainCentralized<mlp;r=0.65;nIL=1 (10-7-10), uniform-a-0, flat, 30 s",
+            shape="biped-4x3", sensors="uniform-a-0", mapper="brainCentralized<mlp;r=0.65;nIL=1", terrain="flat",
+            T=30.0, seed=0, oracle_cfg=1),
+    3: dict(name="config3: worm-8x2, brainPhaseVals;f=1, hilly-1-10-0, 60 s", shape="worm-8x2", sensors="",
+            mapper="brainPhaseVals;f=1", terrain="hilly-1-10-0", T=60.0, seed=1, oracle_cfg=3),
+    4: dict(name="config4: comb-7x2, brainHomoDist;s=1<mlp;r=0.65;nIL=1 (8-5-5), uniform-t+vxy+a-0, steppy-0.25-1-0, 30 s",
+            shape="comb-7x2", sensors="uniform-t+vxy+a-0", mapper="brainHomoDist;s=1<mlp;r=0.65;nIL=1",
+            terrain="steppy-0.25-1-0", T=30.0, seed=2, oracle_cfg=4),
+}
+
+
+def algorithmic_flops_per_robot(res, n_vox, n_springs, n_ropes, n_welds) -> float:
+    """Flops of one episode from the oracle's operation tallies."""
+    steps = res.n_steps
+    f = FLOPS
+    return (res.n_spring_vel * f["spring_vel"] + steps * n_springs * f["spring_init"]
+            + res.n_rope_vel * f["rope_vel"] + steps * n_ropes * f["rope_init"] + res.n_rope_pos * f["rope_vel"]
+            + res.n_weld_vel * f["weld_vel"] + steps * n_welds * f["weld_init"] + res.n_weld_pos * f["weld_pos"]
+            + res.n_contact_pt_vel * f["contact_pt_vel"] + res.n_contact_pt_pos * f["contact_pt_pos"]
+            + res.n_manifolds * 2 * f["contact_init"] + res.n_detect_pairs * f["detect_pair"]
+            + steps * n_vox * 4 * f["body_step"] + steps * n_vox * f["voxel_act"])
+
+
+def cpu_port(w, sample, threads):
+    """Time the oracle on `sample` robots of workload w with `threads` host threads; returns (voxel-steps/s, flops/robot)."""
+    from oracle import model as O
+    m = O.config_model(w["oracle_cfg"], final_t=w["T"])
+    g = np.random.default_rng(w["seed"]).uniform(-1, 1, (sample, m.genome_len()))
+    O.lib()
+    t0 = time.perf_counter()
+    fit, results = m.eval_batch(g, n_threads=threads, want_results=True)
+    dt = time.perf_counter() - t0
+    import ctypes as C
+    mask = m.mask
+    cnt = [C.c_int() for _ in range(4)]
+    O.lib().vo_counts(C.byref(m.params), m.w, m.h, mask.ctypes.data_as(C.c_void_p), *[C.byref(c) for c in cnt])
+    nv, ns, nr, nw = [c.value for c in cnt]
+    flops = float(np.mean([algorithmic_flops_per_robot(r, nv, ns, nr, nw) for r in results]))
+    steps = results[0].n_steps
+    return sample * nv * steps / dt, flops, steps, nv, dt
+
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(index)],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self) -> dict:
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], None, set()
+        for r in rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.strip().lower() == "active":
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peak_fp32_tflops():
+    peaks = {}
+    pth = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pth):
+        peaks = json.load(open(pth))
+    mhz = peaks.get("sm_max_mhz", 1965.0)
+    return 148 * 128 * 2 * mhz * 1e6 / 1e12, peaks.get("hbm_gbs", 6650.0), ("measured" if peaks else "fallback")
+
+
+def run_reference(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample = args.ref_sample
+    for _ in range(args.warmup):
+        cpu_port(w, max(threads, sample // 8), threads)
+    vals, tot = [], 0.0
+    for _ in range(args.steps):
+        v, flops, steps, nv, dt = cpu_port(w, sample, threads)
+        vals.append(v); tot += dt
+    value = float(np.mean(vals))
+    line = {"impl": "reference", "metric": "voxel-steps/sec", "value": value, "unit": "voxel-steps/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": w["name"], "robots_per_step": sample, "physics_steps": steps, "voxels": nv},
+            "evals_per_sec": value / (nv * steps),
+            "cpu_baseline": {"value": value, "unit": "voxel-steps/s", "cores": threads, "kind": "port",
+                             "sample": f"{sample} robots of the same workload per step, C port of the reference algorithm "
+                                       "(oracle/vsr_oracle.c); the Java reference itself cannot run here (no JVM, 2dhmsr/dyn4j un-vendored)"},
+            "e2e": {"value": value, "unit": "voxel-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--robots", type=int, default=4096, help="robots per GPU per step")
+    ap.add_argument("--workload", type=int, default=2, choices=sorted(WORKLOADS))
+    ap.add_argument("--ref-sample", type=int, default=256)
+    ap.add_argument("--cpu-sample", type=int, default=192)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return run_reference(args, w)
+
+    import torch
+    import torch.distributed as dist
+    from vsrevolution_b200.locomotion import population_evaluator
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    ev = population_evaluator(w["shape"], w["sensors"], w["mapper"], w["terrain"], w["T"], 1.0, devices=[local])
+    G, nv = ev.genome_len, ev.n_voxels
+    n = args.robots
+    # synthetic genomes U(-1,1) (UniformDoubleFactory(-1,1), builder/solver/DoublesStandard.java:52-53); rank-distinct
+    host_g = np.random.default_rng(w["seed"] + 1000 * rank).uniform(-1, 1, (n, G))
+    pinned_g = torch.from_numpy(host_g).pin_memory()
+    host_fit = np.empty(n)
+    d_g = torch.from_numpy(host_g).to(dev)
+    d_fit = torch.empty(n, dtype=torch.float64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    from vsrevolution_b200 import _ffi
+    n_steps = _ffi.episode_steps(w["T"], 1.0)[0]
+
+    def device_step():
+        ev.ctx.eval_device(d_g.data_ptr(), n, d_fit.data_ptr(), 0, torch.cuda.current_stream().cuda_stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        device_step()
+    barrier()
+    launches0 = ev.kernel_launches()
+    sampler = ClockSampler(local) if rank == 0 else None
+    # ---- timed: device-resident -------------------------------------------------------------------
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kernel_ms = []
+    barrier()
+    for a, b in evs:
+        flush.fill_(1)  # L2 flush between timed iterations (256 MiB write)
+        a.record()
+        device_step()
+        b.record()
+        kernel_ms.append(ev.ctx.last_kernel_ms())  # CUDA events around the kernel on its launch stream; syncs
+    barrier()
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    # ---- timed: end to end through the host API (pinned host genomes -> fitness on host) --------------
+    pg = pinned_g.numpy()
+    for _ in range(2):
+        ev.ctx.eval_into(pg, host_fit)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ev.ctx.eval_into(pg, host_fit)
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    launches = ev.kernel_launches() - launches0
+    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = t.tolist()
+    fit_ok = bool(np.isfinite(host_fit).all()) and bool(torch.isfinite(d_fit).all().item())
+
+    if rank == 0:
+        units = world * n * nv * n_steps * args.steps  # voxel-steps over all ranks and steps
+        value = units / (dev_ms * 1e-3)
+        e2e = units / (e2e_ms * 1e-3)
+        line = {"metric": "voxel-steps/sec", "value": value, "unit": "voxel-steps/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": w["name"], "robots_per_gpu": n, "physics_steps": n_steps, "voxels": nv,
+                           "genome_len": G, "parallelism": f"robots sharded by index over {world} GPU(s), no collective",
+                           "l2": "256 MiB device write between timed iterations", "kernel": ev.ctx.kernel_info()},
+                "evals_per_sec": value / (nv * n_steps),
+                "e2e": {"value": e2e, "unit": "voxel-steps/s", "h2d_bytes_per_step": n * G * 8, "d2h_bytes_per_step": n * 8,
+                        "evals_per_sec": e2e / (nv * n_steps), "ms_per_step": e2e_ms / args.steps},
+                "gpu_launches": int(launches), "clocks": clocks, "fitness_finite": fit_ok}
+        # roofline of the episode kernel (FP32 issue bound)
+        peak, hbm_peak, src = peak_fp32_tflops()
+        cpu = None
+        flops_per_robot = None
+        if not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            v, flops_per_robot, _, _, cdt = cpu_port(w, args.cpu_sample, threads)
+            cpu = {"value": v, "unit": "voxel-steps/s", "cores": threads, "kind": "port",
+                   "sample": f"{args.cpu_sample} robots of the same workload ({cdt:.1f} s wall), oracle/vsr_oracle.c double precision"}
+        kms = float(np.mean(kernel_ms))
+        if flops_per_robot:
+            ach = flops_per_robot * n / (kms * 1e-3) / 1e12
+            sust = (clocks or {}).get("sm_mhz") or None
+            line["roofline"] = {"bound": "fp32", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                                "traffic": None, "kernel": "vsr_episode_kernel<float,4>", "kernel_ms": kms,
+                                "algorithmic_flops_per_voxel_step": flops_per_robot / (nv * n_steps),
+                                "peak_source": f"148 SM x 128 lanes x 2 x sm_max_mhz ({src} MEASURED_PEAKS.json)",
+                                "frac_at_observed_clock": (ach / (148 * 128 * 2 * sust * 1e6 / 1e12)) if sust else None,
+                                "hbm": {"achieved_gbs": (n * G * 8 + n * 8) / (kms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
+                                        "note": "state is register/shared-memory resident; HBM carries genomes in, fitness out"}}
+        line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,100 @@
+"""CPU-only checks of the drop-in boundary: the C-ABI library loads, exports every symbol include/vsr_eval.h
+declares, its integer/naming layer is bit-identical to the oracle's tables, and it refuses to run without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def F():
+    import __graft_entry__ as g
+    from vsrevolution_b200 import _ffi
+    if not os.path.exists(_ffi.LIB_PATH):
+        g.build()
+    return _ffi
+
+
+def test_library_exports_every_declared_symbol(F):
+    hdr = open(os.path.join(ROOT, "include", "vsr_eval.h")).read()
+    declared = set(re.findall(r"\b(vsr_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 20
+    lib = C.CDLL(F.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in vsr_eval.h but not exported"
+    assert declared == set(F.EXPORTED_SYMBOLS)
+
+
+def test_shapes_match_oracle_tables(F, oracle):
+    for name in ("biped-4x3", "worm-8x2", "comb-7x2", "box-1x1", "box-3x5", "tripod-5x3", "biped-7x4", "comb-8x3"):
+        assert np.array_equal(F.shape_mask(name), oracle.build_shape(name)), name
+    with pytest.raises(F.VsrIllegalArgument):
+        F.shape_mask("snake-3x3")
+
+
+def test_terrains_bit_exact_vs_oracle(F, oracle):
+    for name in ("flat", "hilly-1-10-0", "hilly-0.5-5-42", "steppy-0.25-1-0", "steppy-1-10-7", "downhill-30", "uphill-10"):
+        xs, ys = F.terrain(name)
+        oxs, oys = oracle.create_terrain(name)
+        assert np.array_equal(xs, oxs) and np.array_equal(ys, oys), name
+    with pytest.raises(F.VsrIllegalArgument):
+        F.terrain("lunar-1")
+
+
+def test_java_random_replay(F, oracle):
+    r = oracle.JavaRandom(12345)
+    exp = np.array([r.next_gaussian() for _ in range(64)])
+    assert np.array_equal(F.java_random_gaussians(12345, 64), exp)
+    assert F.java_random_gaussians(0, 1)[0] == 0.8025330637390305
+
+
+def test_mlp_sizing_bit_exact(F, oracle):
+    for n_in in range(1, 60, 3):
+        for n_out in (1, 5, 10, 17):
+            for r in (0.3, 0.65, 1.0, 1.7):
+                for nil in (0, 1, 2, 3, 4, 5):
+                    a = F.mlp_inner_neurons(n_in, n_out, r, nil)
+                    assert a == oracle.inner_neurons(n_in, n_out, r, nil), (n_in, n_out, r, nil)
+                    if all(v > 0 for v in a):
+                        assert F.mlp_count_weights([n_in, *a, n_out]) == oracle.count_weights([n_in, *a, n_out])
+    neurons = [10, 7, 10]
+    # flat order: layer -> to-neuron -> (bias, from-neurons)
+    assert F.mlp_weight_index(neurons, 0, 0, 0) == 0 and F.mlp_weight_index(neurons, 0, 1, 0) == 11
+    assert F.mlp_weight_index(neurons, 1, 0, 0) == 77 and F.mlp_weight_index(neurons, 1, 9, 7) == 156
+
+
+def test_episode_steps_bit_exact(F, oracle):
+    for T, tr in ((30.0, 1.0), (10.0, 1.0), (60.0, 1.0), (5.0, 0.0), (2.0, 0.5), (0.5, 0.0)):
+        assert F.episode_steps(T, tr) == oracle.episode_steps(T, tr)
+
+
+def test_sensor_config(F, oracle):
+    for name in ("uniform-a-0", "uniform-t+vxy+a-0", "uniform-a+vx+vy+r+t-0.01"):
+        a, b = F.sensor_config(name), oracle.sensor_config(name)
+        assert len(a) == len(b)
+        for x, y in zip(a, b):
+            for f in ("kind", "axes", "rotated", "soft_norm", "dom_min", "dom_max", "avg_window", "noise_sigma"):
+                assert getattr(x, f) == getattr(y, f), (name, f)
+
+
+def test_no_gpu_means_loud_failure_not_fallback(F):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    e = F.env_default()
+    with pytest.raises(F.VsrError) as ei:
+        F.Context(e, *F.terrain("flat"))
+    assert ei.value.code == F.VSR_ECUDA and "no CPU fallback" in str(ei.value)
+
+
+def test_create_rejects_bad_env(F):
+    e = F.env_default()
+    h = C.c_void_p()
+    assert F.lib().vsr_ctx_create(C.byref(e), C.byref(h)) == F.VSR_EINVAL  # no terrain
+    assert b"terrain" in F.lib().vsr_last_error(None)
+    assert F.lib().vsr_ctx_create(None, C.byref(h)) == F.VSR_EINVAL
+    assert F.lib().vsr_genome_len(None) == F.VSR_EINVAL

@@ -1,0 +1,189 @@
+"""Host-side mirror of the task boundary: `Locomotion.apply(robot) -> Outcome`, batched.
+
+Mirrors
+  Settings                      org.dyn4j.dynamics.Settings                       (locomotion/Starter.java:67)
+  Locomotion(finalT, terrain, settings), .apply, createTerrain                    (locomotion/Starter.java:83-94)
+  Outcome.getVelocity/getDistance/getTime/subOutcome                              (locomotion/Starter.java:174,430-433)
+  buildLocomotionTask                                                             (locomotion/Starter.java:83-94)
+plus `apply_all(robots)`: the whole population in one vsr_eval call.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Sequence
+
+import numpy as np
+
+from . import _ffi
+from .builder import build_mapper
+from .robot import CentralizedSensing, DistributedSensing, MultiLayerPerceptron, PhaseSin, Robot, RobotUtils
+
+
+@dataclass
+class Settings:
+    """dyn4j Settings() defaults (the only dyn4j symbol the reference touches)."""
+    step_frequency: float = 1.0 / 60.0
+    velocity_constraint_solver_iterations: int = 10
+    position_constraint_solver_iterations: int = 10
+
+
+@dataclass
+class Outcome:
+    """What survives of 2dhmsr's Outcome on the device: the observation window [transient_t, final_t)."""
+    velocity: float
+    distance: float
+    time: float
+    first_x: float
+    last_x: float
+    start_t: float
+    end_t: float
+
+    def get_velocity(self) -> float:
+        return self.velocity
+
+    def get_distance(self) -> float:
+        return self.distance
+
+    def get_time(self) -> float:
+        return self.time
+
+    def sub_outcome(self, start_t: float, end_t: float) -> "Outcome":
+        if start_t != self.start_t or end_t != self.end_t:
+            raise _ffi.VsrIllegalArgument(_ffi.VSR_EINVAL, "the device only keeps the window given to Locomotion(transient_t=...)")
+        return self
+
+
+def shard_range(n: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous index range of robots owned by `rank`: [rank*ceil(n/world), ...)."""
+    per = (n + world - 1) // world
+    lo = min(n, rank * per)
+    return lo, min(n, lo + per)
+
+
+class Locomotion:
+    """`new Locomotion(finalT, groundProfile, settings)`; `transient_t` folds the reference's
+    `.subOutcome(episodeTransientTime, episodeTime)` (Starter.java:430-433) into the same device pass."""
+
+    def __init__(self, final_t: float, ground_profile, settings: Settings | None = None, transient_t: float = 0.0,
+                 precision: int = 32, devices: Sequence[int] | None = None):
+        self.final_t, self.transient_t = float(final_t), float(transient_t)
+        self.xs = np.ascontiguousarray(ground_profile[0], dtype=np.float64)
+        self.ys = np.ascontiguousarray(ground_profile[1], dtype=np.float64)
+        self.settings = settings or Settings()
+        self.precision = precision
+        self.devices = list(devices) if devices else []
+        self._ctxs: dict = {}
+
+    @staticmethod
+    def create_terrain(name: str):
+        return _ffi.terrain(name)
+
+    # -- context cache: one vsr_ctx per (body, sensors, controller structure) ---------------------------
+    def _context(self, robot: Robot) -> _ffi.Context:
+        body = robot.get_voxels()
+        mask = body.mask()
+        voxels = [v for v in body.values() if v is not None]
+        if not voxels:
+            raise _ffi.VsrIllegalArgument(_ffi.VSR_EINVAL, "Target robot has no voxels")
+        skey = voxels[0].sensor_key()
+        if any(v.sensor_key() != skey for v in voxels):
+            raise _ffi.VsrError(_ffi.VSR_EUNSUPPORTED, "per-voxel sensor lists must be uniform in this build")
+        c = robot.get_controller()
+        if isinstance(c, PhaseSin):
+            ckey = ("phase", c.frequency, c.amplitude)
+        elif isinstance(c, CentralizedSensing):
+            ckey = ("central", tuple(self._mlp(c.function).neurons))
+        elif isinstance(c, DistributedSensing):
+            f = next(f for f in c.get_functions().values() if f is not None)
+            ckey = ("dist", c.signals, tuple(self._mlp(f).neurons))
+        else:
+            raise _ffi.VsrError(_ffi.VSR_EUNSUPPORTED, f"controller {type(c).__name__} is outside the hot path")
+        key = (mask.tobytes(), mask.shape, skey, ckey)
+        ctx = self._ctxs.get(key)
+        if ctx is None:
+            e = _ffi.env_default()
+            e.dt = self.settings.step_frequency
+            e.vel_iters = self.settings.velocity_constraint_solver_iterations
+            e.pos_iters = self.settings.position_constraint_solver_iterations
+            e.final_t, e.transient_t, e.precision = self.final_t, self.transient_t, self.precision
+            e.n_devices = len(self.devices)
+            for i, d in enumerate(self.devices):
+                e.devices[i] = d
+            ctx = _ffi.Context(e, self.xs, self.ys)
+            ctx.body_set(mask, voxels[0].sensors)
+            if ckey[0] == "phase":
+                ctx.controller_set(_ffi.CTRL_PHASE_SIN, (), 0, c.frequency, c.amplitude)
+            elif ckey[0] == "central":
+                ctx.controller_set(_ffi.CTRL_MLP_CENTRALIZED, ckey[1])
+            else:
+                ctx.controller_set(_ffi.CTRL_MLP_DISTRIBUTED_HOMO, ckey[2], c.signals)
+            self._ctxs[key] = ctx
+        return ctx
+
+    @staticmethod
+    def _mlp(f) -> MultiLayerPerceptron:
+        if not isinstance(f, MultiLayerPerceptron):
+            raise _ffi.VsrError(_ffi.VSR_EUNSUPPORTED, "only MultiLayerPerceptron functions are built (builder/function/MLP.java)")
+        return f
+
+    @staticmethod
+    def genome_of(robot: Robot) -> np.ndarray:
+        """Flatten the controller parameters in the order the kernel expects (== the mappers' genome order)."""
+        c = robot.get_controller()
+        if isinstance(c, PhaseSin):
+            return np.array([p for p in c.phases.values() if p is not None], dtype=np.float64)
+        if isinstance(c, CentralizedSensing):
+            return Locomotion._mlp(c.function).get_params()
+        fs = [f for f in c.get_functions().values() if f is not None]
+        w0 = Locomotion._mlp(fs[0]).get_params()
+        if any(f is not fs[0] and not np.array_equal(Locomotion._mlp(f).get_params(), w0) for f in fs[1:]):
+            raise _ffi.VsrError(_ffi.VSR_EUNSUPPORTED, "heterogeneous DistributedSensing is outside this build")
+        return w0
+
+    def apply_all(self, robots: Sequence[Robot]) -> list[Outcome]:
+        if not robots:
+            return []
+        ctx = self._context(robots[0])
+        genomes = np.stack([self.genome_of(r) for r in robots])
+        _, res = ctx.eval(genomes, want_results=True)
+        return [Outcome(float(r["velocity"]), float(r["distance"]), float(r["time"]), float(r["first_x"]), float(r["last_x"]),
+                        self.transient_t, self.final_t) for r in res]
+
+    def apply(self, robot: Robot) -> Outcome:
+        return self.apply_all([robot])[0]
+
+
+def build_locomotion_task(terrain_name: str, episode_t: float, transient_t: float = 0.0, **kw) -> Locomotion:
+    """Starter.buildLocomotionTask (Starter.java:83-94) for fixed (non `-rnd`) terrains."""
+    if "-rnd" in terrain_name:
+        raise _ffi.VsrError(_ffi.VSR_EUNSUPPORTED, "per-evaluation random terrains (-rnd) are a 'next' row (SURVEY.md 8f-4)")
+    return Locomotion(episode_t, Locomotion.create_terrain(terrain_name), Settings(), transient_t, **kw)
+
+
+class PopulationEvaluator:
+    """genome matrix -> fitness vector for one (shape, sensors, mapper, terrain): what a batching JGEA evolver calls
+    once per generation.  The genome layout IS the mapper's layout, so rows go to the device untouched."""
+
+    def __init__(self, shape: str, sensor_config: str, mapper: str, terrain: str, episode_t: float, transient_t: float,
+                 precision: int = 32, devices: Sequence[int] | None = None):
+        self.task = build_locomotion_task(terrain, episode_t, transient_t, precision=precision, devices=devices)
+        body = RobotUtils.build_sensorizing_function(sensor_config)(RobotUtils.build_shape(shape))
+        self.target = Robot(None, body)
+        self.mapper = build_mapper(mapper)
+        self.genome_len = len(self.mapper.example_for(self.target))
+        proto = self.mapper.build_for(self.target)(np.zeros(self.genome_len))
+        self.ctx = self.task._context(proto)
+        if self.ctx.genome_len != self.genome_len:
+            raise _ffi.VsrIllegalArgument(_ffi.VSR_EDIM, f"mapper genome length {self.genome_len} != device {self.ctx.genome_len}")
+        self.n_voxels = self.ctx.n_voxels
+
+    def evaluate(self, genomes: np.ndarray) -> np.ndarray:
+        return self.ctx.eval(genomes)
+
+    def kernel_launches(self) -> int:
+        return self.ctx.kernel_launches()
+
+
+def population_evaluator(shape: str, sensor_config: str, mapper: str, terrain: str, episode_t: float,
+                         transient_t: float, **kw) -> PopulationEvaluator:
+    return PopulationEvaluator(shape, sensor_config, mapper, terrain, episode_t, transient_t, **kw)

@@ -1,0 +1,228 @@
+"""Host-side mirror of the 2dhmsr types the reference hands to the hot path (Robot = body grid + sensors +
+controller).  These are plain descriptions: all simulation happens in libvsr_eval.so.
+
+Mirrors (names and argument meaning) of, as used by the reference:
+  Grid                      it.units.erallab.hmsrobots.util.Grid            (builder/robot/BrainPhaseValues.java:38-46)
+  Voxel(sensors)            ...core.objects.Voxel                           (builder/robot/SensorBrainCentralized.java:81-87)
+  Robot(controller, voxels) ...core.objects.Robot                           (builder/robot/BrainCentralized.java:42-45)
+  PhaseSin(f, a, phases)    ...core.controllers.PhaseSin                    (builder/robot/BrainPhaseValues.java:47-50)
+  CentralizedSensing        ...core.controllers.CentralizedSensing          (builder/robot/BrainCentralized.java:28-43)
+  DistributedSensing        ...core.controllers.DistributedSensing          (builder/robot/BrainHomoDistributed.java:76-82)
+  MultiLayerPerceptron      ...core.controllers.MultiLayerPerceptron        (builder/function/MLP.java:63-69)
+  RealFunction.build        ...core.controllers.RealFunction                (builder/robot/BrainCentralized.java:52-56)
+  RobotUtils.buildShape / buildSensorizingFunction                          (locomotion/Starter.java:402-406)
+"""
+from __future__ import annotations
+
+import copy
+from dataclasses import dataclass, field
+from typing import Callable, Generic, Iterator, Optional, Sequence, TypeVar
+
+import numpy as np
+
+from . import _ffi
+
+T = TypeVar("T")
+
+
+class Grid(Generic[T]):
+    """w x h grid; get(x, y) = ts[y*w + x]; values() and iteration are row-major (y outer, x inner), y=0 bottom."""
+
+    @dataclass(frozen=True)
+    class Key:
+        x: int
+        y: int
+
+    @dataclass(frozen=True)
+    class Entry(Generic[T]):
+        key: "Grid.Key"
+        value: T
+
+    def __init__(self, w: int, h: int, filler=None):
+        self.w, self.h = w, h
+        if callable(filler):
+            self._ts = [filler(i % w, i // w) for i in range(w * h)]
+        else:
+            self._ts = [filler for _ in range(w * h)]
+
+    @staticmethod
+    def create(other: "Grid", fn: Optional[Callable] = None) -> "Grid":
+        g = Grid(other.w, other.h)
+        if fn is not None:
+            g._ts = [fn(v) for v in other._ts]
+        return g
+
+    def get(self, x: int, y: int):
+        if x < 0 or x >= self.w or y < 0 or y >= self.h:
+            return None
+        return self._ts[y * self.w + x]
+
+    def set(self, x: int, y: int, v) -> None:
+        self._ts[y * self.w + x] = v
+
+    def values(self) -> list:
+        return list(self._ts)
+
+    def __iter__(self) -> Iterator["Grid.Entry"]:
+        for i, v in enumerate(self._ts):
+            yield Grid.Entry(Grid.Key(i % self.w, i // self.w), v)
+
+    def count(self, pred: Callable) -> int:
+        return sum(1 for v in self._ts if pred(v))
+
+    def mask(self) -> np.ndarray:
+        return np.array([0 if v is None or v is False else 1 for v in self._ts], dtype=np.uint8).reshape(self.h, self.w)
+
+
+@dataclass
+class Voxel:
+    sensors: list = field(default_factory=list)  # list[_ffi.SensorDesc]
+
+    def sensor_dim(self) -> int:
+        return sum(bin(s.axes & 3).count("1") if s.kind == _ffi.SENSOR_VELOCITY else 1 for s in self.sensors)
+
+    def sensor_key(self) -> tuple:
+        return tuple((s.kind, s.axes, s.rotated, s.soft_norm, s.dom_min, s.dom_max, s.avg_window, s.noise_sigma)
+                     for s in self.sensors)
+
+
+# ---- functions ---------------------------------------------------------------------------------------
+class TimedRealFunction:
+    def get_input_dimension(self) -> int:
+        raise NotImplementedError
+
+    def get_output_dimension(self) -> int:
+        raise NotImplementedError
+
+
+class RealFunction(TimedRealFunction):
+    """Shape-only placeholder, RealFunction.build(f, nIn, nOut) in the reference's exampleFor()."""
+
+    def __init__(self, n_in: int, n_out: int):
+        self.n_in, self.n_out = n_in, n_out
+
+    @staticmethod
+    def build(_f, n_in: int, n_out: int) -> "RealFunction":
+        return RealFunction(n_in, n_out)
+
+    def get_input_dimension(self) -> int:
+        return self.n_in
+
+    def get_output_dimension(self) -> int:
+        return self.n_out
+
+
+class MultiLayerPerceptron(TimedRealFunction):
+    TANH = "tanh"
+
+    def __init__(self, activation: str, n_in: int, inner: Sequence[int], n_out: int, weights: Sequence[float]):
+        if activation != self.TANH:
+            raise _ffi.VsrError(_ffi.VSR_EUNSUPPORTED, "only the TANH activation (builder/function/MLP.java:20-22) is built")
+        self.neurons = [n_in, *inner, n_out]
+        self.weights = np.asarray(weights, dtype=np.float64)
+        n = self.count_weights(self.neurons)
+        if n != len(self.weights):
+            raise _ffi.VsrIllegalArgument(_ffi.VSR_EDIM, f"Wrong number of values for weights: {n} expected, {len(self.weights)} found")
+
+    @staticmethod
+    def count_neurons(n_in: int, inner: Sequence[int], n_out: int) -> list[int]:
+        return [n_in, *inner, n_out]
+
+    @staticmethod
+    def count_weights(neurons_or_in, inner=None, n_out=None) -> int:
+        neurons = neurons_or_in if inner is None else [neurons_or_in, *inner, n_out]
+        return _ffi.mlp_count_weights(list(neurons))
+
+    def get_input_dimension(self) -> int:
+        return self.neurons[0]
+
+    def get_output_dimension(self) -> int:
+        return self.neurons[-1]
+
+    def get_params(self) -> np.ndarray:
+        return self.weights
+
+
+# ---- controllers ---------------------------------------------------------------------------------------
+class Controller:
+    @staticmethod
+    def empty() -> "Controller":
+        return Controller()
+
+
+class PhaseSin(Controller):
+    def __init__(self, frequency: float, amplitude: float, phases: Grid):
+        self.frequency, self.amplitude, self.phases = frequency, amplitude, phases
+
+
+class CentralizedSensing(Controller):
+    def __init__(self, body: Grid, function: TimedRealFunction):
+        self.function = function
+        self.n_in, self.n_out = self.n_of_inputs(body), self.n_of_outputs(body)
+
+    @staticmethod
+    def n_of_inputs(body: Grid) -> int:
+        return sum(v.sensor_dim() for v in body.values() if v is not None)
+
+    @staticmethod
+    def n_of_outputs(body: Grid) -> int:
+        return body.count(lambda v: v is not None)
+
+
+class DistributedSensing(Controller):
+    N_DIRS = 4
+
+    def __init__(self, body: Grid, signals: int):
+        self.signals = signals
+        self.functions: Grid = Grid.create(body)
+
+    @staticmethod
+    def n_of_inputs(voxel: Voxel, signals: int) -> int:
+        return voxel.sensor_dim() + signals * DistributedSensing.N_DIRS
+
+    @staticmethod
+    def n_of_outputs(voxel: Voxel, signals: int) -> int:
+        return 1 + signals * DistributedSensing.N_DIRS
+
+    def get_functions(self) -> Grid:
+        return self.functions
+
+
+@dataclass
+class Robot:
+    controller: Controller
+    voxels: Grid
+
+    def get_voxels(self) -> Grid:
+        return self.voxels
+
+    def get_controller(self) -> Controller:
+        return self.controller
+
+
+class SerializationUtils:
+    @staticmethod
+    def clone(obj):
+        return copy.deepcopy(obj)
+
+
+class RobotUtils:
+    @staticmethod
+    def build_shape(name: str) -> Grid:
+        m = _ffi.shape_mask(name)
+        return Grid(m.shape[1], m.shape[0], lambda x, y: bool(m[y, x]))
+
+    @staticmethod
+    def build_sensorizing_function(name: str) -> Callable[[Grid], Grid]:
+        sensors = _ffi.sensor_config(name) if name else []
+
+        def fn(body: Grid) -> Grid:
+            return Grid(body.w, body.h, lambda x, y: Voxel(list(sensors)) if body.get(x, y) else None)
+
+        return fn
+
+    @staticmethod
+    def build_robot_transformation(name: str, _random=None) -> Callable[[Robot], Robot]:
+        if name != "identity":
+            raise _ffi.VsrError(_ffi.VSR_EUNSUPPORTED, f"transformation {name} is outside the hot path (SURVEY.md 8a-19)")
+        return lambda r: r
