@@ -14,7 +14,11 @@
 
 namespace {
 
-constexpr int kWarps = 4;
+// launch shapes (warps per CTA, min CTAs per SM -> register cap); picked per context (VSR_LAUNCH_SHAPE)
+struct Shape { int warps, minb; };
+constexpr Shape kShapes[] = {{4, 2}, {5, 2}, {8, 1}, {10, 1}, {4, 3}, {4, 4}};
+constexpr int kNumShapes = sizeof(kShapes) / sizeof(kShapes[0]);
+constexpr int kDefaultShape = 1;
 
 thread_local std::string g_create_error;
 
@@ -57,6 +61,8 @@ struct vsr_ctx {
   vsr::KParams kp;
   std::vector<uint8_t> win_tab;
   size_t smem_bytes = 0;
+  int shape = kDefaultShape, warps = 4;
+  const void* kernel = nullptr;
   std::vector<DeviceState> devs;
   std::string err;
   int64_t launches = 0;
@@ -107,13 +113,35 @@ int genome_len_of(const vsr_ctx* c) {
 
 size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
 
-template <class R>
-void launch_kernel(const vsr::KParams& kp, int grid, size_t smem, cudaStream_t st) {
-  vsr::vsr_episode_kernel<R, kWarps><<<grid, kWarps * 32, smem, st>>>(kp);
+template <int W, int B>
+const void* f32_kernel(int ctrl) {
+  switch (ctrl) {
+    case VSR_CTRL_PHASE_SIN: return (const void*)vsr::vsr_episode_kernel<float, VSR_CTRL_PHASE_SIN, W, B>;
+    case VSR_CTRL_MLP_CENTRALIZED: return (const void*)vsr::vsr_episode_kernel<float, VSR_CTRL_MLP_CENTRALIZED, W, B>;
+    default: return (const void*)vsr::vsr_episode_kernel<float, VSR_CTRL_MLP_DISTRIBUTED_HOMO, W, B>;
+  }
 }
 
-const void* kernel_ptr(int precision) {
-  return precision == 64 ? (const void*)vsr::vsr_episode_kernel<double, kWarps> : (const void*)vsr::vsr_episode_kernel<float, kWarps>;
+// FP64 parity build: one shape only
+constexpr int kWarps64 = 4;
+const void* f64_kernel(int ctrl) {
+  switch (ctrl) {
+    case VSR_CTRL_PHASE_SIN: return (const void*)vsr::vsr_episode_kernel<double, VSR_CTRL_PHASE_SIN, kWarps64, 1>;
+    case VSR_CTRL_MLP_CENTRALIZED: return (const void*)vsr::vsr_episode_kernel<double, VSR_CTRL_MLP_CENTRALIZED, kWarps64, 1>;
+    default: return (const void*)vsr::vsr_episode_kernel<double, VSR_CTRL_MLP_DISTRIBUTED_HOMO, kWarps64, 1>;
+  }
+}
+
+const void* kernel_ptr(int precision, int ctrl, int shape) {
+  if (precision == 64) return f64_kernel(ctrl);
+  switch (shape) {
+    case 0: return f32_kernel<4, 2>(ctrl);
+    case 1: return f32_kernel<5, 2>(ctrl);
+    case 2: return f32_kernel<8, 1>(ctrl);
+    case 3: return f32_kernel<10, 1>(ctrl);
+    case 4: return f32_kernel<4, 3>(ctrl);
+    default: return f32_kernel<4, 4>(ctrl);
+  }
 }
 
 // (re)derive everything that depends on env + body + controller
@@ -151,6 +179,21 @@ int finalize(vsr_ctx* ctx) {
     k.sp_beta = e.dt * w * w / c;
   }
   k.weld_anchor = m;
+  {
+    vsr::KConstF& c = k.cf;
+    c.c_dt = (float)k.dt; c.c_half = (float)k.half; c.c_im = (float)k.inv_m; c.c_ii = (float)k.inv_i; c.c_mu = (float)k.mu;
+    c.c_lin_tol = (float)k.lin_tol; c.c_ang_tol = (float)k.ang_tol; c.c_max_corr = (float)k.max_lin_corr; c.c_baum = (float)k.baumgarte;
+    c.c_gdt = (float)(k.g * k.dt); c.c_lin_f = (float)k.lin_f; c.c_ang_f = (float)k.ang_f;
+    c.c_sp_sigma = (float)k.sp_sigma; c.c_sp_boversig = (float)(k.sp_beta / k.sp_sigma); c.c_sp_cfrac = (float)k.sp_cfrac;
+    c.c_rope_lower = (float)k.rope_lower; c.c_rope_E = (float)(1.0 / (2.0 * k.inv_m));
+    c.c_wa = (float)m; c.c_wA = (float)(2.0 * k.inv_m); c.c_wh = (float)(0.5 * k.inv_i);
+    c.c_wD = (float)(1.0 / ((2.0 * k.inv_m) * (2.0 * k.inv_m + 0.5 * k.inv_i * m * m)));
+    c.c_w_i2i = (float)(1.0 / (2.0 * k.inv_i));
+    c.c_rest_vel = (float)k.rest_vel; c.c_rest_e = (float)k.rest_e;
+    c.c_max_trans = (float)k.max_trans; c.c_max_trans2 = (float)(k.max_trans * k.max_trans); c.c_max_rot = (float)k.max_rot;
+    c.c_inv_area2 = (float)(0.5 / (L * L)); c.c_mass_off = (float)(L / 2 - k.half); c.c_base_pad = 0;
+    for (int i = 0; i < 3; i++) { c.c_range_min[i] = (float)k.range_min[i]; c.c_range_rest[i] = (float)k.range_rest[i]; c.c_range_max[i] = (float)k.range_max[i]; }
+  }
   k.scaff_mask = e.scaffolding_mask; k.limit_contraction = e.limit_contraction;
   // body
   k.n_vox = ctx->n_vox;
@@ -191,6 +234,10 @@ int finalize(vsr_ctx* ctx) {
   if (rc) return fail(ctx, rc, "bad episode times");
   if (!kf) return fail(ctx, VSR_EINVAL, "no observation falls inside [transient_t, final_t)");
   k.n_steps = ns; k.k_first = kf; k.k_last = kl;
+  {
+    volatile double t = 0.0;
+    for (int s = 1; s <= ns; s++) { t = t + e.dt; if (s == kf) k.t_first = t; if (s == kl) k.t_last = t; }
+  }
   // sensors
   k.n_sensors = (int)ctx->sensors.size();
   int off = 0, navg = 0;
@@ -199,7 +246,7 @@ int finalize(vsr_ctx* ctx) {
     const vsr_sensor_desc& s = ctx->sensors[i];
     vsr::SensorK& sk = k.sensors[i];
     sk.kind = s.kind; sk.axes = s.axes; sk.rotated = s.rotated; sk.soft_norm = s.soft_norm;
-    sk.dom_min = s.dom_min; sk.dom_max = s.dom_max;
+    sk.dom_min = s.dom_min; sk.dom_inv = s.soft_norm ? 1.0 / (s.dom_max - s.dom_min) : 1.0;
     sk.off = off; sk.dim = sensor_dim(s);
     sk.avg = -1;
     if (s.avg_window > 0) {
@@ -236,12 +283,13 @@ int finalize(vsr_ctx* ctx) {
   for (int i = 0; i < k.n_layers; i++) { k.layers[i] = ctx->layers[i]; k.max_neurons = std::max(k.max_neurons, ctx->layers[i]); }
   // shared memory layout (per warp)
   const size_t rs = e.precision == 64 ? 8 : 4;
-  int S = 64;
+  // contact-pool slots per warp: 4/3 manifolds per voxel lane (every bottom mass of every robot touching, plus
+  // polygon-boundary doubles); overflow is counted in vsr_result.contact_overflow
+  int S = std::max(16, std::min(64, k.robots_per_warp * ctx->n_vox * 4 / 3));
   if (const char* ev = std::getenv("VSR_POOL_SLOTS")) S = std::max(8, std::min(255, std::atoi(ev)));
   k.pool_slots = S;
   size_t o = 0;
-  k.off_pool_p = (int)o; o = align16(o + 2 * vsr::kPoolPersist * S * rs);
-  k.off_pool_s = (int)o; o = align16(o + vsr::kPoolSolve * S * rs);
+  k.off_pool_p = (int)o; o = align16(o + (size_t)vsr::kPoolStride * S * rs);
   k.off_pool_m = (int)o; o = align16(o + 2 * S * 4);
   k.off_pool_cnt = (int)o; o = align16(o + 4);
   k.off_w = (int)o;
@@ -251,13 +299,31 @@ int finalize(vsr_ctx* ctx) {
   if (ctx->kind == VSR_CTRL_MLP_DISTRIBUTED_HOMO) o = align16(o + (size_t)2 * k.max_neurons * 32 * rs);
   k.off_sig = (int)o;
   if (ctx->kind == VSR_CTRL_MLP_DISTRIBUTED_HOMO) o = align16(o + (size_t)2 * 32 * 4 * std::max(1, k.signals) * rs);
+  k.off_bias = (int)o;
+  o = align16(o + (size_t)18 * 32 * rs);
+  o = (o + 31) & ~size_t(31);
+  k.off_arm = (int)o;
+  o = align16(o + (size_t)8 * 32 * 4 * rs);
+  k.off_eff = (int)o;
+  o = align16(o + (size_t)8 * 32 * 2 * rs);
+  k.off_park = (int)o;
+  o = align16(o + (size_t)vsr::kPark * 32 * rs);
+  k.off_cold = (int)o;
+  o = align16(o + (size_t)navg * 32 * 12); // Average running sums + counts
   k.smem_warp_stride = (int)o;
-  ctx->smem_bytes = o * kWarps;
+  k.sync_mask = 59; // step start, before velocity loop, before position phase, before/after detect (tools/bench sweep)
+  if (const char* ev = std::getenv("VSR_SYNC_MASK")) k.sync_mask = std::atoi(ev);
+  ctx->shape = kDefaultShape;
+  if (const char* ev = std::getenv("VSR_LAUNCH_SHAPE")) ctx->shape = std::max(0, std::min(kNumShapes - 1, std::atoi(ev)));
+  ctx->warps = e.precision == 64 ? kWarps64 : kShapes[ctx->shape].warps;
+  ctx->kernel = kernel_ptr(e.precision, ctx->kind, ctx->shape);
+  ctx->smem_bytes = o * ctx->warps;
+  if (k.n_t > 16383) return fail(ctx, VSR_EUNSUPPORTED, "terrains with more than 16383 vertices are not supported");
   if (ctx->smem_bytes > 227 * 1024) return fail(ctx, VSR_EUNSUPPORTED, "controller too large for shared memory");
   // per-device uploads
   for (auto& d : ctx->devs) {
     CK(cudaSetDevice(d.dev));
-    CK(cudaFuncSetAttribute(kernel_ptr(e.precision), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_bytes));
+    CK(cudaFuncSetAttribute(ctx->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_bytes));
     if (d.d_win) { cudaFree(d.d_win); d.d_win = nullptr; }
     CK(cudaMalloc(&d.d_win, ctx->win_tab.size()));
     CK(cudaMemcpy(d.d_win, ctx->win_tab.data(), ctx->win_tab.size(), cudaMemcpyHostToDevice));
@@ -284,8 +350,9 @@ int ensure_capacity(vsr_ctx* ctx, DeviceState& d, size_t n) {
   return VSR_OK;
 }
 
-int grid_for(const vsr::KParams& k, size_t n) {
-  const size_t per_cta = (size_t)kWarps * k.robots_per_warp;
+int grid_for(const vsr_ctx* ctx, size_t n) {
+  const vsr::KParams& k = ctx->kp;
+  const size_t per_cta = (size_t)ctx->warps * k.robots_per_warp;
   return (int)((n + per_cta - 1) / per_cta);
 }
 
@@ -293,7 +360,7 @@ int ensure_hist(vsr_ctx* ctx, DeviceState& d, int grid) {
   const vsr::KParams& k = ctx->kp;
   if (!k.n_avg) return VSR_OK;
   const size_t rs = ctx->env.precision == 64 ? 8 : 4;
-  size_t bytes = (size_t)k.hist_cap * k.n_avg * grid * kWarps * 32 * rs;
+  size_t bytes = (size_t)k.hist_cap * k.n_avg * grid * ctx->warps * 32 * rs;
   if (bytes > d.hist_bytes) {
     if (d.d_hist) cudaFree(d.d_hist);
     d.hist_bytes = 0;
@@ -308,15 +375,15 @@ int enqueue(vsr_ctx* ctx, DeviceState& d, const double* d_genomes, size_t n, dou
             cudaStream_t st, double* trv, double* trb, double* trc, int trace_steps, bool time_it) {
   if (n == 0) return VSR_OK;
   vsr::KParams k = ctx->kp;
-  const int grid = grid_for(k, n);
+  const int grid = grid_for(ctx, n);
   int rc = ensure_hist(ctx, d, grid);
   if (rc) return rc;
   k.tx = d.d_tx; k.ty = d.d_ty; k.win_tab = d.d_win; k.hist = d.d_hist;
   k.genomes = d_genomes; k.fitness = d_fitness; k.results = d_results; k.n_robots = (int)n;
   k.tr_vertices = trv; k.tr_bodies = trb; k.tr_ctrl = trc; k.trace_steps = trace_steps;
   if (time_it) CK(cudaEventRecord(d.ev0, st));
-  if (ctx->env.precision == 64) launch_kernel<double>(k, grid, ctx->smem_bytes, st);
-  else launch_kernel<float>(k, grid, ctx->smem_bytes, st);
+  void* args[] = {&k};
+  CK(cudaLaunchKernel(ctx->kernel, dim3(grid), dim3(ctx->warps * 32), args, ctx->smem_bytes, st));
   CK(cudaGetLastError());
   if (time_it) { CK(cudaEventRecord(d.ev1, st)); d.timed = true; }
   ctx->launches++;
@@ -549,15 +616,12 @@ int vsr_kernel_info(const vsr_ctx* ctx_c, int32_t* regs, int32_t* smem, int32_t*
   if (!ctx->ready) return fail(ctx, VSR_ESTATE, "body and controller must be set first");
   CK(cudaSetDevice(ctx->devs[0].dev));
   cudaFuncAttributes a;
-  CK(cudaFuncGetAttributes(&a, kernel_ptr(ctx->env.precision)));
+  CK(cudaFuncGetAttributes(&a, ctx->kernel));
   int nb = 0;
-  if (ctx->env.precision == 64)
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, vsr::vsr_episode_kernel<double, kWarps>, kWarps * 32, ctx->smem_bytes));
-  else
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, vsr::vsr_episode_kernel<float, kWarps>, kWarps * 32, ctx->smem_bytes));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ctx->kernel, ctx->warps * 32, ctx->smem_bytes));
   if (regs) *regs = a.numRegs;
   if (smem) *smem = (int)ctx->smem_bytes;
-  if (threads) *threads = kWarps * 32;
+  if (threads) *threads = ctx->warps * 32;
   if (rpw) *rpw = ctx->kp.robots_per_warp;
   if (ctas_per_sm) *ctas_per_sm = nb;
   return VSR_OK;

@@ -13,6 +13,9 @@
 //   * controller (MLP / PhaseSin / DistributedSensing) runs per robot on the same lanes once per step
 //   * positions are stored relative to a per-lane integer origin so FP32 keeps ~1e-7 absolute resolution
 //   * HBM traffic: genome in (G doubles), one vsr_result out per robot; nothing else during the episode
+//   * the warps of a CTA are re-aligned once per step (__syncthreads) so they share instruction fetches:
+//     the step body is several thousand instructions and the first version of this kernel spent 80% of
+//     its cycles in `no_instruction` stalls (profiles/r1_ncu_summary.md)
 //
 // Constraint order == the oracle's canonical order (oracle/vsr_oracle.c header).
 #pragma once
@@ -27,18 +30,31 @@ constexpr int kMaxVox = 32;
 constexpr int kMaxSensors = 6;
 constexpr int kMaxLayers = 8;
 constexpr int kMaxMan = 3;       // manifolds per corner mass (ground polygons it can touch at once)
+constexpr int kMaxLaneMan = 8;   // manifolds per voxel
 constexpr int kMaxAvg = 6;       // averaged readings per voxel
 constexpr int kPoolPersist = 12; // NX NY (PX PY D JN JT)x2
 constexpr int kPoolSolve = 18;   // (RX RY MN MT VB LX LY)x2 K12 IK11 IK12 IK22
+constexpr int kPark = 23;         // X Y A (12) + polygon cache (6) + origin (2) + rest (3)
+constexpr int kPoolStride = 2 * kPoolPersist + kPoolSolve + 1; // 43 words per slot: odd -> conflict-free across slots
 
 struct SensorK {
   int kind, axes, rotated, soft_norm;
-  double dom_min, dom_max;
-  int avg;      // index into the averaged-reading table or -1
-  int off, dim; // offset / size inside the voxel's reading vector
+  double dom_min, dom_inv; // soft norm: (x - dom_min) * dom_inv
+  int avg;                 // index into the averaged-reading table or -1
+  int off, dim;            // offset / size inside the voxel's reading vector
+};
+
+// FP32 copies of the scalar constants: the FP32 kernel reads them straight from the constant bank
+// (no double->float conversion, no long-lived register)
+struct KConstF {
+  float c_dt, c_half, c_im, c_ii, c_mu, c_lin_tol, c_ang_tol, c_max_corr, c_baum, c_gdt, c_lin_f, c_ang_f, c_sp_sigma, c_sp_boversig,
+      c_sp_cfrac, c_rope_lower, c_rope_E, c_wa, c_wA, c_wh, c_wD, c_w_i2i, c_rest_vel, c_rest_e, c_max_trans, c_max_trans2, c_max_rot,
+      c_inv_area2, c_mass_off, c_base_pad;
+  float c_range_min[3], c_range_rest[3], c_range_max[3];
 };
 
 struct KParams {
+  KConstF cf;
   // dyn4j settings
   double dt, g, baumgarte, lin_tol, ang_tol, max_lin_corr, max_trans, max_rot, rest_vel;
   int vel_iters, pos_iters;
@@ -68,6 +84,7 @@ struct KParams {
   double freq, amp;
   // episode
   int n_steps, k_first, k_last;
+  double t_first, t_last; // accumulated times of the first/last kept observation (host-emulated, same IEEE adds)
   // io
   const double* genomes;
   double* fitness;
@@ -79,35 +96,98 @@ struct KParams {
   // shared-memory layout (bytes from the CTA's dynamic smem base; per warp strides)
   int pool_slots;
   int smem_warp_stride; // bytes per warp
-  int off_pool_p, off_pool_s, off_pool_m, off_pool_cnt, off_w, off_act, off_sig;
+  int off_pool_p, off_pool_m, off_pool_cnt, off_w, off_act, off_sig, off_bias, off_arm, off_eff, off_park, off_cold;
+  int sync_mask; // phase-alignment barriers (bit0 step start, bit1 before velocity loop, bit2 every velocity
+                 // iteration, bit3 before position phase, bit4 before detect, bit5 before sensing)
 };
 
 // ------------------------------------------------------------------------------------------------
-// small math helpers (precise versions; the FP32 build uses no fast-math intrinsics except rsqrt-free sqrt)
+// math: the FP32 build uses single-instruction MUFU reciprocals / rsqrt and short polynomial
+// sincos / tanh (all within a few ulp); the FP64 build uses the precise libm calls.
 // ------------------------------------------------------------------------------------------------
 template <class R> struct M;
 template <> struct M<float> {
-  static __device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
-  static __device__ __forceinline__ void sincos_(float a, float* s, float* c) { sincosf(a, s, c); }
-  static __device__ __forceinline__ float tanh_(float x) { return tanhf(x); }
-  static __device__ __forceinline__ float atan2_(float y, float x) { return atan2f(y, x); }
+  static __device__ __forceinline__ float rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+  static __device__ __forceinline__ float rsqrt_(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
   static __device__ __forceinline__ float abs_(float x) { return fabsf(x); }
   static __device__ __forceinline__ float max_(float a, float b) { return fmaxf(a, b); }
   static __device__ __forceinline__ float min_(float a, float b) { return fminf(a, b); }
   static __device__ __forceinline__ float rint_(float a) { return rintf(a); }
+  // Cody-Waite reduction by pi/2 + minimax polynomials on [-pi/4, pi/4]; |a| < ~1e5
+  static __device__ __forceinline__ void sincos_(float a, float* sn, float* cs) {
+    const float k = rintf(a * 0.636619772367581343f);
+    float r = fmaf(k, -1.57079625129699707031f, a);
+    r = fmaf(k, -7.54978941586159635335e-08f, r);
+    const float r2 = r * r;
+    float s = fmaf(r2, 2.86567956e-6f, -1.98559923e-4f);
+    s = fmaf(s, r2, 8.33338592e-3f);
+    s = fmaf(s, r2, -1.66666672e-1f);
+    s = fmaf(s * r2, r, r);
+    float c = fmaf(r2, 2.44677067e-5f, -1.38877297e-3f);
+    c = fmaf(c, r2, 4.16666567e-2f);
+    c = fmaf(c, r2, -0.5f);
+    c = fmaf(c, r2, 1.0f);
+    const int q = (int)k;
+    const float ss = (q & 1) ? c : s, cc = (q & 1) ? s : c;
+    *sn = (q & 2) ? -ss : ss;
+    *cs = ((q + 1) & 2) ? -cc : cc;
+  }
+  // rotate (c,s) by a small angle d (position-solver corrections); falls back to the full evaluation
+  static __device__ __forceinline__ void rotate(float& a, float& c, float& s, float d) {
+    a += d;
+    if (fabsf(d) < 0.125f) {
+      const float d2 = d * d;
+      const float sd = d * fmaf(d2, fmaf(d2, 8.33333333e-3f, -1.66666667e-1f), 1.0f);
+      const float cd = fmaf(d2, fmaf(d2, fmaf(d2, -1.38888889e-3f, 4.16666667e-2f), -0.5f), 1.0f);
+      const float c2 = c * cd - s * sd;
+      s = s * cd + c * sd;
+      c = c2;
+    } else {
+      sincos_(a, &s, &c);
+    }
+  }
+  static __device__ __forceinline__ float tanh_(float x) {
+    // 1 - 2/(e^{2x}+1); ex2.approx + rcp.approx, abs error ~2e-7
+    const float xc = fminf(fmaxf(x, -15.f), 15.f);
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(xc * 2.88539008177792681472f));
+    return 1.0f - 2.0f * rcp(e + 1.0f);
+  }
+  static __device__ __forceinline__ float atan2_(float y, float x) { return atan2f(y, x); }
+  // a * sin(2 pi f t + phase): the turn count is reduced in double, the sine is FP32
+  static __device__ __forceinline__ float phase_sin(double amp, double freq, double t, float phase) {
+    double u = freq * t;
+    u -= floor(u);
+    float s, c;
+    sincos_(fmaf((float)u, 6.28318530717958647692f, phase), &s, &c);
+    return (float)amp * s;
+  }
 };
 template <> struct M<double> {
-  static __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
-  static __device__ __forceinline__ void sincos_(double a, double* s, double* c) { sincos(a, s, c); }
-  static __device__ __forceinline__ double tanh_(double x) { return tanh(x); }
-  static __device__ __forceinline__ double atan2_(double y, double x) { return atan2(y, x); }
+  static __device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
+  static __device__ __forceinline__ double rsqrt_(double x) { return 1.0 / sqrt(x); }
   static __device__ __forceinline__ double abs_(double x) { return fabs(x); }
   static __device__ __forceinline__ double max_(double a, double b) { return fmax(a, b); }
   static __device__ __forceinline__ double min_(double a, double b) { return fmin(a, b); }
   static __device__ __forceinline__ double rint_(double a) { return rint(a); }
+  static __device__ __forceinline__ void sincos_(double a, double* s, double* c) { sincos(a, s, c); }
+  static __device__ __forceinline__ void rotate(double& a, double& c, double& s, double d) { a += d; sincos(a, &s, &c); }
+  static __device__ __forceinline__ double tanh_(double x) { return tanh(x); }
+  static __device__ __forceinline__ double atan2_(double y, double x) { return atan2(y, x); }
+  static __device__ __forceinline__ double phase_sin(double amp, double freq, double t, double phase) {
+    return amp * sin(2.0 * 3.14159265358979323846 * freq * t + phase);
+  }
 };
 
+template <class R> struct alignas(4 * sizeof(R)) V4 { R x, y, z, w; };
+template <class R> struct alignas(2 * sizeof(R)) V2 { R x, y; };
+// compiler barrier on a value: stops loop-invariant code motion from pinning derived terms in registers
+__device__ __forceinline__ void opaque(float& x) { asm volatile("" : "+f"(x)); }
+__device__ __forceinline__ void opaque(double& x) { asm volatile("" : "+d"(x)); }
+
 #define FULL 0xffffffffu
+#define SEL4(arr, k) ((k) == 0 ? arr[0] : ((k) == 1 ? arr[1] : ((k) == 2 ? arr[2] : arr[3])))
+#define PUT4(arr, k, v) { arr[0] = (k) == 0 ? (v) : arr[0]; arr[1] = (k) == 1 ? (v) : arr[1]; arr[2] = (k) == 2 ? (v) : arr[2]; arr[3] = (k) == 3 ? (v) : arr[3]; }
 
 // spring table: X(index, bodyA, bodyB, sx1, sy1, sx2, sy2, rangeKind, groupBit)
 // canonical order (oracle build_robot): SIDE_INTERNAL, SIDE_EXTERNAL, SIDE_CROSS a, SIDE_CROSS b, CENTRAL_CROSS;
@@ -120,125 +200,176 @@ template <> struct M<double> {
   X(12, 0, 1, +1, -1, -1, +1, 1, 4) X(13, 2, 3, -1, -1, +1, +1, 1, 4) X(14, 1, 2, -1, -1, +1, +1, 1, 4)    \
   X(15, 3, 0, +1, +1, -1, -1, 1, 4) X(16, 0, 2, 0, 0, 0, 0, 2, 8) X(17, 1, 3, 0, 0, 0, 0, 2, 8)
 
+// the same 18 springs as 9 pairs of body-disjoint (hence independent) solves, in canonical order:
+// X(i, a, b, j, c, d): spring i joins bodies (a,b), spring j joins (c,d)
+#define VSR_SPRING_PAIRS(X)                                                                             \
+  X(0, 0, 1, 1, 2, 3, 1) X(2, 1, 2, 3, 3, 0, 1) X(4, 0, 1, 5, 2, 3, 2) X(6, 1, 2, 7, 3, 0, 2)           \
+  X(8, 0, 1, 9, 2, 3, 4) X(10, 1, 2, 11, 3, 0, 4) X(12, 0, 1, 13, 2, 3, 4) X(14, 1, 2, 15, 3, 0, 4)
+
 // rope table: X(index, bodyA, bodyB)
 #define VSR_ROPES(X) X(0, 0, 1) X(1, 2, 3) X(2, 1, 2) X(3, 3, 0)
 
 // ------------------------------------------------------------------------------------------------
 // narrowphase: corner-mass box vs one ground polygon (SAT + reference-face clipping)
-// ground polygon CCW: V0=(x0,base) V1=(x1,base) V2=(x1,y1) V3=(x0,y0)
+// ground polygon CCW: V0=(x0,base) V1=(x1,base) V2=(x1,y1) V3=(x0,y0); box centre (bcx,bcy), half side hh
 // ------------------------------------------------------------------------------------------------
 template <class R>
-__device__ __noinline__ int collide_box_ground(R x0, R y0, R x1, R y1, R base, const R* bx, const R* by, R c, R s,
-                                               R lin_tol, R* onx, R* ony, R* opx, R* opy, R* odepth, int* oid) {
-  const R gx[4] = {x0, x1, x1, x0}, gy[4] = {base, base, y1, y0};
-  R gnx[4], gny[4];
+__device__ __forceinline__ int collide_box_ground(R x0, R y0, R x1, R y1, R base, R bcx, R bcy, R c, R s, R hh, R lin_tol,
+                                                  R& onx, R& ony, R* opx, R* opy, R* odepth, int* oid) {
+  const R hc = hh * c, hs = hh * s;
+  const R bx[4] = {bcx - hc + hs, bcx + hc + hs, bcx + hc - hs, bcx - hc - hs};
+  const R by[4] = {bcy - hs - hc, bcy + hs - hc, bcy + hs + hc, bcy - hs + hc};
+  // ground top-edge normal (edge 2: V2 -> V3); edges 1 / 3 are the vertical sides (+x / -x); edge 0 (bottom,
+  // ground_thickness below the surface) can never be the axis of least penetration.
+  R tnx, tny;
   {
-    R ex = x0 - x1, ey = y0 - y1;
-    R len = M<R>::sqrt_(ex * ex + ey * ey);
-    gnx[0] = 0; gny[0] = -1;
-    gnx[1] = 1; gny[1] = 0;
-    gnx[2] = ey / len; gny[2] = -ex / len;
-    gnx[3] = -1; gny[3] = 0;
+    const R ex = x0 - x1, ey = y0 - y1;
+    const R il = M<R>::rsqrt_(ex * ex + ey * ey);
+    tnx = ey * il; tny = -ex * il;
   }
-  const R bnx[4] = {s, c, -s, -c}, bny[4] = {-c, s, c, -s};
-  // separation of the box from each ground edge (bottom edge 0 can never be the maximum: it is
-  // ground_thickness below the surface)
-  R sA = -1e30f;
+  // separation of the box from the ground's edges 1, 2, 3 (first maximum wins, like the oracle's scan)
+  const R bminx = M<R>::min_(M<R>::min_(bx[0], bx[1]), M<R>::min_(bx[2], bx[3]));
+  const R bmaxx = M<R>::max_(M<R>::max_(bx[0], bx[1]), M<R>::max_(bx[2], bx[3]));
+  R st = tnx * (bx[0] - x1) + tny * (by[0] - y1);
+#pragma unroll
+  for (int j = 1; j < 4; j++) st = M<R>::min_(st, tnx * (bx[j] - x1) + tny * (by[j] - y1));
+  R sA = bminx - x1;
   int eA = 1;
-#pragma unroll
-  for (int i = 1; i < 4; i++) {
-    R sm = 1e30f;
-#pragma unroll
-    for (int j = 0; j < 4; j++) sm = M<R>::min_(sm, gnx[i] * (bx[j] - gx[i]) + gny[i] * (by[j] - gy[i]));
-    if (sm > sA) { sA = sm; eA = i; }
-  }
+  if (st > sA) { sA = st; eA = 2; }
+  if (x0 - bmaxx > sA) { sA = x0 - bmaxx; eA = 3; }
   if (sA > 0) return 0;
-  R sB = -1e30f;
-  int eB = 0;
+  // separation of the ground from the box's edges: normals n0=(s,-c) n1=(c,s) n2=-n0 n3=-n1, each at distance hh
+  // from the centre: sep_i = min_j n_i.(g_j - centre) - hh
+  const R gx[4] = {x0, x1, x1, x0}, gy[4] = {base, base, y1, y0};
+  R umin = 1e30f, umax = -1e30f, wmin = 1e30f, wmax = -1e30f;
 #pragma unroll
-  for (int i = 0; i < 4; i++) {
-    R sm = 1e30f;
-#pragma unroll
-    for (int j = 0; j < 4; j++) sm = M<R>::min_(sm, bnx[i] * (gx[j] - bx[i]) + bny[i] * (gy[j] - by[i]));
-    if (sm > sB) { sB = sm; eB = i; }
+  for (int j = 0; j < 4; j++) {
+    const R dx = gx[j] - bcx, dy = gy[j] - bcy;
+    const R u = s * dx - c * dy, w = c * dx + s * dy;
+    umin = M<R>::min_(umin, u); umax = M<R>::max_(umax, u);
+    wmin = M<R>::min_(wmin, w); wmax = M<R>::max_(wmax, w);
   }
+  R sB = umin - hh;
+  int eB = 0;
+  if (wmin - hh > sB) { sB = wmin - hh; eB = 1; }
+  if (-umax - hh > sB) { sB = -umax - hh; eB = 2; }
+  if (-wmax - hh > sB) { sB = -wmax - hh; eB = 3; }
   if (sB > 0) return 0;
   const int flip = sB > sA + R(0.1) * lin_tol;
-  const int e = flip ? eB : eA;
+  const int e = flip ? eB : eA, e1 = (e + 1) & 3;
+  const R bnx[4] = {s, c, -s, -c}, bny[4] = {-c, s, c, -s};
+  const R gnx[4] = {0, 1, tnx, -1}, gny[4] = {-1, 0, tny, 0};
   R nx, ny, v1x, v1y, v2x, v2y;
+  // reference edge (select chains keep every array index static -> registers, no local memory)
   if (flip) {
-    nx = bnx[e]; ny = bny[e];
-    v1x = bx[e]; v1y = by[e]; v2x = bx[(e + 1) & 3]; v2y = by[(e + 1) & 3];
+    nx = SEL4(bnx, e); ny = SEL4(bny, e);
+    v1x = SEL4(bx, e); v1y = SEL4(by, e); v2x = SEL4(bx, e1); v2y = SEL4(by, e1);
   } else {
-    nx = gnx[e]; ny = gny[e];
-    v1x = gx[e]; v1y = gy[e]; v2x = gx[(e + 1) & 3]; v2y = gy[(e + 1) & 3];
+    nx = SEL4(gnx, e); ny = SEL4(gny, e);
+    v1x = SEL4(gx, e); v1y = SEL4(gy, e); v2x = SEL4(gx, e1); v2y = SEL4(gy, e1);
   }
+  // incident edge: most anti-parallel normal of the other polygon, first minimum wins
   int ie = 0;
   R mind = 1e30f;
 #pragma unroll
   for (int j = 0; j < 4; j++) {
-    R d = flip ? nx * gnx[j] + ny * gny[j] : nx * bnx[j] + ny * bny[j];
+    const R d = flip ? nx * gnx[j] + ny * gny[j] : nx * bnx[j] + ny * bny[j];
     if (d < mind) { mind = d; ie = j; }
   }
-  R cx[2], cy[2];
+  const int ie1 = (ie + 1) & 3;
+  R cx0, cy0, cx1, cy1;
   if (flip) {
-    cx[0] = gx[ie]; cy[0] = gy[ie]; cx[1] = gx[(ie + 1) & 3]; cy[1] = gy[(ie + 1) & 3];
+    cx0 = SEL4(gx, ie); cy0 = SEL4(gy, ie); cx1 = SEL4(gx, ie1); cy1 = SEL4(gy, ie1);
   } else {
-    cx[0] = bx[ie]; cy[0] = by[ie]; cx[1] = bx[(ie + 1) & 3]; cy[1] = by[(ie + 1) & 3];
+    cx0 = SEL4(bx, ie); cy0 = SEL4(by, ie); cx1 = SEL4(bx, ie1); cy1 = SEL4(by, ie1);
   }
   R tx = v2x - v1x, ty = v2y - v1y;
-  R tl = M<R>::sqrt_(tx * tx + ty * ty);
-  tx /= tl; ty /= tl;
-  {
-    R o = tx * v1x + ty * v1y;
-    R d0 = tx * cx[0] + ty * cy[0] - o, d1 = tx * cx[1] + ty * cy[1] - o;
+  const R itl = M<R>::rsqrt_(tx * tx + ty * ty);
+  tx *= itl; ty *= itl;
+  // clip the incident edge against the two side planes of the reference edge
+#pragma unroll
+  for (int side = 0; side < 2; side++) {
+    const R o = side == 0 ? tx * v1x + ty * v1y : tx * v2x + ty * v2y;
+    const R p0 = tx * cx0 + ty * cy0, p1 = tx * cx1 + ty * cy1;
+    const R d0 = side == 0 ? p0 - o : o - p0, d1 = side == 0 ? p1 - o : o - p1;
     if (d0 < 0 && d1 < 0) return 0;
     if (d0 < 0 || d1 < 0) {
-      R u = d0 / (d0 - d1);
-      R ix = cx[0] + u * (cx[1] - cx[0]), iy = cy[0] + u * (cy[1] - cy[0]);
-      if (d0 < 0) { cx[0] = ix; cy[0] = iy; } else { cx[1] = ix; cy[1] = iy; }
-    }
-  }
-  {
-    R o = tx * v2x + ty * v2y;
-    R d0 = o - (tx * cx[0] + ty * cy[0]), d1 = o - (tx * cx[1] + ty * cy[1]);
-    if (d0 < 0 && d1 < 0) return 0;
-    if (d0 < 0 || d1 < 0) {
-      R u = d0 / (d0 - d1);
-      R ix = cx[0] + u * (cx[1] - cx[0]), iy = cy[0] + u * (cy[1] - cy[0]);
-      if (d0 < 0) { cx[0] = ix; cy[0] = iy; } else { cx[1] = ix; cy[1] = iy; }
+      const R u = d0 * M<R>::rcp(d0 - d1);
+      const R ix = cx0 + u * (cx1 - cx0), iy = cy0 + u * (cy1 - cy0);
+      if (d0 < 0) { cx0 = ix; cy0 = iy; } else { cx1 = ix; cy1 = iy; }
     }
   }
   int np = 0;
-#pragma unroll
-  for (int q = 0; q < 2; q++) {
-    R sep = nx * (cx[q] - v1x) + ny * (cy[q] - v1y);
-    if (sep <= 0) {
-      opx[np] = cx[q]; opy[np] = cy[q]; odepth[np] = -sep;
-      oid[np] = (flip << 5) | (e << 3) | (ie << 1) | q;
-      np++;
-    }
+  const R sep0 = nx * (cx0 - v1x) + ny * (cy0 - v1y), sep1 = nx * (cx1 - v1x) + ny * (cy1 - v1y);
+  const int idb = (flip << 5) | (e << 3) | (ie << 1);
+  if (sep0 <= 0) { opx[0] = cx0; opy[0] = cy0; odepth[0] = -sep0; oid[0] = idb; np = 1; }
+  if (sep1 <= 0) {
+    if (np) { opx[1] = cx1; opy[1] = cy1; odepth[1] = -sep1; oid[1] = idb | 1; }
+    else { opx[0] = cx1; opy[0] = cy1; odepth[0] = -sep1; oid[0] = idb | 1; }
+    np++;
   }
-  *onx = flip ? -nx : nx;
-  *ony = flip ? -ny : ny;
+  onx = flip ? -nx : nx;
+  ony = flip ? -ny : ny;
+  return np;
+}
+
+// Fast narrowphase: the box lies at least kFastMargin inside the polygon's x-range, so the
+// ground's top edge is provably the SAT reference face (no flip, side edges cannot win) and the incident box
+// edge needs no clipping.  Same formulas as the general path -> identical normal / points / depths / ids.
+// Returns -1 when the penetration is too deep for that argument (caller falls back to the general path).
+constexpr float kFastMargin = 1.25f, kFastDepth = 0.3f;
+template <class R>
+__device__ __forceinline__ int collide_box_top(R x1, R y1, R pnx, R pny, R bcx, R bcy, R c, R s, R hh,
+                                               R& onx, R& ony, R* opx, R* opy, R* odepth, int* oid) {
+  const R hc = hh * c, hs = hh * s;
+  const R bx[4] = {bcx - hc + hs, bcx + hc + hs, bcx + hc - hs, bcx - hc - hs};
+  const R by[4] = {bcy - hs - hc, bcy + hs - hc, bcy + hs + hc, bcy - hs + hc};
+  R sep[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) sep[j] = pnx * (bx[j] - x1) + pny * (by[j] - y1);
+  const R sA = M<R>::min_(M<R>::min_(sep[0], sep[1]), M<R>::min_(sep[2], sep[3]));
+  if (sA > 0) return 0;
+  if (sA < -R(kFastDepth)) return -1;
+  // incident edge: most anti-parallel box normal {(s,-c),(c,s),(-s,c),(-c,-s)}, first minimum wins
+  const R d0 = pnx * s - pny * c, d1 = pnx * c + pny * s;
+  int ie = 0;
+  R mind = d0;
+  if (d1 < mind) { mind = d1; ie = 1; }
+  if (-d0 < mind) { mind = -d0; ie = 2; }
+  if (-d1 < mind) { mind = -d1; ie = 3; }
+  const int ie1 = (ie + 1) & 3;
+  const R s0 = SEL4(sep, ie), s1 = SEL4(sep, ie1);
+  const int idb = (2 << 3) | (ie << 1);
+  int np = 0;
+  if (s0 <= 0) { opx[0] = SEL4(bx, ie); opy[0] = SEL4(by, ie); odepth[0] = -s0; oid[0] = idb; np = 1; }
+  if (s1 <= 0) {
+    const R cx1 = SEL4(bx, ie1), cy1 = SEL4(by, ie1);
+    if (np) { opx[1] = cx1; opy[1] = cy1; odepth[1] = -s1; oid[1] = idb | 1; }
+    else { opx[0] = cx1; opy[0] = cy1; odepth[0] = -s1; oid[0] = idb | 1; }
+    np++;
+  }
+  onx = pnx; ony = pny;
   return np;
 }
 
 // ------------------------------------------------------------------------------------------------
 // the episode kernel
 // ------------------------------------------------------------------------------------------------
-template <class R, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) vsr_episode_kernel(const __grid_constant__ KParams P) {
+template <class R, int CTRL, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __grid_constant__ KParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned char* wsm = smem_raw + (size_t)warp * P.smem_warp_stride;
-  R* poolP = reinterpret_cast<R*>(wsm + P.off_pool_p);   // [2][kPoolPersist][S]
-  R* poolS = reinterpret_cast<R*>(wsm + P.off_pool_s);   // [kPoolSolve][S]
+  R* pool = reinterpret_cast<R*>(wsm + P.off_pool_p);      // [S][kPoolStride]: persist[2][12], solve[18], pad
   int* poolM = reinterpret_cast<int*>(wsm + P.off_pool_m); // [2][S]
   int* poolCnt = reinterpret_cast<int*>(wsm + P.off_pool_cnt);
-  R* wts = reinterpret_cast<R*>(wsm + P.off_w);           // [robots_per_warp][genome_len]
-  R* act = reinterpret_cast<R*>(wsm + P.off_act);         // centralized: [rpw][2][maxN]; distributed: [2][maxN][32]
-  R* sig = reinterpret_cast<R*>(wsm + P.off_sig);         // distributed: [2][32][4*signals]
+  R* wts = reinterpret_cast<R*>(wsm + P.off_w);            // [robots_per_warp][genome_len]
+  R* act = reinterpret_cast<R*>(wsm + P.off_act);          // centralized: [rpw][2][maxN]; distributed: [2][maxN][32]
+  R* sig = reinterpret_cast<R*>(wsm + P.off_sig);          // distributed: [2][32][4*signals]
+  R* sbias = reinterpret_cast<R*>(wsm + P.off_bias);       // [18][32] per-step spring bias / sigma
+  R* spark = reinterpret_cast<R*>(wsm + P.off_park);       // [kPark][32] cold state parked across the velocity loop
+  V2<R>* seff = reinterpret_cast<V2<R>*>(wsm + P.off_eff);   // [8][32] effective masses E of springs 0..15, pairs packed
+  V4<R>* sarm = reinterpret_cast<V4<R>*>(wsm + P.off_arm); // [8][32] spring lever arms (r x n) of springs 0..15, pairs packed
   const int S = P.pool_slots;
 
   const int L = P.lanes_per_robot;
@@ -251,21 +382,55 @@ __global__ void __launch_bounds__(WARPS * 32) vsr_episode_kernel(const __grid_co
   const int gl = (blockIdx.x * WARPS + warp) * 32 + lane; // global lane (history ring column)
   const int total_lanes = gridDim.x * WARPS * 32;
 
-  // neighbours as lane ids (self when absent, so shuffles stay in range)
+  // neighbours as lane ids packed in one register (self when absent, so shuffles stay in range) + validity bits
   const int vi = valid ? v : 0;
-  const int ln = (valid && P.nb_l[vi] >= 0) ? base_lane + P.nb_l[vi] : -1;
-  const int rn = (valid && P.nb_r[vi] >= 0) ? base_lane + P.nb_r[vi] : -1;
-  const int dn = (valid && P.nb_d[vi] >= 0) ? base_lane + P.nb_d[vi] : -1;
-  const int un = (valid && P.nb_u[vi] >= 0) ? base_lane + P.nb_u[vi] : -1;
-  const int ln_s = ln < 0 ? lane : ln, rn_s = rn < 0 ? lane : rn, dn_s = dn < 0 ? lane : dn, un_s = un < 0 ? lane : un;
+  unsigned nbr, nbv;
+  {
+    const int l_ = (valid && P.nb_l[vi] >= 0) ? base_lane + P.nb_l[vi] : -1, r_ = (valid && P.nb_r[vi] >= 0) ? base_lane + P.nb_r[vi] : -1;
+    const int d_ = (valid && P.nb_d[vi] >= 0) ? base_lane + P.nb_d[vi] : -1, u_ = (valid && P.nb_u[vi] >= 0) ? base_lane + P.nb_u[vi] : -1;
+    nbr = (unsigned)(l_ < 0 ? lane : l_) | ((unsigned)(r_ < 0 ? lane : r_) << 8) | ((unsigned)(d_ < 0 ? lane : d_) << 16) | ((unsigned)(u_ < 0 ? lane : u_) << 24);
+    nbv = (l_ >= 0 ? 1u : 0u) | (r_ >= 0 ? 2u : 0u) | (d_ >= 0 ? 4u : 0u) | (u_ >= 0 ? 8u : 0u);
+  }
+#define ln_s ((int)(nbr & 31u))
+#define rn_s ((int)((nbr >> 8) & 31u))
+#define dn_s ((int)((nbr >> 16) & 31u))
+#define un_s ((int)(nbr >> 24))
+#define ln (((nbv & 1u) != 0) ? ln_s : -1)
+#define rn (((nbv & 2u) != 0) ? rn_s : -1)
+#define dn (((nbv & 4u) != 0) ? dn_s : -1)
+#define un (((nbv & 8u) != 0) ? un_s : -1)
 
-  // constants
-  const R dt = (R)P.dt, half = (R)P.half, im = (R)P.inv_m, ii = (R)P.inv_i, mu = (R)P.mu;
-  const R lin_tol = (R)P.lin_tol, ang_tol = (R)P.ang_tol, max_corr = (R)P.max_lin_corr, baum = (R)P.baumgarte;
-  const R gdt = valid ? (R)(P.g * P.dt) : R(0);
-  const R lin_f = (R)P.lin_f, ang_f = (R)P.ang_f;
-  const R sp_sigma = (R)P.sp_sigma, sp_beta = (R)P.sp_beta, sp_cfrac = (R)P.sp_cfrac;
-  const R rope_lower = (R)P.rope_lower, rope_E = R(1) / (im + im);
+  // constants: macros, not variables -- every use reads the constant bank directly (FP32: KConstF floats;
+  // FP64: derived from the double fields), so none of them occupies a long-lived register
+#define KC(f, d) (sizeof(R) == 4 ? (R)P.cf.c_##f : (R)(d))
+#define K_dt KC(dt, P.dt)
+#define K_half KC(half, P.half)
+#define K_im KC(im, P.inv_m)
+#define K_ii KC(ii, P.inv_i)
+#define K_mu KC(mu, P.mu)
+#define K_lin_tol KC(lin_tol, P.lin_tol)
+#define K_ang_tol KC(ang_tol, P.ang_tol)
+#define K_max_corr KC(max_corr, P.max_lin_corr)
+#define K_baum KC(baum, P.baumgarte)
+#define K_lin_f KC(lin_f, P.lin_f)
+#define K_ang_f KC(ang_f, P.ang_f)
+#define K_sp_sigma KC(sp_sigma, P.sp_sigma)
+#define K_sp_boversig KC(sp_boversig, P.sp_beta / P.sp_sigma)
+#define K_sp_cfrac KC(sp_cfrac, P.sp_cfrac)
+#define K_rope_lower KC(rope_lower, P.rope_lower)
+#define K_rope_E KC(rope_E, 1.0 / (2.0 * P.inv_m))
+#define K_wa KC(wa, P.weld_anchor)
+#define K_wA KC(wA, 2.0 * P.inv_m)
+#define K_wh KC(wh, 0.5 * P.inv_i)
+#define K_wD KC(wD, 1.0 / ((2.0 * P.inv_m) * (2.0 * P.inv_m + 0.5 * P.inv_i * P.weld_anchor * P.weld_anchor)))
+#define K_w_i2i KC(w_i2i, 1.0 / (2.0 * P.inv_i))
+#define K_rest_vel KC(rest_vel, P.rest_vel)
+#define K_rest_e KC(rest_e, P.rest_e)
+#define K_max_trans KC(max_trans, P.max_trans)
+#define K_max_trans2 KC(max_trans2, P.max_trans * P.max_trans)
+#define K_max_rot KC(max_rot, P.max_rot)
+#define K_inv_area2 KC(inv_area2, 0.5 / (P.side_len * P.side_len))
+  const R gdt = valid ? KC(gdt, P.g * P.dt) : R(0);
   const int scaff = P.scaff_mask;
 
   // ---- state ----------------------------------------------------------------------------------
@@ -276,7 +441,7 @@ __global__ void __launch_bounds__(WARPS * 32) vsr_episode_kernel(const __grid_co
     const double cx0 = valid ? P.vox_x0[vi] : 0.0, cy0 = valid ? P.vox_y0[vi] : 1.0e4;
     ox = (R)rint(cx0); oy = (R)rint(cy0);
     const R lx = (R)(cx0 - (double)ox), ly = (R)(cy0 - (double)oy);
-    const R off = (R)(P.side_len / 2 - P.half);
+    const R off = KC(mass_off, P.side_len / 2 - P.half);
     const R sxk[4] = {-1, +1, +1, -1}, syk[4] = {+1, +1, -1, -1};
 #pragma unroll
     for (int k = 0; k < 4; k++) {
@@ -284,128 +449,152 @@ __global__ void __launch_bounds__(WARPS * 32) vsr_episode_kernel(const __grid_co
       A[k] = 0; CS[k] = 1; SN[k] = 0; VX[k] = 0; VY[k] = 0; W[k] = 0;
     }
   }
-  R rest[3] = {(R)P.range_rest[0], (R)P.range_rest[1], (R)P.range_rest[2]};
-  R simp[18];
+  R rest[3] = {KC(range_rest[0], P.range_rest[0]), KC(range_rest[1], P.range_rest[1]), KC(range_rest[2], P.range_rest[2])};
+  R simp[18]; // accumulated spring impulses (warm start); during the velocity loop: impulse + bias/sigma
 #pragma unroll
   for (int i = 0; i < 18; i++) simp[i] = 0;
   R rimp[4] = {0, 0, 0, 0};
   R wimp[4][3];
 #pragma unroll
   for (int i = 0; i < 4; i++) wimp[i][0] = wimp[i][1] = wimp[i][2] = 0;
-  // contact slot lists: per mass [cnt:8 | s2:8 | s1:8 | s0:8]
-  unsigned clist[4] = {0, 0, 0, 0};
+  // contact manifold slots of this lane: up to 8 pool slots (8 bits each), ordered by (mass, polygon)
+  unsigned clo = 0, chi = 0;
+  int ccnt = 0;
   int par = 0; // parity of the current persistent pool buffer
   int kh = 1;  // terrain polygon hint
   int overflow = 0;
 
   // ---- controller state --------------------------------------------------------------------------
   R phase = 0;
-  if (P.ctrl_kind == VSR_CTRL_PHASE_SIN) {
+  if (CTRL == VSR_CTRL_PHASE_SIN) {
     if (valid) phase = (R)P.genomes[(size_t)robot * P.genome_len + v];
   } else {
-    // genome upload: the warp's robots are consecutive rows -> one contiguous range of doubles.
+    // K2 genome upload: the warp's robots are consecutive rows -> one contiguous range of doubles,
+    // read with 128-bit loads (double2) after a scalar head for 16-byte alignment.
     const int r0 = (blockIdx.x * WARPS + warp) * P.robots_per_warp;
     int nr = P.n_robots - r0;
     nr = nr < 0 ? 0 : (nr > P.robots_per_warp ? P.robots_per_warp : nr);
     const size_t first = (size_t)r0 * P.genome_len, count = (size_t)nr * P.genome_len;
     const double* src = P.genomes + first;
-    // 128-bit vectorised body (double2), scalar head/tail for alignment
-    size_t head = ((reinterpret_cast<uintptr_t>(src) & 15) && count) ? 1 : 0;
+    const size_t head = ((reinterpret_cast<uintptr_t>(src) & 15) && count) ? 1 : 0;
     for (size_t i = lane; i < head; i += 32) wts[i] = (R)src[i];
     const size_t nvec = (count - head) / 2;
     const double2* src2 = reinterpret_cast<const double2*>(src + head);
     for (size_t i = lane; i < nvec; i += 32) {
-      double2 d = __ldg(&src2[i]);
+      const double2 d = __ldg(&src2[i]);
       wts[head + 2 * i] = (R)d.x;
       wts[head + 2 * i + 1] = (R)d.y;
     }
     for (size_t i = head + 2 * nvec + lane; i < count; i += 32) wts[i] = (R)src[i];
-    if (P.ctrl_kind == VSR_CTRL_MLP_DISTRIBUTED_HOMO)
+    if (CTRL == VSR_CTRL_MLP_DISTRIBUTED_HOMO)
       for (int i = lane; i < 2 * 32 * 4 * P.signals; i += 32) sig[i] = 0;
   }
   if (lane == 0) *poolCnt = 0;
   __syncwarp();
-  double avg_sum[kMaxAvg];
-  int avg_cnt[kMaxAvg];
-#pragma unroll
-  for (int i = 0; i < kMaxAvg; i++) { avg_sum[i] = 0; avg_cnt[i] = 0; }
+  // cold per-lane state kept in shared memory (touched once per step at most): running sums of the Average
+  // sensors, and the first/last observation
+  double* savg = reinterpret_cast<double*>(wsm + P.off_cold);           // [n_avg][32]
+  int* savg_cnt = reinterpret_cast<int*>(savg + P.n_avg * 32);          // [n_avg][32]
+  for (int i = 0; i < P.n_avg; i++) { savg[i * 32 + lane] = 0; savg_cnt[i * 32 + lane] = 0; }
   int sig_par = 0;
-  double cx_first = 0, cx_last = 0, t_first = 0, t_last = 0;
   R ctrl_f = 0;
 
-  // ---- helpers (lambdas capture state by reference; everything is inlined) -----------------------
-  auto pP = [&](int p, int f, int s) -> R& { return poolP[(p * kPoolPersist + f) * S + s]; };
-  auto pS = [&](int f, int s) -> R& { return poolS[f * S + s]; };
+  auto pP = [&](int p, int f, int s) -> R& { return pool[s * kPoolStride + p * kPoolPersist + f]; };
+  auto pS = [&](int f, int s) -> R& { return pool[s * kPoolStride + 2 * kPoolPersist + f]; };
+  auto slot_of = [&](int e) -> int { return ((e < 4 ? clo >> (8 * e) : chi >> (8 * (e - 4))) & 0xff); };
 
-  // detection of all 4 corner masses of this lane against the ground; fills the pool (parity par^1)
+  // per-lane cached ground polygon (the one under the voxel centre), in the lane's local frame
+  int pk = 0;
+  R px0 = 0, px1 = 0, py0 = 0, py1 = 0, pnx = 0, pny = 1;
+  // detection of all 4 corner masses of this lane against the ground; fills the pool (parity par^1).
+  // One copy of the narrowphase: the mass loop is NOT unrolled, masses are read with select chains.
   auto detect = [&]() {
     __syncwarp();
     if (lane == 0) *poolCnt = 0;
     __syncwarp();
     const int np_ = par ^ 1;
     const double oxd = (double)ox, oyd = (double)oy;
-    unsigned nlist[4];
-#pragma unroll
+    unsigned nlo = 0, nhi = 0;
+    int ncnt = 0;
+    if (valid) {
+      const R cxl = R(0.25) * (X[0] + X[1] + X[2] + X[3]);
+      if (!pk || cxl < px0 || cxl > px1) { // (re)load the polygon under the voxel centre
+        const double cxw = oxd + (double)cxl;
+        int kk = kh;
+        while (kk > 1 && __ldg(&P.tx[kk - 1]) > cxw) kk--;
+        while (kk < P.n_t - 1 && __ldg(&P.tx[kk]) <= cxw) kk++;
+        kh = kk; pk = kk;
+        px0 = (R)(__ldg(&P.tx[kk - 1]) - oxd); px1 = (R)(__ldg(&P.tx[kk]) - oxd);
+        py0 = (R)(__ldg(&P.ty[kk - 1]) - oyd); py1 = (R)(__ldg(&P.ty[kk]) - oyd);
+        const R ex = px0 - px1, ey = py0 - py1;
+        const R il = M<R>::rsqrt_(ex * ex + ey * ey);
+        pnx = ey * il; pny = -ex * il;
+      }
+    }
+    const R pymax = M<R>::max_(py0, py1);
+#pragma unroll 1
     for (int k = 0; k < 4; k++) {
-      nlist[k] = 0;
-      if (!valid) continue;
-      const R ext = half * (M<R>::abs_(CS[k]) + M<R>::abs_(SN[k]));
-      const double ax0 = oxd + (double)(X[k] - ext), ax1 = oxd + (double)(X[k] + ext), ay0 = oyd + (double)(Y[k] - ext);
-      // smallest polygon index kk (polygon kk spans tx[kk-1]..tx[kk]) with tx[kk] >= ax0
-      int kk = kh;
-      while (kk > 1 && __ldg(&P.tx[kk - 1]) >= ax0) kk--;
-      while (kk < P.n_t - 1 && __ldg(&P.tx[kk]) < ax0) kk++;
-      if (k == 0) kh = kk;
-      R bx[4], by[4];
-      {
-        const R hc = half * CS[k], hs = half * SN[k];
-        bx[0] = X[k] - hc + hs; by[0] = Y[k] - hs - hc;
-        bx[1] = X[k] + hc + hs; by[1] = Y[k] + hs - hc;
-        bx[2] = X[k] + hc - hs; by[2] = Y[k] + hs + hc;
-        bx[3] = X[k] - hc - hs; by[3] = Y[k] - hs + hc;
+      if (!valid) break;
+      const R xk = SEL4(X, k), yk = SEL4(Y, k), ck = SEL4(CS, k), sk = SEL4(SN, k);
+      const R ext = K_half * (M<R>::abs_(ck) + M<R>::abs_(sk));
+      const bool fast = xk - ext >= px0 + R(kFastMargin) && xk + ext <= px1 - R(kFastMargin);
+      if (fast && yk - ext > pymax) continue; // broadphase: above the polygon's AABB
+      double ax0 = 0, ax1 = 0, ay0 = 0;
+      int kk = pk, kend = pk;
+      if (!fast) {
+        ax0 = oxd + (double)(xk - ext); ax1 = oxd + (double)(xk + ext); ay0 = oyd + (double)(yk - ext);
+        // smallest polygon index kk (polygon kk spans tx[kk-1]..tx[kk]) with tx[kk] >= ax0
+        while (kk > 1 && __ldg(&P.tx[kk - 1]) >= ax0) kk--;
+        while (kk < P.n_t - 1 && __ldg(&P.tx[kk]) < ax0) kk++;
+        kend = P.n_t - 1;
       }
       int cnt = 0;
-      for (; kk <= P.n_t - 1 && cnt < kMaxMan; kk++) {
-        const double x0 = __ldg(&P.tx[kk - 1]);
-        if (x0 > ax1) break;
-        const double x1 = __ldg(&P.tx[kk]), y0 = __ldg(&P.ty[kk - 1]), y1 = __ldg(&P.ty[kk]);
-        if (ax1 < x0 || ax0 > x1) continue;
-        if (ay0 > fmax(y0, y1)) continue;
+      for (; kk <= kend && cnt < kMaxMan; kk++) {
         R nx, ny, px[2], py[2], dp[2];
         int id[2];
-        const int np = collide_box_ground<R>((R)(x0 - oxd), (R)(y0 - oyd), (R)(x1 - oxd), (R)(y1 - oyd),
-                                             (R)(P.base_y - oyd), bx, by, CS[k], SN[k], lin_tol, &nx, &ny, px, py, dp, id);
+        int np = -1;
+        R gx0 = px0, gy0 = py0, gx1 = px1, gy1 = py1;
+        if (fast) {
+          np = collide_box_top<R>(px1, py1, pnx, pny, xk, yk, ck, sk, K_half, nx, ny, px, py, dp, id);
+        } else {
+          const double x0 = __ldg(&P.tx[kk - 1]);
+          if (x0 > ax1) break;
+          const double x1 = __ldg(&P.tx[kk]), y0 = __ldg(&P.ty[kk - 1]), y1 = __ldg(&P.ty[kk]);
+          if (ax1 < x0 || ax0 > x1) continue;
+          if (ay0 > fmax(y0, y1)) continue;
+          gx0 = (R)(x0 - oxd); gy0 = (R)(y0 - oyd); gx1 = (R)(x1 - oxd); gy1 = (R)(y1 - oyd);
+        }
+        if (np < 0)
+          np = collide_box_ground<R>(gx0, gy0, gx1, gy1, (R)(P.base_y - oyd), xk, yk, ck, sk, K_half, K_lin_tol, nx, ny, px, py, dp, id);
         if (!np) continue;
+        if (ncnt >= kMaxLaneMan) { overflow++; continue; }
         const int s = atomicAdd(poolCnt, 1);
         if (s >= S) { overflow++; continue; }
-        R jn[2] = {0, 0}, jt[2] = {0, 0};
-        // warm start from the previous manifold with the same polygon
-        const int ocnt = clist[k] >> 24;
-        for (int o = 0; o < ocnt; o++) {
-          const int os = (clist[k] >> (8 * o)) & 0xff;
+        R jn0 = 0, jt0 = 0, jn1 = 0, jt1 = 0;
+        // warm start from the previous manifold of the same (mass, polygon)
+        const int key = kk | (k << 14);
+        for (int o = 0; o < ccnt; o++) {
+          const int os = slot_of(o);
           const int ometa = poolM[par * S + os];
-          if ((ometa & 0xffff) != kk) continue;
+          if ((ometa & 0xffff) != key) continue;
           const int onp = (ometa >> 16) & 3;
-          for (int q = 0; q < np; q++)
-            for (int r = 0; r < onp; r++)
-              if (((ometa >> (18 + 6 * r)) & 63) == id[q]) {
-                jn[q] = pP(par, 2 + 5 * r + 3, os);
-                jt[q] = pP(par, 2 + 5 * r + 4, os);
-              }
+          for (int r = 0; r < onp; r++) {
+            const int oidr = (ometa >> (18 + 6 * r)) & 63;
+            const R ojn = pP(par, 2 + 5 * r + 3, os), ojt = pP(par, 2 + 5 * r + 4, os);
+            if (oidr == id[0]) { jn0 = ojn; jt0 = ojt; }
+            if (np > 1 && oidr == id[1]) { jn1 = ojn; jt1 = ojt; }
+          }
         }
         pP(np_, 0, s) = nx; pP(np_, 1, s) = ny;
-        for (int q = 0; q < np; q++) {
-          pP(np_, 2 + 5 * q + 0, s) = px[q]; pP(np_, 2 + 5 * q + 1, s) = py[q]; pP(np_, 2 + 5 * q + 2, s) = dp[q];
-          pP(np_, 2 + 5 * q + 3, s) = jn[q]; pP(np_, 2 + 5 * q + 4, s) = jt[q];
-        }
-        poolM[np_ * S + s] = kk | (np << 16) | (id[0] << 18) | ((np > 1 ? id[1] : 0) << 24);
-        nlist[k] |= (unsigned)s << (8 * cnt);
+        pP(np_, 2, s) = px[0]; pP(np_, 3, s) = py[0]; pP(np_, 4, s) = dp[0]; pP(np_, 5, s) = jn0; pP(np_, 6, s) = jt0;
+        if (np > 1) { pP(np_, 7, s) = px[1]; pP(np_, 8, s) = py[1]; pP(np_, 9, s) = dp[1]; pP(np_, 10, s) = jn1; pP(np_, 11, s) = jt1; }
+        poolM[np_ * S + s] = key | (np << 16) | (id[0] << 18) | ((np > 1 ? id[1] : 0) << 24);
+        if (ncnt < 4) nlo |= (unsigned)s << (8 * ncnt); else nhi |= (unsigned)s << (8 * (ncnt - 4));
+        ncnt++;
         cnt++;
       }
-      nlist[k] |= (unsigned)cnt << 24;
     }
-#pragma unroll
-    for (int k = 0; k < 4; k++) clist[k] = nlist[k];
+    clo = nlo; chi = nhi; ccnt = ncnt;
     par ^= 1;
     __syncwarp();
   };
@@ -414,103 +603,127 @@ __global__ void __launch_bounds__(WARPS * 32) vsr_episode_kernel(const __grid_co
 
   double t = 0.0;
   // =================================================================================================
+#pragma unroll 1
   for (int step = 1; step <= P.n_steps; step++) {
+#define PHASE_SYNC(bit) if (P.sync_mask & (bit)) __syncthreads(); /* re-align the CTA's warps: shared instruction stream */
+    PHASE_SYNC(1)
     t += P.dt;
+    // ---- park cold state in shared memory (phase 1: what neither the constraint initialisation nor the velocity
+    // loop reads: angles, cached polygon, lane origin).  Keeps the live set inside the 168-register budget of 3
+    // warps per SMSP, so no spill sits on the loop's dependency chain (profiles/r1_ncu_summary.md).
+    {
+#pragma unroll
+      for (int k = 0; k < 4; k++) spark[(8 + k) * 32 + lane] = A[k];
+      spark[12 * 32 + lane] = px0; spark[13 * 32 + lane] = px1; spark[14 * 32 + lane] = py0; spark[15 * 32 + lane] = py1;
+      spark[16 * 32 + lane] = pnx; spark[17 * 32 + lane] = pny;
+      spark[18 * 32 + lane] = ox; spark[19 * 32 + lane] = oy;
+      asm volatile("" ::: "memory");
+    }
     // ---- integrate velocities: gravity, then damping ---------------------------------------------
 #pragma unroll
     for (int k = 0; k < 4; k++) {
       VY[k] += gdt;
-      VX[k] *= lin_f; VY[k] *= lin_f; W[k] *= ang_f;
+      VX[k] *= K_lin_f; VY[k] *= K_lin_f; W[k] *= K_ang_f;
     }
-    // ---- contacts: initialise (+ restitution bias from pre-warm-start velocities), then warm start --
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const int cnt = clist[k] >> 24;
-      for (int o = 0; o < cnt; o++) {
-        const int s = (clist[k] >> (8 * o)) & 0xff;
-        int meta = poolM[par * S + s];
-        int np = (meta >> 16) & 3;
-        const R nx = pP(par, 0, s), ny = pP(par, 1, s), tx = ny, ty = -nx;
-        R rn[2] = {0, 0};
-        for (int q = 0; q < np; q++) {
-          const R rx = pP(par, 2 + 5 * q, s) - X[k], ry = pP(par, 2 + 5 * q + 1, s) - Y[k];
-          rn[q] = rx * ny - ry * nx;
-          const R rt = rx * ty - ry * tx;
-          pS(7 * q + 0, s) = rx; pS(7 * q + 1, s) = ry;
-          pS(7 * q + 2, s) = R(1) / (im + ii * rn[q] * rn[q]);
-          pS(7 * q + 3, s) = R(1) / (im + ii * rt * rt);
-          const R vx = VX[k] - W[k] * ry, vy = VY[k] + W[k] * rx;
-          const R vn = nx * vx + ny * vy;
-          pS(7 * q + 4, s) = vn < -(R)P.rest_vel ? -(R)P.rest_e * vn : R(0);
-          pS(7 * q + 5, s) = CS[k] * rx + SN[k] * ry;
-          pS(7 * q + 6, s) = -SN[k] * rx + CS[k] * ry;
-        }
-        meta &= ~(1 << 30);
-        if (np == 2) {
-          const R K11 = im + ii * rn[0] * rn[0], K22 = im + ii * rn[1] * rn[1], K12 = im + ii * rn[0] * rn[1];
-          const R det = K11 * K22 - K12 * K12;
-          if (K11 * K11 < R(100) * det) {
-            meta |= 1 << 30;
-            const R idet = det != 0 ? R(1) / det : R(0);
-            pS(14, s) = K12; pS(15, s) = K22 * idet; pS(16, s) = -K12 * idet; pS(17, s) = K11 * idet;
-          } else {
-            np = 1;
-            meta = (meta & ~(3 << 16)) | (1 << 16);
-          }
-        }
-        poolM[par * S + s] = meta;
+    // ---- contacts: initialise (+ restitution bias from pre-warm-start velocities) -------------------
+#pragma unroll 1
+    for (int e = 0; e < ccnt; e++) {
+      const int s = slot_of(e);
+      int meta = poolM[par * S + s];
+      const int k = (meta >> 14) & 3;
+      const int np = (meta >> 16) & 3;
+      const R xk = SEL4(X, k), yk = SEL4(Y, k), ck = SEL4(CS, k), sk = SEL4(SN, k);
+      const R vxk = SEL4(VX, k), vyk = SEL4(VY, k), wk = SEL4(W, k);
+      const R nx = pP(par, 0, s), ny = pP(par, 1, s), tx = ny, ty = -nx;
+      R rn0 = 0, rn1 = 0;
+      for (int q = 0; q < np; q++) {
+        const R rx = pP(par, 2 + 5 * q, s) - xk, ry = pP(par, 2 + 5 * q + 1, s) - yk;
+        const R rnq = rx * ny - ry * nx, rt = rx * ty - ry * tx;
+        if (q == 0) rn0 = rnq; else rn1 = rnq;
+        pS(7 * q + 0, s) = rx; pS(7 * q + 1, s) = ry;
+        pS(7 * q + 2, s) = M<R>::rcp(K_im + K_ii * rnq * rnq);
+        pS(7 * q + 3, s) = M<R>::rcp(K_im + K_ii * rt * rt);
+        const R vn = nx * (vxk - wk * ry) + ny * (vyk + wk * rx);
+        pS(7 * q + 4, s) = vn < -K_rest_vel ? -K_rest_e * vn : R(0);
+        pS(7 * q + 5, s) = ck * rx + sk * ry;
+        pS(7 * q + 6, s) = -sk * rx + ck * ry;
       }
-    }
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const int cnt = clist[k] >> 24;
-      for (int o = 0; o < cnt; o++) {
-        const int s = (clist[k] >> (8 * o)) & 0xff;
-        const int np = (poolM[par * S + s] >> 16) & 3;
-        const R nx = pP(par, 0, s), ny = pP(par, 1, s), tx = ny, ty = -nx;
-        for (int q = 0; q < np; q++) {
-          const R jn = pP(par, 2 + 5 * q + 3, s), jt = pP(par, 2 + 5 * q + 4, s);
-          const R Jx = nx * jn + tx * jt, Jy = ny * jn + ty * jt;
-          VX[k] += im * Jx; VY[k] += im * Jy; W[k] += ii * (pS(7 * q, s) * Jy - pS(7 * q + 1, s) * Jx);
+      meta &= ~(1 << 30);
+      if (np == 2) {
+        const R K11 = K_im + K_ii * rn0 * rn0, K22 = K_im + K_ii * rn1 * rn1, K12 = K_im + K_ii * rn0 * rn1;
+        const R det = K11 * K22 - K12 * K12;
+        if (K11 * K11 < R(100) * det) {
+          meta |= 1 << 30;
+          const R idet = det != 0 ? M<R>::rcp(det) : R(0);
+          pS(14, s) = K12; pS(15, s) = K22 * idet; pS(16, s) = -K12 * idet; pS(17, s) = K11 * idet;
+        } else {
+          meta = (meta & ~(3 << 16)) | (1 << 16);
         }
       }
+      poolM[par * S + s] = meta;
+    }
+    // ---- contacts: warm start -------------------------------------------------------------------------
+#pragma unroll 1
+    for (int e = 0; e < ccnt; e++) {
+      const int s = slot_of(e);
+      const int meta = poolM[par * S + s];
+      const int k = (meta >> 14) & 3, np = (meta >> 16) & 3;
+      R vxk = SEL4(VX, k), vyk = SEL4(VY, k), wk = SEL4(W, k);
+      const R nx = pP(par, 0, s), ny = pP(par, 1, s), tx = ny, ty = -nx;
+      for (int q = 0; q < np; q++) {
+        const R jn = pP(par, 2 + 5 * q + 3, s), jt = pP(par, 2 + 5 * q + 4, s);
+        const R Jx = nx * jn + tx * jt, Jy = ny * jn + ty * jt;
+        vxk += K_im * Jx; vyk += K_im * Jy; wk += K_ii * (pS(7 * q, s) * Jy - pS(7 * q + 1, s) * Jx);
+      }
+      PUT4(VX, k, vxk) PUT4(VY, k, vyk) PUT4(W, k, wk)
     }
     // ---- springs: initialise + warm start ---------------------------------------------------------
-    R HC[4], HS[4];
+    R snx[18], sny[18], sE16 = 0, sE17 = 0;
+    V4<R> arm4;
+    V2<R> eff2;
+    {
+      R HC[4], HS[4];
 #pragma unroll
-    for (int k = 0; k < 4; k++) { HC[k] = half * CS[k]; HS[k] = half * SN[k]; }
-    R snx[18], sny[18], sc1[18], sc2[18], sE[18], sB[18];
-#define SPRING_INIT(i, a, b, sx1, sy1, sx2, sy2, kind, bit)                                     \
-  if (scaff & bit) {                                                                            \
-    const R r1x = (sx1)*HC[a] - (sy1)*HS[a], r1y = (sx1)*HS[a] + (sy1)*HC[a];                   \
-    const R r2x = (sx2)*HC[b] - (sy2)*HS[b], r2y = (sx2)*HS[b] + (sy2)*HC[b];                   \
-    R nx = (X[a] + r1x) - (X[b] + r2x), ny = (Y[a] + r1y) - (Y[b] + r2y);                       \
-    const R len = M<R>::sqrt_(nx * nx + ny * ny);                                               \
-    if (len < lin_tol) { nx = 0; ny = 0; } else { const R il = R(1) / len; nx *= il; ny *= il; } \
-    const R cr1 = r1x * ny - r1y * nx, cr2 = r2x * ny - r2y * nx;                               \
-    const R inv_mass = im + ii * cr1 * cr1 + im + ii * cr2 * cr2;                               \
-    const R E = sp_cfrac / inv_mass;                                                            \
-    snx[i] = nx; sny[i] = ny; sc1[i] = cr1; sc2[i] = cr2; sE[i] = E;                            \
-    sB[i] = E * ((len - rest[kind]) * sp_beta);                                                 \
-    const R m_ = simp[i] * im, q_ = simp[i] * ii;                                               \
-    VX[a] += nx * m_; VY[a] += ny * m_; W[a] += q_ * cr1;                                       \
-    VX[b] -= nx * m_; VY[b] -= ny * m_; W[b] -= q_ * cr2;                                       \
+      for (int k = 0; k < 4; k++) { HC[k] = K_half * CS[k]; HS[k] = K_half * SN[k]; }
+#define SPRING_INIT(i, a, b, sx1, sy1, sx2, sy2, kind, bit)                                      \
+  if (scaff & bit) {                                                                             \
+    const R r1x = (sx1)*HC[a] - (sy1)*HS[a], r1y = (sx1)*HS[a] + (sy1)*HC[a];                    \
+    const R r2x = (sx2)*HC[b] - (sy2)*HS[b], r2y = (sx2)*HS[b] + (sy2)*HC[b];                    \
+    R nx = (X[a] + r1x) - (X[b] + r2x), ny = (Y[a] + r1y) - (Y[b] + r2y);                        \
+    const R l2 = nx * nx + ny * ny;                                                              \
+    const R il = M<R>::rsqrt_(l2);                                                               \
+    const R len = l2 * il;                                                                       \
+    if (!(len >= K_lin_tol)) { nx = 0; ny = 0; } else { nx *= il; ny *= il; }                      \
+    const R cr1 = r1x * ny - r1y * nx, cr2 = r2x * ny - r2y * nx;                                \
+    const R E = K_sp_cfrac * M<R>::rcp(K_im + K_ii * cr1 * cr1 + K_im + K_ii * cr2 * cr2);                 \
+    snx[i] = nx; sny[i] = ny;                                                                    \
+    if ((i) < 16) {                                                                              \
+      if (((i) & 1) == 0) { arm4.x = cr1; arm4.y = cr2; eff2.x = E; }                            \
+      else { arm4.z = cr1; arm4.w = cr2; eff2.y = E; sarm[((i) >> 1) * 32 + lane] = arm4; seff[((i) >> 1) * 32 + lane] = eff2; } \
+    } else if ((i) == 16) sE16 = E; else sE17 = E;                                               \
+    const R m_ = simp[i] * K_im, q_ = simp[i] * K_ii;                                                \
+    VX[a] += nx * m_; VY[a] += ny * m_; W[a] += q_ * cr1;                                        \
+    VX[b] -= nx * m_; VY[b] -= ny * m_; W[b] -= q_ * cr2;                                        \
+    const R bs = E * ((len - rest[kind]) * K_sp_boversig); /* bias / sigma */                      \
+    sbias[i * 32 + lane] = bs;                                                                   \
+    simp[i] += bs;                                                                               \
   }
-    VSR_SPRINGS(SPRING_INIT)
+      VSR_SPRINGS(SPRING_INIT)
 #undef SPRING_INIT
+    }
     // ---- ropes: initialise + warm start -------------------------------------------------------------
-    R rnx[4], rny[4];
     bool ract[4];
     bool any_rope = false;
 #define ROPE_INIT(i, a, b)                                                                  \
   {                                                                                         \
     R nx = X[a] - X[b], ny = Y[a] - Y[b];                                                   \
-    const R len = M<R>::sqrt_(nx * nx + ny * ny);                                           \
-    if (len < lin_tol) { nx = 0; ny = 0; } else { const R il = R(1) / len; nx *= il; ny *= il; } \
-    rnx[i] = nx; rny[i] = ny;                                                               \
-    ract[i] = P.limit_contraction && len < rope_lower;                                      \
+    const R l2 = nx * nx + ny * ny;                                                         \
+    const R il = M<R>::rsqrt_(l2);                                                          \
+    const R len = l2 * il;                                                                  \
+    if (!(len >= K_lin_tol)) { nx = 0; ny = 0; } else { nx *= il; ny *= il; }                 \
+    ract[i] = P.limit_contraction && len < K_rope_lower;                                      \
     if (!ract[i]) rimp[i] = 0;                                                              \
-    const R m_ = rimp[i] * im;                                                              \
+    const R m_ = rimp[i] * K_im;                                                              \
     VX[a] += nx * m_; VY[a] += ny * m_; VX[b] -= nx * m_; VY[b] -= ny * m_;                 \
     any_rope |= ract[i];                                                                    \
   }
@@ -520,22 +733,21 @@ __global__ void __launch_bounds__(WARPS * 32) vsr_episode_kernel(const __grid_co
     // ---- welds: r2 of the partner mass, warm start ----------------------------------------------------
     // owner welds: 0 = (my NW, left NE) 1 = (my SW, left SE) 2 = (my SW, below NW) 3 = (my SE, below NE)
     // local anchor 2 = body1 - body2 at assembly: horizontal (+m, 0), vertical (0, +m)
-    const R wa = (R)P.weld_anchor;
     R wr2x[4], wr2y[4];
     {
       const R c1 = __shfl_sync(FULL, CS[1], ln_s), s1 = __shfl_sync(FULL, SN[1], ln_s);
       const R c2 = __shfl_sync(FULL, CS[2], ln_s), s2 = __shfl_sync(FULL, SN[2], ln_s);
-      wr2x[0] = wa * c1; wr2y[0] = wa * s1; wr2x[1] = wa * c2; wr2y[1] = wa * s2;
+      wr2x[0] = K_wa * c1; wr2y[0] = K_wa * s1; wr2x[1] = K_wa * c2; wr2y[1] = K_wa * s2;
       const R c0 = __shfl_sync(FULL, CS[0], dn_s), s0 = __shfl_sync(FULL, SN[0], dn_s);
       const R c1d = __shfl_sync(FULL, CS[1], dn_s), s1d = __shfl_sync(FULL, SN[1], dn_s);
-      wr2x[2] = -wa * s0; wr2y[2] = wa * c0; wr2x[3] = -wa * s1d; wr2y[3] = wa * c1d;
+      wr2x[2] = -K_wa * s0; wr2y[2] = K_wa * c0; wr2x[3] = -K_wa * s1d; wr2y[3] = K_wa * c1d;
     }
     // apply impulse l (3) of owner weld to body1 (mine) and return the partner's delta
 #define WELD_APPLY(wi, k1, lx_, ly_, lz_, dvx, dvy, dw)                   \
   {                                                                      \
-    VX[k1] += im * (lx_); VY[k1] += im * (ly_); W[k1] += ii * (lz_);     \
-    dvx = -im * (lx_); dvy = -im * (ly_);                                \
-    dw = -ii * (wr2x[wi] * (ly_) - wr2y[wi] * (lx_) + (lz_));            \
+    VX[k1] += K_im * (lx_); VY[k1] += K_im * (ly_); W[k1] += K_ii * (lz_);     \
+    dvx = -K_im * (lx_); dvy = -K_im * (ly_);                                \
+    dw = -K_ii * (wr2x[wi] * (ly_) - wr2y[wi] * (lx_) + (lz_));            \
   }
     {
       // horizontal round warm start
@@ -557,49 +769,77 @@ __global__ void __launch_bounds__(WARPS * 32) vsr_episode_kernel(const __grid_co
       const R f0 = __shfl_sync(FULL, d1x, un_s), f1 = __shfl_sync(FULL, d1y, un_s), f2 = __shfl_sync(FULL, d1w, un_s);
       if (un >= 0) { VX[0] += e0; VY[0] += e1; W[0] += e2; VX[1] += f0; VY[1] += f1; W[1] += f2; }
     }
-    // weld solve constants (r1 = 0 closed form)
-    const R wA = im + im, wh = ii * R(0.5);
-    const R wD = R(1) / (wA * (wA + wh * wa * wa));
     // solve K l = -C for a weld with r1 = 0 and partner arm (r2x, r2y)
 #define WELD_SOLVE(r2x, r2y, Cx, Cy, Cz, lx_, ly_, lz_)                                  \
   {                                                                                     \
     const R bx_ = -(Cx) - (r2y) * (Cz) * R(0.5), by_ = -(Cy) + (r2x) * (Cz) * R(0.5);   \
-    const R k00 = wA + wh * (r2x) * (r2x), k01 = wh * (r2x) * (r2y), k11 = wA + wh * (r2y) * (r2y); \
-    lx_ = wD * (k00 * bx_ + k01 * by_);                                                 \
-    ly_ = wD * (k01 * bx_ + k11 * by_);                                                 \
-    lz_ = -(Cz) / (ii + ii) + ((r2y)*lx_ - (r2x)*ly_) * R(0.5);                         \
+    const R k00 = K_wA + K_wh * (r2x) * (r2x), k01 = K_wh * (r2x) * (r2y), k11 = K_wA + K_wh * (r2y) * (r2y); \
+    lx_ = K_wD * (k00 * bx_ + k01 * by_);                                                 \
+    ly_ = K_wD * (k01 * bx_ + k11 * by_);                                                 \
+    lz_ = -(Cz) * K_w_i2i + ((r2y)*lx_ - (r2x)*ly_) * R(0.5);                             \
   }
 
+    // ---- park phase 2: positions and spring targets (read again only after the velocity loop) ----------------
+    {
+#pragma unroll
+      for (int k = 0; k < 4; k++) { spark[(k) * 32 + lane] = X[k]; spark[(4 + k) * 32 + lane] = Y[k]; }
+      spark[20 * 32 + lane] = rest[0]; spark[21 * 32 + lane] = rest[1]; spark[22 * 32 + lane] = rest[2];
+      asm volatile("" ::: "memory");
+    }
     // ---- velocity iterations ------------------------------------------------------------------------
+    PHASE_SYNC(2)
+#pragma unroll 1
     for (int it = 0; it < P.vel_iters; it++) {
-#define SPRING_SOLVE(i, a, b, sx1, sy1, sx2, sy2, kind, bit)                             \
-  if (scaff & bit) {                                                                    \
-    R jv = snx[i] * (VX[a] - VX[b]);                                                    \
-    jv += sny[i] * (VY[a] - VY[b]);                                                     \
-    jv += sc1[i] * W[a];                                                                \
-    jv -= sc2[i] * W[b];                                                                \
-    const R l_ = sE[i] * jv + sB[i] + sp_sigma * simp[i]; /* = -lambda */               \
-    simp[i] -= l_;                                                                      \
-    const R m_ = l_ * im, q_ = l_ * ii;                                                 \
-    VX[a] -= snx[i] * m_; VY[a] -= sny[i] * m_; W[a] -= q_ * sc1[i];                    \
-    VX[b] += snx[i] * m_; VY[b] += sny[i] * m_; W[b] += q_ * sc2[i];                    \
+      PHASE_SYNC(4)
+#pragma unroll
+      for (int i = 0; i < 4; i++) { opaque(wr2x[i]); opaque(wr2y[i]); } // keep the weld K terms out of long-lived registers
+      // springs: lambda' = E*Jv + sigma*(impulse + bias/sigma); impulse' -= lambda'  (DESIGN.md 4.2).
+      // Two body-disjoint springs are solved side by side (explicit ILP 2: the lane's dependency chain is
+      // the bottleneck, not the FMA pipe); one LDS.128 brings both springs' lever arms.
+#define SPRING_SOLVE2(i, a, b, j, c, d, bit)                                                     \
+  if (scaff & bit) {                                                                            \
+    const V4<R> arm = sarm[((i) >> 1) * 32 + lane];                                             \
+    const V2<R> eff = seff[((i) >> 1) * 32 + lane];                                             \
+    R jv0 = snx[i] * (VX[a] - VX[b]), jv1 = snx[j] * (VX[c] - VX[d]);                           \
+    jv0 += sny[i] * (VY[a] - VY[b]); jv1 += sny[j] * (VY[c] - VY[d]);                           \
+    jv0 += arm.x * W[a]; jv1 += arm.z * W[c];                                                   \
+    jv0 -= arm.y * W[b]; jv1 -= arm.w * W[d];                                                   \
+    const R l0 = eff.x * jv0 + K_sp_sigma * simp[i], l1 = eff.y * jv1 + K_sp_sigma * simp[j];   \
+    simp[i] -= l0; simp[j] -= l1;                                                               \
+    const R m0 = l0 * K_im, m1 = l1 * K_im, q0 = l0 * K_ii, q1 = l1 * K_ii;                             \
+    VX[a] -= snx[i] * m0; VX[c] -= snx[j] * m1; VY[a] -= sny[i] * m0; VY[c] -= sny[j] * m1;     \
+    VX[b] += snx[i] * m0; VX[d] += snx[j] * m1; VY[b] += sny[i] * m0; VY[d] += sny[j] * m1;     \
+    W[a] -= q0 * arm.x; W[c] -= q1 * arm.z; W[b] += q0 * arm.y; W[d] += q1 * arm.w;             \
   }
-      VSR_SPRINGS(SPRING_SOLVE)
-#undef SPRING_SOLVE
+      VSR_SPRING_PAIRS(SPRING_SOLVE2)
+#undef SPRING_SOLVE2
+      if (scaff & 8) { // central cross (0,2) and (1,3): anchors at the centres, r x n = 0
+        R jv0 = snx[16] * (VX[0] - VX[2]), jv1 = snx[17] * (VX[1] - VX[3]);
+        jv0 += sny[16] * (VY[0] - VY[2]); jv1 += sny[17] * (VY[1] - VY[3]);
+        const R l0 = sE16 * jv0 + K_sp_sigma * simp[16], l1 = sE17 * jv1 + K_sp_sigma * simp[17];
+        simp[16] -= l0; simp[17] -= l1;
+        const R m0 = l0 * K_im, m1 = l1 * K_im;
+        VX[0] -= snx[16] * m0; VX[1] -= snx[17] * m1; VY[0] -= sny[16] * m0; VY[1] -= sny[17] * m1;
+        VX[2] += snx[16] * m0; VX[3] += snx[17] * m1; VY[2] += sny[16] * m0; VY[3] += sny[17] * m1;
+      }
       if (warp_rope) {
 #define ROPE_SOLVE(i, a, b)                                                        \
   if (ract[i]) {                                                                   \
-    const R jv = rnx[i] * (VX[a] - VX[b]) + rny[i] * (VY[a] - VY[b]);              \
-    R l_ = -rope_E * jv;                                                           \
+    R rnx_ = spark[(a) * 32 + lane] - spark[(b) * 32 + lane], rny_ = spark[(4 + a) * 32 + lane] - spark[(4 + b) * 32 + lane]; \
+    { const R l2_ = rnx_ * rnx_ + rny_ * rny_; const R il_ = M<R>::rsqrt_(l2_);                    \
+      if (!(l2_ * il_ >= K_lin_tol)) { rnx_ = 0; rny_ = 0; } else { rnx_ *= il_; rny_ *= il_; } }  \
+    const R jv = rnx_ * (VX[a] - VX[b]) + rny_ * (VY[a] - VY[b]);                  \
+    R l_ = -K_rope_E * jv;                                                           \
     const R old = rimp[i];                                                         \
     rimp[i] = M<R>::max_(old + l_, R(0));                                          \
     l_ = rimp[i] - old;                                                            \
-    const R m_ = l_ * im;                                                          \
-    VX[a] += rnx[i] * m_; VY[a] += rny[i] * m_; VX[b] -= rnx[i] * m_; VY[b] -= rny[i] * m_; \
+    const R m_ = l_ * K_im;                                                          \
+    VX[a] += rnx_ * m_; VY[a] += rny_ * m_; VX[b] -= rnx_ * m_; VY[b] -= rny_ * m_;         \
   }
         VSR_ROPES(ROPE_SOLVE)
 #undef ROPE_SOLVE
       }
+#ifndef VSR_PROBE_NO_WELD_LOOP
       // welds, horizontal round: partner = left neighbour's NE(1) / SE(2)
       {
         const R p0x = __shfl_sync(FULL, VX[1], ln_s), p0y = __shfl_sync(FULL, VY[1], ln_s), p0w = __shfl_sync(FULL, W[1], ln_s);
@@ -636,80 +876,96 @@ __global__ void __launch_bounds__(WARPS * 32) vsr_episode_kernel(const __grid_co
         const R f0 = __shfl_sync(FULL, d1x, un_s), f1 = __shfl_sync(FULL, d1y, un_s), f2 = __shfl_sync(FULL, d1w, un_s);
         if (un >= 0) { VX[0] += e0; VY[0] += e1; W[0] += e2; VX[1] += f0; VY[1] += f1; W[1] += f2; }
       }
-      // contacts of my 4 corner masses
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const int cnt = clist[k] >> 24;
-        for (int o = 0; o < cnt; o++) {
-          const int s = (clist[k] >> (8 * o)) & 0xff;
-          const int meta = poolM[par * S + s];
-          const int np = (meta >> 16) & 3;
-          const R nx = pP(par, 0, s), ny = pP(par, 1, s), tx = ny, ty = -nx;
-          for (int q = 0; q < np; q++) { // friction first
+#endif
+#ifndef VSR_PROBE_NO_CONTACT_LOOP
+      // contacts of my corner masses (one copy of the solver; masses via select chains)
+#pragma unroll 1
+      for (int e = 0; e < ccnt; e++) {
+        const int s = slot_of(e);
+        const int meta = poolM[par * S + s];
+        const int k = (meta >> 14) & 3, np = (meta >> 16) & 3;
+        R vxk = SEL4(VX, k), vyk = SEL4(VY, k), wk = SEL4(W, k);
+        const R nx = pP(par, 0, s), ny = pP(par, 1, s), tx = ny, ty = -nx;
+        for (int q = 0; q < np; q++) { // friction first
+          const R rx = pS(7 * q, s), ry = pS(7 * q + 1, s);
+          R l_ = -pS(7 * q + 3, s) * (tx * (vxk - wk * ry) + ty * (vyk + wk * rx));
+          const R maxf = K_mu * pP(par, 2 + 5 * q + 3, s);
+          const R old = pP(par, 2 + 5 * q + 4, s);
+          const R nj = M<R>::max_(-maxf, M<R>::min_(old + l_, maxf));
+          l_ = nj - old;
+          pP(par, 2 + 5 * q + 4, s) = nj;
+          const R Jx = tx * l_, Jy = ty * l_;
+          vxk += K_im * Jx; vyk += K_im * Jy; wk += K_ii * (rx * Jy - ry * Jx);
+        }
+        if (!(meta & (1 << 30))) {
+          for (int q = 0; q < np; q++) {
             const R rx = pS(7 * q, s), ry = pS(7 * q + 1, s);
-            const R vx = VX[k] - W[k] * ry, vy = VY[k] + W[k] * rx;
-            R l_ = -pS(7 * q + 3, s) * (tx * vx + ty * vy);
-            const R maxf = mu * pP(par, 2 + 5 * q + 3, s);
-            const R old = pP(par, 2 + 5 * q + 4, s);
-            const R nj = M<R>::max_(-maxf, M<R>::min_(old + l_, maxf));
+            R l_ = -pS(7 * q + 2, s) * (nx * (vxk - wk * ry) + ny * (vyk + wk * rx) - pS(7 * q + 4, s));
+            const R old = pP(par, 2 + 5 * q + 3, s);
+            const R nj = M<R>::max_(old + l_, R(0));
             l_ = nj - old;
-            pP(par, 2 + 5 * q + 4, s) = nj;
-            const R Jx = tx * l_, Jy = ty * l_;
-            VX[k] += im * Jx; VY[k] += im * Jy; W[k] += ii * (rx * Jy - ry * Jx);
+            pP(par, 2 + 5 * q + 3, s) = nj;
+            const R Jx = nx * l_, Jy = ny * l_;
+            vxk += K_im * Jx; vyk += K_im * Jy; wk += K_ii * (rx * Jy - ry * Jx);
           }
-          if (!(meta & (1 << 30))) {
-            for (int q = 0; q < np; q++) {
-              const R rx = pS(7 * q, s), ry = pS(7 * q + 1, s);
-              const R vx = VX[k] - W[k] * ry, vy = VY[k] + W[k] * rx;
-              R l_ = -pS(7 * q + 2, s) * (nx * vx + ny * vy - pS(7 * q + 4, s));
-              const R old = pP(par, 2 + 5 * q + 3, s);
-              const R nj = M<R>::max_(old + l_, R(0));
-              l_ = nj - old;
-              pP(par, 2 + 5 * q + 3, s) = nj;
-              const R Jx = nx * l_, Jy = ny * l_;
-              VX[k] += im * Jx; VY[k] += im * Jy; W[k] += ii * (rx * Jy - ry * Jx);
-            }
-          } else { // 2-point block solver
-            const R r1x = pS(0, s), r1y = pS(1, s), r2x = pS(7, s), r2y = pS(8, s);
-            const R a1 = pP(par, 5, s), a2 = pP(par, 10, s);
-            const R vn1 = nx * (VX[k] - W[k] * r1y) + ny * (VY[k] + W[k] * r1x);
-            const R vn2 = nx * (VX[k] - W[k] * r2y) + ny * (VY[k] + W[k] * r2x);
-            const R K11 = R(1) / pS(2, s), K22 = R(1) / pS(9, s), K12 = pS(14, s);
-            const R b1 = vn1 - pS(4, s) - (K11 * a1 + K12 * a2);
-            const R b2 = vn2 - pS(11, s) - (K12 * a1 + K22 * a2);
-            R x1 = -(pS(15, s) * b1 + pS(16, s) * b2), x2 = -(pS(16, s) * b1 + pS(17, s) * b2);
-            if (!(x1 >= 0 && x2 >= 0)) {
-              x1 = -b1 * pS(2, s); x2 = 0;
-              if (!(x1 >= 0 && K12 * x1 + b2 >= 0)) {
-                x1 = 0; x2 = -b2 * pS(9, s);
-                if (!(x2 >= 0 && K12 * x2 + b1 >= 0)) {
-                  x1 = 0; x2 = 0;
-                  if (!(b1 >= 0 && b2 >= 0)) { x1 = a1; x2 = a2; }
-                }
+        } else { // 2-point block solver
+          const R r1x = pS(0, s), r1y = pS(1, s), r2x = pS(7, s), r2y = pS(8, s);
+          const R a1 = pP(par, 5, s), a2 = pP(par, 10, s);
+          const R vn1 = nx * (vxk - wk * r1y) + ny * (vyk + wk * r1x);
+          const R vn2 = nx * (vxk - wk * r2y) + ny * (vyk + wk * r2x);
+          const R mn1 = pS(2, s), mn2 = pS(9, s), K12 = pS(14, s);
+          const R rn1 = r1x * ny - r1y * nx, rn2 = r2x * ny - r2y * nx;
+          const R K11 = K_im + K_ii * rn1 * rn1, K22 = K_im + K_ii * rn2 * rn2;
+          const R b1 = vn1 - pS(4, s) - (K11 * a1 + K12 * a2);
+          const R b2 = vn2 - pS(11, s) - (K12 * a1 + K22 * a2);
+          R x1 = -(pS(15, s) * b1 + pS(16, s) * b2), x2 = -(pS(16, s) * b1 + pS(17, s) * b2);
+          if (!(x1 >= 0 && x2 >= 0)) {
+            x1 = -b1 * mn1; x2 = 0;
+            if (!(x1 >= 0 && K12 * x1 + b2 >= 0)) {
+              x1 = 0; x2 = -b2 * mn2;
+              if (!(x2 >= 0 && K12 * x2 + b1 >= 0)) {
+                x1 = 0; x2 = 0;
+                if (!(b1 >= 0 && b2 >= 0)) { x1 = a1; x2 = a2; }
               }
             }
-            const R d1 = x1 - a1, d2 = x2 - a2;
-            pP(par, 5, s) = x1; pP(par, 10, s) = x2;
-            const R J1x = nx * d1, J1y = ny * d1, J2x = nx * d2, J2y = ny * d2;
-            VX[k] += im * (J1x + J2x); VY[k] += im * (J1y + J2y);
-            W[k] += ii * ((r1x * J1y - r1y * J1x) + (r2x * J2y - r2y * J2x));
           }
+          const R d1 = x1 - a1, d2 = x2 - a2;
+          pP(par, 5, s) = x1; pP(par, 10, s) = x2;
+          const R J1x = nx * d1, J1y = ny * d1, J2x = nx * d2, J2y = ny * d2;
+          vxk += K_im * (J1x + J2x); vyk += K_im * (J1y + J2y);
+          wk += K_ii * ((r1x * J1y - r1y * J1x) + (r2x * J2y - r2y * J2x));
         }
+        PUT4(VX, k, vxk) PUT4(VY, k, vyk) PUT4(W, k, wk)
       }
+#endif
     } // velocity iterations
+    // spring accumulators back to pure impulses (warm start of the next step)
+#define SPRING_FIN(i, a, b, sx1, sy1, sx2, sy2, kind, bit) if (scaff & bit) simp[i] -= sbias[i * 32 + lane];
+    VSR_SPRINGS(SPRING_FIN)
+#undef SPRING_FIN
 
     // ---- integrate positions (per-step clamps) -----------------------------------------------------
+    PHASE_SYNC(8)
+    {
+      asm volatile("" ::: "memory");
+#pragma unroll
+      for (int k = 0; k < 4; k++) { X[k] = spark[(k) * 32 + lane]; Y[k] = spark[(4 + k) * 32 + lane]; A[k] = spark[(8 + k) * 32 + lane]; }
+      px0 = spark[12 * 32 + lane]; px1 = spark[13 * 32 + lane]; py0 = spark[14 * 32 + lane]; py1 = spark[15 * 32 + lane];
+      pnx = spark[16 * 32 + lane]; pny = spark[17 * 32 + lane];
+      ox = spark[18 * 32 + lane]; oy = spark[19 * 32 + lane];
+      rest[0] = spark[20 * 32 + lane]; rest[1] = spark[21 * 32 + lane]; rest[2] = spark[22 * 32 + lane];
+    }
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-      R txx = VX[k] * dt, tyy = VY[k] * dt, r = W[k] * dt;
+      R txx = VX[k] * K_dt, tyy = VY[k] * K_dt, r = W[k] * K_dt;
       const R t2 = txx * txx + tyy * tyy;
-      if (t2 > (R)(P.max_trans * P.max_trans)) {
-        const R ratio = (R)P.max_trans / M<R>::sqrt_(t2);
-        VX[k] *= ratio; VY[k] *= ratio; txx = VX[k] * dt; tyy = VY[k] * dt;
+      if (t2 > K_max_trans2) {
+        const R ratio = K_max_trans * M<R>::rsqrt_(t2);
+        VX[k] *= ratio; VY[k] *= ratio; txx = VX[k] * K_dt; tyy = VY[k] * K_dt;
       }
-      if (M<R>::abs_(r) > (R)P.max_rot) {
-        const R ratio = (R)P.max_rot / M<R>::abs_(r);
-        W[k] *= ratio; r = W[k] * dt;
+      if (M<R>::abs_(r) > K_max_rot) {
+        const R ratio = K_max_rot * M<R>::rcp(M<R>::abs_(r));
+        W[k] *= ratio; r = W[k] * K_dt;
       }
       X[k] += txx; Y[k] += tyy; A[k] += r;
       M<R>::sincos_(A[k], &SN[k], &CS[k]);
@@ -722,93 +978,97 @@ __global__ void __launch_bounds__(WARPS * 32) vsr_episode_kernel(const __grid_co
       const R dox = __shfl_sync(FULL, ox, dn_s) - ox, doy = __shfl_sync(FULL, oy, dn_s) - oy;
       const unsigned robot_mask = lane_used ? (((L >= 32) ? FULL : ((1u << L) - 1u)) << base_lane) : (1u << lane);
       bool active = true;
+#pragma unroll 1
       for (int it = 0; it < P.pos_iters; it++) {
         bool ok = true;
         // contacts
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-          const int cnt = active ? (clist[k] >> 24) : 0;
-          for (int o = 0; o < cnt; o++) {
-            const int s = (clist[k] >> (8 * o)) & 0xff;
-            const int np = (poolM[par * S + s] >> 16) & 3;
-            const R nx = pP(par, 0, s), ny = pP(par, 1, s);
-            for (int q = 0; q < np; q++) {
-              const R lx = pS(7 * q + 5, s), ly = pS(7 * q + 6, s);
-              const R rx = CS[k] * lx - SN[k] * ly, ry = SN[k] * lx + CS[k] * ly;
-              const R sep = nx * (X[k] + rx - pP(par, 2 + 5 * q, s)) + ny * (Y[k] + ry - pP(par, 2 + 5 * q + 1, s)) -
-                            pP(par, 2 + 5 * q + 2, s);
-              if (sep < -R(3) * lin_tol) ok = false;
-              R C = baum * (sep + lin_tol);
-              C = M<R>::min_(C, R(0));
-              C = M<R>::max_(C, -max_corr);
-              const R rn_ = rx * ny - ry * nx;
-              const R K = im + ii * rn_ * rn_;
-              const R l_ = K > 0 ? -C / K : R(0);
-              X[k] += im * nx * l_; Y[k] += im * ny * l_; A[k] += ii * rn_ * l_;
-              M<R>::sincos_(A[k], &SN[k], &CS[k]);
-            }
+        const int ccnt_a = active ? ccnt : 0;
+#pragma unroll 1
+        for (int e = 0; e < ccnt_a; e++) {
+          const int s = slot_of(e);
+          const int meta = poolM[par * S + s];
+          const int k = (meta >> 14) & 3, np = (meta >> 16) & 3;
+          R xk = SEL4(X, k), yk = SEL4(Y, k), ak = SEL4(A, k), ck = SEL4(CS, k), sk = SEL4(SN, k);
+          const R nx = pP(par, 0, s), ny = pP(par, 1, s);
+          for (int q = 0; q < np; q++) {
+            const R lx = pS(7 * q + 5, s), ly = pS(7 * q + 6, s);
+            const R rx = ck * lx - sk * ly, ry = sk * lx + ck * ly;
+            const R sep = nx * (xk + rx - pP(par, 2 + 5 * q, s)) + ny * (yk + ry - pP(par, 2 + 5 * q + 1, s)) - pP(par, 2 + 5 * q + 2, s);
+            if (sep < -R(3) * K_lin_tol) ok = false;
+            R C = K_baum * (sep + K_lin_tol);
+            C = M<R>::min_(C, R(0));
+            C = M<R>::max_(C, -K_max_corr);
+            const R rn_ = rx * ny - ry * nx;
+            const R l_ = -C * M<R>::rcp(K_im + K_ii * rn_ * rn_);
+            xk += K_im * nx * l_; yk += K_im * ny * l_;
+            M<R>::rotate(ak, ck, sk, K_ii * rn_ * l_);
           }
+          PUT4(X, k, xk) PUT4(Y, k, yk) PUT4(A, k, ak) PUT4(CS, k, ck) PUT4(SN, k, sk)
         }
         // ropes
         if (warp_rope) {
 #define ROPE_POS(i, a, b)                                                                  \
   if (ract[i] && active) {                                                                 \
     R nx = X[a] - X[b], ny = Y[a] - Y[b];                                                  \
-    const R len = M<R>::sqrt_(nx * nx + ny * ny);                                          \
-    if (len < lin_tol) { nx = 0; ny = 0; } else { const R il = R(1) / len; nx *= il; ny *= il; } \
-    R C = len - rope_lower;                                                                \
-    if (!(-C < lin_tol)) ok = false;                                                       \
+    const R l2 = nx * nx + ny * ny;                                                        \
+    const R il = M<R>::rsqrt_(l2);                                                         \
+    const R len = l2 * il;                                                                 \
+    if (!(len >= K_lin_tol)) { nx = 0; ny = 0; } else { nx *= il; ny *= il; }                \
+    R C = len - K_rope_lower;                                                                \
+    if (!(-C < K_lin_tol)) ok = false;                                                       \
     C = M<R>::min_(C, R(0));                                                               \
-    C = M<R>::max_(C, -max_corr);                                                          \
-    const R l_ = -rope_E * C;                                                              \
-    const R m_ = l_ * im;                                                                  \
+    C = M<R>::max_(C, -K_max_corr);                                                          \
+    const R l_ = -K_rope_E * C;                                                              \
+    const R m_ = l_ * K_im;                                                                  \
     X[a] += nx * m_; Y[a] += ny * m_; X[b] -= nx * m_; Y[b] -= ny * m_;                    \
   }
           VSR_ROPES(ROPE_POS)
 #undef ROPE_POS
         }
-        // weld position solve for owner weld (body1 = mine k1, partner pose pulled)
-#define WELD_POS(k1, px_, py_, pa_, ax_, ay_, dpx, dpy, dpa)                                     \
+        // weld position solve for owner weld (body1 = mine k1; partner pose + rotation pulled)
+#define WELD_POS(k1, px_, py_, pa_, pc_, ps_, ax_, ay_, dpx, dpy, dpa)                            \
   {                                                                                             \
-    R s2, c2;                                                                                   \
-    M<R>::sincos_(pa_, &s2, &c2);                                                               \
-    const R r2x = c2 * (ax_) - s2 * (ay_), r2y = s2 * (ax_) + c2 * (ay_);                       \
+    const R r2x = (pc_) * (ax_) - (ps_) * (ay_), r2y = (ps_) * (ax_) + (pc_) * (ay_);           \
     const R Cx = X[k1] - ((px_) + r2x), Cy = Y[k1] - ((py_) + r2y), Cz = A[k1] - (pa_);         \
-    if (!(M<R>::sqrt_(Cx * Cx + Cy * Cy) <= lin_tol && M<R>::abs_(Cz) <= ang_tol)) ok = false;  \
+    if (!(Cx * Cx + Cy * Cy <= K_lin_tol * K_lin_tol && M<R>::abs_(Cz) <= K_ang_tol)) ok = false;     \
     R lx_, ly_, lz_;                                                                            \
     WELD_SOLVE(r2x, r2y, Cx, Cy, Cz, lx_, ly_, lz_)                                             \
-    X[k1] += im * lx_; Y[k1] += im * ly_; A[k1] += ii * lz_;                                    \
-    M<R>::sincos_(A[k1], &SN[k1], &CS[k1]);                                                     \
-    dpx = -im * lx_; dpy = -im * ly_; dpa = -ii * (r2x * ly_ - r2y * lx_ + lz_);                \
+    X[k1] += K_im * lx_; Y[k1] += K_im * ly_;                                                       \
+    M<R>::rotate(A[k1], CS[k1], SN[k1], K_ii * lz_);                                              \
+    dpx = -K_im * lx_; dpy = -K_im * ly_; dpa = -K_ii * (r2x * ly_ - r2y * lx_ + lz_);                \
   }
         {
           const R p0x = __shfl_sync(FULL, X[1], ln_s) + lox, p0y = __shfl_sync(FULL, Y[1], ln_s) + loy, p0a = __shfl_sync(FULL, A[1], ln_s);
+          const R p0c = __shfl_sync(FULL, CS[1], ln_s), p0s = __shfl_sync(FULL, SN[1], ln_s);
           const R p1x = __shfl_sync(FULL, X[2], ln_s) + lox, p1y = __shfl_sync(FULL, Y[2], ln_s) + loy, p1a = __shfl_sync(FULL, A[2], ln_s);
+          const R p1c = __shfl_sync(FULL, CS[2], ln_s), p1s = __shfl_sync(FULL, SN[2], ln_s);
           R d0x = 0, d0y = 0, d0a = 0, d1x = 0, d1y = 0, d1a = 0;
           if (ln >= 0 && active) {
-            WELD_POS(0, p0x, p0y, p0a, wa, R(0), d0x, d0y, d0a)
-            WELD_POS(3, p1x, p1y, p1a, wa, R(0), d1x, d1y, d1a)
+            WELD_POS(0, p0x, p0y, p0a, p0c, p0s, K_wa, R(0), d0x, d0y, d0a)
+            WELD_POS(3, p1x, p1y, p1a, p1c, p1s, K_wa, R(0), d1x, d1y, d1a)
           }
           const R a0 = __shfl_sync(FULL, d0x, rn_s), a1 = __shfl_sync(FULL, d0y, rn_s), a2 = __shfl_sync(FULL, d0a, rn_s);
           const R b0 = __shfl_sync(FULL, d1x, rn_s), b1 = __shfl_sync(FULL, d1y, rn_s), b2 = __shfl_sync(FULL, d1a, rn_s);
           if (rn >= 0 && active) {
-            X[1] += a0; Y[1] += a1; A[1] += a2; M<R>::sincos_(A[1], &SN[1], &CS[1]);
-            X[2] += b0; Y[2] += b1; A[2] += b2; M<R>::sincos_(A[2], &SN[2], &CS[2]);
+            X[1] += a0; Y[1] += a1; M<R>::rotate(A[1], CS[1], SN[1], a2);
+            X[2] += b0; Y[2] += b1; M<R>::rotate(A[2], CS[2], SN[2], b2);
           }
         }
         {
           const R p0x = __shfl_sync(FULL, X[0], dn_s) + dox, p0y = __shfl_sync(FULL, Y[0], dn_s) + doy, p0a = __shfl_sync(FULL, A[0], dn_s);
+          const R p0c = __shfl_sync(FULL, CS[0], dn_s), p0s = __shfl_sync(FULL, SN[0], dn_s);
           const R p1x = __shfl_sync(FULL, X[1], dn_s) + dox, p1y = __shfl_sync(FULL, Y[1], dn_s) + doy, p1a = __shfl_sync(FULL, A[1], dn_s);
+          const R p1c = __shfl_sync(FULL, CS[1], dn_s), p1s = __shfl_sync(FULL, SN[1], dn_s);
           R d0x = 0, d0y = 0, d0a = 0, d1x = 0, d1y = 0, d1a = 0;
           if (dn >= 0 && active) {
-            WELD_POS(3, p0x, p0y, p0a, R(0), wa, d0x, d0y, d0a)
-            WELD_POS(2, p1x, p1y, p1a, R(0), wa, d1x, d1y, d1a)
+            WELD_POS(3, p0x, p0y, p0a, p0c, p0s, R(0), K_wa, d0x, d0y, d0a)
+            WELD_POS(2, p1x, p1y, p1a, p1c, p1s, R(0), K_wa, d1x, d1y, d1a)
           }
           const R e0 = __shfl_sync(FULL, d0x, un_s), e1 = __shfl_sync(FULL, d0y, un_s), e2 = __shfl_sync(FULL, d0a, un_s);
           const R f0 = __shfl_sync(FULL, d1x, un_s), f1 = __shfl_sync(FULL, d1y, un_s), f2 = __shfl_sync(FULL, d1a, un_s);
           if (un >= 0 && active) {
-            X[0] += e0; Y[0] += e1; A[0] += e2; M<R>::sincos_(A[0], &SN[0], &CS[0]);
-            X[1] += f0; Y[1] += f1; A[1] += f2; M<R>::sincos_(A[1], &SN[1], &CS[1]);
+            X[0] += e0; Y[0] += e1; M<R>::rotate(A[0], CS[0], SN[0], e2);
+            X[1] += f0; Y[1] += f1; M<R>::rotate(A[1], CS[1], SN[1], f2);
           }
         }
 #undef WELD_POS
@@ -827,10 +1087,13 @@ __global__ void __launch_bounds__(WARPS * 32) vsr_episode_kernel(const __grid_co
         ox += sx; oy += sy;
 #pragma unroll
         for (int k = 0; k < 4; k++) { X[k] -= sx; Y[k] -= sy; }
+        pk = 0; // cached polygon is expressed in the old frame
       }
     }
     // ---- detect for the next step / touch sensors -----------------------------------------------------
+    PHASE_SYNC(16)
     detect();
+    PHASE_SYNC(32)
 
     // ---- robot.act(t): sensors -> controller -> applyForce ---------------------------------------------
     // outer voxel-poly vertices (NW NE SE SW), local frame
@@ -839,35 +1102,38 @@ __global__ void __launch_bounds__(WARPS * 32) vsr_episode_kernel(const __grid_co
       const R sxk[4] = {-1, +1, +1, -1}, syk[4] = {+1, +1, -1, -1};
 #pragma unroll
       for (int k = 0; k < 4; k++) {
-        const R lx = sxk[k] * half, ly = syk[k] * half;
+        const R lx = sxk[k] * K_half, ly = syk[k] * K_half;
         qx[k] = X[k] + CS[k] * lx - SN[k] * ly;
         qy[k] = Y[k] + SN[k] * lx + CS[k] * ly;
       }
     }
     R f = 0;
-    if (P.ctrl_kind == VSR_CTRL_PHASE_SIN) {
-      f = (R)(P.amp * sin(2.0 * 3.14159265358979323846 * P.freq * t + (double)phase));
+    if (CTRL == VSR_CTRL_PHASE_SIN) {
+      f = M<R>::phase_sin(P.amp, P.freq, t, phase);
     } else {
       // sensor readings of this voxel
       R rd[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) rd[i] = 0;
       R vang = 0;
       bool have_ang = false;
+#pragma unroll 1
       for (int si = 0; si < P.n_sensors; si++) {
         const SensorK& sk = P.sensors[si];
-        R raw[2] = {0, 0};
+        R raw0 = 0, raw1 = 0;
         if (sk.kind == VSR_SENSOR_AREA_RATIO) {
           R a2 = 0;
 #pragma unroll
           for (int i = 0; i < 4; i++) { const int j = (i + 1) & 3; a2 += qx[i] * qy[j] - qx[j] * qy[i]; }
-          raw[0] = M<R>::abs_(a2) * R(0.5) / (R)(P.side_len * P.side_len);
+          raw0 = M<R>::abs_(a2) * K_inv_area2;
         } else if (sk.kind == VSR_SENSOR_TOUCH) {
-          raw[0] = ((clist[0] | clist[1] | clist[2] | clist[3]) >> 24) ? R(1) : R(0);
+          raw0 = ccnt ? R(1) : R(0);
         } else {
           if (!have_ang) {
             vang = (M<R>::atan2_(Y[1] - Y[0], X[1] - X[0]) + M<R>::atan2_(Y[2] - Y[3], X[2] - X[3])) * R(0.5);
             have_ang = true;
           }
-          if (sk.kind == VSR_SENSOR_ANGLE) raw[0] = vang;
+          if (sk.kind == VSR_SENSOR_ANGLE) raw0 = vang;
           else {
             R vx = R(0.25) * (VX[0] + VX[1] + VX[2] + VX[3]), vy = R(0.25) * (VY[0] + VY[1] + VY[2] + VY[3]);
             if (sk.rotated) {
@@ -876,45 +1142,49 @@ __global__ void __launch_bounds__(WARPS * 32) vsr_episode_kernel(const __grid_co
               const R rx = cs_ * vx - sn_ * vy, ry = sn_ * vx + cs_ * vy;
               vx = rx; vy = ry;
             }
-            int o = 0;
-            if (sk.axes & 1) raw[o++] = vx;
-            if (sk.axes & 2) raw[o++] = vy;
+            if ((sk.axes & 3) == 3) { raw0 = vx; raw1 = vy; }
+            else raw0 = (sk.axes & 1) ? vx : vy;
           }
         }
         for (int d = 0; d < sk.dim; d++) {
-          R val = raw[d];
+          R val = d == 0 ? raw0 : raw1;
           if (sk.avg >= 0) {
             // Average: mean of the last win readings (window table emulates the t_j >= t - w test in double)
             const int ai = sk.avg + d;
             const int slot = (step - 1) % P.hist_cap;
             R* hist = reinterpret_cast<R*>(P.hist);
             hist[((size_t)slot * P.n_avg + ai) * total_lanes + gl] = val;
-            double sum = avg_sum[ai] + (double)val;
-            int cnt = avg_cnt[ai] + 1;
+            double sum = savg[ai * 32 + lane] + (double)val;
+            int cnt = savg_cnt[ai * 32 + lane] + 1;
             const int win = P.win_tab[(size_t)ai * (P.n_steps + 1) + step];
             while (cnt > win) {
               const int oslot = (step - cnt + P.hist_cap * 4) % P.hist_cap;
               sum -= (double)hist[((size_t)oslot * P.n_avg + ai) * total_lanes + gl];
               cnt--;
             }
-            avg_sum[ai] = sum; avg_cnt[ai] = cnt;
+            savg[ai * 32 + lane] = sum; savg_cnt[ai * 32 + lane] = cnt;
             val = (R)(sum / cnt);
           }
           if (sk.soft_norm) {
-            const R vv = (val - (R)sk.dom_min) / (R)(sk.dom_max - sk.dom_min);
+            const R vv = (val - (R)sk.dom_min) * (R)sk.dom_inv;
             val = M<R>::tanh_((vv * R(2) - R(1)) * R(2)) * R(0.5) + R(0.5);
           }
-          rd[sk.off + d] = val;
+          const int ri = sk.off + d;
+#pragma unroll
+          for (int z = 0; z < 8; z++) if (z == ri) rd[z] = val;
         }
       }
       const int D = P.sens_dim, maxN = P.max_neurons;
-      if (P.ctrl_kind == VSR_CTRL_MLP_CENTRALIZED) {
+      if (CTRL == VSR_CTRL_MLP_CENTRALIZED) {
         R* a0 = act + (size_t)(lane_used ? rw : 0) * 2 * maxN;
         const R* w_ = wts + (size_t)(lane_used ? rw : 0) * P.genome_len;
-        if (valid)
-          for (int d = 0; d < D; d++) a0[v * D + d] = P.in_act ? M<R>::tanh_(rd[d]) : rd[d];
+        if (valid) {
+#pragma unroll
+          for (int d = 0; d < 8; d++) if (d < D) a0[v * D + d] = P.in_act ? M<R>::tanh_(rd[d]) : rd[d];
+        }
         __syncwarp();
         int cur = 0, o = 0;
+#pragma unroll 1
         for (int l = 1; l < P.n_layers; l++) {
           const int nf = P.layers[l - 1], nt = P.layers[l];
           const R* in = a0 + cur * maxN;
@@ -934,21 +1204,25 @@ __global__ void __launch_bounds__(WARPS * 32) vsr_episode_kernel(const __grid_co
         __syncwarp();
       } else { // homogeneous DistributedSensing: every voxel runs the same MLP on its own inputs
         const int sg = P.signals;
-        R* a0 = act;                    // [2][maxN][32]
+        R* a0 = act; // [2][maxN][32]
         const R* w_ = wts + (size_t)(lane_used ? rw : 0) * P.genome_len;
         const R* sin_ = sig + (size_t)sig_par * 32 * 4 * sg;
         R* sout = sig + (size_t)(sig_par ^ 1) * 32 * 4 * sg;
         int ni = 0;
-        for (int d = 0; d < D; d++) a0[(ni++) * 32 + lane] = P.in_act ? M<R>::tanh_(rd[d]) : rd[d];
+#pragma unroll
+        for (int d = 0; d < 8; d++) if (d < D) a0[(ni++) * 32 + lane] = P.in_act ? M<R>::tanh_(rd[d]) : rd[d];
         // Dir N(0,-1) E(1,0) S(0,1) W(-1,0); read the neighbour's signal emitted towards me (opposite side)
-        const int nbl[4] = {dn, rn, un, ln};
-        const int opp[4] = {2, 3, 0, 1};
-        for (int d = 0; d < 4; d++)
+#pragma unroll
+        for (int d = 0; d < 4; d++) {
+          const int nbl = d == 0 ? dn : (d == 1 ? rn : (d == 2 ? un : ln));
+          const int opp = (d + 2) & 3;
           for (int s_ = 0; s_ < sg; s_++) {
-            const R x_ = nbl[d] >= 0 ? sin_[(nbl[d] * 4 + opp[d]) * sg + s_] : R(0);
+            const R x_ = nbl >= 0 ? sin_[(nbl * 4 + opp) * sg + s_] : R(0);
             a0[(ni++) * 32 + lane] = P.in_act ? M<R>::tanh_(x_) : x_;
           }
+        }
         int cur = 0, o = 0;
+#pragma unroll 1
         for (int l = 1; l < P.n_layers; l++) {
           const int nf = P.layers[l - 1], nt = P.layers[l];
           const R* in = a0 + (size_t)cur * maxN * 32;
@@ -974,8 +1248,8 @@ __global__ void __launch_bounds__(WARPS * 32) vsr_episode_kernel(const __grid_co
     ctrl_f = f;
 #pragma unroll
     for (int kq = 0; kq < 3; kq++) {
-      const R rr = (R)P.range_rest[kq];
-      rest[kq] = f >= 0 ? rr - (rr - (R)P.range_min[kq]) * f : rr + ((R)P.range_max[kq] - rr) * -f;
+      const R rr = KC(range_rest[kq], P.range_rest[kq]);
+      rest[kq] = f >= 0 ? rr - (rr - KC(range_min[kq], P.range_min[kq])) * f : rr + (KC(range_max[kq], P.range_max[kq]) - rr) * -f;
     }
 
     // ---- observation: robot centre x at the first / last kept step --------------------------------------
@@ -984,8 +1258,22 @@ __global__ void __launch_bounds__(WARPS * 32) vsr_episode_kernel(const __grid_co
       double sum = 0;
       for (int j = 0; j < L; j++) sum += __shfl_sync(FULL, cxv, (base_lane + j) & 31);
       sum /= L;
-      if (step == P.k_first) { cx_first = sum; t_first = t; }
-      if (step == P.k_last) { cx_last = sum; t_last = t; }
+      // K3 result pack: the first observation waits in the fitness slot (global) until the last one arrives
+      if (valid && v == 0) {
+        if (step == P.k_first) P.fitness[robot] = sum;
+        if (step == P.k_last) {
+          const double cx_first = P.k_last == P.k_first ? sum : P.fitness[robot];
+          const double dist = sum - cx_first, tm = P.t_last - P.t_first;
+          const double vel = dist / tm;
+          P.fitness[robot] = vel;
+          if (P.results) {
+            vsr_result r;
+            r.velocity = vel; r.distance = dist; r.time = tm; r.first_x = cx_first; r.last_x = sum;
+            r.n_steps = P.n_steps; r.k_first = P.k_first; r.k_last = P.k_last; r.contact_overflow = 0;
+            P.results[robot] = r;
+          }
+        }
+      }
     }
     // ---- trace (parity tests; robot 0 only) ---------------------------------------------------------------
     if (P.trace_steps > 0 && step <= P.trace_steps && valid && robot == 0) {
@@ -1006,21 +1294,47 @@ __global__ void __launch_bounds__(WARPS * 32) vsr_episode_kernel(const __grid_co
     }
   } // steps
 
-  // ---- epilogue: K3 result pack --------------------------------------------------------------------------
+  // ---- epilogue: contact-pool overflow count (fitness / result were written at step k_last) ---------------
   const int ovf = __reduce_add_sync(FULL, overflow);
-  if (valid && v == 0) {
-    const double dist = cx_last - cx_first, tm = t_last - t_first;
-    const double vel = dist / tm;
-    P.fitness[robot] = vel;
-    if (P.results) {
-      vsr_result r;
-      r.velocity = vel; r.distance = dist; r.time = tm; r.first_x = cx_first; r.last_x = cx_last;
-      r.n_steps = P.n_steps; r.k_first = P.k_first; r.k_last = P.k_last; r.contact_overflow = ovf;
-      P.results[robot] = r;
-    }
-  }
+  if (valid && v == 0 && P.results && ovf) P.results[robot].contact_overflow = ovf;
 #undef WELD_APPLY
 #undef WELD_SOLVE
+#undef ln_s
+#undef rn_s
+#undef dn_s
+#undef un_s
+#undef ln
+#undef rn
+#undef dn
+#undef un
+#undef K_dt
+#undef K_half
+#undef K_im
+#undef K_ii
+#undef K_mu
+#undef K_lin_tol
+#undef K_ang_tol
+#undef K_max_corr
+#undef K_baum
+#undef K_lin_f
+#undef K_ang_f
+#undef K_sp_sigma
+#undef K_sp_boversig
+#undef K_sp_cfrac
+#undef K_rope_lower
+#undef K_rope_E
+#undef K_wa
+#undef K_wA
+#undef K_wh
+#undef K_wD
+#undef K_w_i2i
+#undef K_rest_vel
+#undef K_rest_e
+#undef K_max_trans
+#undef K_max_trans2
+#undef K_max_rot
+#undef K_inv_area2
+#undef KC
 }
 
 } // namespace vsr
