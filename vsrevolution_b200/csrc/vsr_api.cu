@@ -283,15 +283,18 @@ int finalize(vsr_ctx* ctx) {
   for (int i = 0; i < k.n_layers; i++) { k.layers[i] = ctx->layers[i]; k.max_neurons = std::max(k.max_neurons, ctx->layers[i]); }
   // shared memory layout (per warp)
   const size_t rs = e.precision == 64 ? 8 : 4;
-  // contact-pool slots per warp: 4/3 manifolds per voxel lane (every bottom mass of every robot touching, plus
+  // contact-pool slots per warp: 6/5 manifolds per voxel lane (every bottom mass of every robot touching, plus
   // polygon-boundary doubles); overflow is counted in vsr_result.contact_overflow
-  int S = std::max(16, std::min(64, k.robots_per_warp * ctx->n_vox * 4 / 3));
+  int S = std::max(16, std::min(64, k.robots_per_warp * ctx->n_vox * 6 / 5));
   if (const char* ev = std::getenv("VSR_POOL_SLOTS")) S = std::max(8, std::min(255, std::atoi(ev)));
   k.pool_slots = S;
   size_t o = 0;
   k.off_pool_p = (int)o; o = align16(o + (size_t)vsr::kPoolStride * S * rs);
   k.off_pool_m = (int)o; o = align16(o + 2 * S * 4);
   k.off_pool_cnt = (int)o; o = align16(o + 4);
+  k.off_pool_o = (int)o; o = align16(o + S * 4);
+  o = (o + 31) & ~size_t(31);
+  k.off_stage = (int)o; o = align16(o + (size_t)3 * 32 * 4 * rs);
   k.off_w = (int)o;
   if (ctx->kind != VSR_CTRL_PHASE_SIN) o = align16(o + (size_t)k.robots_per_warp * glen * rs);
   k.off_act = (int)o;
@@ -306,6 +309,9 @@ int finalize(vsr_ctx* ctx) {
   o = align16(o + (size_t)8 * 32 * 4 * rs);
   k.off_eff = (int)o;
   o = align16(o + (size_t)8 * 32 * 2 * rs);
+  o = (o + 31) & ~size_t(31);
+  k.off_nrm = (int)o;
+  o = align16(o + (size_t)2 * 32 * 4 * rs);
   k.off_park = (int)o;
   o = align16(o + (size_t)vsr::kPark * 32 * rs);
   k.off_cold = (int)o;

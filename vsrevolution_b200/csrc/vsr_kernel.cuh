@@ -96,7 +96,7 @@ struct KParams {
   // shared-memory layout (bytes from the CTA's dynamic smem base; per warp strides)
   int pool_slots;
   int smem_warp_stride; // bytes per warp
-  int off_pool_p, off_pool_m, off_pool_cnt, off_w, off_act, off_sig, off_bias, off_arm, off_eff, off_park, off_cold;
+  int off_pool_p, off_pool_m, off_pool_cnt, off_w, off_act, off_sig, off_bias, off_arm, off_eff, off_nrm, off_park, off_cold, off_stage, off_pool_o;
   int sync_mask; // phase-alignment barriers (bit0 step start, bit1 before velocity loop, bit2 every velocity
                  // iteration, bit3 before position phase, bit4 before detect, bit5 before sensing)
 };
@@ -317,7 +317,7 @@ __device__ __forceinline__ int collide_box_ground(R x0, R y0, R x1, R y1, R base
 // ground's top edge is provably the SAT reference face (no flip, side edges cannot win) and the incident box
 // edge needs no clipping.  Same formulas as the general path -> identical normal / points / depths / ids.
 // Returns -1 when the penetration is too deep for that argument (caller falls back to the general path).
-constexpr float kFastMargin = 1.25f, kFastDepth = 0.3f;
+constexpr float kFastMargin = 0.96f, kFastDepth = 0.05f; // margin > 2*half + depth (0.9 + 0.05), DESIGN.md 4.4
 template <class R>
 __device__ __forceinline__ int collide_box_top(R x1, R y1, R pnx, R pny, R bcx, R bcy, R c, R s, R hh,
                                                R& onx, R& ony, R* opx, R* opy, R* odepth, int* oid) {
@@ -363,12 +363,15 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
   R* pool = reinterpret_cast<R*>(wsm + P.off_pool_p);      // [S][kPoolStride]: persist[2][12], solve[18], pad
   int* poolM = reinterpret_cast<int*>(wsm + P.off_pool_m); // [2][S]
   int* poolCnt = reinterpret_cast<int*>(wsm + P.off_pool_cnt);
+  int* poolO = reinterpret_cast<int*>(wsm + P.off_pool_o);     // [S] owner lane | rank-within-mass << 5
+  V4<R>* stage = reinterpret_cast<V4<R>*>(wsm + P.off_stage);  // [3][32] corner-mass velocities (vx, vy, w) x 4 masses per lane
   R* wts = reinterpret_cast<R*>(wsm + P.off_w);            // [robots_per_warp][genome_len]
   R* act = reinterpret_cast<R*>(wsm + P.off_act);          // centralized: [rpw][2][maxN]; distributed: [2][maxN][32]
   R* sig = reinterpret_cast<R*>(wsm + P.off_sig);          // distributed: [2][32][4*signals]
   R* sbias = reinterpret_cast<R*>(wsm + P.off_bias);       // [18][32] per-step spring bias / sigma
   R* spark = reinterpret_cast<R*>(wsm + P.off_park);       // [kPark][32] cold state parked across the velocity loop
   V2<R>* seff = reinterpret_cast<V2<R>*>(wsm + P.off_eff);   // [8][32] effective masses E of springs 0..15, pairs packed
+  V4<R>* snrm = reinterpret_cast<V4<R>*>(wsm + P.off_nrm);   // [2][32] unit normals of springs 12..15 (pairs 6, 7): register relief
   V4<R>* sarm = reinterpret_cast<V4<R>*>(wsm + P.off_arm); // [8][32] spring lever arms (r x n) of springs 0..15, pairs packed
   const int S = P.pool_slots;
 
@@ -503,6 +506,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
   auto pS = [&](int f, int s) -> R& { return pool[s * kPoolStride + 2 * kPoolPersist + f]; };
   auto slot_of = [&](int e) -> int { return ((e < 4 ? clo >> (8 * e) : chi >> (8 * (e - 4))) & 0xff); };
 
+  int man_total = 0, man_rank = 0; // warp-uniform: manifolds in the pool, highest rank of a manifold within its mass
   // per-lane cached ground polygon (the one under the voxel centre), in the lane's local frame
   int pk = 0;
   R px0 = 0, px1 = 0, py0 = 0, py1 = 0, pnx = 0, pny = 1;
@@ -515,7 +519,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
     const int np_ = par ^ 1;
     const double oxd = (double)ox, oyd = (double)oy;
     unsigned nlo = 0, nhi = 0;
-    int ncnt = 0;
+    int ncnt = 0, lane_rank = 0;
     if (valid) {
       const R cxl = R(0.25) * (X[0] + X[1] + X[2] + X[3]);
       if (!pk || cxl < px0 || cxl > px1) { // (re)load the polygon under the voxel centre
@@ -589,6 +593,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
         pP(np_, 2, s) = px[0]; pP(np_, 3, s) = py[0]; pP(np_, 4, s) = dp[0]; pP(np_, 5, s) = jn0; pP(np_, 6, s) = jt0;
         if (np > 1) { pP(np_, 7, s) = px[1]; pP(np_, 8, s) = py[1]; pP(np_, 9, s) = dp[1]; pP(np_, 10, s) = jn1; pP(np_, 11, s) = jt1; }
         poolM[np_ * S + s] = key | (np << 16) | (id[0] << 18) | ((np > 1 ? id[1] : 0) << 24);
+        poolO[s] = lane | (cnt << 5);
+        if (cnt > lane_rank) lane_rank = cnt;
         if (ncnt < 4) nlo |= (unsigned)s << (8 * ncnt); else nhi |= (unsigned)s << (8 * (ncnt - 4));
         ncnt++;
         cnt++;
@@ -597,6 +603,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
     clo = nlo; chi = nhi; ccnt = ncnt;
     par ^= 1;
     __syncwarp();
+    man_total = min(*poolCnt, S);
+    man_rank = __reduce_max_sync(FULL, lane_rank);
   };
 
   detect(); // World.step's first-step detect()
@@ -678,7 +686,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
       PUT4(VX, k, vxk) PUT4(VY, k, vyk) PUT4(W, k, wk)
     }
     // ---- springs: initialise + warm start ---------------------------------------------------------
-    R snx[18], sny[18], sE16 = 0, sE17 = 0;
+    R snx[18], sny[18], sE16 = 0, sE17 = 0; // entries 12..15 unused (those normals live in shared memory)
+    V4<R> nrm4;
     V4<R> arm4;
     V2<R> eff2;
     {
@@ -696,7 +705,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
     if (!(len >= K_lin_tol)) { nx = 0; ny = 0; } else { nx *= il; ny *= il; }                      \
     const R cr1 = r1x * ny - r1y * nx, cr2 = r2x * ny - r2y * nx;                                \
     const R E = K_sp_cfrac * M<R>::rcp(K_im + K_ii * cr1 * cr1 + K_im + K_ii * cr2 * cr2);                 \
-    snx[i] = nx; sny[i] = ny;                                                                    \
+    if ((i) < 12 || (i) >= 16) { snx[i] = nx; sny[i] = ny; }                                     \
+    else if (((i) & 1) == 0) { nrm4.x = nx; nrm4.y = ny; }                                       \
+    else { nrm4.z = nx; nrm4.w = ny; snrm[(((i) - 12) >> 1) * 32 + lane] = nrm4; }               \
     if ((i) < 16) {                                                                              \
       if (((i) & 1) == 0) { arm4.x = cr1; arm4.y = cr2; eff2.x = E; }                            \
       else { arm4.z = cr1; arm4.w = cr2; eff2.y = E; sarm[((i) >> 1) * 32 + lane] = arm4; seff[((i) >> 1) * 32 + lane] = eff2; } \
@@ -800,15 +811,18 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
   if (scaff & bit) {                                                                            \
     const V4<R> arm = sarm[((i) >> 1) * 32 + lane];                                             \
     const V2<R> eff = seff[((i) >> 1) * 32 + lane];                                             \
-    R jv0 = snx[i] * (VX[a] - VX[b]), jv1 = snx[j] * (VX[c] - VX[d]);                           \
-    jv0 += sny[i] * (VY[a] - VY[b]); jv1 += sny[j] * (VY[c] - VY[d]);                           \
+    R nxi, nyi, nxj, nyj;                                                                       \
+    if ((i) >= 12) { const V4<R> n4 = snrm[(((i) - 12) >> 1) * 32 + lane]; nxi = n4.x; nyi = n4.y; nxj = n4.z; nyj = n4.w; } \
+    else { nxi = snx[(i) < 12 ? (i) : 0]; nyi = sny[(i) < 12 ? (i) : 0]; nxj = snx[(j) < 12 ? (j) : 0]; nyj = sny[(j) < 12 ? (j) : 0]; } \
+    R jv0 = nxi * (VX[a] - VX[b]), jv1 = nxj * (VX[c] - VX[d]);                                 \
+    jv0 += nyi * (VY[a] - VY[b]); jv1 += nyj * (VY[c] - VY[d]);                                 \
     jv0 += arm.x * W[a]; jv1 += arm.z * W[c];                                                   \
     jv0 -= arm.y * W[b]; jv1 -= arm.w * W[d];                                                   \
     const R l0 = eff.x * jv0 + K_sp_sigma * simp[i], l1 = eff.y * jv1 + K_sp_sigma * simp[j];   \
     simp[i] -= l0; simp[j] -= l1;                                                               \
-    const R m0 = l0 * K_im, m1 = l1 * K_im, q0 = l0 * K_ii, q1 = l1 * K_ii;                             \
-    VX[a] -= snx[i] * m0; VX[c] -= snx[j] * m1; VY[a] -= sny[i] * m0; VY[c] -= sny[j] * m1;     \
-    VX[b] += snx[i] * m0; VX[d] += snx[j] * m1; VY[b] += sny[i] * m0; VY[d] += sny[j] * m1;     \
+    const R m0 = l0 * K_im, m1 = l1 * K_im, q0 = l0 * K_ii, q1 = l1 * K_ii;                     \
+    VX[a] -= nxi * m0; VX[c] -= nxj * m1; VY[a] -= nyi * m0; VY[c] -= nyj * m1;                 \
+    VX[b] += nxi * m0; VX[d] += nxj * m1; VY[b] += nyi * m0; VY[d] += nyj * m1;                 \
     W[a] -= q0 * arm.x; W[c] -= q1 * arm.z; W[b] += q0 * arm.y; W[d] += q1 * arm.w;             \
   }
       VSR_SPRING_PAIRS(SPRING_SOLVE2)
@@ -878,64 +892,88 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
       }
 #endif
 #ifndef VSR_PROBE_NO_CONTACT_LOOP
-      // contacts of my corner masses (one copy of the solver; masses via select chains)
+      // contacts, transposed: every lane solves ONE manifold of the warp's pool (lane = pool slot); the corner
+      // masses' velocities travel through shared memory.  Manifolds of the same mass are taken in rank passes,
+      // so each body still sees its constraints in the canonical order (ground is static: bodies are independent).
+      if (man_total > 0) {
+        {
+          V4<R> t4;
+          t4.x = VX[0]; t4.y = VX[1]; t4.z = VX[2]; t4.w = VX[3]; stage[0 * 32 + lane] = t4;
+          t4.x = VY[0]; t4.y = VY[1]; t4.z = VY[2]; t4.w = VY[3]; stage[1 * 32 + lane] = t4;
+          t4.x = W[0]; t4.y = W[1]; t4.z = W[2]; t4.w = W[3]; stage[2 * 32 + lane] = t4;
+        }
+        __syncwarp();
+        R* stg = reinterpret_cast<R*>(stage);
 #pragma unroll 1
-      for (int e = 0; e < ccnt; e++) {
-        const int s = slot_of(e);
-        const int meta = poolM[par * S + s];
-        const int k = (meta >> 14) & 3, np = (meta >> 16) & 3;
-        R vxk = SEL4(VX, k), vyk = SEL4(VY, k), wk = SEL4(W, k);
+        for (int pass = 0; pass <= man_rank; pass++) {
+#pragma unroll 1
+          for (int s = lane; s < man_total; s += 32) {
+            const int own = poolO[s];
+            if ((own >> 5) != pass) continue;
+            const int meta = poolM[par * S + s];
+            const int np = (meta >> 16) & 3;
+            const int mi = (own & 31) * 4 + ((meta >> 14) & 3); // corner mass = owner lane * 4 + k
+            R vxk = stg[mi], vyk = stg[128 + mi], wk = stg[256 + mi];
         const R nx = pP(par, 0, s), ny = pP(par, 1, s), tx = ny, ty = -nx;
-        for (int q = 0; q < np; q++) { // friction first
-          const R rx = pS(7 * q, s), ry = pS(7 * q + 1, s);
-          R l_ = -pS(7 * q + 3, s) * (tx * (vxk - wk * ry) + ty * (vyk + wk * rx));
-          const R maxf = K_mu * pP(par, 2 + 5 * q + 3, s);
-          const R old = pP(par, 2 + 5 * q + 4, s);
-          const R nj = M<R>::max_(-maxf, M<R>::min_(old + l_, maxf));
-          l_ = nj - old;
-          pP(par, 2 + 5 * q + 4, s) = nj;
-          const R Jx = tx * l_, Jy = ty * l_;
-          vxk += K_im * Jx; vyk += K_im * Jy; wk += K_ii * (rx * Jy - ry * Jx);
-        }
-        if (!(meta & (1 << 30))) {
-          for (int q = 0; q < np; q++) {
-            const R rx = pS(7 * q, s), ry = pS(7 * q + 1, s);
-            R l_ = -pS(7 * q + 2, s) * (nx * (vxk - wk * ry) + ny * (vyk + wk * rx) - pS(7 * q + 4, s));
-            const R old = pP(par, 2 + 5 * q + 3, s);
-            const R nj = M<R>::max_(old + l_, R(0));
-            l_ = nj - old;
-            pP(par, 2 + 5 * q + 3, s) = nj;
-            const R Jx = nx * l_, Jy = ny * l_;
-            vxk += K_im * Jx; vyk += K_im * Jy; wk += K_ii * (rx * Jy - ry * Jx);
-          }
-        } else { // 2-point block solver
-          const R r1x = pS(0, s), r1y = pS(1, s), r2x = pS(7, s), r2y = pS(8, s);
-          const R a1 = pP(par, 5, s), a2 = pP(par, 10, s);
-          const R vn1 = nx * (vxk - wk * r1y) + ny * (vyk + wk * r1x);
-          const R vn2 = nx * (vxk - wk * r2y) + ny * (vyk + wk * r2x);
-          const R mn1 = pS(2, s), mn2 = pS(9, s), K12 = pS(14, s);
-          const R rn1 = r1x * ny - r1y * nx, rn2 = r2x * ny - r2y * nx;
-          const R K11 = K_im + K_ii * rn1 * rn1, K22 = K_im + K_ii * rn2 * rn2;
-          const R b1 = vn1 - pS(4, s) - (K11 * a1 + K12 * a2);
-          const R b2 = vn2 - pS(11, s) - (K12 * a1 + K22 * a2);
-          R x1 = -(pS(15, s) * b1 + pS(16, s) * b2), x2 = -(pS(16, s) * b1 + pS(17, s) * b2);
-          if (!(x1 >= 0 && x2 >= 0)) {
-            x1 = -b1 * mn1; x2 = 0;
-            if (!(x1 >= 0 && K12 * x1 + b2 >= 0)) {
-              x1 = 0; x2 = -b2 * mn2;
-              if (!(x2 >= 0 && K12 * x2 + b1 >= 0)) {
-                x1 = 0; x2 = 0;
-                if (!(b1 >= 0 && b2 >= 0)) { x1 = a1; x2 = a2; }
-              }
+            for (int q = 0; q < np; q++) { // friction first
+              const R rx = pS(7 * q, s), ry = pS(7 * q + 1, s);
+              R l_ = -pS(7 * q + 3, s) * (tx * (vxk - wk * ry) + ty * (vyk + wk * rx));
+              const R maxf = K_mu * pP(par, 2 + 5 * q + 3, s);
+              const R old = pP(par, 2 + 5 * q + 4, s);
+              const R nj = M<R>::max_(-maxf, M<R>::min_(old + l_, maxf));
+              l_ = nj - old;
+              pP(par, 2 + 5 * q + 4, s) = nj;
+              const R Jx = tx * l_, Jy = ty * l_;
+              vxk += K_im * Jx; vyk += K_im * Jy; wk += K_ii * (rx * Jy - ry * Jx);
             }
+            if (!(meta & (1 << 30))) {
+              for (int q = 0; q < np; q++) {
+                const R rx = pS(7 * q, s), ry = pS(7 * q + 1, s);
+                R l_ = -pS(7 * q + 2, s) * (nx * (vxk - wk * ry) + ny * (vyk + wk * rx) - pS(7 * q + 4, s));
+                const R old = pP(par, 2 + 5 * q + 3, s);
+                const R nj = M<R>::max_(old + l_, R(0));
+                l_ = nj - old;
+                pP(par, 2 + 5 * q + 3, s) = nj;
+                const R Jx = nx * l_, Jy = ny * l_;
+                vxk += K_im * Jx; vyk += K_im * Jy; wk += K_ii * (rx * Jy - ry * Jx);
+              }
+            } else { // 2-point block solver
+              const R r1x = pS(0, s), r1y = pS(1, s), r2x = pS(7, s), r2y = pS(8, s);
+              const R a1 = pP(par, 5, s), a2 = pP(par, 10, s);
+              const R vn1 = nx * (vxk - wk * r1y) + ny * (vyk + wk * r1x);
+              const R vn2 = nx * (vxk - wk * r2y) + ny * (vyk + wk * r2x);
+              const R mn1 = pS(2, s), mn2 = pS(9, s), K12 = pS(14, s);
+              const R rn1 = r1x * ny - r1y * nx, rn2 = r2x * ny - r2y * nx;
+              const R K11 = K_im + K_ii * rn1 * rn1, K22 = K_im + K_ii * rn2 * rn2;
+              const R b1 = vn1 - pS(4, s) - (K11 * a1 + K12 * a2);
+              const R b2 = vn2 - pS(11, s) - (K12 * a1 + K22 * a2);
+              R x1 = -(pS(15, s) * b1 + pS(16, s) * b2), x2 = -(pS(16, s) * b1 + pS(17, s) * b2);
+              if (!(x1 >= 0 && x2 >= 0)) {
+                x1 = -b1 * mn1; x2 = 0;
+                if (!(x1 >= 0 && K12 * x1 + b2 >= 0)) {
+                  x1 = 0; x2 = -b2 * mn2;
+                  if (!(x2 >= 0 && K12 * x2 + b1 >= 0)) {
+                    x1 = 0; x2 = 0;
+                    if (!(b1 >= 0 && b2 >= 0)) { x1 = a1; x2 = a2; }
+                  }
+                }
+              }
+              const R d1 = x1 - a1, d2 = x2 - a2;
+              pP(par, 5, s) = x1; pP(par, 10, s) = x2;
+              const R J1x = nx * d1, J1y = ny * d1, J2x = nx * d2, J2y = ny * d2;
+              vxk += K_im * (J1x + J2x); vyk += K_im * (J1y + J2y);
+              wk += K_ii * ((r1x * J1y - r1y * J1x) + (r2x * J2y - r2y * J2x));
+            }
+            stg[mi] = vxk; stg[128 + mi] = vyk; stg[256 + mi] = wk;
           }
-          const R d1 = x1 - a1, d2 = x2 - a2;
-          pP(par, 5, s) = x1; pP(par, 10, s) = x2;
-          const R J1x = nx * d1, J1y = ny * d1, J2x = nx * d2, J2y = ny * d2;
-          vxk += K_im * (J1x + J2x); vyk += K_im * (J1y + J2y);
-          wk += K_ii * ((r1x * J1y - r1y * J1x) + (r2x * J2y - r2y * J2x));
+          __syncwarp();
         }
-        PUT4(VX, k, vxk) PUT4(VY, k, vyk) PUT4(W, k, wk)
+        if (ccnt) {
+          V4<R> t4;
+          t4 = stage[0 * 32 + lane]; VX[0] = t4.x; VX[1] = t4.y; VX[2] = t4.z; VX[3] = t4.w;
+          t4 = stage[1 * 32 + lane]; VY[0] = t4.x; VY[1] = t4.y; VY[2] = t4.z; VY[3] = t4.w;
+          t4 = stage[2 * 32 + lane]; W[0] = t4.x; W[1] = t4.y; W[2] = t4.z; W[3] = t4.w;
+        }
       }
 #endif
     } // velocity iterations
