@@ -16,7 +16,7 @@ namespace {
 
 // launch shapes (warps per CTA, min CTAs per SM -> register cap); picked per context (VSR_LAUNCH_SHAPE)
 struct Shape { int warps, minb; };
-constexpr Shape kShapes[] = {{4, 2}, {5, 2}, {8, 1}, {10, 1}, {4, 3}, {4, 4}};
+constexpr Shape kShapes[] = {{4, 2}, {5, 2}, {8, 1}, {10, 1}, {2, 5}, {3, 3}};
 constexpr int kNumShapes = sizeof(kShapes) / sizeof(kShapes[0]);
 constexpr int kDefaultShape = 1;
 
@@ -139,8 +139,8 @@ const void* kernel_ptr(int precision, int ctrl, int shape) {
     case 1: return f32_kernel<5, 2>(ctrl);
     case 2: return f32_kernel<8, 1>(ctrl);
     case 3: return f32_kernel<10, 1>(ctrl);
-    case 4: return f32_kernel<4, 3>(ctrl);
-    default: return f32_kernel<4, 4>(ctrl);
+    case 4: return f32_kernel<2, 5>(ctrl);
+    default: return f32_kernel<3, 3>(ctrl);
   }
 }
 
@@ -294,12 +294,15 @@ int finalize(vsr_ctx* ctx) {
   k.off_pool_cnt = (int)o; o = align16(o + 4);
   k.off_pool_o = (int)o; o = align16(o + S * 4);
   o = (o + 31) & ~size_t(31);
-  k.off_stage = (int)o; o = align16(o + (size_t)3 * 32 * 4 * rs);
+  // velocity staging of the transposed contact solve and the controller's activation scratch are used in disjoint
+  // phases of a step: one region, sized for the larger
+  size_t act_bytes = 0;
+  if (ctx->kind == VSR_CTRL_MLP_CENTRALIZED) act_bytes = (size_t)k.robots_per_warp * 2 * k.max_neurons * rs;
+  if (ctx->kind == VSR_CTRL_MLP_DISTRIBUTED_HOMO) act_bytes = (size_t)2 * k.max_neurons * 32 * rs;
+  k.off_stage = (int)o; k.off_act = (int)o;
+  o = align16(o + std::max((size_t)3 * 32 * 4 * rs, act_bytes));
   k.off_w = (int)o;
   if (ctx->kind != VSR_CTRL_PHASE_SIN) o = align16(o + (size_t)k.robots_per_warp * glen * rs);
-  k.off_act = (int)o;
-  if (ctx->kind == VSR_CTRL_MLP_CENTRALIZED) o = align16(o + (size_t)k.robots_per_warp * 2 * k.max_neurons * rs);
-  if (ctx->kind == VSR_CTRL_MLP_DISTRIBUTED_HOMO) o = align16(o + (size_t)2 * k.max_neurons * 32 * rs);
   k.off_sig = (int)o;
   if (ctx->kind == VSR_CTRL_MLP_DISTRIBUTED_HOMO) o = align16(o + (size_t)2 * 32 * 4 * std::max(1, k.signals) * rs);
   k.off_bias = (int)o;
@@ -316,6 +319,7 @@ int finalize(vsr_ctx* ctx) {
   o = align16(o + (size_t)vsr::kPark * 32 * rs);
   k.off_cold = (int)o;
   o = align16(o + (size_t)navg * 32 * 12); // Average running sums + counts
+  o = (o + 31) & ~size_t(31);
   k.smem_warp_stride = (int)o;
   k.sync_mask = 59; // step start, before velocity loop, before position phase, before/after detect (tools/bench sweep)
   if (const char* ev = std::getenv("VSR_SYNC_MASK")) k.sync_mask = std::atoi(ev);
