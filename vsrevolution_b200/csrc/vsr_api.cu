@@ -14,9 +14,11 @@
 
 namespace {
 
-// launch shapes (warps per CTA, min CTAs per SM -> register cap); picked per context (VSR_LAUNCH_SHAPE)
+// launch shapes (warps per CTA, min CTAs per SM -> register cap): 0/2 = 255 registers, 8 warps/SM (no spills, best
+// per-warp latency, 3552 bipeds per wave); 1/3 = 168 registers, 10 warps/SM (4440 bipeds per wave; default).
+// VSR_LAUNCH_SHAPE overrides (tuning only).
 struct Shape { int warps, minb; };
-constexpr Shape kShapes[] = {{4, 2}, {5, 2}, {8, 1}, {10, 1}, {2, 5}, {3, 3}};
+constexpr Shape kShapes[] = {{4, 2}, {5, 2}, {8, 1}, {10, 1}};
 constexpr int kNumShapes = sizeof(kShapes) / sizeof(kShapes[0]);
 constexpr int kDefaultShape = 1;
 
@@ -138,9 +140,7 @@ const void* kernel_ptr(int precision, int ctrl, int shape) {
     case 0: return f32_kernel<4, 2>(ctrl);
     case 1: return f32_kernel<5, 2>(ctrl);
     case 2: return f32_kernel<8, 1>(ctrl);
-    case 3: return f32_kernel<10, 1>(ctrl);
-    case 4: return f32_kernel<2, 5>(ctrl);
-    default: return f32_kernel<3, 3>(ctrl);
+    default: return f32_kernel<10, 1>(ctrl);
   }
 }
 
