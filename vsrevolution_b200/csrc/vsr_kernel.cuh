@@ -32,10 +32,15 @@ constexpr int kMaxLayers = 8;
 constexpr int kMaxMan = 3;       // manifolds per corner mass (ground polygons it can touch at once)
 constexpr int kMaxLaneMan = 8;   // manifolds per voxel
 constexpr int kMaxAvg = 6;       // averaged readings per voxel
-constexpr int kPoolPersist = 12; // NX NY (PX PY D JN JT)x2
-constexpr int kPoolSolve = 18;   // (RX RY MN MT VB LX LY)x2 K12 IK11 IK12 IK22
+constexpr int kPoolPersist = 12;
+constexpr int kPoolSolve = 24;
 constexpr int kPark = 23;         // X Y A (12) + polygon cache (6) + origin (2) + rest (3)
-constexpr int kPoolStride = 2 * kPoolPersist + kPoolSolve + 1; // 43 words per slot: odd -> conflict-free across slots
+// contact-pool slot (R words), 16-byte aligned vectors; stride 44 = 4 x odd -> 128-bit accesses of 8 consecutive slots hit
+// all 32 banks once.  Persistent half p (double-buffered for warm starting) at 12*p:
+//   [0..3] nx ny px0 py0 | [4..7] d0 px1 py1 d1 | [8..11] jn0 jt0 jn1 jt1
+// solver half at 24 (rebuilt every step by the contact initialisation; Jacobian rows rn = r x n, rt = r x t):
+//   [24..27] rn0 rt0 mN0 mT0 | [28..31] rn1 rt1 mN1 mT1 | [32..35] vb0 vb1 K12 iK11 | [36..39] iK12 iK22 - - | [40..43] lx0 ly0 lx1 ly1
+constexpr int kPoolStride = 44;
 
 struct SensorK {
   int kind, axes, rotated, soft_norm;
@@ -98,7 +103,8 @@ struct KParams {
   int smem_warp_stride; // bytes per warp
   int off_pool_p, off_pool_m, off_pool_cnt, off_w, off_act, off_sig, off_bias, off_arm, off_eff, off_nrm, off_park, off_cold, off_stage, off_pool_o;
   int sync_mask; // phase-alignment barriers (bit0 step start, bit1 before velocity loop, bit2 every velocity
-                 // iteration, bit3 before position phase, bit4 before detect, bit5 before sensing)
+                 // iteration, bit3 before position phase, bit4 before detect, bit5 before sensing, bit6 before spring
+                 // init, bit7 before weld init, bit8 after the velocity loop, bit9 after the position phase, bit10 after control)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -360,7 +366,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned char* wsm = smem_raw + (size_t)warp * P.smem_warp_stride;
-  R* pool = reinterpret_cast<R*>(wsm + P.off_pool_p);      // [S][kPoolStride]: persist[2][12], solve[18], pad
+  R* pool = reinterpret_cast<R*>(wsm + P.off_pool_p);      // [S][kPoolStride]: persist[2][12], solve[20]
   int* poolM = reinterpret_cast<int*>(wsm + P.off_pool_m); // [2][S]
   int* poolCnt = reinterpret_cast<int*>(wsm + P.off_pool_cnt);
   int* poolO = reinterpret_cast<int*>(wsm + P.off_pool_o);     // [S] owner lane | rank-within-mass << 5
@@ -502,8 +508,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
   int sig_par = 0;
   R ctrl_f = 0;
 
-  auto pP = [&](int p, int f, int s) -> R& { return pool[s * kPoolStride + p * kPoolPersist + f]; };
-  auto pS = [&](int f, int s) -> R& { return pool[s * kPoolStride + 2 * kPoolPersist + f]; };
+  auto ld4 = [](const R* q) -> V4<R> { return *reinterpret_cast<const V4<R>*>(q); };
+  auto st4 = [](R* q, const V4<R>& v) { *reinterpret_cast<V4<R>*>(q) = v; };
   auto slot_of = [&](int e) -> int { return ((e < 4 ? clo >> (8 * e) : chi >> (8 * (e - 4))) & 0xff); };
 
   int man_total = 0, man_rank = 0; // warp-uniform: manifolds in the pool, highest rank of a manifold within its mass
@@ -582,16 +588,21 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
           const int ometa = poolM[par * S + os];
           if ((ometa & 0xffff) != key) continue;
           const int onp = (ometa >> 16) & 3;
+          const V4<R> oi = ld4(pool + os * kPoolStride + par * kPoolPersist + 8);
           for (int r = 0; r < onp; r++) {
             const int oidr = (ometa >> (18 + 6 * r)) & 63;
-            const R ojn = pP(par, 2 + 5 * r + 3, os), ojt = pP(par, 2 + 5 * r + 4, os);
+            const R ojn = r == 0 ? oi.x : oi.z, ojt = r == 0 ? oi.y : oi.w;
             if (oidr == id[0]) { jn0 = ojn; jt0 = ojt; }
             if (np > 1 && oidr == id[1]) { jn1 = ojn; jt1 = ojt; }
           }
         }
-        pP(np_, 0, s) = nx; pP(np_, 1, s) = ny;
-        pP(np_, 2, s) = px[0]; pP(np_, 3, s) = py[0]; pP(np_, 4, s) = dp[0]; pP(np_, 5, s) = jn0; pP(np_, 6, s) = jt0;
-        if (np > 1) { pP(np_, 7, s) = px[1]; pP(np_, 8, s) = py[1]; pP(np_, 9, s) = dp[1]; pP(np_, 10, s) = jn1; pP(np_, 11, s) = jt1; }
+        {
+          R* sp = pool + s * kPoolStride + np_ * kPoolPersist;
+          V4<R> v4;
+          v4.x = nx; v4.y = ny; v4.z = px[0]; v4.w = py[0]; st4(sp, v4);
+          v4.x = dp[0]; v4.y = np > 1 ? px[1] : R(0); v4.z = np > 1 ? py[1] : R(0); v4.w = np > 1 ? dp[1] : R(0); st4(sp + 4, v4);
+          v4.x = jn0; v4.y = jt0; v4.z = jn1; v4.w = jt1; st4(sp + 8, v4);
+        }
         poolM[np_ * S + s] = key | (np << 16) | (id[0] << 18) | ((np > 1 ? id[1] : 0) << 24);
         poolO[s] = lane | (cnt << 5);
         if (cnt > lane_rank) lane_rank = cnt;
@@ -640,35 +651,39 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
       int meta = poolM[par * S + s];
       const int k = (meta >> 14) & 3;
       const int np = (meta >> 16) & 3;
+      R* sp = pool + s * kPoolStride;
+      const V4<R> pa = ld4(sp + par * kPoolPersist), pb = ld4(sp + par * kPoolPersist + 4);
       const R xk = SEL4(X, k), yk = SEL4(Y, k), ck = SEL4(CS, k), sk = SEL4(SN, k);
       const R vxk = SEL4(VX, k), vyk = SEL4(VY, k), wk = SEL4(W, k);
-      const R nx = pP(par, 0, s), ny = pP(par, 1, s), tx = ny, ty = -nx;
-      R rn0 = 0, rn1 = 0;
-      for (int q = 0; q < np; q++) {
-        const R rx = pP(par, 2 + 5 * q, s) - xk, ry = pP(par, 2 + 5 * q + 1, s) - yk;
-        const R rnq = rx * ny - ry * nx, rt = rx * ty - ry * tx;
-        if (q == 0) rn0 = rnq; else rn1 = rnq;
-        pS(7 * q + 0, s) = rx; pS(7 * q + 1, s) = ry;
-        pS(7 * q + 2, s) = M<R>::rcp(K_im + K_ii * rnq * rnq);
-        pS(7 * q + 3, s) = M<R>::rcp(K_im + K_ii * rt * rt);
-        const R vn = nx * (vxk - wk * ry) + ny * (vyk + wk * rx);
-        pS(7 * q + 4, s) = vn < -K_rest_vel ? -K_rest_e * vn : R(0);
-        pS(7 * q + 5, s) = ck * rx + sk * ry;
-        pS(7 * q + 6, s) = -sk * rx + ck * ry;
-      }
+      const R nx = pa.x, ny = pa.y;
+      // Jacobian rows of a contact point: normal (nx, ny, rn), tangent t = (ny, -nx): (ny, -nx, rt)
+      const R r0x = pa.z - xk, r0y = pa.w - yk, r1x = pb.y - xk, r1y = pb.z - yk;
+      const R rn0 = r0x * ny - r0y * nx, rt0 = -(r0x * nx + r0y * ny);
+      const R rn1 = np > 1 ? r1x * ny - r1y * nx : R(0), rt1 = np > 1 ? -(r1x * nx + r1y * ny) : R(0);
+      const R vn0 = nx * vxk + ny * vyk + rn0 * wk, vn1 = nx * vxk + ny * vyk + rn1 * wk;
+      V4<R> v4;
+      v4.x = rn0; v4.y = rt0; v4.z = M<R>::rcp(K_im + K_ii * rn0 * rn0); v4.w = M<R>::rcp(K_im + K_ii * rt0 * rt0); st4(sp + 24, v4);
+      v4.x = rn1; v4.y = rt1; v4.z = M<R>::rcp(K_im + K_ii * rn1 * rn1); v4.w = M<R>::rcp(K_im + K_ii * rt1 * rt1); st4(sp + 28, v4);
+      R K12 = 0, i11 = 0, i12 = 0, i22 = 0;
       meta &= ~(1 << 30);
       if (np == 2) {
-        const R K11 = K_im + K_ii * rn0 * rn0, K22 = K_im + K_ii * rn1 * rn1, K12 = K_im + K_ii * rn0 * rn1;
+        const R K11 = K_im + K_ii * rn0 * rn0, K22 = K_im + K_ii * rn1 * rn1;
+        K12 = K_im + K_ii * rn0 * rn1;
         const R det = K11 * K22 - K12 * K12;
         if (K11 * K11 < R(100) * det) {
           meta |= 1 << 30;
           const R idet = det != 0 ? M<R>::rcp(det) : R(0);
-          pS(14, s) = K12; pS(15, s) = K22 * idet; pS(16, s) = -K12 * idet; pS(17, s) = K11 * idet;
+          i11 = K22 * idet; i12 = -K12 * idet; i22 = K11 * idet;
         } else {
-          meta = (meta & ~(3 << 16)) | (1 << 16);
+          meta = (meta & ~(3 << 16)) | (1 << 16); // ill conditioned: keep the first point only
         }
       }
+      v4.x = vn0 < -K_rest_vel ? -K_rest_e * vn0 : R(0); v4.y = (np > 1 && vn1 < -K_rest_vel) ? -K_rest_e * vn1 : R(0); v4.z = K12; v4.w = i11;
+      st4(sp + 32, v4);
+      v4.x = i12; v4.y = i22; v4.z = 0; v4.w = 0; st4(sp + 36, v4);
+      v4.x = ck * r0x + sk * r0y; v4.y = -sk * r0x + ck * r0y; v4.z = ck * r1x + sk * r1y; v4.w = -sk * r1x + ck * r1y; st4(sp + 40, v4);
       poolM[par * S + s] = meta;
+      // warm start of this manifold happens below, after every manifold has sampled the pre-warm-start velocities
     }
     // ---- contacts: warm start -------------------------------------------------------------------------
 #pragma unroll 1
@@ -676,16 +691,23 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
       const int s = slot_of(e);
       const int meta = poolM[par * S + s];
       const int k = (meta >> 14) & 3, np = (meta >> 16) & 3;
+      const R* sp = pool + s * kPoolStride;
+      const V4<R> pa = ld4(sp + par * kPoolPersist), imp = ld4(sp + par * kPoolPersist + 8);
+      const V4<R> j0 = ld4(sp + 24), j1 = ld4(sp + 28);
+      const R nx = pa.x, ny = pa.y;
       R vxk = SEL4(VX, k), vyk = SEL4(VY, k), wk = SEL4(W, k);
-      const R nx = pP(par, 0, s), ny = pP(par, 1, s), tx = ny, ty = -nx;
-      for (int q = 0; q < np; q++) {
-        const R jn = pP(par, 2 + 5 * q + 3, s), jt = pP(par, 2 + 5 * q + 4, s);
-        const R Jx = nx * jn + tx * jt, Jy = ny * jn + ty * jt;
-        vxk += K_im * Jx; vyk += K_im * Jy; wk += K_ii * (pS(7 * q, s) * Jy - pS(7 * q + 1, s) * Jx);
+      {
+        const R Jx = nx * imp.x + ny * imp.y, Jy = ny * imp.x - nx * imp.y;
+        vxk += K_im * Jx; vyk += K_im * Jy; wk += K_ii * (j0.x * imp.x + j0.y * imp.y);
+      }
+      if (np > 1) {
+        const R Jx = nx * imp.z + ny * imp.w, Jy = ny * imp.z - nx * imp.w;
+        vxk += K_im * Jx; vyk += K_im * Jy; wk += K_ii * (j1.x * imp.z + j1.y * imp.w);
       }
       PUT4(VX, k, vxk) PUT4(VY, k, vyk) PUT4(W, k, wk)
     }
     // ---- springs: initialise + warm start ---------------------------------------------------------
+    PHASE_SYNC(64)
     R snx[18], sny[18], sE16 = 0, sE17 = 0; // entries 12..15 unused (those normals live in shared memory)
     V4<R> nrm4;
     V4<R> arm4;
@@ -742,6 +764,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
 #undef ROPE_INIT
     const bool warp_rope = __any_sync(FULL, any_rope);
     // ---- welds: r2 of the partner mass, warm start ----------------------------------------------------
+    PHASE_SYNC(128)
     // owner welds: 0 = (my NW, left NE) 1 = (my SW, left SE) 2 = (my SW, below NW) 3 = (my SE, below NE)
     // local anchor 2 = body1 - body2 at assembly: horizontal (+m, 0), vertical (0, +m)
     R wr2x[4], wr2y[4];
@@ -914,44 +937,46 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
             const int np = (meta >> 16) & 3;
             const int mi = (own & 31) * 4 + ((meta >> 14) & 3); // corner mass = owner lane * 4 + k
             R vxk = stg[mi], vyk = stg[128 + mi], wk = stg[256 + mi];
-        const R nx = pP(par, 0, s), ny = pP(par, 1, s), tx = ny, ty = -nx;
-            for (int q = 0; q < np; q++) { // friction first
-              const R rx = pS(7 * q, s), ry = pS(7 * q + 1, s);
-              R l_ = -pS(7 * q + 3, s) * (tx * (vxk - wk * ry) + ty * (vyk + wk * rx));
-              const R maxf = K_mu * pP(par, 2 + 5 * q + 3, s);
-              const R old = pP(par, 2 + 5 * q + 4, s);
-              const R nj = M<R>::max_(-maxf, M<R>::min_(old + l_, maxf));
-              l_ = nj - old;
-              pP(par, 2 + 5 * q + 4, s) = nj;
-              const R Jx = tx * l_, Jy = ty * l_;
-              vxk += K_im * Jx; vyk += K_im * Jy; wk += K_ii * (rx * Jy - ry * Jx);
+            R* sp = pool + s * kPoolStride;
+            const V2<R> nn = *reinterpret_cast<const V2<R>*>(sp + par * kPoolPersist);
+            V4<R> imp = ld4(sp + par * kPoolPersist + 8);
+            const V4<R> j0 = ld4(sp + 24), j1 = ld4(sp + 28), cc = ld4(sp + 32);
+            const R nx = nn.x, ny = nn.y;
+            // friction rows first (tangent t = (ny, -nx)), clamped by mu * (accumulated normal impulse)
+            {
+              R l_ = -j0.w * (ny * vxk - nx * vyk + j0.y * wk);
+              const R maxf = K_mu * imp.x;
+              const R nj = M<R>::max_(-maxf, M<R>::min_(imp.y + l_, maxf));
+              l_ = nj - imp.y; imp.y = nj;
+              const R a_ = K_im * l_;
+              vxk += a_ * ny; vyk -= a_ * nx; wk += (K_ii * l_) * j0.y;
             }
-            if (!(meta & (1 << 30))) {
-              for (int q = 0; q < np; q++) {
-                const R rx = pS(7 * q, s), ry = pS(7 * q + 1, s);
-                R l_ = -pS(7 * q + 2, s) * (nx * (vxk - wk * ry) + ny * (vyk + wk * rx) - pS(7 * q + 4, s));
-                const R old = pP(par, 2 + 5 * q + 3, s);
-                const R nj = M<R>::max_(old + l_, R(0));
-                l_ = nj - old;
-                pP(par, 2 + 5 * q + 3, s) = nj;
-                const R Jx = nx * l_, Jy = ny * l_;
-                vxk += K_im * Jx; vyk += K_im * Jy; wk += K_ii * (rx * Jy - ry * Jx);
-              }
+            if (np > 1) {
+              R l_ = -j1.w * (ny * vxk - nx * vyk + j1.y * wk);
+              const R maxf = K_mu * imp.z;
+              const R nj = M<R>::max_(-maxf, M<R>::min_(imp.w + l_, maxf));
+              l_ = nj - imp.w; imp.w = nj;
+              const R a_ = K_im * l_;
+              vxk += a_ * ny; vyk -= a_ * nx; wk += (K_ii * l_) * j1.y;
+            }
+            if (!(meta & (1 << 30))) { // normal rows one by one (single point, or ill-conditioned pair reduced to one)
+              R l_ = -j0.z * (nx * vxk + ny * vyk + j0.x * wk - cc.x);
+              const R nj = M<R>::max_(imp.x + l_, R(0));
+              l_ = nj - imp.x; imp.x = nj;
+              const R a_ = K_im * l_;
+              vxk += a_ * nx; vyk += a_ * ny; wk += (K_ii * l_) * j0.x;
             } else { // 2-point block solver
-              const R r1x = pS(0, s), r1y = pS(1, s), r2x = pS(7, s), r2y = pS(8, s);
-              const R a1 = pP(par, 5, s), a2 = pP(par, 10, s);
-              const R vn1 = nx * (vxk - wk * r1y) + ny * (vyk + wk * r1x);
-              const R vn2 = nx * (vxk - wk * r2y) + ny * (vyk + wk * r2x);
-              const R mn1 = pS(2, s), mn2 = pS(9, s), K12 = pS(14, s);
-              const R rn1 = r1x * ny - r1y * nx, rn2 = r2x * ny - r2y * nx;
-              const R K11 = K_im + K_ii * rn1 * rn1, K22 = K_im + K_ii * rn2 * rn2;
-              const R b1 = vn1 - pS(4, s) - (K11 * a1 + K12 * a2);
-              const R b2 = vn2 - pS(11, s) - (K12 * a1 + K22 * a2);
-              R x1 = -(pS(15, s) * b1 + pS(16, s) * b2), x2 = -(pS(16, s) * b1 + pS(17, s) * b2);
+              const V2<R> ik = *reinterpret_cast<const V2<R>*>(sp + 36);
+              const R a1 = imp.x, a2 = imp.z, K12 = cc.z;
+              const R vn1 = nx * vxk + ny * vyk + j0.x * wk, vn2 = nx * vxk + ny * vyk + j1.x * wk;
+              const R K11 = K_im + K_ii * j0.x * j0.x, K22 = K_im + K_ii * j1.x * j1.x;
+              const R b1 = vn1 - cc.x - (K11 * a1 + K12 * a2);
+              const R b2 = vn2 - cc.y - (K12 * a1 + K22 * a2);
+              R x1 = -(cc.w * b1 + ik.x * b2), x2 = -(ik.x * b1 + ik.y * b2);
               if (!(x1 >= 0 && x2 >= 0)) {
-                x1 = -b1 * mn1; x2 = 0;
+                x1 = -b1 * j0.z; x2 = 0;
                 if (!(x1 >= 0 && K12 * x1 + b2 >= 0)) {
-                  x1 = 0; x2 = -b2 * mn2;
+                  x1 = 0; x2 = -b2 * j1.z;
                   if (!(x2 >= 0 && K12 * x2 + b1 >= 0)) {
                     x1 = 0; x2 = 0;
                     if (!(b1 >= 0 && b2 >= 0)) { x1 = a1; x2 = a2; }
@@ -959,11 +984,11 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
                 }
               }
               const R d1 = x1 - a1, d2 = x2 - a2;
-              pP(par, 5, s) = x1; pP(par, 10, s) = x2;
-              const R J1x = nx * d1, J1y = ny * d1, J2x = nx * d2, J2y = ny * d2;
-              vxk += K_im * (J1x + J2x); vyk += K_im * (J1y + J2y);
-              wk += K_ii * ((r1x * J1y - r1y * J1x) + (r2x * J2y - r2y * J2x));
+              imp.x = x1; imp.z = x2;
+              const R a_ = K_im * (d1 + d2);
+              vxk += a_ * nx; vyk += a_ * ny; wk += K_ii * (j0.x * d1 + j1.x * d2);
             }
+            st4(sp + par * kPoolPersist + 8, imp);
             stg[mi] = vxk; stg[128 + mi] = vyk; stg[256 + mi] = wk;
           }
           __syncwarp();
@@ -978,6 +1003,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
 #endif
     } // velocity iterations
     // spring accumulators back to pure impulses (warm start of the next step)
+    PHASE_SYNC(256)
 #define SPRING_FIN(i, a, b, sx1, sy1, sx2, sy2, kind, bit) if (scaff & bit) simp[i] -= sbias[i * 32 + lane];
     VSR_SPRINGS(SPRING_FIN)
 #undef SPRING_FIN
@@ -1027,11 +1053,14 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
           const int meta = poolM[par * S + s];
           const int k = (meta >> 14) & 3, np = (meta >> 16) & 3;
           R xk = SEL4(X, k), yk = SEL4(Y, k), ak = SEL4(A, k), ck = SEL4(CS, k), sk = SEL4(SN, k);
-          const R nx = pP(par, 0, s), ny = pP(par, 1, s);
+          const R* sp = pool + s * kPoolStride;
+          const V4<R> pa = ld4(sp + par * kPoolPersist), pb = ld4(sp + par * kPoolPersist + 4), pl = ld4(sp + 40);
+          const R nx = pa.x, ny = pa.y;
           for (int q = 0; q < np; q++) {
-            const R lx = pS(7 * q + 5, s), ly = pS(7 * q + 6, s);
+            const R lx = q == 0 ? pl.x : pl.z, ly = q == 0 ? pl.y : pl.w;
+            const R cpx = q == 0 ? pa.z : pb.y, cpy = q == 0 ? pa.w : pb.z, cdp = q == 0 ? pb.x : pb.w;
             const R rx = ck * lx - sk * ly, ry = sk * lx + ck * ly;
-            const R sep = nx * (xk + rx - pP(par, 2 + 5 * q, s)) + ny * (yk + ry - pP(par, 2 + 5 * q + 1, s)) - pP(par, 2 + 5 * q + 2, s);
+            const R sep = nx * (xk + rx - cpx) + ny * (yk + ry - cpy) - cdp;
             if (sep < -R(3) * K_lin_tol) ok = false;
             R C = K_baum * (sep + K_lin_tol);
             C = M<R>::min_(C, R(0));
@@ -1118,6 +1147,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
     }
 
     // ---- re-centre the lane origin (integer shifts; keeps |local| small) -------------------------------
+    PHASE_SYNC(512)
     {
       const R mx = R(0.25) * (X[0] + X[1] + X[2] + X[3]), my = R(0.25) * (Y[0] + Y[1] + Y[2] + Y[3]);
       if (M<R>::abs_(mx) > R(1) || M<R>::abs_(my) > R(1)) {
@@ -1281,6 +1311,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
         __syncwarp();
       }
     }
+    PHASE_SYNC(1024)
     // Voxel.applyForce(f), ForceMethod.DISTANCE
     if (M<R>::abs_(f) > R(1)) f = f > 0 ? R(1) : R(-1);
     ctrl_f = f;
