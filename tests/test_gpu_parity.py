@@ -184,6 +184,20 @@ def test_full_size_batch_properties(F, oracle):
     ctx.close()
 
 
+def test_steppy_terrain_never_overflows_the_contact_pool(F, oracle):
+    """Config 4 terrain (narrow steps): a corner mass can touch 3 polygons; the per-warp pool must hold them all."""
+    m = oracle.config_model(4, final_t=10.0)
+    ctx = make_ctx(F, m)
+    g = np.random.default_rng(2).uniform(-1, 1, (4096, ctx.genome_len))
+    fit, res = ctx.eval(g, want_results=True)
+    assert np.isfinite(fit).all()
+    assert int((res["contact_overflow"] > 0).sum()) == 0
+    idx = np.arange(0, 4096, 128)
+    ref = m.eval_batch(g[idx], n_threads=8)
+    assert np.median(np.abs(fit[idx] - ref)) < 2e-3
+    ctx.close()
+
+
 def test_eval_device_equals_host_path(F, oracle):
     import torch
     m = oracle.config_model(3, final_t=3.0)

@@ -283,9 +283,15 @@ int finalize(vsr_ctx* ctx) {
   for (int i = 0; i < k.n_layers; i++) { k.layers[i] = ctx->layers[i]; k.max_neurons = std::max(k.max_neurons, ctx->layers[i]); }
   // shared memory layout (per warp)
   const size_t rs = e.precision == 64 ? 8 : 4;
-  // contact-pool slots per warp: 6/5 manifolds per voxel lane (every bottom mass of every robot touching, plus
-  // polygon-boundary doubles); overflow is counted in vsr_result.contact_overflow
-  int S = std::max(16, std::min(64, k.robots_per_warp * ctx->n_vox * 6 / 5));
+  // contact-pool slots per warp.  Wide polygons (flat, hilly): 6/5 manifolds per voxel lane covers every bottom mass of
+  // every robot touching plus polygon-boundary doubles.  Narrow polygons (steppy: segments of 0.5-1.5): a mass can touch
+  // up to 3 polygons, so 2 per lane (capped by the 8-bit slot ids).  Overflow is never silent: it is counted in
+  // vsr_result.contact_overflow and the tests assert it stays 0.
+  double min_seg = INFINITY;
+  for (size_t i = 1; i < ctx->tx.size(); i++) min_seg = std::fmin(min_seg, ctx->tx[i] - ctx->tx[i - 1]);
+  const bool narrow = min_seg < 2.0 * m;
+  int S = narrow ? std::max(16, std::min(96, k.robots_per_warp * ctx->n_vox * 2))
+                 : std::max(16, std::min(64, k.robots_per_warp * ctx->n_vox * 6 / 5));
   if (const char* ev = std::getenv("VSR_POOL_SLOTS")) S = std::max(8, std::min(255, std::atoi(ev)));
   k.pool_slots = S;
   size_t o = 0;
@@ -323,7 +329,11 @@ int finalize(vsr_ctx* ctx) {
   k.smem_warp_stride = (int)o;
   k.sync_mask = 59; // step start, before velocity loop, before position phase, before/after detect (tools/bench sweep)
   if (const char* ev = std::getenv("VSR_SYNC_MASK")) k.sync_mask = std::atoi(ev);
+  // launch shape: 2 CTAs x 5 warps (168 registers, 10 warps/SM) when their shared memory fits an SM; otherwise one CTA of
+  // 8 warps (255 registers) -- e.g. narrow-step terrains with their larger contact pool
+  const size_t smem_sm = 227 * 1024 - 2 * 1024;
   ctx->shape = kDefaultShape;
+  if (2 * 5 * o > smem_sm && 8 * o + 1024 <= 227 * 1024) ctx->shape = 2;
   if (const char* ev = std::getenv("VSR_LAUNCH_SHAPE")) ctx->shape = std::max(0, std::min(kNumShapes - 1, std::atoi(ev)));
   ctx->warps = e.precision == 64 ? kWarps64 : kShapes[ctx->shape].warps;
   ctx->kernel = kernel_ptr(e.precision, ctx->kind, ctx->shape);
