@@ -73,7 +73,7 @@ typedef struct {
   int32_t soft_norm;  /* SoftNormalization wrapper */
   double dom_min, dom_max;
   double avg_window;  /* Average wrapper window [s], 0 = none */
-  double noise_sigma; /* Noisy wrapper; must be 0 in this build (VSR_EUNSUPPORTED otherwise) */
+  double noise_sigma; /* Noisy(sensor, sigma, seed 0) wrapper: + nextGaussian()*sigma*|domain| (java.util.Random replayed on the host) */
 } vsr_sensor_desc;
 
 /* ---- controllers: CentralizedSensing (builder/robot/BrainCentralized.java:42-45), PhaseSin

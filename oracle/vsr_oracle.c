@@ -23,7 +23,7 @@
  *   for every voxel in grid order: its springs then its ropes; then all horizontal welds; then all
  *   vertical welds; then contacts body by body.  Position iterations: contacts, then ropes, then welds.
  * Not modelled (documented in DESIGN.md): body sleeping, continuous collision detection, robot
- * self-collision (filtered out in 2dhmsr), Noisy sensors.
+ * self-collision (filtered out in 2dhmsr).
  */
 #include "vsr_oracle.h"
 
@@ -907,8 +907,28 @@ static double robot_center_x(const World* W) {
   return s / W->n_vox;
 }
 
+/* java.util.Random (LCG + polar nextGaussian): the Noisy sensor wrapper draws from `new Random(seed)`; 2dhmsr's
+ * RobotUtils.buildSensorizingFunction builds every wrapper as `new Noisy(sensor, sigma, 0)` [U], so all voxels see the
+ * same sequence: one stream per sensor of the per-voxel list. */
+typedef struct { uint64_t seed; int have; double next_g; } JRandom;
+static void jr_init(JRandom* r, int64_t seed) { r->seed = ((uint64_t)seed ^ 0x5DEECE66DULL) & ((1ULL << 48) - 1); r->have = 0; r->next_g = 0; }
+static int32_t jr_next(JRandom* r, int bits) {
+  r->seed = (r->seed * 0x5DEECE66DULL + 0xBULL) & ((1ULL << 48) - 1);
+  return (int32_t)((int64_t)r->seed >> (48 - bits));
+}
+static double jr_double(JRandom* r) { return (double)(((int64_t)jr_next(r, 26) << 27) + jr_next(r, 27)) * (1.0 / (double)(1LL << 53)); }
+static double jr_gaussian(JRandom* r) {
+  if (r->have) { r->have = 0; return r->next_g; }
+  double v1, v2, s;
+  do { v1 = 2 * jr_double(r) - 1; v2 = 2 * jr_double(r) - 1; s = v1 * v1 + v2 * v2; } while (s >= 1 || s == 0);
+  double mul = sqrt(-2 * log(s) / s);
+  r->next_g = v2 * mul; r->have = 1;
+  return v1 * mul;
+}
+
 typedef struct {
   int n_sensors, dim; /* per voxel */
+  JRandom rng[8];     /* Noisy: one stream per sensor */
   const vo_sensor* sensors;
   int* off;           /* [n_sensors] offset of each sensor's readings in the voxel's reading vector */
   double* readings;   /* [n_vox][dim] */
@@ -963,6 +983,13 @@ static void sense(World* W, Sensing* S, double t) {
       }
     }
   S->hist_n++;
+  double noise[8][2] = {{0}};
+  for (int si = 0; si < S->n_sensors; si++) {
+    const vo_sensor* s = &S->sensors[si];
+    if (s->noise_sigma > 0)
+      for (int d = 0; d < sensor_dim(s); d++) /* Noisy.sense: value + nextGaussian() * sigma * |domain| of the wrapped sensor */
+        noise[si][d] = jr_gaussian(&S->rng[si]) * s->noise_sigma * (s->soft_norm ? 1.0 : fabs(s->dom_max - s->dom_min));
+  }
   for (int v = 0; v < W->n_vox; v++)
     for (int si = 0; si < S->n_sensors; si++) {
       const vo_sensor* s = &S->sensors[si];
@@ -983,7 +1010,7 @@ static void sense(World* W, Sensing* S, double t) {
           val = sum / n;
         }
         if (s->soft_norm) val = soft_norm(val, s->dom_min, s->dom_max);
-        S->readings[idx] = val;
+        S->readings[idx] = val + noise[si][d];
       }
     }
 }
@@ -1084,8 +1111,7 @@ int vo_run(const vo_params* p, int w, int h, const uint8_t* mask,
            int trace_steps, double* trace_vertices, double* trace_bodies, double* trace_ctrl,
            vo_result* out) {
   if (!p || !mask || !ctrl || !out || w <= 0 || h <= 0 || n_terrain < 2) return -1;
-  for (int i = 0; i < n_sensors; i++)
-    if (sensors[i].noise_sigma > 0) return -3;
+  if (n_sensors > 8) return -3;
   int glen = vo_genome_len(w, h, mask, sensors, n_sensors, ctrl);
   if (glen < 0) return glen;
   if (glen != genome_len) return -4;
@@ -1125,6 +1151,7 @@ int vo_run(const vo_params* p, int w, int h, const uint8_t* mask,
   memset(&S, 0, sizeof(S));
   S.n_sensors = n_sensors;
   S.sensors = sensors;
+  for (int i = 0; i < 8; i++) jr_init(&S.rng[i], 0);
   S.off = (int*)malloc(sizeof(int) * (n_sensors > 0 ? n_sensors : 1));
   double max_window = 0;
   for (int i = 0; i < n_sensors; i++) {

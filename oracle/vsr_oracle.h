@@ -73,7 +73,7 @@ typedef struct {
   int    soft_norm;   /* wrap in SoftNormalization */
   double dom_min, dom_max;
   double avg_window;  /* >0: wrap in Average(window seconds) */
-  double noise_sigma; /* >0: Noisy -- NOT implemented by the oracle (returns error) */
+  double noise_sigma; /* >0: Noisy(sensor, sigma, seed 0): + nextGaussian()*sigma*|domain| per reading per step */
 } vo_sensor;
 
 enum { VO_CTRL_PHASE_SIN = 0, VO_CTRL_MLP_CENTRALIZED = 1, VO_CTRL_MLP_DISTRIBUTED_HOMO = 2 };

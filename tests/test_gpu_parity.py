@@ -141,10 +141,6 @@ def test_edge_cases_and_errors(F, oracle):
     with pytest.raises(F.VsrError) as ei:
         ctx.body_set(big, [])
     assert ei.value.code == F.VSR_EUNSUPPORTED
-    noisy = F.sensor_config("uniform-a-0.01")
-    with pytest.raises(F.VsrError) as ei:
-        ctx.body_set(m.mask, noisy)
-    assert ei.value.code == F.VSR_EUNSUPPORTED
     ctx.close()
 
 
@@ -182,6 +178,28 @@ def test_full_size_batch_properties(F, oracle):
     assert np.median(np.abs(a[idx] - ref)) < 2e-3
     assert abs(np.abs(a).max()) < 5.0                                       # biped top speed is a few units/s at most
     ctx.close()
+
+
+def test_noisy_sensors_replay_java_random(F, oracle):
+    """The reference's default sensor config `uniform-a-0.01` (Starter.java:152): Noisy(sensor, 0.01, seed 0).
+    Oracle (C java.util.Random) and library (C++ java.util.Random, table on the device) are independent replays."""
+    p = oracle.default_params(3.0, 1.0)
+    m = oracle.Model("biped-4x3", "flat", "uniform-a-0.01", oracle.CTRL_MLP_CENTRALIZED, p)
+    clean = oracle.Model("biped-4x3", "flat", "uniform-a-0", oracle.CTRL_MLP_CENTRALIZED, p)
+    g = np.random.default_rng(0).uniform(-1, 1, (3, m.genome_len()))
+    ctx = make_ctx(F, m, 64)
+    for r in range(3):
+        _, otv, otb, otc = m.run(g[r], trace_steps=40)
+        _, _, _, ctc = clean.run(g[r], trace_steps=40)
+        res, tv, tb, tc = ctx.trace(g[r], 40)
+        assert np.abs(tb - otb).max() < 1e-9 and np.abs(tc - otc).max() < 1e-9
+        assert np.abs(otc - ctc).max() > 1e-4  # the noise really reaches the controller
+    ctx.close()
+    ctx32 = make_ctx(F, m, 32)
+    _, otv, _, otc = m.run(g[0], trace_steps=10)
+    _, tv, _, tc = ctx32.trace(g[0], 10)
+    assert np.abs(tv - otv).max() / 3.0 < 1e-4 and np.abs(tc - otc).max() < 1e-5
+    ctx32.close()
 
 
 def test_steppy_terrain_never_overflows_the_contact_pool(F, oracle):

@@ -154,3 +154,24 @@ def test_determinism_and_counts(oracle):
     assert r1.n_weld_vel == r1.n_steps * 10 * 24
     fit = m.eval_batch(np.stack([g, g, -g]), n_threads=3)
     assert fit[0] == r1.velocity == fit[1]
+
+
+def test_noisy_sensor_adds_first_gaussians_of_random_0(oracle):
+    """Noisy(sensor, sigma, 0): the c-th reading of a 1-dim sensor gets the c-th Gaussian of Random(0) times sigma.
+    Checked through a 1-voxel robot whose MLP is the identity-like map out = tanh(w * tanh(reading))."""
+    p = oracle.default_params(0.2, 0.0)
+    p.gravity_y = 0.0
+    outs = {}
+    for cfg in ("uniform-a-0", "uniform-a-0.05"):
+        m = oracle.Model("box-1x1", "flat", cfg, oracle.CTRL_MLP_CENTRALIZED, p, n_inner=0)
+        assert m.genome_len() == 2  # bias + 1 weight
+        _, _, _, tc = m.run(np.array([0.0, 1.0]), trace_steps=3)
+        outs[cfg] = tc[:, 0]
+    r = oracle.JavaRandom(0)
+    gs = [r.next_gaussian() for _ in range(3)]
+    for k in range(3):
+        clean_reading = math.atanh(math.atanh(outs["uniform-a-0"][k]))
+        noisy_reading = math.atanh(math.atanh(outs["uniform-a-0.05"][k]))
+        # step 1 is exact; later steps feed back through the controlled area, so only the first is a closed form
+        if k == 0:
+            assert abs(noisy_reading - clean_reading - gs[0] * 0.05) < 1e-12

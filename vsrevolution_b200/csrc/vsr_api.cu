@@ -30,6 +30,7 @@ struct DeviceState {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   double *d_tx = nullptr, *d_ty = nullptr;
   uint8_t* d_win = nullptr;
+  double* d_noise = nullptr;
   void* d_hist = nullptr;
   size_t hist_bytes = 0;
   double* d_genomes = nullptr;
@@ -62,6 +63,7 @@ struct vsr_ctx {
   bool ready = false;
   vsr::KParams kp;
   std::vector<uint8_t> win_tab;
+  std::vector<double> noise_tab; // Noisy sensors: [sens_dim][n_steps+1]
   size_t smem_bytes = 0;
   int shape = kDefaultShape, warps = 4;
   const void* kernel = nullptr;
@@ -275,6 +277,26 @@ int finalize(vsr_ctx* ctx) {
       }
   }
   k.hist_cap = max_win + 2;
+  // Noisy wrappers: `new Noisy(sensor, sigma, 0)` on every voxel [U] -> one java.util.Random(0) stream per sensor, one
+  // Gaussian per reading per step, scaled by sigma * |domain of the wrapped sensor| ([0,1] after SoftNormalization)
+  ctx->noise_tab.clear();
+  {
+    bool any = false;
+    for (auto& sd : ctx->sensors) any |= sd.noise_sigma > 0;
+    if (any) {
+      ctx->noise_tab.assign((size_t)k.sens_dim * (ns + 1), 0.0);
+      for (int i = 0; i < k.n_sensors; i++) {
+        const vsr_sensor_desc& sd = ctx->sensors[i];
+        if (!(sd.noise_sigma > 0)) continue;
+        const int dim = k.sensors[i].dim;
+        std::vector<double> g((size_t)dim * ns);
+        vsr_java_random_gaussians(0, g.data(), dim * ns);
+        const double scale = sd.noise_sigma * (sd.soft_norm ? 1.0 : std::fabs(sd.dom_max - sd.dom_min));
+        for (int st = 1; st <= ns; st++)
+          for (int d = 0; d < dim; d++) ctx->noise_tab[(size_t)(k.sensors[i].off + d) * (ns + 1) + st] = g[(size_t)(st - 1) * dim + d] * scale;
+      }
+    }
+  }
   // controller
   k.ctrl_kind = ctx->kind; k.signals = ctx->signals; k.in_act = ctx->in_act; k.freq = ctx->freq; k.amp = ctx->amp;
   k.genome_len = glen;
@@ -347,6 +369,11 @@ int finalize(vsr_ctx* ctx) {
     if (d.d_win) { cudaFree(d.d_win); d.d_win = nullptr; }
     CK(cudaMalloc(&d.d_win, ctx->win_tab.size()));
     CK(cudaMemcpy(d.d_win, ctx->win_tab.data(), ctx->win_tab.size(), cudaMemcpyHostToDevice));
+    if (d.d_noise) { cudaFree(d.d_noise); d.d_noise = nullptr; }
+    if (!ctx->noise_tab.empty()) {
+      CK(cudaMalloc(&d.d_noise, ctx->noise_tab.size() * sizeof(double)));
+      CK(cudaMemcpy(d.d_noise, ctx->noise_tab.data(), ctx->noise_tab.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
   }
   ctx->ready = true;
   return VSR_OK;
@@ -398,7 +425,7 @@ int enqueue(vsr_ctx* ctx, DeviceState& d, const double* d_genomes, size_t n, dou
   const int grid = grid_for(ctx, n);
   int rc = ensure_hist(ctx, d, grid);
   if (rc) return rc;
-  k.tx = d.d_tx; k.ty = d.d_ty; k.win_tab = d.d_win; k.hist = d.d_hist;
+  k.tx = d.d_tx; k.ty = d.d_ty; k.win_tab = d.d_win; k.hist = d.d_hist; k.noise = d.d_noise;
   k.genomes = d_genomes; k.fitness = d_fitness; k.results = d_results; k.n_robots = (int)n;
   k.tr_vertices = trv; k.tr_bodies = trb; k.tr_ctrl = trc; k.trace_steps = trace_steps;
   if (time_it) CK(cudaEventRecord(d.ev0, st));
@@ -487,7 +514,7 @@ void vsr_ctx_destroy(vsr_ctx* c) {
   for (auto& d : c->devs) {
     cudaSetDevice(d.dev);
     if (d.stream) cudaStreamSynchronize(d.stream);
-    cudaFree(d.d_tx); cudaFree(d.d_ty); cudaFree(d.d_win); cudaFree(d.d_hist);
+    cudaFree(d.d_tx); cudaFree(d.d_ty); cudaFree(d.d_win); cudaFree(d.d_hist); cudaFree(d.d_noise);
     cudaFree(d.d_genomes); cudaFree(d.d_fitness); cudaFree(d.d_results);
     cudaFreeHost(d.h_genomes); cudaFreeHost(d.h_fitness); cudaFreeHost(d.h_results);
     if (d.ev0) cudaEventDestroy(d.ev0);
@@ -508,7 +535,7 @@ int vsr_body_set(vsr_ctx* ctx, int32_t w, int32_t h, const uint8_t* mask, const 
   if (nv == 0) return fail(ctx, VSR_EINVAL, "Target robot has no voxels");
   if (nv > vsr::kMaxVox) return fail(ctx, VSR_EUNSUPPORTED, "bodies with more than 32 voxels are not supported by this build");
   for (int i = 0; i < n_sensors; i++) {
-    if (sensors[i].noise_sigma != 0) return fail(ctx, VSR_EUNSUPPORTED, "Noisy sensors (sigma > 0) are not supported by this build");
+    if (sensors[i].noise_sigma < 0) return fail(ctx, VSR_EINVAL, "negative noise sigma");
     if (sensors[i].kind < 0 || sensors[i].kind > VSR_SENSOR_ANGLE) return fail(ctx, VSR_EINVAL, "unknown sensor kind");
     if (sensors[i].kind == VSR_SENSOR_VELOCITY && !(sensors[i].axes & 3)) return fail(ctx, VSR_EINVAL, "velocity sensor without axes");
     if (sensors[i].soft_norm && !(sensors[i].dom_max > sensors[i].dom_min)) return fail(ctx, VSR_EINVAL, "empty sensor domain");

@@ -83,6 +83,7 @@ struct KParams {
   int n_sensors, sens_dim, n_avg, hist_cap;
   SensorK sensors[kMaxSensors];
   const uint8_t* win_tab; // [n_avg][n_steps+1] window length (in readings) at step k
+  const double* noise;    // Noisy sensors: [sens_dim][n_steps+1] additive noise of reading r at step k (NULL = none)
   void* hist;             // R[hist_cap][n_avg][total_lanes] ring of raw readings
   // controller
   int ctrl_kind, n_layers, layers[kMaxLayers], signals, in_act, genome_len, max_neurons;
@@ -1238,6 +1239,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
             val = M<R>::tanh_((vv * R(2) - R(1)) * R(2)) * R(0.5) + R(0.5);
           }
           const int ri = sk.off + d;
+          if (P.noise) val += (R)__ldg(&P.noise[(size_t)ri * (P.n_steps + 1) + step]); // Noisy wrapper (host-replayed java.util.Random)
 #pragma unroll
           for (int z = 0; z < 8; z++) if (z == ri) rd[z] = val;
         }
