@@ -159,6 +159,8 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=256)
     ap.add_argument("--cpu-sample", type=int, default=192)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ga-generations", type=int, default=3,
+                    help="also time this many generations of the device-resident numGA loop (config 5); 0 = skip")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -230,10 +232,31 @@ def main():
     barrier()
     clocks = sampler.stop() if sampler else None
     launches = ev.kernel_launches() - launches0
-    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
+    # ---- config 5: the same evaluator inside the numGA generation loop (device-resident genomes) ---------
+    ga_ms, ga_info = 0.0, None
+    if args.ga_generations > 0:
+        from vsrevolution_b200.solver import num_ga
+        n_pop = n * world  # whole-job population; every rank evaluates its n robots and the ranks exchange 8 B per robot
+        loop = num_ga().build({"nPop": str(n_pop), "nEval": "0"}).build(ev, seed=w["seed"], process_group=dist.group.WORLD if world > 1 else None)
+        loop.init()
+        loop.step()
+        l0, g0 = ev.kernel_launches(), loop.ga.kernel_launches
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.ga_generations):
+            loop.step()
+        best = loop.ga.best_fitness()  # 8-byte D2H: the only thing that leaves the device
+        ga_ms = (time.perf_counter() - t0) * 1e3
+        ga_kernel_ms = ev.ctx.last_kernel_ms()  # episode kernel of the last generation (evolved genomes, not the random ones)
+        barrier()
+        ga_info = {"n_pop": n_pop, "generations": args.ga_generations, "best_fitness": best, "tournament": loop.ga.tournament_size,
+                   "episode_kernel_ms": ga_kernel_ms,
+                   "gpu_launches": int(ev.kernel_launches() - l0 + loop.ga.kernel_launches - g0)}
+        launches += ga_info["gpu_launches"]
+    t = torch.tensor([dev_ms, e2e_ms, ga_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = t.tolist()
+    dev_ms, e2e_ms, ga_ms = t.tolist()
     fit_ok = bool(np.isfinite(host_fit).all()) and bool(torch.isfinite(d_fit).all().item())
 
     if rank == 0:
@@ -250,6 +273,14 @@ def main():
                 "e2e": {"value": e2e, "unit": "voxel-steps/s", "h2d_bytes_per_step": n * G * 8, "d2h_bytes_per_step": n * 8,
                         "evals_per_sec": e2e / (nv * n_steps), "ms_per_step": e2e_ms / args.steps},
                 "gpu_launches": int(launches), "clocks": clocks, "fitness_finite": fit_ok}
+        if ga_info:
+            per_gen = ga_ms / args.ga_generations
+            ga_info.update({"ms_per_generation": per_gen, "evals_per_sec": ga_info["n_pop"] / (per_gen * 1e-3),
+                            "voxel_steps_per_sec": ga_info["n_pop"] * nv * n_steps / (per_gen * 1e-3),
+                            "loop_overhead_frac": max(0.0, 1.0 - ga_info["episode_kernel_ms"] / per_gen),
+                            "what": "numGA = DoublesStandard(0.75,0.05,3,0.35): tournament + uniform crossover + Gaussian mutation + "
+                                    "evaluation + (mu+lambda) truncation, genomes resident in HBM, wall clock incl. best-fitness D2H"})
+            line["generation_loop"] = ga_info
         # roofline of the episode kernel (FP32 issue bound)
         peak, hbm_peak, src = peak_fp32_tflops()
         cpu = None

@@ -1,0 +1,138 @@
+"""GPU parity of the device-resident generation loop (include/vsr_ga.h) against oracle/ga.py, through the C ABI.
+
+Integer decisions (parents, crossover masks via the genes they pick, survivors, ranks) must match index for index; genes
+carry a Gaussian computed with device libm (log/sqrt/cos in double), so they are compared to 1e-12 absolute.  The fitness
+values are whatever the episode kernel returns: the oracle GA is fed the device's own fitness vector, so the test is exact
+and independent of the (chaotic) physics.
+"""
+import numpy as np
+import pytest
+
+from oracle import ga as OG
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ev():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from vsrevolution_b200.locomotion import population_evaluator
+    return population_evaluator("biped-4x3", "uniform-a-0", "brainCentralized<mlp;r=0.65;nIL=1", "flat", 2.0, 0.5)
+
+
+@pytest.mark.parametrize("remap", [False, True])
+def test_generation_loop_matches_oracle_index_for_index(ev, remap):
+    from vsrevolution_b200 import _ffi
+    n, G = 96, ev.genome_len
+    ga = _ffi.GeneticAlgorithm(ev.ctx, n, seed=11, remap=remap)
+    og = OG.NumGA(n, G, seed=11, remap=remap)
+    assert ga.tournament_size == og.nt == 5
+    ga.init()
+    pop, fit = ga.population()
+    g0 = og.initial_genomes()
+    f0 = ev.evaluate(g0)  # same kernel, same genomes: deterministic
+    o = og.set_population(g0, f0)
+    assert np.array_equal(ga.survivors(), o)
+    assert np.array_equal(pop, og.pop) and np.array_equal(fit, og.fit)  # uniform init is exact arithmetic
+    assert ga.generation == 0 and ga.evaluations == n
+    for gen in range(1, 4):
+        ga.step()
+        off, par, off_fit = ga.offspring()
+        opar = og.select(gen)
+        assert np.array_equal(par, opar)
+        ooff = og.vary(gen, opar)
+        assert np.abs(off - ooff).max() < 1e-12
+        # feed the oracle the device's genomes and fitness, so the merge is compared exactly
+        if remap:
+            allfit = ev.evaluate(np.concatenate([og.pop, off]))
+            origin = og.merge(off, allfit[n:], allfit[:n])
+        else:
+            origin = og.merge(off, off_fit)
+        pop, fit = ga.population()
+        assert np.array_equal(ga.survivors(), origin)
+        assert np.array_equal(pop, og.pop) and np.array_equal(fit, og.fit)
+        assert np.all(np.diff(fit) <= 0)
+        assert ga.generation == gen
+    assert ga.evaluations == n + 3 * (2 * n if remap else n)
+    bg, bf = ga.best()
+    assert bf == fit[0] and np.array_equal(bg, pop[0])
+    ga.close()
+
+
+def test_split_begin_end_and_shards_equal_the_single_call(ev):
+    """Two GA replicas evaluating half of every batch each (the N>1 path, exchanged by hand here) == one unsharded GA."""
+    import torch
+    from vsrevolution_b200 import _ffi
+    from vsrevolution_b200.solver import _DeviceDoubles
+    n = 50  # odd split: per = 25; with remap off counts are 50
+    whole = _ffi.GeneticAlgorithm(ev.ctx, n, seed=4)
+    whole.init()
+    for _ in range(2):
+        whole.step()
+    ref_pop, ref_fit = whole.population()
+    whole.close()
+    # replicas share the context (serialised), each with its own GA state
+    reps = [_ffi.GeneticAlgorithm(ev.ctx, n, seed=4) for _ in range(2)]
+    for r, g in enumerate(reps):
+        g.set_shard(r, 2)
+
+    def exchange():
+        views = []
+        for g in reps:
+            ptr, count, lo, hi, _ = g.pending()
+            g.sync()
+            views.append((torch.as_tensor(_DeviceDoubles(ptr, count), device="cuda"), lo, hi))
+        for i, (v, lo, hi) in enumerate(views):
+            for j, (w, _, _) in enumerate(views):
+                if i != j:
+                    w[lo:hi] = v[lo:hi]
+        torch.cuda.synchronize()
+
+    for g in reps:
+        g.init_begin()
+    exchange()
+    for g in reps:
+        g.init_end()
+    for _ in range(2):
+        for g in reps:
+            g.step_begin()
+        exchange()
+        for g in reps:
+            g.step_end()
+    for g in reps:
+        pop, fit = g.population()
+        assert np.array_equal(pop, ref_pop) and np.array_equal(fit, ref_fit)
+        g.close()
+
+
+def test_set_population_sorts_and_nan_ranks_last(ev):
+    from vsrevolution_b200 import _ffi
+    n, G = 8, ev.genome_len
+    ga = _ffi.GeneticAlgorithm(ev.ctx, n, seed=0)
+    genomes = np.arange(n * G, dtype=np.float64).reshape(n, G)
+    fit = np.array([0.5, np.nan, 2.0, 2.0, -1.0, np.inf, -np.inf, 0.0])
+    ga.set_population(genomes, fit)
+    pop, f = ga.population()
+    o = OG.order(fit)
+    assert np.array_equal(ga.survivors(), o)
+    assert np.array_equal(pop, genomes[o])
+    assert np.array_equal(f, fit[o], equal_nan=True)
+    with pytest.raises(_ffi.VsrIllegalArgument):
+        ga.set_population(genomes[:4], fit[:4])
+    with pytest.raises(_ffi.VsrError):
+        ga.step_end()
+    ga.close()
+
+
+def test_solver_mirror_improves_fitness(ev):
+    from vsrevolution_b200.solver import num_ga
+    log = []
+    solver = num_ga().build({"nPop": "256", "nEval": str(256 * 6)}).build(ev, seed=2)
+    genome, best = solver.solve(listener=log.append)
+    assert solver.ga.evaluations == 256 * 6 and solver.ga.generation == 5
+    assert [e["iterations"] for e in log] == [0, 1, 2, 3, 4]
+    bests = [e["best.fitness"] for e in log] + [best]
+    assert all(b >= a for a, b in zip(bests, bests[1:]))
+    assert np.isclose(ev.evaluate(genome[None, :])[0], best, rtol=0, atol=0)  # deterministic re-evaluation of the best

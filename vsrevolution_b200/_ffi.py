@@ -56,6 +56,12 @@ class VsrIllegalArgument(VsrError, ValueError):
     """Maps VSR_EINVAL / VSR_EDIM, like the IllegalArgumentException the reference mappers throw."""
 
 
+class GaDesc(C.Structure):
+    _fields_ = [("n_pop", C.c_int32), ("xover_prob", C.c_double), ("tournament_rate", C.c_double),
+                ("min_tournament", C.c_int32), ("sigma_mut", C.c_double), ("init_min", C.c_double),
+                ("init_max", C.c_double), ("seed", C.c_uint64), ("remap", C.c_int32)]
+
+
 _lib = None
 
 _SIGS = {
@@ -87,7 +93,35 @@ _SIGS = {
     "vsr_java_random_gaussians": (C.c_int, [C.c_int64, C.c_void_p, C.c_int32]),
 }
 
+# include/vsr_ga.h
+_GA_SIGS = {
+    "vsr_ga_default": (C.c_int, [C.POINTER(GaDesc)]),
+    "vsr_ga_tournament_size": (C.c_int, [C.POINTER(GaDesc)]),
+    "vsr_ga_create": (C.c_int, [C.c_void_p, C.POINTER(GaDesc), C.POINTER(C.c_void_p)]),
+    "vsr_ga_destroy": (None, [C.c_void_p]),
+    "vsr_ga_last_error": (C.c_char_p, [C.c_void_p]),
+    "vsr_ga_set_shard": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
+    "vsr_ga_init": (C.c_int, [C.c_void_p]),
+    "vsr_ga_init_begin": (C.c_int, [C.c_void_p]),
+    "vsr_ga_init_end": (C.c_int, [C.c_void_p]),
+    "vsr_ga_step": (C.c_int, [C.c_void_p]),
+    "vsr_ga_step_begin": (C.c_int, [C.c_void_p]),
+    "vsr_ga_step_end": (C.c_int, [C.c_void_p]),
+    "vsr_ga_pending": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                 C.POINTER(C.c_int32), C.POINTER(C.c_void_p)]),
+    "vsr_ga_sync": (C.c_int, [C.c_void_p]),
+    "vsr_ga_best": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vsr_ga_population": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vsr_ga_offspring": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vsr_ga_survivors": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "vsr_ga_set_population": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vsr_ga_generation": (C.c_int64, [C.c_void_p]),
+    "vsr_ga_evaluations": (C.c_int64, [C.c_void_p]),
+    "vsr_ga_kernel_launches": (C.c_int64, [C.c_void_p]),
+}
+
 EXPORTED_SYMBOLS = tuple(_SIGS)
+GA_EXPORTED_SYMBOLS = tuple(_GA_SIGS)
 
 
 def lib():
@@ -98,7 +132,7 @@ def lib():
             raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                               "(there is no CPU fallback)")
         L = C.CDLL(LIB_PATH)
-        for name, (res, args) in _SIGS.items():
+        for name, (res, args) in {**_SIGS, **_GA_SIGS}.items():
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
@@ -223,6 +257,123 @@ class Context:
         a = np.zeros(n, dtype=np.int32)
         check(lib().vsr_voxel_cells(self._h, _ptr(a), n), self._h)
         return a
+
+
+class GeneticAlgorithm:
+    """Thin RAII wrapper of vsr_ga (include/vsr_ga.h): the device-resident `numGA` generation loop."""
+
+    def __init__(self, ctx: Context, n_pop: int, seed: int = 0, remap: bool = False, **params):
+        self._h = C.c_void_p()
+        self.ctx = ctx  # the GA borrows the context: keep it alive
+        d = GaDesc()
+        check(lib().vsr_ga_default(C.byref(d)))
+        d.n_pop, d.seed, d.remap = n_pop, seed, int(remap)
+        for k, v in params.items():
+            if not hasattr(d, k):
+                raise VsrIllegalArgument(VSR_EINVAL, f"unknown GA parameter {k}")
+            setattr(d, k, v)
+        self.desc = d
+        rc = lib().vsr_ga_create(ctx._h, C.byref(d), C.byref(self._h))
+        if rc == VSR_EINVAL:
+            raise VsrIllegalArgument(rc, "bad GA parameters")
+        if rc < 0:
+            raise VsrError(rc, "vsr_ga_create failed")
+        self.n_pop, self.genome_len = n_pop, ctx.genome_len
+        self.tournament_size = lib().vsr_ga_tournament_size(C.byref(d))
+
+    def _ck(self, rc: int):
+        if rc >= 0:
+            return rc
+        msg = lib().vsr_ga_last_error(self._h)
+        msg = msg.decode() if msg else ""
+        raise (VsrIllegalArgument if rc in (VSR_EINVAL, VSR_EDIM) else VsrError)(rc, msg)
+
+    def close(self):
+        if self._h:
+            lib().vsr_ga_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_shard(self, rank: int, world: int):
+        self._ck(lib().vsr_ga_set_shard(self._h, rank, world))
+
+    def init(self):
+        self._ck(lib().vsr_ga_init(self._h))
+
+    def step(self):
+        self._ck(lib().vsr_ga_step(self._h))
+
+    def init_begin(self):
+        self._ck(lib().vsr_ga_init_begin(self._h))
+
+    def init_end(self):
+        self._ck(lib().vsr_ga_init_end(self._h))
+
+    def step_begin(self):
+        self._ck(lib().vsr_ga_step_begin(self._h))
+
+    def step_end(self):
+        self._ck(lib().vsr_ga_step_end(self._h))
+
+    def pending(self):
+        """(device pointer, count, lo, hi, stream) of the fitness vector the generation in flight is filling."""
+        p, st = C.c_void_p(), C.c_void_p()
+        cnt, lo, hi = C.c_int32(), C.c_int32(), C.c_int32()
+        self._ck(lib().vsr_ga_pending(self._h, C.byref(p), C.byref(cnt), C.byref(lo), C.byref(hi), C.byref(st)))
+        return p.value, cnt.value, lo.value, hi.value, st.value or 0
+
+    def sync(self):
+        self._ck(lib().vsr_ga_sync(self._h))
+
+    def best(self):
+        g, f = np.empty(self.genome_len), np.empty(1)
+        self._ck(lib().vsr_ga_best(self._h, _ptr(g), _ptr(f)))
+        return g, float(f[0])
+
+    def best_fitness(self) -> float:
+        f = np.empty(1)
+        self._ck(lib().vsr_ga_best(self._h, None, _ptr(f)))
+        return float(f[0])
+
+    def population(self):
+        g, f = np.empty((self.n_pop, self.genome_len)), np.empty(self.n_pop)
+        self._ck(lib().vsr_ga_population(self._h, _ptr(g), _ptr(f)))
+        return g, f
+
+    def offspring(self):
+        g, f = np.empty((self.n_pop, self.genome_len)), np.empty(self.n_pop)
+        p = np.empty((self.n_pop, 2), dtype=np.int32)
+        self._ck(lib().vsr_ga_offspring(self._h, _ptr(g), _ptr(p), _ptr(f)))
+        return g, p, f
+
+    def survivors(self) -> np.ndarray:
+        o = np.empty(self.n_pop, dtype=np.int32)
+        self._ck(lib().vsr_ga_survivors(self._h, _ptr(o)))
+        return o
+
+    def set_population(self, genomes: np.ndarray, fitness: np.ndarray):
+        g = np.ascontiguousarray(genomes, dtype=np.float64)
+        f = np.ascontiguousarray(fitness, dtype=np.float64)
+        if g.shape != (self.n_pop, self.genome_len) or f.shape != (self.n_pop,):
+            raise VsrIllegalArgument(VSR_EDIM, f"population must be [{self.n_pop}][{self.genome_len}] + [{self.n_pop}]")
+        self._ck(lib().vsr_ga_set_population(self._h, _ptr(g), _ptr(f)))
+
+    @property
+    def generation(self) -> int:
+        return lib().vsr_ga_generation(self._h)
+
+    @property
+    def evaluations(self) -> int:
+        return lib().vsr_ga_evaluations(self._h)
+
+    @property
+    def kernel_launches(self) -> int:
+        return lib().vsr_ga_kernel_launches(self._h)
 
 
 # ---- naming / integer layer ------------------------------------------------------------------------

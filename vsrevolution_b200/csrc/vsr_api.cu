@@ -10,6 +10,7 @@
 #include <string>
 #include <vector>
 
+#include "vsr_internal.h"
 #include "vsr_kernel.cuh"
 
 namespace {
@@ -28,6 +29,7 @@ struct DeviceState {
   int dev = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev_join = nullptr; // eval_range: this device's slice is back on the primary device
   double *d_tx = nullptr, *d_ty = nullptr;
   uint8_t* d_win = nullptr;
   double* d_noise = nullptr;
@@ -117,32 +119,15 @@ int genome_len_of(const vsr_ctx* c) {
 
 size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
 
-template <int W, int B>
-const void* f32_kernel(int ctrl) {
-  switch (ctrl) {
-    case VSR_CTRL_PHASE_SIN: return (const void*)vsr::vsr_episode_kernel<float, VSR_CTRL_PHASE_SIN, W, B>;
-    case VSR_CTRL_MLP_CENTRALIZED: return (const void*)vsr::vsr_episode_kernel<float, VSR_CTRL_MLP_CENTRALIZED, W, B>;
-    default: return (const void*)vsr::vsr_episode_kernel<float, VSR_CTRL_MLP_DISTRIBUTED_HOMO, W, B>;
-  }
-}
-
-// FP64 parity build: one shape only
+// kernel instantiations live in vsr_kernel_inst.cu (one object per launch shape, compiled in parallel)
 constexpr int kWarps64 = 4;
-const void* f64_kernel(int ctrl) {
-  switch (ctrl) {
-    case VSR_CTRL_PHASE_SIN: return (const void*)vsr::vsr_episode_kernel<double, VSR_CTRL_PHASE_SIN, kWarps64, 1>;
-    case VSR_CTRL_MLP_CENTRALIZED: return (const void*)vsr::vsr_episode_kernel<double, VSR_CTRL_MLP_CENTRALIZED, kWarps64, 1>;
-    default: return (const void*)vsr::vsr_episode_kernel<double, VSR_CTRL_MLP_DISTRIBUTED_HOMO, kWarps64, 1>;
-  }
-}
-
 const void* kernel_ptr(int precision, int ctrl, int shape) {
-  if (precision == 64) return f64_kernel(ctrl);
+  if (precision == 64) return vsr_internal::kernel_f64(ctrl);
   switch (shape) {
-    case 0: return f32_kernel<4, 2>(ctrl);
-    case 1: return f32_kernel<5, 2>(ctrl);
-    case 2: return f32_kernel<8, 1>(ctrl);
-    default: return f32_kernel<10, 1>(ctrl);
+    case 0: return vsr_internal::kernel_f32_s0(ctrl);
+    case 1: return vsr_internal::kernel_f32_s1(ctrl);
+    case 2: return vsr_internal::kernel_f32_s2(ctrl);
+    default: return vsr_internal::kernel_f32_s3(ctrl);
   }
 }
 
@@ -439,6 +424,53 @@ int enqueue(vsr_ctx* ctx, DeviceState& d, const double* d_genomes, size_t n, dou
 
 } // namespace
 
+// ---- internal surface for vsr_ga.cu (vsr_internal.h) ---------------------------------------------------
+namespace vsr_internal {
+int primary_device(const vsr_ctx* ctx) { return ctx->devs[0].dev; }
+cudaStream_t primary_stream(const vsr_ctx* ctx) { return ctx->devs[0].stream; }
+bool ready(const vsr_ctx* ctx) { return ctx && ctx->ready; }
+int genome_len(const vsr_ctx* ctx) { return ctx->kp.genome_len; }
+const std::string& last_error(const vsr_ctx* ctx) { return ctx->err; }
+
+int eval_range(vsr_ctx* ctx, const double* d_genomes, size_t lo, size_t hi, double* d_fitness, cudaStream_t st) {
+  if (hi <= lo) return VSR_OK;
+  const size_t G = (size_t)ctx->kp.genome_len, nd = ctx->devs.size(), cnt = hi - lo, per = (cnt + nd - 1) / nd;
+  DeviceState& d0 = ctx->devs[0];
+  cudaEvent_t fork = nullptr;
+  if (nd > 1) {
+    // the genomes are produced on `st`: the other devices' streams wait for them
+    CK(cudaSetDevice(d0.dev));
+    CK(cudaEventRecord(d0.ev_join, st));
+    fork = d0.ev_join;
+  }
+  for (size_t i = 1; i < nd; i++) {
+    DeviceState& d = ctx->devs[i];
+    const size_t a = std::min(hi, lo + i * per), b = std::min(hi, a + per);
+    if (b <= a) continue;
+    int rc = ensure_capacity(ctx, d, b - a);
+    if (rc) return rc;
+    CK(cudaSetDevice(d.dev));
+    CK(cudaStreamWaitEvent(d.stream, fork, 0));
+    CK(cudaMemcpyPeerAsync(d.d_genomes, d.dev, d_genomes + a * G, d0.dev, (b - a) * G * sizeof(double), d.stream));
+    rc = enqueue(ctx, d, d.d_genomes, b - a, d.d_fitness, nullptr, d.stream, nullptr, nullptr, nullptr, 0, false);
+    if (rc) return rc;
+    CK(cudaMemcpyPeerAsync(d_fitness + a, d0.dev, d.d_fitness, d.dev, (b - a) * sizeof(double), d.stream));
+    CK(cudaEventRecord(d.ev_join, d.stream));
+  }
+  CK(cudaSetDevice(d0.dev));
+  {
+    const size_t b = std::min(hi, lo + per);
+    int rc = enqueue(ctx, d0, d_genomes + lo * G, b - lo, d_fitness + lo, nullptr, st, nullptr, nullptr, nullptr, 0, true);
+    if (rc) return rc;
+  }
+  for (size_t i = 1; i < nd; i++) {
+    const size_t a = std::min(hi, lo + i * per), b = std::min(hi, a + per);
+    if (b > a) CK(cudaStreamWaitEvent(st, ctx->devs[i].ev_join, 0));
+  }
+  return VSR_OK;
+}
+} // namespace vsr_internal
+
 extern "C" {
 
 int vsr_env_default(vsr_env_desc* e) {
@@ -500,6 +532,7 @@ int vsr_ctx_create(const vsr_env_desc* env, vsr_ctx** out) {
     };
     bool ok = ck(cudaSetDevice(d.dev), "cudaSetDevice") && ck(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking), "cudaStreamCreate") &&
               ck(cudaEventCreate(&d.ev0), "cudaEventCreate") && ck(cudaEventCreate(&d.ev1), "cudaEventCreate") &&
+              ck(cudaEventCreateWithFlags(&d.ev_join, cudaEventDisableTiming), "cudaEventCreate") &&
               ck(cudaMalloc(&d.d_tx, sizeof(double) * c->tx.size()), "cudaMalloc") && ck(cudaMalloc(&d.d_ty, sizeof(double) * c->ty.size()), "cudaMalloc") &&
               ck(cudaMemcpy(d.d_tx, c->tx.data(), sizeof(double) * c->tx.size(), cudaMemcpyHostToDevice), "cudaMemcpy") &&
               ck(cudaMemcpy(d.d_ty, c->ty.data(), sizeof(double) * c->ty.size(), cudaMemcpyHostToDevice), "cudaMemcpy");
@@ -519,6 +552,7 @@ void vsr_ctx_destroy(vsr_ctx* c) {
     cudaFreeHost(d.h_genomes); cudaFreeHost(d.h_fitness); cudaFreeHost(d.h_results);
     if (d.ev0) cudaEventDestroy(d.ev0);
     if (d.ev1) cudaEventDestroy(d.ev1);
+    if (d.ev_join) cudaEventDestroy(d.ev_join);
     if (d.stream) cudaStreamDestroy(d.stream);
   }
   delete c;

@@ -1,0 +1,33 @@
+// vsr_kernel_inst.cu -- instantiates vsr_episode_kernel for ONE launch shape per object file (-DVSR_INST=0..3: FP32 shapes
+// {4,2} {5,2} {8,1} {10,1} warps x min CTAs/SM; 4: the FP64 parity build), so the shapes compile in parallel.
+#include "vsr_internal.h"
+#include "vsr_kernel.cuh"
+
+#ifndef VSR_INST
+#error "compile with -DVSR_INST=0..4"
+#endif
+
+namespace {
+template <typename R, int W, int B>
+const void* pick(int ctrl) {
+  switch (ctrl) {
+    case VSR_CTRL_PHASE_SIN: return (const void*)vsr::vsr_episode_kernel<R, VSR_CTRL_PHASE_SIN, W, B>;
+    case VSR_CTRL_MLP_CENTRALIZED: return (const void*)vsr::vsr_episode_kernel<R, VSR_CTRL_MLP_CENTRALIZED, W, B>;
+    default: return (const void*)vsr::vsr_episode_kernel<R, VSR_CTRL_MLP_DISTRIBUTED_HOMO, W, B>;
+  }
+}
+} // namespace
+
+namespace vsr_internal {
+#if VSR_INST == 0
+const void* kernel_f32_s0(int ctrl) { return pick<float, 4, 2>(ctrl); }
+#elif VSR_INST == 1
+const void* kernel_f32_s1(int ctrl) { return pick<float, 5, 2>(ctrl); }
+#elif VSR_INST == 2
+const void* kernel_f32_s2(int ctrl) { return pick<float, 8, 1>(ctrl); }
+#elif VSR_INST == 3
+const void* kernel_f32_s3(int ctrl) { return pick<float, 10, 1>(ctrl); }
+#else
+const void* kernel_f64(int ctrl) { return pick<double, 4, 1>(ctrl); }
+#endif
+} // namespace vsr_internal

@@ -1,0 +1,115 @@
+"""Host-side mirror of the solver the hot path sits in: `numGA` = `new DoublesStandard(0.75, 0.05, 3, 0.35)`
+(locomotion/Starter.java:178; builder/solver/DoublesStandard.java:41-71), run as a device-resident generation loop
+(include/vsr_ga.h): genomes never leave HBM, one episode-kernel launch per generation, only the best individual (and,
+on request, the population) comes back.
+
+    solver = DoublesStandard(0.75, 0.05, 3, 0.35).build({"nPop": "4096", "nEval": "40960"}).build(evaluator)
+    best_genome, best_fitness = solver.solve(listener=print)
+
+Multi-GPU: one process per GPU, GA state replicated (same seed -> identical offspring on every rank), each
+rank evaluates its contiguous shard and the ranks all-gather 8 bytes per robot per generation (`torch.distributed`).
+"""
+from __future__ import annotations
+
+from typing import Callable
+
+import numpy as np
+
+from . import _ffi
+from .locomotion import PopulationEvaluator
+
+
+class _DeviceDoubles:
+    """A device buffer of float64 exposed through __cuda_array_interface__, so torch can alias it without a copy."""
+
+    def __init__(self, ptr: int, n: int, stream: int = 0):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2, "strides": None}
+
+
+class GenerationLoop:
+    """StandardEvolver(..., overlapping=true, remap) restated on the device; stop condition nOfFitnessEvaluations(nEval)."""
+
+    def __init__(self, evaluator: PopulationEvaluator, n_pop: int, n_eval: int, x_over_prob: float, tournament_rate: float,
+                 min_n_tournament: int, sigma_mut: float, remap: bool = False, seed: int = 0, process_group=None):
+        self.evaluator = evaluator
+        self.n_pop, self.n_eval = n_pop, n_eval
+        self.ga = _ffi.GeneticAlgorithm(evaluator.ctx, n_pop, seed=seed, remap=remap, xover_prob=x_over_prob,
+                                        tournament_rate=tournament_rate, min_tournament=min_n_tournament, sigma_mut=sigma_mut)
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None:
+            import torch.distributed as dist
+            self.world = dist.get_world_size(process_group)
+            self.ga.set_shard(dist.get_rank(process_group), self.world)
+
+    # one exchange: every rank contributes its shard of the pending fitness vector
+    def _exchange(self):
+        if self.world == 1:
+            return
+        import torch
+        import torch.distributed as dist
+        ptr, count, lo, hi, _ = self.ga.pending()
+        per = (count + self.world - 1) // self.world
+        self.ga.sync()  # shard evaluated
+        whole = torch.as_tensor(_DeviceDoubles(ptr, per * self.world), device="cuda")  # padded to world * per (<= 7 spare slots)
+        mine = whole[dist.get_rank(self.pg) * per:(dist.get_rank(self.pg) + 1) * per].clone()
+        dist.all_gather_into_tensor(whole, mine, group=self.pg)
+        torch.cuda.current_stream().synchronize()
+
+    def init(self):
+        self.ga.init_begin()
+        self._exchange()
+        self.ga.init_end()
+
+    def step(self):
+        self.ga.step_begin()
+        self._exchange()
+        self.ga.step_end()
+
+    def solve(self, listener: Callable[[dict], None] | None = None):
+        self.init()
+        while self.ga.evaluations < self.n_eval:
+            if listener is not None:
+                listener({"iterations": self.ga.generation, "evals": self.ga.evaluations, "best.fitness": self.ga.best_fitness()})
+            self.step()
+        return self.ga.best()
+
+
+class _SolverBuilder:
+    def __init__(self, outer: "DoublesStandard", n_pop: int, n_eval: int, remap: bool):
+        self.outer, self.n_pop, self.n_eval, self.remap = outer, n_pop, n_eval, remap
+
+    def build(self, evaluator: PopulationEvaluator, seed: int = 0, process_group=None) -> GenerationLoop:
+        o = self.outer
+        return GenerationLoop(evaluator, self.n_pop, self.n_eval, o.x_over_prob, o.tournament_rate, o.min_n_tournament, o.sigma_mut,
+                              self.remap, seed, process_group)
+
+
+class DoublesStandard:
+    """builder/solver/DoublesStandard.java: (xOverProb, tournamentRate, minNTournament, sigmaMut); `build(params)` reads
+    nPop, nEval, diversity, remap (:42-45)."""
+
+    def __init__(self, x_over_prob: float, tournament_rate: float, min_n_tournament: int, sigma_mut: float):
+        self.x_over_prob, self.tournament_rate = x_over_prob, tournament_rate
+        self.min_n_tournament, self.sigma_mut = min_n_tournament, sigma_mut
+
+    def build(self, params: dict) -> _SolverBuilder:
+        try:
+            n_pop, n_eval = int(params["nPop"]), int(params["nEval"])
+        except KeyError as e:  # Integer.parseInt(null) -> NumberFormatException in the reference
+            raise _ffi.VsrIllegalArgument(_ffi.VSR_EINVAL, f"missing solver parameter {e.args[0]}")
+        if str(params.get("diversity", "false")).lower() == "true":
+            raise _ffi.VsrError(_ffi.VSR_EUNSUPPORTED, "StandardWithEnforcedDiversityEvolver is outside the hot path (SURVEY.md 8)")
+        return _SolverBuilder(self, n_pop, n_eval, str(params.get("remap", "false")).lower() == "true")
+
+
+def num_ga() -> DoublesStandard:
+    """`numGA` (locomotion/Starter.java:178)."""
+    return DoublesStandard(0.75, 0.05, 3, 0.35)
+
+
+def tournament_size(n_pop: int, tournament_rate: float = 0.05, min_n_tournament: int = 3) -> int:
+    d = _ffi.GaDesc()
+    _ffi.check(_ffi.lib().vsr_ga_default(d))
+    d.n_pop, d.tournament_rate, d.min_tournament = n_pop, tournament_rate, min_n_tournament
+    return _ffi.check(_ffi.lib().vsr_ga_tournament_size(d))
