@@ -14,11 +14,9 @@ def region(f, ln):
     for i, n in marks:
         if ln >= i: name = f"{i}:{n}"
     return name
-so = os.path.join(os.path.dirname(__file__), "..", "vsrevolution_b200", "libvsr_eval.so")
-d = tempfile.mkdtemp()
-subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=d, stdout=subprocess.DEVNULL)
-cub = [f for f in glob.glob(d + "/*.cubin") if "names" not in f][0]
-txt = subprocess.run(["nvdisasm", "--print-line-info", cub], capture_output=True, text=True).stdout.splitlines()
+sys.path.insert(0, os.path.dirname(__file__))
+from _sass import kernel_sass
+txt = kernel_sass(sub)
 inside = False; cur = None; line_of = {}; static = collections.Counter()
 for line in txt:
     if line.startswith(".text."): inside = sub in line; continue

@@ -2,11 +2,9 @@
 usage: python tools/sass_lines.py <mangled-substring> [bucket]"""
 import collections, re, subprocess, sys, tempfile, os, glob
 sub = sys.argv[1]; bucket = int(sys.argv[2]) if len(sys.argv) > 2 else 10
-so = os.path.join(os.path.dirname(__file__), "..", "vsrevolution_b200", "libvsr_eval.so")
-d = tempfile.mkdtemp()
-subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=d, stdout=subprocess.DEVNULL)
-cub = [f for f in glob.glob(d + "/*.cubin") if "names" not in f][0]
-txt = subprocess.run(["nvdisasm", "--print-line-info", cub], capture_output=True, text=True).stdout.splitlines()
+sys.path.insert(0, os.path.dirname(__file__))
+from _sass import kernel_sass
+txt = kernel_sass(sub)
 inside = False; cur = None; cnt = collections.Counter(); ops = collections.Counter()
 for line in txt:
     if line.startswith(".text."):

@@ -1,11 +1,9 @@
 """List local-memory spill slots of one kernel variant with the source lines of their stores/loads."""
 import subprocess, re, glob, os, tempfile, collections, sys
 sub = sys.argv[1]
-so = os.path.join(os.path.dirname(__file__), "..", "vsrevolution_b200", "libvsr_eval.so")
-d = tempfile.mkdtemp()
-subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=d, stdout=subprocess.DEVNULL)
-cub = [f for f in glob.glob(d + "/*.cubin") if "names" not in f][0]
-txt = subprocess.run(["nvdisasm", "--print-line-info", cub], capture_output=True, text=True).stdout.splitlines()
+sys.path.insert(0, os.path.dirname(__file__))
+from _sass import kernel_sass
+txt = kernel_sass(sub)
 inside = False; cur = None
 st = collections.defaultdict(list); ld = collections.defaultdict(list)
 for line in txt:

@@ -121,13 +121,13 @@ size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
 
 // kernel instantiations live in vsr_kernel_inst.cu (one object per launch shape, compiled in parallel)
 constexpr int kWarps64 = 4;
-const void* kernel_ptr(int precision, int ctrl, int shape) {
+const void* kernel_ptr(int precision, int ctrl, int shape, int full_scaff) {
   if (precision == 64) return vsr_internal::kernel_f64(ctrl);
   switch (shape) {
-    case 0: return vsr_internal::kernel_f32_s0(ctrl);
-    case 1: return vsr_internal::kernel_f32_s1(ctrl);
-    case 2: return vsr_internal::kernel_f32_s2(ctrl);
-    default: return vsr_internal::kernel_f32_s3(ctrl);
+    case 0: return vsr_internal::kernel_f32_s0(ctrl, full_scaff);
+    case 1: return vsr_internal::kernel_f32_s1(ctrl, full_scaff);
+    case 2: return vsr_internal::kernel_f32_s2(ctrl, full_scaff);
+    default: return vsr_internal::kernel_f32_s3(ctrl, full_scaff);
   }
 }
 
@@ -343,7 +343,7 @@ int finalize(vsr_ctx* ctx) {
   if (2 * 5 * o > smem_sm && 8 * o + 1024 <= 227 * 1024) ctx->shape = 2;
   if (const char* ev = std::getenv("VSR_LAUNCH_SHAPE")) ctx->shape = std::max(0, std::min(kNumShapes - 1, std::atoi(ev)));
   ctx->warps = e.precision == 64 ? kWarps64 : kShapes[ctx->shape].warps;
-  ctx->kernel = kernel_ptr(e.precision, ctx->kind, ctx->shape);
+  ctx->kernel = kernel_ptr(e.precision, ctx->kind, ctx->shape, e.scaffolding_mask == 0xF && !std::getenv("VSR_GENERIC_SCAFF"));
   ctx->smem_bytes = o * ctx->warps;
   if (k.n_t > 16383) return fail(ctx, VSR_EUNSUPPORTED, "terrains with more than 16383 vertices are not supported");
   if (ctx->smem_bytes > 227 * 1024) return fail(ctx, VSR_EUNSUPPORTED, "controller too large for shared memory");

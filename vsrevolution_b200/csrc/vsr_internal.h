@@ -20,9 +20,9 @@ VSR_HIDDEN int genome_len(const vsr_ctx* ctx);
 VSR_HIDDEN int eval_range(vsr_ctx* ctx, const double* d_genomes, size_t lo, size_t hi, double* d_fitness, cudaStream_t st);
 VSR_HIDDEN const std::string& last_error(const vsr_ctx* ctx);
 // episode-kernel instantiations (vsr_kernel_inst.cu): launch shapes 0..3 of the FP32 build, the FP64 parity build
-VSR_HIDDEN const void* kernel_f32_s0(int ctrl);
-VSR_HIDDEN const void* kernel_f32_s1(int ctrl);
-VSR_HIDDEN const void* kernel_f32_s2(int ctrl);
-VSR_HIDDEN const void* kernel_f32_s3(int ctrl);
+VSR_HIDDEN const void* kernel_f32_s0(int ctrl, int full_scaff);
+VSR_HIDDEN const void* kernel_f32_s1(int ctrl, int full_scaff);
+VSR_HIDDEN const void* kernel_f32_s2(int ctrl, int full_scaff);
+VSR_HIDDEN const void* kernel_f32_s3(int ctrl, int full_scaff);
 VSR_HIDDEN const void* kernel_f64(int ctrl);
 } // namespace vsr_internal

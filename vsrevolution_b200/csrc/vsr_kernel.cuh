@@ -41,6 +41,9 @@ constexpr int kPark = 23;         // X Y A (12) + polygon cache (6) + origin (2)
 // solver half at 24 (rebuilt every step by the contact initialisation; Jacobian rows rn = r x n, rt = r x t):
 //   [24..27] rn0 rt0 mN0 mT0 | [28..31] rn1 rt1 mN1 mT1 | [32..35] vb0 vb1 K12 iK11 | [36..39] iK12 iK22 - - | [40..43] lx0 ly0 lx1 ly1
 constexpr int kPoolStride = 44;
+// phase-alignment barriers of the specialised build (bits: KParams::sync_mask): step start, before the velocity loop, before
+// the position phase, before / after detect (tools/bench sweep); the generic build reads the mask from P (tuning only)
+constexpr int kSyncMaskDefault = 59;
 
 struct SensorK {
   int kind, axes, rotated, soft_norm;
@@ -362,7 +365,8 @@ __device__ __forceinline__ int collide_box_top(R x1, R y1, R pnx, R pny, R bcx, 
 // ------------------------------------------------------------------------------------------------
 // the episode kernel
 // ------------------------------------------------------------------------------------------------
-template <class R, int CTRL, int WARPS, int MINB>
+// SCAFF >= 0: the scaffolding mask is a compile-time constant (0xF, the Voxel default: no branch per spring); -1: read from P
+template <class R, int CTRL, int WARPS, int MINB, int SCAFF = -1>
 __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __grid_constant__ KParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -441,7 +445,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
 #define K_max_rot KC(max_rot, P.max_rot)
 #define K_inv_area2 KC(inv_area2, 0.5 / (P.side_len * P.side_len))
   const R gdt = valid ? KC(gdt, P.g * P.dt) : R(0);
-  const int scaff = P.scaff_mask;
+  const int scaff = SCAFF >= 0 ? SCAFF : P.scaff_mask;
 
   // ---- state ----------------------------------------------------------------------------------
   // per-lane integer origin (world = origin + local); corner masses NW NE SE SW
@@ -625,7 +629,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
   // =================================================================================================
 #pragma unroll 1
   for (int step = 1; step <= P.n_steps; step++) {
-#define PHASE_SYNC(bit) if (P.sync_mask & (bit)) __syncthreads(); /* re-align the CTA's warps: shared instruction stream */
+#define PHASE_SYNC(bit) if ((SCAFF >= 0 ? kSyncMaskDefault : P.sync_mask) & (bit)) __syncthreads(); /* re-align the CTA's warps: shared instruction stream */
     PHASE_SYNC(1)
     t += P.dt;
     // ---- park cold state in shared memory (phase 1: what neither the constraint initialisation nor the velocity

@@ -8,26 +8,29 @@
 #endif
 
 namespace {
-template <typename R, int W, int B>
+template <typename R, int W, int B, int SCAFF>
 const void* pick(int ctrl) {
   switch (ctrl) {
-    case VSR_CTRL_PHASE_SIN: return (const void*)vsr::vsr_episode_kernel<R, VSR_CTRL_PHASE_SIN, W, B>;
-    case VSR_CTRL_MLP_CENTRALIZED: return (const void*)vsr::vsr_episode_kernel<R, VSR_CTRL_MLP_CENTRALIZED, W, B>;
-    default: return (const void*)vsr::vsr_episode_kernel<R, VSR_CTRL_MLP_DISTRIBUTED_HOMO, W, B>;
+    case VSR_CTRL_PHASE_SIN: return (const void*)vsr::vsr_episode_kernel<R, VSR_CTRL_PHASE_SIN, W, B, SCAFF>;
+    case VSR_CTRL_MLP_CENTRALIZED: return (const void*)vsr::vsr_episode_kernel<R, VSR_CTRL_MLP_CENTRALIZED, W, B, SCAFF>;
+    default: return (const void*)vsr::vsr_episode_kernel<R, VSR_CTRL_MLP_DISTRIBUTED_HOMO, W, B, SCAFF>;
   }
 }
+// full_scaff: all four scaffoldings enabled (the Voxel default) -> the build with the mask folded at compile time
+template <typename R, int W, int B>
+const void* pick2(int ctrl, int full_scaff) { return full_scaff ? pick<R, W, B, 0xF>(ctrl) : pick<R, W, B, -1>(ctrl); }
 } // namespace
 
 namespace vsr_internal {
 #if VSR_INST == 0
-const void* kernel_f32_s0(int ctrl) { return pick<float, 4, 2>(ctrl); }
+const void* kernel_f32_s0(int ctrl, int full_scaff) { return pick2<float, 4, 2>(ctrl, full_scaff); }
 #elif VSR_INST == 1
-const void* kernel_f32_s1(int ctrl) { return pick<float, 5, 2>(ctrl); }
+const void* kernel_f32_s1(int ctrl, int full_scaff) { return pick2<float, 5, 2>(ctrl, full_scaff); }
 #elif VSR_INST == 2
-const void* kernel_f32_s2(int ctrl) { return pick<float, 8, 1>(ctrl); }
+const void* kernel_f32_s2(int ctrl, int full_scaff) { return pick2<float, 8, 1>(ctrl, full_scaff); }
 #elif VSR_INST == 3
-const void* kernel_f32_s3(int ctrl) { return pick<float, 10, 1>(ctrl); }
+const void* kernel_f32_s3(int ctrl, int full_scaff) { return pick2<float, 10, 1>(ctrl, full_scaff); }
 #else
-const void* kernel_f64(int ctrl) { return pick<double, 4, 1>(ctrl); }
+const void* kernel_f64(int ctrl) { return pick<double, 4, 1, -1>(ctrl); }
 #endif
 } // namespace vsr_internal
