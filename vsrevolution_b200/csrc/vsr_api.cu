@@ -215,6 +215,7 @@ int finalize(vsr_ctx* ctx) {
   }
   k.n_t = (int)ctx->tx.size();
   k.base_y = *std::min_element(ctx->ty.begin(), ctx->ty.end()) - e.ground_thickness;
+  k.ty_max = *std::max_element(ctx->ty.begin(), ctx->ty.end());
   // episode
   int ns, kf, kl;
   int rc = vsr_episode_steps(e.final_t, e.transient_t, e.dt, &ns, &kf, &kl);
@@ -306,6 +307,7 @@ int finalize(vsr_ctx* ctx) {
   k.off_pool_m = (int)o; o = align16(o + 2 * S * 4);
   k.off_pool_cnt = (int)o; o = align16(o + 4);
   k.off_pool_o = (int)o; o = align16(o + S * 4);
+  k.off_mslots = (int)o; o = align16(o + 32 * 4 * 4); // mass -> manifold slots
   o = (o + 31) & ~size_t(31);
   // velocity staging of the transposed contact solve and the controller's activation scratch are used in disjoint
   // phases of a step: one region, sized for the larger
@@ -318,6 +320,7 @@ int finalize(vsr_ctx* ctx) {
   if (ctx->kind != VSR_CTRL_PHASE_SIN) o = align16(o + (size_t)k.robots_per_warp * glen * rs);
   k.off_sig = (int)o;
   if (ctx->kind == VSR_CTRL_MLP_DISTRIBUTED_HOMO) o = align16(o + (size_t)2 * 32 * 4 * std::max(1, k.signals) * rs);
+  o = (o + 31) & ~size_t(31); // also staged as V4 rows by the position phase
   k.off_bias = (int)o;
   o = align16(o + (size_t)18 * 32 * rs);
   o = (o + 31) & ~size_t(31);
@@ -338,7 +341,7 @@ int finalize(vsr_ctx* ctx) {
   if (const char* ev = std::getenv("VSR_SYNC_MASK")) k.sync_mask = std::atoi(ev);
   // launch shape: 2 CTAs x 5 warps (168 registers, 10 warps/SM) when their shared memory fits an SM; otherwise one CTA of
   // 8 warps (255 registers) -- e.g. narrow-step terrains with their larger contact pool
-  const size_t smem_sm = 227 * 1024 - 2 * 1024;
+  const size_t smem_sm = 228 * 1024 - 2 * 1024; // 228 KB per SM, 1 KB reserved per resident CTA
   ctx->shape = kDefaultShape;
   if (2 * 5 * o > smem_sm && 8 * o + 1024 <= 227 * 1024) ctx->shape = 2;
   if (const char* ev = std::getenv("VSR_LAUNCH_SHAPE")) ctx->shape = std::max(0, std::min(kNumShapes - 1, std::atoi(ev)));

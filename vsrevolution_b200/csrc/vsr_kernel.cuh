@@ -81,7 +81,7 @@ struct KParams {
   const double* tx;
   const double* ty;
   int n_t;
-  double base_y;
+  double base_y, ty_max; // bottom of the ground body; highest terrain vertex
   // sensors
   int n_sensors, sens_dim, n_avg, hist_cap;
   SensorK sensors[kMaxSensors];
@@ -105,7 +105,7 @@ struct KParams {
   // shared-memory layout (bytes from the CTA's dynamic smem base; per warp strides)
   int pool_slots;
   int smem_warp_stride; // bytes per warp
-  int off_pool_p, off_pool_m, off_pool_cnt, off_w, off_act, off_sig, off_bias, off_arm, off_eff, off_nrm, off_park, off_cold, off_stage, off_pool_o;
+  int off_pool_p, off_pool_m, off_pool_cnt, off_w, off_act, off_sig, off_bias, off_arm, off_eff, off_nrm, off_park, off_cold, off_stage, off_pool_o, off_mslots;
   int sync_mask; // phase-alignment barriers (bit0 step start, bit1 before velocity loop, bit2 every velocity
                  // iteration, bit3 before position phase, bit4 before detect, bit5 before sensing, bit6 before spring
                  // init, bit7 before weld init, bit8 after the velocity loop, bit9 after the position phase, bit10 after control)
@@ -471,9 +471,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
   R wimp[4][3];
 #pragma unroll
   for (int i = 0; i < 4; i++) wimp[i][0] = wimp[i][1] = wimp[i][2] = 0;
-  // contact manifold slots of this lane: up to 8 pool slots (8 bits each), ordered by (mass, polygon)
-  unsigned clo = 0, chi = 0;
-  int ccnt = 0;
+  bool touching = false; // any corner mass of this voxel has a manifold (Touch sensor; gates the velocity reloads)
   int par = 0; // parity of the current persistent pool buffer
   int kh = 1;  // terrain polygon hint
   int overflow = 0;
@@ -515,47 +513,100 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
 
   auto ld4 = [](const R* q) -> V4<R> { return *reinterpret_cast<const V4<R>*>(q); };
   auto st4 = [](R* q, const V4<R>& v) { *reinterpret_cast<V4<R>*>(q) = v; };
-  auto slot_of = [&](int e) -> int { return ((e < 4 ? clo >> (8 * e) : chi >> (8 * (e - 4))) & 0xff); };
-
   int man_total = 0, man_rank = 0; // warp-uniform: manifolds in the pool, highest rank of a manifold within its mass
   // per-lane cached ground polygon (the one under the voxel centre), in the lane's local frame
   int pk = 0;
   R px0 = 0, px1 = 0, py0 = 0, py1 = 0, pnx = 0, pny = 1;
-  // detection of all 4 corner masses of this lane against the ground; fills the pool (parity par^1).
-  // One copy of the narrowphase: the mass loop is NOT unrolled, masses are read with select chains.
+  R* stg = reinterpret_cast<R*>(stage);
+  // mass -> manifold slots of the current pool parity: byte r = 1 + slot of the rank-r manifold of that mass (0 = none)
+  unsigned* massSlots = reinterpret_cast<unsigned*>(wsm + P.off_mslots); // [32 lanes][4 masses]
+  // detect-time aliases inside the staging area: CS [32][4] | SN [32][4] | candidate list (128 bytes) | polygon hint [32]
+  unsigned char* cand = reinterpret_cast<unsigned char*>(stg + 256);
+  int* spk = reinterpret_cast<int*>(cand + 128);
+  for (int i = lane; i < 128; i += 32) massSlots[i] = 0;
+
+  // Ground contact detection, TRANSPOSED: the voxel lanes run a broadphase over their 4 corner masses and park the mass
+  // poses in shared memory; the surviving (lane, mass) candidates are compacted over the warp and every lane then runs the
+  // narrowphase of ONE candidate (lane = candidate, not lane = voxel): the few masses near the ground no longer serialise
+  // on their owner lane while the other lanes idle.  The candidate lane also builds everything of the contact constraint
+  // that depends on geometry only (Jacobian rows, effective masses, block matrix, local anchors); the restitution bias
+  // needs the next step's velocities and is added at the top of the step.  Fills pool parity par^1, then flips par.
   auto detect = [&]() {
     __syncwarp();
-    if (lane == 0) *poolCnt = 0;
-    __syncwarp();
     const int np_ = par ^ 1;
-    const double oxd = (double)ox, oyd = (double)oy;
-    unsigned nlo = 0, nhi = 0;
-    int ncnt = 0, lane_rank = 0;
-    if (valid) {
-      const R cxl = R(0.25) * (X[0] + X[1] + X[2] + X[3]);
-      if (!pk || cxl < px0 || cxl > px1) { // (re)load the polygon under the voxel centre
-        const double cxw = oxd + (double)cxl;
-        int kk = kh;
-        while (kk > 1 && __ldg(&P.tx[kk - 1]) > cxw) kk--;
-        while (kk < P.n_t - 1 && __ldg(&P.tx[kk]) <= cxw) kk++;
-        kh = kk; pk = kk;
-        px0 = (R)(__ldg(&P.tx[kk - 1]) - oxd); px1 = (R)(__ldg(&P.tx[kk]) - oxd);
-        py0 = (R)(__ldg(&P.ty[kk - 1]) - oyd); py1 = (R)(__ldg(&P.ty[kk]) - oyd);
-        const R ex = px0 - px1, ey = py0 - py1;
-        const R il = M<R>::rsqrt_(ex * ex + ey * ey);
-        pnx = ey * il; pny = -ex * il;
+    unsigned cmask = 0;
+    {
+      const double oxd = (double)ox, oyd = (double)oy;
+      if (valid) {
+        const R cxl = R(0.25) * (X[0] + X[1] + X[2] + X[3]);
+        if (!pk || cxl < px0 || cxl > px1) { // (re)load the polygon under the voxel centre
+          const double cxw = oxd + (double)cxl;
+          int kk = kh;
+          while (kk > 1 && __ldg(&P.tx[kk - 1]) > cxw) kk--;
+          while (kk < P.n_t - 1 && __ldg(&P.tx[kk]) <= cxw) kk++;
+          kh = kk; pk = kk;
+          px0 = (R)(__ldg(&P.tx[kk - 1]) - oxd); px1 = (R)(__ldg(&P.tx[kk]) - oxd);
+          py0 = (R)(__ldg(&P.ty[kk - 1]) - oyd); py1 = (R)(__ldg(&P.ty[kk]) - oyd);
+          const R ex = px0 - px1, ey = py0 - py1;
+          const R il = M<R>::rsqrt_(ex * ex + ey * ey);
+          pnx = ey * il; pny = -ex * il;
+        }
+        // broadphase: a mass well inside the cached polygon's x-range is tested against that polygon's AABB, any other
+        // mass against the highest terrain vertex
+        const R pymax = M<R>::max_(py0, py1), ytop = (R)(P.ty_max - oyd);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const R ext = K_half * (M<R>::abs_(CS[k]) + M<R>::abs_(SN[k]));
+          const bool fast = X[k] - ext >= px0 + R(kFastMargin) && X[k] + ext <= px1 - R(kFastMargin);
+          if (!(Y[k] - ext > (fast ? pymax : ytop))) cmask |= 1u << k;
+        }
       }
     }
-    const R pymax = M<R>::max_(py0, py1);
+    // park the poses (read back after the velocity loop; read by the candidate lanes below)
+    {
+#pragma unroll
+      for (int k = 0; k < 4; k++) { spark[k * 32 + lane] = X[k]; spark[(4 + k) * 32 + lane] = Y[k]; spark[(8 + k) * 32 + lane] = A[k]; }
+      spark[12 * 32 + lane] = px0; spark[13 * 32 + lane] = px1; spark[14 * 32 + lane] = py0; spark[15 * 32 + lane] = py1;
+      spark[16 * 32 + lane] = pnx; spark[17 * 32 + lane] = pny;
+      spark[18 * 32 + lane] = ox; spark[19 * 32 + lane] = oy;
+      V4<R> t4;
+      t4.x = CS[0]; t4.y = CS[1]; t4.z = CS[2]; t4.w = CS[3]; stage[0 * 32 + lane] = t4;
+      t4.x = SN[0]; t4.y = SN[1]; t4.z = SN[2]; t4.w = SN[3]; stage[1 * 32 + lane] = t4;
+      spk[lane] = pk;
+      uint4 ms = reinterpret_cast<uint4*>(massSlots)[lane]; // masses that are not candidates lose their manifolds
+      if (!(cmask & 1u)) ms.x = 0;
+      if (!(cmask & 2u)) ms.y = 0;
+      if (!(cmask & 4u)) ms.z = 0;
+      if (!(cmask & 8u)) ms.w = 0;
+      reinterpret_cast<uint4*>(massSlots)[lane] = ms;
+    }
+    int ncand = 0;
+    {
+      const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const bool mine = (cmask >> k) & 1u;
+        const unsigned b = __ballot_sync(FULL, mine);
+        if (mine) cand[ncand + __popc(b & lt)] = (unsigned char)(lane | (k << 5));
+        ncand += __popc(b);
+      }
+    }
+    if (lane == 0) *poolCnt = 0;
+    __syncwarp();
+    int lane_rank = 0;
 #pragma unroll 1
-    for (int k = 0; k < 4; k++) {
-      if (!valid) break;
-      const R xk = SEL4(X, k), yk = SEL4(Y, k), ck = SEL4(CS, k), sk = SEL4(SN, k);
+    for (int ci = lane; ci < ncand; ci += 32) {
+      const int c = cand[ci], ol = c & 31, k = c >> 5, mi = ol * 4 + k;
+      const R xk = spark[k * 32 + ol], yk = spark[(4 + k) * 32 + ol], ck = stg[mi], sk = stg[128 + mi];
+      const R qx0 = spark[12 * 32 + ol], qx1 = spark[13 * 32 + ol], qy0 = spark[14 * 32 + ol], qy1 = spark[15 * 32 + ol];
+      const R qnx = spark[16 * 32 + ol], qny = spark[17 * 32 + ol];
+      const double oxd = (double)spark[18 * 32 + ol], oyd = (double)spark[19 * 32 + ol];
+      const int pko = spk[ol];
+      const unsigned prev = massSlots[mi];
       const R ext = K_half * (M<R>::abs_(ck) + M<R>::abs_(sk));
-      const bool fast = xk - ext >= px0 + R(kFastMargin) && xk + ext <= px1 - R(kFastMargin);
-      if (fast && yk - ext > pymax) continue; // broadphase: above the polygon's AABB
+      const bool fast = xk - ext >= qx0 + R(kFastMargin) && xk + ext <= qx1 - R(kFastMargin);
       double ax0 = 0, ax1 = 0, ay0 = 0;
-      int kk = pk, kend = pk;
+      int kk = pko, kend = pko;
       if (!fast) {
         ax0 = oxd + (double)(xk - ext); ax1 = oxd + (double)(xk + ext); ay0 = oyd + (double)(yk - ext);
         // smallest polygon index kk (polygon kk spans tx[kk-1]..tx[kk]) with tx[kk] >= ax0
@@ -564,13 +615,14 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
         kend = P.n_t - 1;
       }
       int cnt = 0;
+      unsigned news = 0;
       for (; kk <= kend && cnt < kMaxMan; kk++) {
         R nx, ny, px[2], py[2], dp[2];
         int id[2];
         int np = -1;
-        R gx0 = px0, gy0 = py0, gx1 = px1, gy1 = py1;
+        R gx0 = qx0, gy0 = qy0, gx1 = qx1, gy1 = qy1;
         if (fast) {
-          np = collide_box_top<R>(px1, py1, pnx, pny, xk, yk, ck, sk, K_half, nx, ny, px, py, dp, id);
+          np = collide_box_top<R>(qx1, qy1, qnx, qny, xk, yk, ck, sk, K_half, nx, ny, px, py, dp, id);
         } else {
           const double x0 = __ldg(&P.tx[kk - 1]);
           if (x0 > ax1) break;
@@ -582,14 +634,14 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
         if (np < 0)
           np = collide_box_ground<R>(gx0, gy0, gx1, gy1, (R)(P.base_y - oyd), xk, yk, ck, sk, K_half, K_lin_tol, nx, ny, px, py, dp, id);
         if (!np) continue;
-        if (ncnt >= kMaxLaneMan) { overflow++; continue; }
         const int s = atomicAdd(poolCnt, 1);
         if (s >= S) { overflow++; continue; }
         R jn0 = 0, jt0 = 0, jn1 = 0, jt1 = 0;
         // warm start from the previous manifold of the same (mass, polygon)
         const int key = kk | (k << 14);
-        for (int o = 0; o < ccnt; o++) {
-          const int os = slot_of(o);
+        for (int o = 0; o < kMaxMan; o++) {
+          const int os = (int)((prev >> (8 * o)) & 0xffu) - 1;
+          if (os < 0) break;
           const int ometa = poolM[par * S + os];
           if ((ometa & 0xffff) != key) continue;
           const int onp = (ometa >> 16) & 3;
@@ -601,26 +653,51 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
             if (np > 1 && oidr == id[1]) { jn1 = ojn; jt1 = ojt; }
           }
         }
-        {
-          R* sp = pool + s * kPoolStride + np_ * kPoolPersist;
-          V4<R> v4;
-          v4.x = nx; v4.y = ny; v4.z = px[0]; v4.w = py[0]; st4(sp, v4);
-          v4.x = dp[0]; v4.y = np > 1 ? px[1] : R(0); v4.z = np > 1 ? py[1] : R(0); v4.w = np > 1 ? dp[1] : R(0); st4(sp + 4, v4);
-          v4.x = jn0; v4.y = jt0; v4.z = jn1; v4.w = jt1; st4(sp + 8, v4);
+        R* sp = pool + s * kPoolStride;
+        V4<R> v4;
+        v4.x = nx; v4.y = ny; v4.z = px[0]; v4.w = py[0]; st4(sp + np_ * kPoolPersist, v4);
+        v4.x = dp[0]; v4.y = np > 1 ? px[1] : R(0); v4.z = np > 1 ? py[1] : R(0); v4.w = np > 1 ? dp[1] : R(0); st4(sp + np_ * kPoolPersist + 4, v4);
+        v4.x = jn0; v4.y = jt0; v4.z = jn1; v4.w = jt1; st4(sp + np_ * kPoolPersist + 8, v4);
+        // geometry part of the contact constraint (ContactConstraint initialisation): Jacobian rows of a contact point:
+        // normal (nx, ny, rn), tangent t = (ny, -nx): (ny, -nx, rt)
+        int meta = key | (np << 16) | (id[0] << 18) | ((np > 1 ? id[1] : 0) << 24);
+        const R r0x = px[0] - xk, r0y = py[0] - yk, r1x = np > 1 ? px[1] - xk : -xk, r1y = np > 1 ? py[1] - yk : -yk;
+        const R rn0 = r0x * ny - r0y * nx, rt0 = -(r0x * nx + r0y * ny);
+        const R rn1 = np > 1 ? r1x * ny - r1y * nx : R(0), rt1 = np > 1 ? -(r1x * nx + r1y * ny) : R(0);
+        v4.x = rn0; v4.y = rt0; v4.z = M<R>::rcp(K_im + K_ii * rn0 * rn0); v4.w = M<R>::rcp(K_im + K_ii * rt0 * rt0); st4(sp + 24, v4);
+        v4.x = rn1; v4.y = rt1; v4.z = M<R>::rcp(K_im + K_ii * rn1 * rn1); v4.w = M<R>::rcp(K_im + K_ii * rt1 * rt1); st4(sp + 28, v4);
+        R K12 = 0, i11 = 0, i12 = 0, i22 = 0;
+        if (np == 2) {
+          const R K11 = K_im + K_ii * rn0 * rn0, K22 = K_im + K_ii * rn1 * rn1;
+          K12 = K_im + K_ii * rn0 * rn1;
+          const R det = K11 * K22 - K12 * K12;
+          if (K11 * K11 < R(100) * det) {
+            meta |= 1 << 30;
+            const R idet = det != 0 ? M<R>::rcp(det) : R(0);
+            i11 = K22 * idet; i12 = -K12 * idet; i22 = K11 * idet;
+          } else {
+            meta = (meta & ~(3 << 16)) | (1 << 16); // ill conditioned: keep the first point only
+          }
         }
-        poolM[np_ * S + s] = key | (np << 16) | (id[0] << 18) | ((np > 1 ? id[1] : 0) << 24);
-        poolO[s] = lane | (cnt << 5);
+        v4.x = 0; v4.y = 0; v4.z = K12; v4.w = i11; st4(sp + 32, v4); // .x .y: restitution bias, set at the top of the step
+        v4.x = i12; v4.y = i22; v4.z = 0; v4.w = 0; st4(sp + 36, v4);
+        v4.x = ck * r0x + sk * r0y; v4.y = -sk * r0x + ck * r0y; v4.z = ck * r1x + sk * r1y; v4.w = -sk * r1x + ck * r1y; st4(sp + 40, v4);
+        poolM[np_ * S + s] = meta;
+        poolO[s] = ol | (cnt << 5);
+        news |= (unsigned)(s + 1) << (8 * cnt);
         if (cnt > lane_rank) lane_rank = cnt;
-        if (ncnt < 4) nlo |= (unsigned)s << (8 * ncnt); else nhi |= (unsigned)s << (8 * (ncnt - 4));
-        ncnt++;
         cnt++;
       }
+      massSlots[mi] = news;
     }
-    clo = nlo; chi = nhi; ccnt = ncnt;
     par ^= 1;
     __syncwarp();
     man_total = min(*poolCnt, S);
     man_rank = __reduce_max_sync(FULL, lane_rank);
+    {
+      const uint4 ms = reinterpret_cast<const uint4*>(massSlots)[lane];
+      touching = valid && (ms.x | ms.y | ms.z | ms.w) != 0;
+    }
   };
 
   detect(); // World.step's first-step detect()
@@ -632,84 +709,70 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
 #define PHASE_SYNC(bit) if ((SCAFF >= 0 ? kSyncMaskDefault : P.sync_mask) & (bit)) __syncthreads(); /* re-align the CTA's warps: shared instruction stream */
     PHASE_SYNC(1)
     t += P.dt;
-    // ---- park cold state in shared memory (phase 1: what neither the constraint initialisation nor the velocity
-    // loop reads: angles, cached polygon, lane origin).  Keeps the live set inside the 168-register budget of 3
-    // warps per SMSP, so no spill sits on the loop's dependency chain (profiles/r1_ncu_summary.md).
-    {
-#pragma unroll
-      for (int k = 0; k < 4; k++) spark[(8 + k) * 32 + lane] = A[k];
-      spark[12 * 32 + lane] = px0; spark[13 * 32 + lane] = px1; spark[14 * 32 + lane] = py0; spark[15 * 32 + lane] = py1;
-      spark[16 * 32 + lane] = pnx; spark[17 * 32 + lane] = pny;
-      spark[18 * 32 + lane] = ox; spark[19 * 32 + lane] = oy;
-      asm volatile("" ::: "memory");
-    }
     // ---- integrate velocities: gravity, then damping ---------------------------------------------
 #pragma unroll
     for (int k = 0; k < 4; k++) {
       VY[k] += gdt;
       VX[k] *= K_lin_f; VY[k] *= K_lin_f; W[k] *= K_ang_f;
     }
-    // ---- contacts: initialise (+ restitution bias from pre-warm-start velocities) -------------------
-#pragma unroll 1
-    for (int e = 0; e < ccnt; e++) {
-      const int s = slot_of(e);
-      int meta = poolM[par * S + s];
-      const int k = (meta >> 14) & 3;
-      const int np = (meta >> 16) & 3;
-      R* sp = pool + s * kPoolStride;
-      const V4<R> pa = ld4(sp + par * kPoolPersist), pb = ld4(sp + par * kPoolPersist + 4);
-      const R xk = SEL4(X, k), yk = SEL4(Y, k), ck = SEL4(CS, k), sk = SEL4(SN, k);
-      const R vxk = SEL4(VX, k), vyk = SEL4(VY, k), wk = SEL4(W, k);
-      const R nx = pa.x, ny = pa.y;
-      // Jacobian rows of a contact point: normal (nx, ny, rn), tangent t = (ny, -nx): (ny, -nx, rt)
-      const R r0x = pa.z - xk, r0y = pa.w - yk, r1x = pb.y - xk, r1y = pb.z - yk;
-      const R rn0 = r0x * ny - r0y * nx, rt0 = -(r0x * nx + r0y * ny);
-      const R rn1 = np > 1 ? r1x * ny - r1y * nx : R(0), rt1 = np > 1 ? -(r1x * nx + r1y * ny) : R(0);
-      const R vn0 = nx * vxk + ny * vyk + rn0 * wk, vn1 = nx * vxk + ny * vyk + rn1 * wk;
-      V4<R> v4;
-      v4.x = rn0; v4.y = rt0; v4.z = M<R>::rcp(K_im + K_ii * rn0 * rn0); v4.w = M<R>::rcp(K_im + K_ii * rt0 * rt0); st4(sp + 24, v4);
-      v4.x = rn1; v4.y = rt1; v4.z = M<R>::rcp(K_im + K_ii * rn1 * rn1); v4.w = M<R>::rcp(K_im + K_ii * rt1 * rt1); st4(sp + 28, v4);
-      R K12 = 0, i11 = 0, i12 = 0, i22 = 0;
-      meta &= ~(1 << 30);
-      if (np == 2) {
-        const R K11 = K_im + K_ii * rn0 * rn0, K22 = K_im + K_ii * rn1 * rn1;
-        K12 = K_im + K_ii * rn0 * rn1;
-        const R det = K11 * K22 - K12 * K12;
-        if (K11 * K11 < R(100) * det) {
-          meta |= 1 << 30;
-          const R idet = det != 0 ? M<R>::rcp(det) : R(0);
-          i11 = K22 * idet; i12 = -K12 * idet; i22 = K11 * idet;
-        } else {
-          meta = (meta & ~(3 << 16)) | (1 << 16); // ill conditioned: keep the first point only
-        }
-      }
-      v4.x = vn0 < -K_rest_vel ? -K_rest_e * vn0 : R(0); v4.y = (np > 1 && vn1 < -K_rest_vel) ? -K_rest_e * vn1 : R(0); v4.z = K12; v4.w = i11;
-      st4(sp + 32, v4);
-      v4.x = i12; v4.y = i22; v4.z = 0; v4.w = 0; st4(sp + 36, v4);
-      v4.x = ck * r0x + sk * r0y; v4.y = -sk * r0x + ck * r0y; v4.z = ck * r1x + sk * r1y; v4.w = -sk * r1x + ck * r1y; st4(sp + 40, v4);
-      poolM[par * S + s] = meta;
-      // warm start of this manifold happens below, after every manifold has sampled the pre-warm-start velocities
-    }
-    // ---- contacts: warm start -------------------------------------------------------------------------
-#pragma unroll 1
-    for (int e = 0; e < ccnt; e++) {
-      const int s = slot_of(e);
-      const int meta = poolM[par * S + s];
-      const int k = (meta >> 14) & 3, np = (meta >> 16) & 3;
-      const R* sp = pool + s * kPoolStride;
-      const V4<R> pa = ld4(sp + par * kPoolPersist), imp = ld4(sp + par * kPoolPersist + 8);
-      const V4<R> j0 = ld4(sp + 24), j1 = ld4(sp + 28);
-      const R nx = pa.x, ny = pa.y;
-      R vxk = SEL4(VX, k), vyk = SEL4(VY, k), wk = SEL4(W, k);
+    // ---- contacts: restitution bias (from the pre-warm-start velocities) + warm start, lane = manifold ----------
+    // (the geometry part of the constraint was built by detect(); cold state X Y A / polygon / origin is parked there too)
+    if (man_total > 0) {
       {
-        const R Jx = nx * imp.x + ny * imp.y, Jy = ny * imp.x - nx * imp.y;
-        vxk += K_im * Jx; vyk += K_im * Jy; wk += K_ii * (j0.x * imp.x + j0.y * imp.y);
+        V4<R> t4;
+        t4.x = VX[0]; t4.y = VX[1]; t4.z = VX[2]; t4.w = VX[3]; stage[0 * 32 + lane] = t4;
+        t4.x = VY[0]; t4.y = VY[1]; t4.z = VY[2]; t4.w = VY[3]; stage[1 * 32 + lane] = t4;
+        t4.x = W[0]; t4.y = W[1]; t4.z = W[2]; t4.w = W[3]; stage[2 * 32 + lane] = t4;
       }
-      if (np > 1) {
-        const R Jx = nx * imp.z + ny * imp.w, Jy = ny * imp.z - nx * imp.w;
-        vxk += K_im * Jx; vyk += K_im * Jy; wk += K_ii * (j1.x * imp.z + j1.y * imp.w);
+      __syncwarp();
+#pragma unroll 1
+      for (int s = lane; s < man_total; s += 32) {
+        const int own = poolO[s], meta = poolM[par * S + s];
+        const int np = (meta >> 16) & 3, mi = (own & 31) * 4 + ((meta >> 14) & 3);
+        R* sp = pool + s * kPoolStride;
+        const V2<R> nn = *reinterpret_cast<const V2<R>*>(sp + par * kPoolPersist);
+        const R rn0 = sp[24], rn1 = sp[28];
+        const R vn = nn.x * stg[mi] + nn.y * stg[128 + mi], wk = stg[256 + mi];
+        const R vn0 = vn + rn0 * wk, vn1 = vn + rn1 * wk;
+        V2<R> vb;
+        vb.x = vn0 < -K_rest_vel ? -K_rest_e * vn0 : R(0);
+        vb.y = (np > 1 && vn1 < -K_rest_vel) ? -K_rest_e * vn1 : R(0);
+        *reinterpret_cast<V2<R>*>(sp + 32) = vb;
       }
-      PUT4(VX, k, vxk) PUT4(VY, k, vyk) PUT4(W, k, wk)
+      __syncwarp();
+#pragma unroll 1
+      for (int pass = 0; pass <= man_rank; pass++) {
+#pragma unroll 1
+        for (int s = lane; s < man_total; s += 32) {
+          const int own = poolO[s];
+          if ((own >> 5) != pass) continue;
+          const int meta = poolM[par * S + s];
+          const int np = (meta >> 16) & 3, mi = (own & 31) * 4 + ((meta >> 14) & 3);
+          const R* sp = pool + s * kPoolStride;
+          const V2<R> nn = *reinterpret_cast<const V2<R>*>(sp + par * kPoolPersist);
+          const V4<R> imp = ld4(sp + par * kPoolPersist + 8);
+          const V2<R> j0 = *reinterpret_cast<const V2<R>*>(sp + 24), j1 = *reinterpret_cast<const V2<R>*>(sp + 28);
+          const R nx = nn.x, ny = nn.y;
+          R vxk = stg[mi], vyk = stg[128 + mi], wk = stg[256 + mi];
+          {
+            const R Jx = nx * imp.x + ny * imp.y, Jy = ny * imp.x - nx * imp.y;
+            vxk += K_im * Jx; vyk += K_im * Jy; wk += K_ii * (j0.x * imp.x + j0.y * imp.y);
+          }
+          if (np > 1) {
+            const R Jx = nx * imp.z + ny * imp.w, Jy = ny * imp.z - nx * imp.w;
+            vxk += K_im * Jx; vyk += K_im * Jy; wk += K_ii * (j1.x * imp.z + j1.y * imp.w);
+          }
+          stg[mi] = vxk; stg[128 + mi] = vyk; stg[256 + mi] = wk;
+        }
+        __syncwarp();
+      }
+      if (touching) {
+        V4<R> t4;
+        t4 = stage[0 * 32 + lane]; VX[0] = t4.x; VX[1] = t4.y; VX[2] = t4.z; VX[3] = t4.w;
+        t4 = stage[1 * 32 + lane]; VY[0] = t4.x; VY[1] = t4.y; VY[2] = t4.z; VY[3] = t4.w;
+        t4 = stage[2 * 32 + lane]; W[0] = t4.x; W[1] = t4.y; W[2] = t4.z; W[3] = t4.w;
+      }
+      __syncwarp(); // the staging area is reused by the velocity loop
     }
     // ---- springs: initialise + warm start ---------------------------------------------------------
     PHASE_SYNC(64)
@@ -818,10 +881,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
     lz_ = -(Cz) * K_w_i2i + ((r2y)*lx_ - (r2x)*ly_) * R(0.5);                             \
   }
 
-    // ---- park phase 2: positions and spring targets (read again only after the velocity loop) ----------------
+    // ---- park the spring targets (read again only after the velocity loop; X Y A were parked by detect()) ---------
     {
-#pragma unroll
-      for (int k = 0; k < 4; k++) { spark[(k) * 32 + lane] = X[k]; spark[(4 + k) * 32 + lane] = Y[k]; }
       spark[20 * 32 + lane] = rest[0]; spark[21 * 32 + lane] = rest[1]; spark[22 * 32 + lane] = rest[2];
       asm volatile("" ::: "memory");
     }
@@ -931,7 +992,6 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
           t4.x = W[0]; t4.y = W[1]; t4.z = W[2]; t4.w = W[3]; stage[2 * 32 + lane] = t4;
         }
         __syncwarp();
-        R* stg = reinterpret_cast<R*>(stage);
 #pragma unroll 1
         for (int pass = 0; pass <= man_rank; pass++) {
 #pragma unroll 1
@@ -998,7 +1058,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
           }
           __syncwarp();
         }
-        if (ccnt) {
+        if (touching) {
           V4<R> t4;
           t4 = stage[0 * 32 + lane]; VX[0] = t4.x; VX[1] = t4.y; VX[2] = t4.z; VX[3] = t4.w;
           t4 = stage[1 * 32 + lane]; VY[0] = t4.x; VY[1] = t4.y; VY[2] = t4.z; VY[3] = t4.w;
@@ -1050,32 +1110,62 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
 #pragma unroll 1
       for (int it = 0; it < P.pos_iters; it++) {
         bool ok = true;
-        // contacts
-        const int ccnt_a = active ? ccnt : 0;
-#pragma unroll 1
-        for (int e = 0; e < ccnt_a; e++) {
-          const int s = slot_of(e);
-          const int meta = poolM[par * S + s];
-          const int k = (meta >> 14) & 3, np = (meta >> 16) & 3;
-          R xk = SEL4(X, k), yk = SEL4(Y, k), ak = SEL4(A, k), ck = SEL4(CS, k), sk = SEL4(SN, k);
-          const R* sp = pool + s * kPoolStride;
-          const V4<R> pa = ld4(sp + par * kPoolPersist), pb = ld4(sp + par * kPoolPersist + 4), pl = ld4(sp + 40);
-          const R nx = pa.x, ny = pa.y;
-          for (int q = 0; q < np; q++) {
-            const R lx = q == 0 ? pl.x : pl.z, ly = q == 0 ? pl.y : pl.w;
-            const R cpx = q == 0 ? pa.z : pb.y, cpy = q == 0 ? pa.w : pb.z, cdp = q == 0 ? pb.x : pb.w;
-            const R rx = ck * lx - sk * ly, ry = sk * lx + ck * ly;
-            const R sep = nx * (xk + rx - cpx) + ny * (yk + ry - cpy) - cdp;
-            if (sep < -R(3) * K_lin_tol) ok = false;
-            R C = K_baum * (sep + K_lin_tol);
-            C = M<R>::min_(C, R(0));
-            C = M<R>::max_(C, -K_max_corr);
-            const R rn_ = rx * ny - ry * nx;
-            const R l_ = -C * M<R>::rcp(K_im + K_ii * rn_ * rn_);
-            xk += K_im * nx * l_; yk += K_im * ny * l_;
-            M<R>::rotate(ak, ck, sk, K_ii * rn_ * l_);
+        // contacts, lane = manifold: the masses' poses travel through shared memory (X Y A in the staging area, CS SN in
+        // the spring-bias area, which is dead outside the velocity loop); rank passes keep the manifolds of one mass in order
+        if (man_total > 0) {
+          V4<R>* pcs = reinterpret_cast<V4<R>*>(sbias);
+          R* pc = sbias;
+          {
+            V4<R> t4;
+            t4.x = X[0]; t4.y = X[1]; t4.z = X[2]; t4.w = X[3]; stage[0 * 32 + lane] = t4;
+            t4.x = Y[0]; t4.y = Y[1]; t4.z = Y[2]; t4.w = Y[3]; stage[1 * 32 + lane] = t4;
+            t4.x = A[0]; t4.y = A[1]; t4.z = A[2]; t4.w = A[3]; stage[2 * 32 + lane] = t4;
+            t4.x = CS[0]; t4.y = CS[1]; t4.z = CS[2]; t4.w = CS[3]; pcs[0 * 32 + lane] = t4;
+            t4.x = SN[0]; t4.y = SN[1]; t4.z = SN[2]; t4.w = SN[3]; pcs[1 * 32 + lane] = t4;
           }
-          PUT4(X, k, xk) PUT4(Y, k, yk) PUT4(A, k, ak) PUT4(CS, k, ck) PUT4(SN, k, sk)
+          const unsigned actm = __ballot_sync(FULL, active);
+          __syncwarp();
+          unsigned mybad = 0;
+#pragma unroll 1
+          for (int pass = 0; pass <= man_rank; pass++) {
+#pragma unroll 1
+            for (int s = lane; s < man_total; s += 32) {
+              const int own = poolO[s];
+              if ((own >> 5) != pass || !((actm >> (own & 31)) & 1u)) continue;
+              const int meta = poolM[par * S + s];
+              const int np = (meta >> 16) & 3, mi = (own & 31) * 4 + ((meta >> 14) & 3);
+              R xk = stg[mi], yk = stg[128 + mi], ak = stg[256 + mi], ck = pc[mi], sk = pc[128 + mi];
+              const R* sp = pool + s * kPoolStride;
+              const V4<R> pa = ld4(sp + par * kPoolPersist), pb = ld4(sp + par * kPoolPersist + 4), pl = ld4(sp + 40);
+              const R nx = pa.x, ny = pa.y;
+              for (int q = 0; q < np; q++) {
+                const R lx = q == 0 ? pl.x : pl.z, ly = q == 0 ? pl.y : pl.w;
+                const R cpx = q == 0 ? pa.z : pb.y, cpy = q == 0 ? pa.w : pb.z, cdp = q == 0 ? pb.x : pb.w;
+                const R rx = ck * lx - sk * ly, ry = sk * lx + ck * ly;
+                const R sep = nx * (xk + rx - cpx) + ny * (yk + ry - cpy) - cdp;
+                if (sep < -R(3) * K_lin_tol) mybad |= 1u << (own & 31);
+                R C = K_baum * (sep + K_lin_tol);
+                C = M<R>::min_(C, R(0));
+                C = M<R>::max_(C, -K_max_corr);
+                const R rn_ = rx * ny - ry * nx;
+                const R l_ = -C * M<R>::rcp(K_im + K_ii * rn_ * rn_);
+                xk += K_im * nx * l_; yk += K_im * ny * l_;
+                M<R>::rotate(ak, ck, sk, K_ii * rn_ * l_);
+              }
+              stg[mi] = xk; stg[128 + mi] = yk; stg[256 + mi] = ak; pc[mi] = ck; pc[128 + mi] = sk;
+            }
+            __syncwarp();
+          }
+          if ((__reduce_or_sync(FULL, mybad) >> lane) & 1u) ok = false;
+          if (touching && active) {
+            V4<R> t4;
+            t4 = stage[0 * 32 + lane]; X[0] = t4.x; X[1] = t4.y; X[2] = t4.z; X[3] = t4.w;
+            t4 = stage[1 * 32 + lane]; Y[0] = t4.x; Y[1] = t4.y; Y[2] = t4.z; Y[3] = t4.w;
+            t4 = stage[2 * 32 + lane]; A[0] = t4.x; A[1] = t4.y; A[2] = t4.z; A[3] = t4.w;
+            t4 = pcs[0 * 32 + lane]; CS[0] = t4.x; CS[1] = t4.y; CS[2] = t4.z; CS[3] = t4.w;
+            t4 = pcs[1 * 32 + lane]; SN[0] = t4.x; SN[1] = t4.y; SN[2] = t4.z; SN[3] = t4.w;
+          }
+          __syncwarp();
         }
         // ropes
         if (warp_rope) {
@@ -1200,7 +1290,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
           for (int i = 0; i < 4; i++) { const int j = (i + 1) & 3; a2 += qx[i] * qy[j] - qx[j] * qy[i]; }
           raw0 = M<R>::abs_(a2) * K_inv_area2;
         } else if (sk.kind == VSR_SENSOR_TOUCH) {
-          raw0 = ccnt ? R(1) : R(0);
+          raw0 = touching ? R(1) : R(0);
         } else {
           if (!have_ang) {
             vang = (M<R>::atan2_(Y[1] - Y[0], X[1] - X[0]) + M<R>::atan2_(Y[2] - Y[3], X[2] - X[3])) * R(0.5);
