@@ -3,11 +3,9 @@ usage: python tools/ncu_by_line.py <report.ncu-rep> <mangled-kernel-substring> <
 import collections, csv, glob, io, os, re, subprocess, sys, tempfile
 rep, sub, per = sys.argv[1], sys.argv[2], float(sys.argv[3])
 bucket = int(sys.argv[4]) if len(sys.argv) > 4 else 1
-so = os.path.join(os.path.dirname(__file__), "..", "vsrevolution_b200", "libvsr_eval.so")
-d = tempfile.mkdtemp()
-subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=d, stdout=subprocess.DEVNULL)
-cub = [f for f in glob.glob(d + "/*.cubin") if "names" not in f][0]
-txt = subprocess.run(["nvdisasm", "--print-line-info", cub], capture_output=True, text=True).stdout.splitlines()
+sys.path.insert(0, os.path.dirname(__file__))
+from _sass import kernel_sass
+txt = kernel_sass(sub)
 inside = False; cur = None; line_of = {}
 for line in txt:
     if line.startswith(".text."): inside = sub in line; continue

@@ -331,6 +331,8 @@ int finalize(vsr_ctx* ctx) {
   o = (o + 31) & ~size_t(31);
   k.off_nrm = (int)o;
   o = align16(o + (size_t)2 * 32 * 4 * rs);
+  k.off_rope = (int)o;
+  o = align16(o + (size_t)2 * 32 * 4 * rs);
   k.off_park = (int)o;
   o = align16(o + (size_t)vsr::kPark * 32 * rs);
   k.off_cold = (int)o;

@@ -30,20 +30,22 @@ constexpr int kMaxVox = 32;
 constexpr int kMaxSensors = 6;
 constexpr int kMaxLayers = 8;
 constexpr int kMaxMan = 3;       // manifolds per corner mass (ground polygons it can touch at once)
-constexpr int kMaxLaneMan = 8;   // manifolds per voxel
 constexpr int kMaxAvg = 6;       // averaged readings per voxel
-constexpr int kPoolPersist = 12;
-constexpr int kPoolSolve = 24;
 constexpr int kPark = 23;         // X Y A (12) + polygon cache (6) + origin (2) + rest (3)
-// contact-pool slot (R words), 16-byte aligned vectors; stride 44 = 4 x odd -> 128-bit accesses of 8 consecutive slots hit
-// all 32 banks once.  Persistent half p (double-buffered for warm starting) at 12*p:
-//   [0..3] nx ny px0 py0 | [4..7] d0 px1 py1 d1 | [8..11] jn0 jt0 jn1 jt1
-// solver half at 24 (rebuilt every step by the contact initialisation; Jacobian rows rn = r x n, rt = r x t):
-//   [24..27] rn0 rt0 mN0 mT0 | [28..31] rn1 rt1 mN1 mT1 | [32..35] vb0 vb1 K12 iK11 | [36..39] iK12 iK22 - - | [40..43] lx0 ly0 lx1 ly1
-constexpr int kPoolStride = 44;
+// contact-pool slot (36 R words, 16-byte aligned vectors; stride 36 = 4 x odd -> 128-bit accesses of 8 consecutive slots
+// hit all 32 banks once):
+//   geometry (rebuilt by every detect):   [0..3] nx ny px0 py0 | [4..7] d0 px1 py1 d1
+//   accumulated impulses, double-buffered by detect parity p for warm starting:   [8 + 4p .. 11 + 4p] jn0 jt0 jn1 jt1
+//   solver part (Jacobian rows rn = r x n, rt = r x t):   [16..19] rn0 rt0 mN0 mT0 | [20..23] rn1 rt1 mN1 mT1 |
+//   [24..27] vb0 vb1 K12 iK11 | [28..31] iK12 iK22 - - | [32..35] lx0 ly0 lx1 ly1
+constexpr int kPI = 8, kPS = 16;
+constexpr int kPoolStride = 36;
 // phase-alignment barriers of the specialised build (bits: KParams::sync_mask): step start, before the velocity loop, before
 // the position phase, before / after detect (tools/bench sweep); the generic build reads the mask from P (tuning only)
-constexpr int kSyncMaskDefault = 59;
+#ifndef VSR_SYNC_MASK_DEFAULT
+#define VSR_SYNC_MASK_DEFAULT 59
+#endif
+constexpr int kSyncMaskDefault = VSR_SYNC_MASK_DEFAULT;
 
 struct SensorK {
   int kind, axes, rotated, soft_norm;
@@ -105,7 +107,7 @@ struct KParams {
   // shared-memory layout (bytes from the CTA's dynamic smem base; per warp strides)
   int pool_slots;
   int smem_warp_stride; // bytes per warp
-  int off_pool_p, off_pool_m, off_pool_cnt, off_w, off_act, off_sig, off_bias, off_arm, off_eff, off_nrm, off_park, off_cold, off_stage, off_pool_o, off_mslots;
+  int off_pool_p, off_pool_m, off_pool_cnt, off_w, off_act, off_sig, off_bias, off_arm, off_eff, off_nrm, off_park, off_cold, off_stage, off_pool_o, off_mslots, off_rope;
   int sync_mask; // phase-alignment barriers (bit0 step start, bit1 before velocity loop, bit2 every velocity
                  // iteration, bit3 before position phase, bit4 before detect, bit5 before sensing, bit6 before spring
                  // init, bit7 before weld init, bit8 after the velocity loop, bit9 after the position phase, bit10 after control)
@@ -383,6 +385,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
   R* spark = reinterpret_cast<R*>(wsm + P.off_park);       // [kPark][32] cold state parked across the velocity loop
   V2<R>* seff = reinterpret_cast<V2<R>*>(wsm + P.off_eff);   // [8][32] effective masses E of springs 0..15, pairs packed
   V4<R>* snrm = reinterpret_cast<V4<R>*>(wsm + P.off_nrm);   // [2][32] unit normals of springs 12..15 (pairs 6, 7): register relief
+  V4<R>* srope = reinterpret_cast<V4<R>*>(wsm + P.off_rope); // [2][32] unit normals of the 4 contraction-limit ropes
   V4<R>* sarm = reinterpret_cast<V4<R>*>(wsm + P.off_arm); // [8][32] spring lever arms (r x n) of springs 0..15, pairs packed
   const int S = P.pool_slots;
 
@@ -645,7 +648,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
           const int ometa = poolM[par * S + os];
           if ((ometa & 0xffff) != key) continue;
           const int onp = (ometa >> 16) & 3;
-          const V4<R> oi = ld4(pool + os * kPoolStride + par * kPoolPersist + 8);
+          const V4<R> oi = ld4(pool + os * kPoolStride + kPI + 4 * par);
           for (int r = 0; r < onp; r++) {
             const int oidr = (ometa >> (18 + 6 * r)) & 63;
             const R ojn = r == 0 ? oi.x : oi.z, ojt = r == 0 ? oi.y : oi.w;
@@ -655,17 +658,17 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
         }
         R* sp = pool + s * kPoolStride;
         V4<R> v4;
-        v4.x = nx; v4.y = ny; v4.z = px[0]; v4.w = py[0]; st4(sp + np_ * kPoolPersist, v4);
-        v4.x = dp[0]; v4.y = np > 1 ? px[1] : R(0); v4.z = np > 1 ? py[1] : R(0); v4.w = np > 1 ? dp[1] : R(0); st4(sp + np_ * kPoolPersist + 4, v4);
-        v4.x = jn0; v4.y = jt0; v4.z = jn1; v4.w = jt1; st4(sp + np_ * kPoolPersist + 8, v4);
+        v4.x = nx; v4.y = ny; v4.z = px[0]; v4.w = py[0]; st4(sp, v4);
+        v4.x = dp[0]; v4.y = np > 1 ? px[1] : R(0); v4.z = np > 1 ? py[1] : R(0); v4.w = np > 1 ? dp[1] : R(0); st4(sp + 4, v4);
+        v4.x = jn0; v4.y = jt0; v4.z = jn1; v4.w = jt1; st4(sp + kPI + 4 * np_, v4);
         // geometry part of the contact constraint (ContactConstraint initialisation): Jacobian rows of a contact point:
         // normal (nx, ny, rn), tangent t = (ny, -nx): (ny, -nx, rt)
         int meta = key | (np << 16) | (id[0] << 18) | ((np > 1 ? id[1] : 0) << 24);
         const R r0x = px[0] - xk, r0y = py[0] - yk, r1x = np > 1 ? px[1] - xk : -xk, r1y = np > 1 ? py[1] - yk : -yk;
         const R rn0 = r0x * ny - r0y * nx, rt0 = -(r0x * nx + r0y * ny);
         const R rn1 = np > 1 ? r1x * ny - r1y * nx : R(0), rt1 = np > 1 ? -(r1x * nx + r1y * ny) : R(0);
-        v4.x = rn0; v4.y = rt0; v4.z = M<R>::rcp(K_im + K_ii * rn0 * rn0); v4.w = M<R>::rcp(K_im + K_ii * rt0 * rt0); st4(sp + 24, v4);
-        v4.x = rn1; v4.y = rt1; v4.z = M<R>::rcp(K_im + K_ii * rn1 * rn1); v4.w = M<R>::rcp(K_im + K_ii * rt1 * rt1); st4(sp + 28, v4);
+        v4.x = rn0; v4.y = rt0; v4.z = M<R>::rcp(K_im + K_ii * rn0 * rn0); v4.w = M<R>::rcp(K_im + K_ii * rt0 * rt0); st4(sp + kPS, v4);
+        v4.x = rn1; v4.y = rt1; v4.z = M<R>::rcp(K_im + K_ii * rn1 * rn1); v4.w = M<R>::rcp(K_im + K_ii * rt1 * rt1); st4(sp + kPS + 4, v4);
         R K12 = 0, i11 = 0, i12 = 0, i22 = 0;
         if (np == 2) {
           const R K11 = K_im + K_ii * rn0 * rn0, K22 = K_im + K_ii * rn1 * rn1;
@@ -679,9 +682,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
             meta = (meta & ~(3 << 16)) | (1 << 16); // ill conditioned: keep the first point only
           }
         }
-        v4.x = 0; v4.y = 0; v4.z = K12; v4.w = i11; st4(sp + 32, v4); // .x .y: restitution bias, set at the top of the step
-        v4.x = i12; v4.y = i22; v4.z = 0; v4.w = 0; st4(sp + 36, v4);
-        v4.x = ck * r0x + sk * r0y; v4.y = -sk * r0x + ck * r0y; v4.z = ck * r1x + sk * r1y; v4.w = -sk * r1x + ck * r1y; st4(sp + 40, v4);
+        v4.x = 0; v4.y = 0; v4.z = K12; v4.w = i11; st4(sp + kPS + 8, v4); // .x .y: restitution bias, set at the top of the step
+        v4.x = i12; v4.y = i22; v4.z = 0; v4.w = 0; st4(sp + kPS + 12, v4);
+        v4.x = ck * r0x + sk * r0y; v4.y = -sk * r0x + ck * r0y; v4.z = ck * r1x + sk * r1y; v4.w = -sk * r1x + ck * r1y; st4(sp + kPS + 16, v4);
         poolM[np_ * S + s] = meta;
         poolO[s] = ol | (cnt << 5);
         news |= (unsigned)(s + 1) << (8 * cnt);
@@ -730,14 +733,14 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
         const int own = poolO[s], meta = poolM[par * S + s];
         const int np = (meta >> 16) & 3, mi = (own & 31) * 4 + ((meta >> 14) & 3);
         R* sp = pool + s * kPoolStride;
-        const V2<R> nn = *reinterpret_cast<const V2<R>*>(sp + par * kPoolPersist);
-        const R rn0 = sp[24], rn1 = sp[28];
+        const V2<R> nn = *reinterpret_cast<const V2<R>*>(sp);
+        const R rn0 = sp[kPS], rn1 = sp[kPS + 4];
         const R vn = nn.x * stg[mi] + nn.y * stg[128 + mi], wk = stg[256 + mi];
         const R vn0 = vn + rn0 * wk, vn1 = vn + rn1 * wk;
         V2<R> vb;
         vb.x = vn0 < -K_rest_vel ? -K_rest_e * vn0 : R(0);
         vb.y = (np > 1 && vn1 < -K_rest_vel) ? -K_rest_e * vn1 : R(0);
-        *reinterpret_cast<V2<R>*>(sp + 32) = vb;
+        *reinterpret_cast<V2<R>*>(sp + kPS + 8) = vb;
       }
       __syncwarp();
 #pragma unroll 1
@@ -749,9 +752,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
           const int meta = poolM[par * S + s];
           const int np = (meta >> 16) & 3, mi = (own & 31) * 4 + ((meta >> 14) & 3);
           const R* sp = pool + s * kPoolStride;
-          const V2<R> nn = *reinterpret_cast<const V2<R>*>(sp + par * kPoolPersist);
-          const V4<R> imp = ld4(sp + par * kPoolPersist + 8);
-          const V2<R> j0 = *reinterpret_cast<const V2<R>*>(sp + 24), j1 = *reinterpret_cast<const V2<R>*>(sp + 28);
+          const V2<R> nn = *reinterpret_cast<const V2<R>*>(sp);
+          const V4<R> imp = ld4(sp + kPI + 4 * par);
+          const V2<R> j0 = *reinterpret_cast<const V2<R>*>(sp + kPS), j1 = *reinterpret_cast<const V2<R>*>(sp + kPS + 4);
           const R nx = nn.x, ny = nn.y;
           R vxk = stg[mi], vyk = stg[128 + mi], wk = stg[256 + mi];
           {
@@ -815,6 +818,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
     // ---- ropes: initialise + warm start -------------------------------------------------------------
     bool ract[4];
     bool any_rope = false;
+    V4<R> rn4;
 #define ROPE_INIT(i, a, b)                                                                  \
   {                                                                                         \
     R nx = X[a] - X[b], ny = Y[a] - Y[b];                                                   \
@@ -823,6 +827,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
     const R len = l2 * il;                                                                  \
     if (!(len >= K_lin_tol)) { nx = 0; ny = 0; } else { nx *= il; ny *= il; }                 \
     ract[i] = P.limit_contraction && len < K_rope_lower;                                      \
+    if (((i) & 1) == 0) { rn4.x = nx; rn4.y = ny; } else { rn4.z = nx; rn4.w = ny; srope[((i) >> 1) * 32 + lane] = rn4; } \
     if (!ract[i]) rimp[i] = 0;                                                              \
     const R m_ = rimp[i] * K_im;                                                              \
     VX[a] += nx * m_; VY[a] += ny * m_; VX[b] -= nx * m_; VY[b] -= ny * m_;                 \
@@ -928,16 +933,14 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
       if (warp_rope) {
 #define ROPE_SOLVE(i, a, b)                                                        \
   if (ract[i]) {                                                                   \
-    R rnx_ = spark[(a) * 32 + lane] - spark[(b) * 32 + lane], rny_ = spark[(4 + a) * 32 + lane] - spark[(4 + b) * 32 + lane]; \
-    { const R l2_ = rnx_ * rnx_ + rny_ * rny_; const R il_ = M<R>::rsqrt_(l2_);                    \
-      if (!(l2_ * il_ >= K_lin_tol)) { rnx_ = 0; rny_ = 0; } else { rnx_ *= il_; rny_ *= il_; } }  \
-    const R jv = rnx_ * (VX[a] - VX[b]) + rny_ * (VY[a] - VY[b]);                  \
+    const V2<R> n_ = *reinterpret_cast<const V2<R>*>(reinterpret_cast<const R*>(srope + ((i) >> 1) * 32 + lane) + ((i) & 1) * 2); \
+    const R jv = n_.x * (VX[a] - VX[b]) + n_.y * (VY[a] - VY[b]);                  \
     R l_ = -K_rope_E * jv;                                                           \
     const R old = rimp[i];                                                         \
     rimp[i] = M<R>::max_(old + l_, R(0));                                          \
     l_ = rimp[i] - old;                                                            \
     const R m_ = l_ * K_im;                                                          \
-    VX[a] += rnx_ * m_; VY[a] += rny_ * m_; VX[b] -= rnx_ * m_; VY[b] -= rny_ * m_;         \
+    VX[a] += n_.x * m_; VY[a] += n_.y * m_; VX[b] -= n_.x * m_; VY[b] -= n_.y * m_;         \
   }
         VSR_ROPES(ROPE_SOLVE)
 #undef ROPE_SOLVE
@@ -1003,9 +1006,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
             const int mi = (own & 31) * 4 + ((meta >> 14) & 3); // corner mass = owner lane * 4 + k
             R vxk = stg[mi], vyk = stg[128 + mi], wk = stg[256 + mi];
             R* sp = pool + s * kPoolStride;
-            const V2<R> nn = *reinterpret_cast<const V2<R>*>(sp + par * kPoolPersist);
-            V4<R> imp = ld4(sp + par * kPoolPersist + 8);
-            const V4<R> j0 = ld4(sp + 24), j1 = ld4(sp + 28), cc = ld4(sp + 32);
+            const V2<R> nn = *reinterpret_cast<const V2<R>*>(sp);
+            V4<R> imp = ld4(sp + kPI + 4 * par);
+            const V4<R> j0 = ld4(sp + kPS), j1 = ld4(sp + kPS + 4), cc = ld4(sp + kPS + 8);
             const R nx = nn.x, ny = nn.y;
             // friction rows first (tangent t = (ny, -nx)), clamped by mu * (accumulated normal impulse)
             {
@@ -1031,7 +1034,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
               const R a_ = K_im * l_;
               vxk += a_ * nx; vyk += a_ * ny; wk += (K_ii * l_) * j0.x;
             } else { // 2-point block solver
-              const V2<R> ik = *reinterpret_cast<const V2<R>*>(sp + 36);
+              const V2<R> ik = *reinterpret_cast<const V2<R>*>(sp + kPS + 12);
               const R a1 = imp.x, a2 = imp.z, K12 = cc.z;
               const R vn1 = nx * vxk + ny * vyk + j0.x * wk, vn2 = nx * vxk + ny * vyk + j1.x * wk;
               const R K11 = K_im + K_ii * j0.x * j0.x, K22 = K_im + K_ii * j1.x * j1.x;
@@ -1053,7 +1056,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
               const R a_ = K_im * (d1 + d2);
               vxk += a_ * nx; vyk += a_ * ny; wk += K_ii * (j0.x * d1 + j1.x * d2);
             }
-            st4(sp + par * kPoolPersist + 8, imp);
+            st4(sp + kPI + 4 * par, imp);
             stg[mi] = vxk; stg[128 + mi] = vyk; stg[256 + mi] = wk;
           }
           __syncwarp();
@@ -1136,7 +1139,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
               const int np = (meta >> 16) & 3, mi = (own & 31) * 4 + ((meta >> 14) & 3);
               R xk = stg[mi], yk = stg[128 + mi], ak = stg[256 + mi], ck = pc[mi], sk = pc[128 + mi];
               const R* sp = pool + s * kPoolStride;
-              const V4<R> pa = ld4(sp + par * kPoolPersist), pb = ld4(sp + par * kPoolPersist + 4), pl = ld4(sp + 40);
+              const V4<R> pa = ld4(sp), pb = ld4(sp + 4), pl = ld4(sp + kPS + 16);
               const R nx = pa.x, ny = pa.y;
               for (int q = 0; q < np; q++) {
                 const R lx = q == 0 ? pl.x : pl.z, ly = q == 0 ? pl.y : pl.w;
