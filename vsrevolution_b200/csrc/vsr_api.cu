@@ -15,13 +15,14 @@
 
 namespace {
 
-// launch shapes (warps per CTA, min CTAs per SM -> register cap): 0/2 = 255 registers, 8 warps/SM (no spills, best
-// per-warp latency, 3552 bipeds per wave); 1/3 = 168 registers, 10 warps/SM (4440 bipeds per wave; default).
+// launch shapes (warps per CTA, min CTAs per SM -> register cap): 0/2 = 255 registers, 8 warps/SM (3552 bipeds per wave);
+// 1/3 = 168 registers, 10 warps/SM (4440 bipeds per wave).  Default 3: ONE CTA of 10 warps per SM, so that all resident
+// warps are phase-aligned by the same barriers and share one instruction stream.
 // VSR_LAUNCH_SHAPE overrides (tuning only).
 struct Shape { int warps, minb; };
 constexpr Shape kShapes[] = {{4, 2}, {5, 2}, {8, 1}, {10, 1}};
 constexpr int kNumShapes = sizeof(kShapes) / sizeof(kShapes[0]);
-constexpr int kDefaultShape = 1;
+constexpr int kDefaultShape = 3;
 
 thread_local std::string g_create_error;
 
@@ -174,7 +175,8 @@ int finalize(vsr_ctx* ctx) {
     c.c_sp_sigma = (float)k.sp_sigma; c.c_sp_boversig = (float)(k.sp_beta / k.sp_sigma); c.c_sp_cfrac = (float)k.sp_cfrac;
     c.c_rope_lower = (float)k.rope_lower; c.c_rope_E = (float)(1.0 / (2.0 * k.inv_m));
     c.c_wa = (float)m; c.c_wA = (float)(2.0 * k.inv_m); c.c_wh = (float)(0.5 * k.inv_i);
-    c.c_wD = (float)(1.0 / ((2.0 * k.inv_m) * (2.0 * k.inv_m + 0.5 * k.inv_i * m * m)));
+    c.c_wDA = (float)(1.0 / (2.0 * k.inv_m + 0.5 * k.inv_i * m * m));
+    c.c_wDh = (float)((0.5 * k.inv_i) / ((2.0 * k.inv_m) * (2.0 * k.inv_m + 0.5 * k.inv_i * m * m)));
     c.c_w_i2i = (float)(1.0 / (2.0 * k.inv_i));
     c.c_rest_vel = (float)k.rest_vel; c.c_rest_e = (float)k.rest_e;
     c.c_max_trans = (float)k.max_trans; c.c_max_trans2 = (float)(k.max_trans * k.max_trans); c.c_max_rot = (float)k.max_rot;
@@ -339,13 +341,13 @@ int finalize(vsr_ctx* ctx) {
   o = align16(o + (size_t)navg * 32 * 12); // Average running sums + counts
   o = (o + 31) & ~size_t(31);
   k.smem_warp_stride = (int)o;
-  k.sync_mask = 59; // step start, before velocity loop, before position phase, before/after detect (tools/bench sweep)
+  k.sync_mask = 115; // step start, before spring init, before velocity loop, before/after detect (tools/ab_run.sh sweeps)
   if (const char* ev = std::getenv("VSR_SYNC_MASK")) k.sync_mask = std::atoi(ev);
   // launch shape: 2 CTAs x 5 warps (168 registers, 10 warps/SM) when their shared memory fits an SM; otherwise one CTA of
   // 8 warps (255 registers) -- e.g. narrow-step terrains with their larger contact pool
   const size_t smem_sm = 228 * 1024 - 2 * 1024; // 228 KB per SM, 1 KB reserved per resident CTA
   ctx->shape = kDefaultShape;
-  if (2 * 5 * o > smem_sm && 8 * o + 1024 <= 227 * 1024) ctx->shape = 2;
+  if (10 * o + 1024 > 227 * 1024 && 8 * o + 1024 <= 227 * 1024) ctx->shape = 2;
   if (const char* ev = std::getenv("VSR_LAUNCH_SHAPE")) ctx->shape = std::max(0, std::min(kNumShapes - 1, std::atoi(ev)));
   ctx->warps = e.precision == 64 ? kWarps64 : kShapes[ctx->shape].warps;
   ctx->kernel = kernel_ptr(e.precision, ctx->kind, ctx->shape, e.scaffolding_mask == 0xF && !std::getenv("VSR_GENERIC_SCAFF"));

@@ -41,9 +41,10 @@ constexpr int kPark = 23;         // X Y A (12) + polygon cache (6) + origin (2)
 constexpr int kPI = 8, kPS = 16;
 constexpr int kPoolStride = 36;
 // phase-alignment barriers of the specialised build (bits: KParams::sync_mask): step start, before the velocity loop, before
-// the position phase, before / after detect (tools/bench sweep); the generic build reads the mask from P (tuning only)
+// the spring initialisation, before / after detect (tools/ab_run.sh sweeps on B200, one 10-warp CTA per SM); the generic
+// build reads the mask from P (tuning only)
 #ifndef VSR_SYNC_MASK_DEFAULT
-#define VSR_SYNC_MASK_DEFAULT 59
+#define VSR_SYNC_MASK_DEFAULT 115
 #endif
 constexpr int kSyncMaskDefault = VSR_SYNC_MASK_DEFAULT;
 
@@ -58,7 +59,7 @@ struct SensorK {
 // (no double->float conversion, no long-lived register)
 struct KConstF {
   float c_dt, c_half, c_im, c_ii, c_mu, c_lin_tol, c_ang_tol, c_max_corr, c_baum, c_gdt, c_lin_f, c_ang_f, c_sp_sigma, c_sp_boversig,
-      c_sp_cfrac, c_rope_lower, c_rope_E, c_wa, c_wA, c_wh, c_wD, c_w_i2i, c_rest_vel, c_rest_e, c_max_trans, c_max_trans2, c_max_rot,
+      c_sp_cfrac, c_rope_lower, c_rope_E, c_wa, c_wA, c_wh, c_wDA, c_wDh, c_w_i2i, c_rest_vel, c_rest_e, c_max_trans, c_max_trans2, c_max_rot,
       c_inv_area2, c_mass_off, c_base_pad;
   float c_range_min[3], c_range_rest[3], c_range_max[3];
 };
@@ -372,6 +373,7 @@ template <class R, int CTRL, int WARPS, int MINB, int SCAFF = -1>
 __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __grid_constant__ KParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gw = blockIdx.x * WARPS + warp; // global robot-warp
   unsigned char* wsm = smem_raw + (size_t)warp * P.smem_warp_stride;
   R* pool = reinterpret_cast<R*>(wsm + P.off_pool_p);      // [S][kPoolStride]: persist[2][12], solve[20]
   int* poolM = reinterpret_cast<int*>(wsm + P.off_pool_m); // [2][S]
@@ -393,10 +395,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
   const int rw = lane / L;                     // robot slot inside the warp
   const int v = lane - rw * L;                 // voxel index inside the robot
   const bool lane_used = rw < P.robots_per_warp;
-  const int robot = (blockIdx.x * WARPS + warp) * P.robots_per_warp + rw;
+  const int robot = gw * P.robots_per_warp + rw;
   const bool valid = lane_used && robot < P.n_robots;
   const int base_lane = rw * L;
-  const int gl = (blockIdx.x * WARPS + warp) * 32 + lane; // global lane (history ring column)
+  const int gl = gw * 32 + lane; // global lane (history ring column)
   const int total_lanes = gridDim.x * WARPS * 32;
 
   // neighbours as lane ids packed in one register (self when absent, so shuffles stay in range) + validity bits
@@ -439,7 +441,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
 #define K_wa KC(wa, P.weld_anchor)
 #define K_wA KC(wA, 2.0 * P.inv_m)
 #define K_wh KC(wh, 0.5 * P.inv_i)
-#define K_wD KC(wD, 1.0 / ((2.0 * P.inv_m) * (2.0 * P.inv_m + 0.5 * P.inv_i * P.weld_anchor * P.weld_anchor)))
+#define K_wDA KC(wDA, 1.0 / (2.0 * P.inv_m + 0.5 * P.inv_i * P.weld_anchor * P.weld_anchor))
+#define K_wDh KC(wDh, (0.5 * P.inv_i) / ((2.0 * P.inv_m) * (2.0 * P.inv_m + 0.5 * P.inv_i * P.weld_anchor * P.weld_anchor)))
 #define K_w_i2i KC(w_i2i, 1.0 / (2.0 * P.inv_i))
 #define K_rest_vel KC(rest_vel, P.rest_vel)
 #define K_rest_e KC(rest_e, P.rest_e)
@@ -486,7 +489,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
   } else {
     // K2 genome upload: the warp's robots are consecutive rows -> one contiguous range of doubles,
     // read with 128-bit loads (double2) after a scalar head for 16-byte alignment.
-    const int r0 = (blockIdx.x * WARPS + warp) * P.robots_per_warp;
+    const int r0 = gw * P.robots_per_warp;
     int nr = P.n_robots - r0;
     nr = nr < 0 ? 0 : (nr > P.robots_per_warp ? P.robots_per_warp : nr);
     const size_t first = (size_t)r0 * P.genome_len, count = (size_t)nr * P.genome_len;
@@ -877,12 +880,13 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
       if (un >= 0) { VX[0] += e0; VY[0] += e1; W[0] += e2; VX[1] += f0; VY[1] += f1; W[1] += f2; }
     }
     // solve K l = -C for a weld with r1 = 0 and partner arm (r2x, r2y)
+    // (the 2x2 block left after eliminating the angular row is D * (A I + h r2 r2^T), so no matrix entries are formed)
 #define WELD_SOLVE(r2x, r2y, Cx, Cy, Cz, lx_, ly_, lz_)                                  \
   {                                                                                     \
     const R bx_ = -(Cx) - (r2y) * (Cz) * R(0.5), by_ = -(Cy) + (r2x) * (Cz) * R(0.5);   \
-    const R k00 = K_wA + K_wh * (r2x) * (r2x), k01 = K_wh * (r2x) * (r2y), k11 = K_wA + K_wh * (r2y) * (r2y); \
-    lx_ = K_wD * (k00 * bx_ + k01 * by_);                                                 \
-    ly_ = K_wD * (k01 * bx_ + k11 * by_);                                                 \
+    const R hd_ = K_wDh * ((r2x) * bx_ + (r2y) * by_);                                  \
+    lx_ = K_wDA * bx_ + hd_ * (r2x);                                                    \
+    ly_ = K_wDA * by_ + hd_ * (r2y);                                                    \
     lz_ = -(Cz) * K_w_i2i + ((r2y)*lx_ - (r2x)*ly_) * R(0.5);                             \
   }
 
@@ -896,8 +900,6 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
 #pragma unroll 1
     for (int it = 0; it < P.vel_iters; it++) {
       PHASE_SYNC(4)
-#pragma unroll
-      for (int i = 0; i < 4; i++) { opaque(wr2x[i]); opaque(wr2y[i]); } // keep the weld K terms out of long-lived registers
       // springs: lambda' = E*Jv + sigma*(impulse + bias/sigma); impulse' -= lambda'  (DESIGN.md 4.2).
       // Two body-disjoint springs are solved side by side (explicit ILP 2: the lane's dependency chain is
       // the bottleneck, not the FMA pipe); one LDS.128 brings both springs' lever arms.
@@ -931,15 +933,15 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
         VX[2] += snx[16] * m0; VX[3] += snx[17] * m1; VY[2] += sny[16] * m0; VY[3] += sny[17] * m1;
       }
       if (warp_rope) {
+      // branch-free: an inactive rope keeps a zero impulse (few lanes have an active rope: a branch per rope diverges)
 #define ROPE_SOLVE(i, a, b)                                                        \
-  if (ract[i]) {                                                                   \
+  {                                                                                \
     const V2<R> n_ = *reinterpret_cast<const V2<R>*>(reinterpret_cast<const R*>(srope + ((i) >> 1) * 32 + lane) + ((i) & 1) * 2); \
     const R jv = n_.x * (VX[a] - VX[b]) + n_.y * (VY[a] - VY[b]);                  \
-    R l_ = -K_rope_E * jv;                                                           \
     const R old = rimp[i];                                                         \
-    rimp[i] = M<R>::max_(old + l_, R(0));                                          \
-    l_ = rimp[i] - old;                                                            \
-    const R m_ = l_ * K_im;                                                          \
+    const R nw = ract[i] ? M<R>::max_(old - K_rope_E * jv, R(0)) : R(0);           \
+    rimp[i] = nw;                                                                  \
+    const R m_ = (nw - old) * K_im;                                                \
     VX[a] += n_.x * m_; VY[a] += n_.y * m_; VX[b] -= n_.x * m_; VY[b] -= n_.y * m_;         \
   }
         VSR_ROPES(ROPE_SOLVE)
@@ -1010,33 +1012,32 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
             V4<R> imp = ld4(sp + kPI + 4 * par);
             const V4<R> j0 = ld4(sp + kPS), j1 = ld4(sp + kPS + 4), cc = ld4(sp + kPS + 8);
             const R nx = nn.x, ny = nn.y;
-            // friction rows first (tangent t = (ny, -nx)), clamped by mu * (accumulated normal impulse)
+            // all rows of a manifold share n and t = (ny, -nx): solve in (normal, tangent, angular) velocity coordinates
+            R vn_ = nx * vxk + ny * vyk, vt_ = ny * vxk - nx * vyk;
+            // friction rows first, clamped by mu * (accumulated normal impulse)
             {
-              R l_ = -j0.w * (ny * vxk - nx * vyk + j0.y * wk);
+              R l_ = -j0.w * (vt_ + j0.y * wk);
               const R maxf = K_mu * imp.x;
               const R nj = M<R>::max_(-maxf, M<R>::min_(imp.y + l_, maxf));
               l_ = nj - imp.y; imp.y = nj;
-              const R a_ = K_im * l_;
-              vxk += a_ * ny; vyk -= a_ * nx; wk += (K_ii * l_) * j0.y;
+              vt_ += K_im * l_; wk += (K_ii * l_) * j0.y;
             }
             if (np > 1) {
-              R l_ = -j1.w * (ny * vxk - nx * vyk + j1.y * wk);
+              R l_ = -j1.w * (vt_ + j1.y * wk);
               const R maxf = K_mu * imp.z;
               const R nj = M<R>::max_(-maxf, M<R>::min_(imp.w + l_, maxf));
               l_ = nj - imp.w; imp.w = nj;
-              const R a_ = K_im * l_;
-              vxk += a_ * ny; vyk -= a_ * nx; wk += (K_ii * l_) * j1.y;
+              vt_ += K_im * l_; wk += (K_ii * l_) * j1.y;
             }
             if (!(meta & (1 << 30))) { // normal rows one by one (single point, or ill-conditioned pair reduced to one)
-              R l_ = -j0.z * (nx * vxk + ny * vyk + j0.x * wk - cc.x);
+              R l_ = -j0.z * (vn_ + j0.x * wk - cc.x);
               const R nj = M<R>::max_(imp.x + l_, R(0));
               l_ = nj - imp.x; imp.x = nj;
-              const R a_ = K_im * l_;
-              vxk += a_ * nx; vyk += a_ * ny; wk += (K_ii * l_) * j0.x;
+              vn_ += K_im * l_; wk += (K_ii * l_) * j0.x;
             } else { // 2-point block solver
               const V2<R> ik = *reinterpret_cast<const V2<R>*>(sp + kPS + 12);
               const R a1 = imp.x, a2 = imp.z, K12 = cc.z;
-              const R vn1 = nx * vxk + ny * vyk + j0.x * wk, vn2 = nx * vxk + ny * vyk + j1.x * wk;
+              const R vn1 = vn_ + j0.x * wk, vn2 = vn_ + j1.x * wk;
               const R K11 = K_im + K_ii * j0.x * j0.x, K22 = K_im + K_ii * j1.x * j1.x;
               const R b1 = vn1 - cc.x - (K11 * a1 + K12 * a2);
               const R b2 = vn2 - cc.y - (K12 * a1 + K22 * a2);
@@ -1053,9 +1054,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
               }
               const R d1 = x1 - a1, d2 = x2 - a2;
               imp.x = x1; imp.z = x2;
-              const R a_ = K_im * (d1 + d2);
-              vxk += a_ * nx; vyk += a_ * ny; wk += K_ii * (j0.x * d1 + j1.x * d2);
+              vn_ += K_im * (d1 + d2); wk += K_ii * (j0.x * d1 + j1.x * d2);
             }
+            vxk = nx * vn_ + ny * vt_; vyk = ny * vn_ - nx * vt_;
             st4(sp + kPI + 4 * par, imp);
             stg[mi] = vxk; stg[128 + mi] = vyk; stg[256 + mi] = wk;
           }
@@ -1494,7 +1495,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
 #undef K_wa
 #undef K_wA
 #undef K_wh
-#undef K_wD
+#undef K_wDA
+#undef K_wDh
 #undef K_w_i2i
 #undef K_rest_vel
 #undef K_rest_e
