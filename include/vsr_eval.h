@@ -89,6 +89,12 @@ typedef struct {
   double first_x, last_x;
   int32_t n_steps, k_first, k_last;
   int32_t contact_overflow; /* >0: the per-warp contact pool overflowed (results unreliable)        */
+  /* energy terms over the kept observations (k_first, k_last], summed over the voxels; they feed Outcome.getControlPower()
+   * = control_energy / time, getAreaRatioPower() = area-ratio energy / time and getCorrectedEfficiency() = distance /
+   * (1 + control_energy) (locomotion/NamedFunctions.java:135-137; the 2dhmsr formulas are recalled [U], so both candidate
+   * area-ratio sums are returned): sum f^2 dt;  sum |a_k - a_{k-1}|;  sum |a_k^2 - a_{k-1}^2|                        */
+  double control_energy, area_ratio_abs, area_ratio_sq;
+  double reserved;
 } vsr_result;
 
 typedef struct vsr_ctx vsr_ctx;

@@ -57,7 +57,7 @@ public class BatchedLocomotion implements Function<Robot, GpuOutcome>, AutoClose
     double[] r = VsrEval.eval(ctx, genomes, robots.size());
     List<GpuOutcome> outcomes = new ArrayList<>(robots.size());
     for (int i = 0; i < robots.size(); i++) {
-      outcomes.add(new GpuOutcome(r[i * 5], r[i * 5 + 1], r[i * 5 + 2], transientT, finalT));
+      outcomes.add(new GpuOutcome(r[i * 8], r[i * 8 + 1], r[i * 8 + 2], r[i * 8 + 5], r[i * 8 + 6], transientT, finalT));
     }
     return outcomes;
   }

@@ -81,10 +81,11 @@ JNIEXPORT jdoubleArray JNICALL Java_it_units_erallab_gpu_VsrEval_eval(JNIEnv* en
   jdoubleArray out = NULL;
   if (rc) throw_status(env, ctx, rc);
   else {
-    out = (*env)->NewDoubleArray(env, n * 5);
+    out = (*env)->NewDoubleArray(env, n * 8);
     for (int i = 0; i < n; i++) {
-      jdouble v[5] = {res[i].velocity, res[i].distance, res[i].time, res[i].first_x, res[i].last_x};
-      (*env)->SetDoubleArrayRegion(env, out, i * 5, 5, v);
+      jdouble v[8] = {res[i].velocity, res[i].distance, res[i].time, res[i].first_x, res[i].last_x,
+                      res[i].control_energy, res[i].area_ratio_abs, res[i].area_ratio_sq};
+      (*env)->SetDoubleArrayRegion(env, out, i * 8, 8, v);
     }
   }
   free(fit); free(res);

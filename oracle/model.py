@@ -245,7 +245,8 @@ class VoResult(C.Structure):
         [("n_steps", C.c_int), ("k_first", C.c_int), ("k_last", C.c_int)] + \
         [(n, C.c_int64) for n in ("n_spring_vel", "n_rope_vel", "n_weld_vel", "n_contact_pt_vel", "n_block_vel",
                                   "n_rope_pos", "n_weld_pos", "n_contact_pt_pos", "n_detect_pairs", "n_pos_iters",
-                                  "n_manifolds")]
+                                  "n_manifolds")] + \
+        [(n, C.c_double) for n in ("control_energy", "area_ratio_abs", "area_ratio_sq")]
 
 
 CTRL_PHASE_SIN, CTRL_MLP_CENTRALIZED, CTRL_MLP_DISTRIBUTED_HOMO = 0, 1, 2

@@ -1173,6 +1173,8 @@ int vo_run(const vo_params* p, int w, int h, const uint8_t* mask,
   double t = 0.0, first_t = 0, last_t = 0, first_x = 0, last_x = 0;
   int k = 0, have_first = 0;
   double in[256], o[256];
+  double* last_area = (double*)calloc((size_t)W->n_vox, sizeof(double));
+  out->control_energy = out->area_ratio_abs = out->area_ratio_sq = 0.0;
   while (t < p->final_t) {
     t += p->dt;
     k++;
@@ -1210,6 +1212,16 @@ int vo_run(const vo_params* p, int w, int h, const uint8_t* mask,
     /* observation */
     double cx = robot_center_x(W);
     if (t >= p->transient_t && t < p->final_t) { /* Outcome.subOutcome: subMap(start, end) */
+      /* energy increments between consecutive kept observations (the first one only sets the reference) */
+      for (int v = 0; v < W->n_vox; v++) {
+        const double a = voxel_area_ratio(W, v), f = W->ctrl_f[v];
+        if (have_first) {
+          out->control_energy += f * f * p->dt;
+          out->area_ratio_abs += fabs(a - last_area[v]);
+          out->area_ratio_sq += fabs(a * a - last_area[v] * last_area[v]);
+        }
+        last_area[v] = a;
+      }
       if (!have_first) { have_first = 1; first_t = t; first_x = cx; out->k_first = k; }
       last_t = t; last_x = cx; out->k_last = k;
     }
@@ -1236,7 +1248,7 @@ int vo_run(const vo_params* p, int w, int h, const uint8_t* mask,
   out->distance = last_x - first_x;
   out->time = last_t - first_t;
   out->velocity = out->distance / out->time;
-  free(S.off); free(S.readings); free(S.hist_t); free(S.hist_v); free(last_sig); free(cur_sig);
+  free(S.off); free(S.readings); free(S.hist_t); free(S.hist_v); free(last_sig); free(cur_sig); free(last_area);
   world_free(W);
   return 0;
 }

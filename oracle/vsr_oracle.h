@@ -99,6 +99,10 @@ typedef struct {
   int64_t n_spring_vel, n_rope_vel, n_weld_vel, n_contact_pt_vel, n_block_vel;
   int64_t n_rope_pos, n_weld_pos, n_contact_pt_pos;
   int64_t n_detect_pairs, n_pos_iters, n_manifolds;
+  /* energy terms over the kept observations (k_first, k_last], summed over the voxels [U] (2dhmsr Voxel.getControlEnergy /
+   * getAreaRatioEnergy feed Outcome.getControlPower / getAreaRatioPower / getCorrectedEfficiency, NamedFunctions.java:135-137):
+   *   control_energy = sum f^2 dt;  area_ratio_abs = sum |a_k - a_{k-1}|;  area_ratio_sq = sum |a_k^2 - a_{k-1}^2|        */
+  double control_energy, area_ratio_abs, area_ratio_sq;
 } vo_result;
 
 void vo_default_params(vo_params* p);

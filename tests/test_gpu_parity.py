@@ -261,3 +261,31 @@ def test_multi_device_sharding_is_exact(F, oracle):
     c2 = make_ctx(F, m, devices=[0, 1])
     assert np.array_equal(c1.eval(g), c2.eval(g))
     c1.close(); c2.close()
+
+
+@pytest.mark.parametrize("cfg", [1, 3, 4])
+def test_outcome_energy_terms_match_oracle(F, oracle, cfg):
+    """vsr_result energy sums (inputs of Outcome.getControlPower / getAreaRatioPower / getCorrectedEfficiency,
+    NamedFunctions.java:135-137) against the oracle on a window short enough to precede the first discrete divergence:
+    FP64 kernel 1e-8 relative (same algorithm, same order); FP32 kernel 5e-2 relative (sum |da| accumulates the FP32
+    trajectory differences of every voxel and step; the FP32 build tracks the oracle to 1e-4 only for the first N steps)."""
+    m = oracle.config_model(cfg, final_t=0.7)
+    m.params.transient_t = 0.2
+    g = np.random.default_rng(CFG_SEED[cfg]).uniform(-1, 1, (6, m.genome_len()))
+    _, ores = m.eval_batch(g, n_threads=4, want_results=True)
+    for prec, tol in ((64, 1e-8), (32, 5e-2)):
+        ctx = make_ctx(F, m, prec)
+        _, res = ctx.eval(g, want_results=True)
+        for i in range(len(g)):
+            assert res["k_first"][i] == ores[i].k_first and res["k_last"][i] == ores[i].k_last
+            for name in ("control_energy", "area_ratio_abs", "area_ratio_sq"):
+                a, b = float(res[name][i]), getattr(ores[i], name)
+                assert abs(a - b) <= tol * max(abs(b), 1e-3), (cfg, prec, i, name, a, b)
+            assert res["control_energy"][i] > 0 and res["area_ratio_abs"][i] > 0
+        # the fitness-only call must give the same fitness (the energy path is results-mode only)
+        assert np.array_equal(ctx.eval(g), res["velocity"])
+        ctx.close()
+    # host mirror getters
+    from vsrevolution_b200.locomotion import Outcome
+    o = Outcome(0.5, 5.0, 10.0, 0.0, 5.0, 1.0, 11.0, control_energy=4.0, area_ratio_energy=2.0)
+    assert o.get_control_power() == 0.4 and o.get_area_ratio_power() == 0.2 and o.get_corrected_efficiency() == 1.0

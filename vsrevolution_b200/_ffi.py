@@ -38,11 +38,13 @@ class SensorDesc(C.Structure):
 
 class Result(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("velocity", "distance", "time", "first_x", "last_x")] + \
-        [(n, C.c_int32) for n in ("n_steps", "k_first", "k_last", "contact_overflow")]
+        [(n, C.c_int32) for n in ("n_steps", "k_first", "k_last", "contact_overflow")] + \
+        [(n, C.c_double) for n in ("control_energy", "area_ratio_abs", "area_ratio_sq", "reserved")]
 
 
 RESULT_DTYPE = np.dtype([("velocity", "f8"), ("distance", "f8"), ("time", "f8"), ("first_x", "f8"), ("last_x", "f8"),
-                         ("n_steps", "i4"), ("k_first", "i4"), ("k_last", "i4"), ("contact_overflow", "i4")])
+                         ("n_steps", "i4"), ("k_first", "i4"), ("k_last", "i4"), ("contact_overflow", "i4"),
+                         ("control_energy", "f8"), ("area_ratio_abs", "f8"), ("area_ratio_sq", "f8"), ("reserved", "f8")])
 assert RESULT_DTYPE.itemsize == C.sizeof(Result)
 
 

@@ -36,6 +36,8 @@ struct DeviceState {
   double* d_noise = nullptr;
   void* d_hist = nullptr;
   size_t hist_bytes = 0;
+  void* d_energy = nullptr; // per-lane energy accumulators (results mode only)
+  size_t energy_bytes = 0;
   double* d_genomes = nullptr;
   double* d_fitness = nullptr;
   vsr_result* d_results = nullptr;
@@ -308,7 +310,7 @@ int finalize(vsr_ctx* ctx) {
   k.off_pool_p = (int)o; o = align16(o + (size_t)vsr::kPoolStride * S * rs);
   k.off_pool_m = (int)o; o = align16(o + 2 * S * 4);
   k.off_pool_cnt = (int)o; o = align16(o + 4);
-  k.off_pool_o = (int)o; o = align16(o + S * 4);
+  k.off_pool_o = (int)o; o = align16(o + 128); // list of touching masses
   k.off_mslots = (int)o; o = align16(o + 32 * 4 * 4); // mass -> manifold slots
   o = (o + 31) & ~size_t(31);
   // velocity staging of the transposed contact solve and the controller's activation scratch are used in disjoint
@@ -409,6 +411,18 @@ int ensure_hist(vsr_ctx* ctx, DeviceState& d, int grid) {
   return VSR_OK;
 }
 
+int ensure_energy(vsr_ctx* ctx, DeviceState& d, int grid) {
+  const size_t rs = ctx->env.precision == 64 ? 8 : 4;
+  const size_t bytes = (size_t)grid * ctx->warps * 32 * 4 * rs;
+  if (bytes > d.energy_bytes) {
+    if (d.d_energy) cudaFree(d.d_energy);
+    d.energy_bytes = 0;
+    CK(cudaMalloc(&d.d_energy, bytes));
+    d.energy_bytes = bytes;
+  }
+  return VSR_OK;
+}
+
 // enqueue the episode kernel for n robots whose genomes are at d_genomes (device)
 int enqueue(vsr_ctx* ctx, DeviceState& d, const double* d_genomes, size_t n, double* d_fitness, vsr_result* d_results,
             cudaStream_t st, double* trv, double* trb, double* trc, int trace_steps, bool time_it) {
@@ -417,6 +431,11 @@ int enqueue(vsr_ctx* ctx, DeviceState& d, const double* d_genomes, size_t n, dou
   const int grid = grid_for(ctx, n);
   int rc = ensure_hist(ctx, d, grid);
   if (rc) return rc;
+  if (d_results) {
+    rc = ensure_energy(ctx, d, grid);
+    if (rc) return rc;
+  }
+  k.energy = d.d_energy;
   k.tx = d.d_tx; k.ty = d.d_ty; k.win_tab = d.d_win; k.hist = d.d_hist; k.noise = d.d_noise;
   k.genomes = d_genomes; k.fitness = d_fitness; k.results = d_results; k.n_robots = (int)n;
   k.tr_vertices = trv; k.tr_bodies = trb; k.tr_ctrl = trc; k.trace_steps = trace_steps;
@@ -554,7 +573,7 @@ void vsr_ctx_destroy(vsr_ctx* c) {
   for (auto& d : c->devs) {
     cudaSetDevice(d.dev);
     if (d.stream) cudaStreamSynchronize(d.stream);
-    cudaFree(d.d_tx); cudaFree(d.d_ty); cudaFree(d.d_win); cudaFree(d.d_hist); cudaFree(d.d_noise);
+    cudaFree(d.d_tx); cudaFree(d.d_ty); cudaFree(d.d_win); cudaFree(d.d_hist); cudaFree(d.d_noise); cudaFree(d.d_energy);
     cudaFree(d.d_genomes); cudaFree(d.d_fitness); cudaFree(d.d_results);
     cudaFreeHost(d.h_genomes); cudaFreeHost(d.h_fitness); cudaFreeHost(d.h_results);
     if (d.ev0) cudaEventDestroy(d.ev0);

@@ -31,7 +31,7 @@ constexpr int kMaxSensors = 6;
 constexpr int kMaxLayers = 8;
 constexpr int kMaxMan = 3;       // manifolds per corner mass (ground polygons it can touch at once)
 constexpr int kMaxAvg = 6;       // averaged readings per voxel
-constexpr int kPark = 23;         // X Y A (12) + polygon cache (6) + origin (2) + rest (3)
+constexpr int kPark = 20;         // X Y A (12) + polygon cache (6) + origin (2)
 // contact-pool slot (36 R words, 16-byte aligned vectors; stride 36 = 4 x odd -> 128-bit accesses of 8 consecutive slots
 // hit all 32 banks once):
 //   geometry (rebuilt by every detect):   [0..3] nx ny px0 py0 | [4..7] d0 px1 py1 d1
@@ -101,6 +101,7 @@ struct KParams {
   const double* genomes;
   double* fitness;
   vsr_result* results;
+  void* energy;          // V4<R>[total lanes]: per-voxel energy accumulators (sum f^2 dt, sum |da|, sum |d(a^2)|, last a); used only with results
   int n_robots;
   // trace (robot 0 only)
   double *tr_vertices, *tr_bodies, *tr_ctrl;
@@ -378,7 +379,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
   R* pool = reinterpret_cast<R*>(wsm + P.off_pool_p);      // [S][kPoolStride]: persist[2][12], solve[20]
   int* poolM = reinterpret_cast<int*>(wsm + P.off_pool_m); // [2][S]
   int* poolCnt = reinterpret_cast<int*>(wsm + P.off_pool_cnt);
-  int* poolO = reinterpret_cast<int*>(wsm + P.off_pool_o);     // [S] owner lane | rank-within-mass << 5
+  unsigned char* tml = reinterpret_cast<unsigned char*>(wsm + P.off_pool_o); // [128] list of the corner masses (lane*4 + k) that have manifolds
   V4<R>* stage = reinterpret_cast<V4<R>*>(wsm + P.off_stage);  // [3][32] corner-mass velocities (vx, vy, w) x 4 masses per lane
   R* wts = reinterpret_cast<R*>(wsm + P.off_w);            // [robots_per_warp][genome_len]
   R* act = reinterpret_cast<R*>(wsm + P.off_act);          // centralized: [rpw][2][maxN]; distributed: [2][maxN][32]
@@ -519,7 +520,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
 
   auto ld4 = [](const R* q) -> V4<R> { return *reinterpret_cast<const V4<R>*>(q); };
   auto st4 = [](R* q, const V4<R>& v) { *reinterpret_cast<V4<R>*>(q) = v; };
-  int man_total = 0, man_rank = 0; // warp-uniform: manifolds in the pool, highest rank of a manifold within its mass
+  int n_tm = 0; // warp-uniform: corner masses of this warp that have at least one manifold (length of tml)
   // per-lane cached ground polygon (the one under the voxel centre), in the lane's local frame
   int pk = 0;
   R px0 = 0, px1 = 0, py0 = 0, py1 = 0, pnx = 0, pny = 1;
@@ -599,7 +600,6 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
     }
     if (lane == 0) *poolCnt = 0;
     __syncwarp();
-    int lane_rank = 0;
 #pragma unroll 1
     for (int ci = lane; ci < ncand; ci += 32) {
       const int c = cand[ci], ol = c & 31, k = c >> 5, mi = ol * 4 + k;
@@ -689,21 +689,30 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
         v4.x = i12; v4.y = i22; v4.z = 0; v4.w = 0; st4(sp + kPS + 12, v4);
         v4.x = ck * r0x + sk * r0y; v4.y = -sk * r0x + ck * r0y; v4.z = ck * r1x + sk * r1y; v4.w = -sk * r1x + ck * r1y; st4(sp + kPS + 16, v4);
         poolM[np_ * S + s] = meta;
-        poolO[s] = ol | (cnt << 5);
         news |= (unsigned)(s + 1) << (8 * cnt);
-        if (cnt > lane_rank) lane_rank = cnt;
         cnt++;
       }
       massSlots[mi] = news;
     }
     par ^= 1;
     __syncwarp();
-    man_total = min(*poolCnt, S);
-    man_rank = __reduce_max_sync(FULL, lane_rank);
+    // list of the touching masses: the contact phases of the step run lane = touching mass
     {
       const uint4 ms = reinterpret_cast<const uint4*>(massSlots)[lane];
+      const unsigned w4[4] = {ms.x, ms.y, ms.z, ms.w};
       touching = valid && (ms.x | ms.y | ms.z | ms.w) != 0;
+      const unsigned lt = (1u << lane) - 1u;
+      int n = 0;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const bool mine = valid && w4[k] != 0;
+        const unsigned b = __ballot_sync(FULL, mine);
+        if (mine) tml[n + __popc(b & lt)] = (unsigned char)(lane * 4 + k);
+        n += __popc(b);
+      }
+      n_tm = n;
     }
+    __syncwarp();
   };
 
   detect(); // World.step's first-step detect()
@@ -721,9 +730,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
       VY[k] += gdt;
       VX[k] *= K_lin_f; VY[k] *= K_lin_f; W[k] *= K_ang_f;
     }
-    // ---- contacts: restitution bias (from the pre-warm-start velocities) + warm start, lane = manifold ----------
+    // ---- contacts: restitution bias (from the pre-warm-start velocities) + warm start, lane = touching mass -----
     // (the geometry part of the constraint was built by detect(); cold state X Y A / polygon / origin is parked there too)
-    if (man_total > 0) {
+    if (n_tm > 0) {
       {
         V4<R> t4;
         t4.x = VX[0]; t4.y = VX[1]; t4.z = VX[2]; t4.w = VX[3]; stage[0 * 32 + lane] = t4;
@@ -732,34 +741,29 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
       }
       __syncwarp();
 #pragma unroll 1
-      for (int s = lane; s < man_total; s += 32) {
-        const int own = poolO[s], meta = poolM[par * S + s];
-        const int np = (meta >> 16) & 3, mi = (own & 31) * 4 + ((meta >> 14) & 3);
-        R* sp = pool + s * kPoolStride;
-        const V2<R> nn = *reinterpret_cast<const V2<R>*>(sp);
-        const R rn0 = sp[kPS], rn1 = sp[kPS + 4];
-        const R vn = nn.x * stg[mi] + nn.y * stg[128 + mi], wk = stg[256 + mi];
-        const R vn0 = vn + rn0 * wk, vn1 = vn + rn1 * wk;
-        V2<R> vb;
-        vb.x = vn0 < -K_rest_vel ? -K_rest_e * vn0 : R(0);
-        vb.y = (np > 1 && vn1 < -K_rest_vel) ? -K_rest_e * vn1 : R(0);
-        *reinterpret_cast<V2<R>*>(sp + kPS + 8) = vb;
-      }
-      __syncwarp();
+      for (int i = lane; i < n_tm; i += 32) {
+        const int mi = tml[i];
+        const unsigned slots = massSlots[mi];
+        const R vx0 = stg[mi], vy0 = stg[128 + mi], w0 = stg[256 + mi]; // pre-warm-start velocity of this mass
+        R vxk = vx0, vyk = vy0, wk = w0;
 #pragma unroll 1
-      for (int pass = 0; pass <= man_rank; pass++) {
-#pragma unroll 1
-        for (int s = lane; s < man_total; s += 32) {
-          const int own = poolO[s];
-          if ((own >> 5) != pass) continue;
+        for (unsigned sl = slots; sl != 0; sl >>= 8) { // slot bytes are packed from rank 0 upwards
+          const int s = (int)(sl & 0xffu) - 1;
           const int meta = poolM[par * S + s];
-          const int np = (meta >> 16) & 3, mi = (own & 31) * 4 + ((meta >> 14) & 3);
-          const R* sp = pool + s * kPoolStride;
+          const int np = (meta >> 16) & 3;
+          R* sp = pool + s * kPoolStride;
           const V2<R> nn = *reinterpret_cast<const V2<R>*>(sp);
           const V4<R> imp = ld4(sp + kPI + 4 * par);
           const V2<R> j0 = *reinterpret_cast<const V2<R>*>(sp + kPS), j1 = *reinterpret_cast<const V2<R>*>(sp + kPS + 4);
           const R nx = nn.x, ny = nn.y;
-          R vxk = stg[mi], vyk = stg[128 + mi], wk = stg[256 + mi];
+          {
+            const R vn = nx * vx0 + ny * vy0;
+            const R vn0 = vn + j0.x * w0, vn1 = vn + j1.x * w0;
+            V2<R> vb;
+            vb.x = vn0 < -K_rest_vel ? -K_rest_e * vn0 : R(0);
+            vb.y = (np > 1 && vn1 < -K_rest_vel) ? -K_rest_e * vn1 : R(0);
+            *reinterpret_cast<V2<R>*>(sp + kPS + 8) = vb;
+          }
           {
             const R Jx = nx * imp.x + ny * imp.y, Jy = ny * imp.x - nx * imp.y;
             vxk += K_im * Jx; vyk += K_im * Jy; wk += K_ii * (j0.x * imp.x + j0.y * imp.y);
@@ -768,10 +772,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
             const R Jx = nx * imp.z + ny * imp.w, Jy = ny * imp.z - nx * imp.w;
             vxk += K_im * Jx; vyk += K_im * Jy; wk += K_ii * (j1.x * imp.z + j1.y * imp.w);
           }
-          stg[mi] = vxk; stg[128 + mi] = vyk; stg[256 + mi] = wk;
         }
-        __syncwarp();
+        stg[mi] = vxk; stg[128 + mi] = vyk; stg[256 + mi] = wk;
       }
+      __syncwarp();
       if (touching) {
         V4<R> t4;
         t4 = stage[0 * 32 + lane]; VX[0] = t4.x; VX[1] = t4.y; VX[2] = t4.z; VX[3] = t4.w;
@@ -890,11 +894,6 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
     lz_ = -(Cz) * K_w_i2i + ((r2y)*lx_ - (r2x)*ly_) * R(0.5);                             \
   }
 
-    // ---- park the spring targets (read again only after the velocity loop; X Y A were parked by detect()) ---------
-    {
-      spark[20 * 32 + lane] = rest[0]; spark[21 * 32 + lane] = rest[1]; spark[22 * 32 + lane] = rest[2];
-      asm volatile("" ::: "memory");
-    }
     // ---- velocity iterations ------------------------------------------------------------------------
     PHASE_SYNC(2)
 #pragma unroll 1
@@ -986,10 +985,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
       }
 #endif
 #ifndef VSR_PROBE_NO_CONTACT_LOOP
-      // contacts, transposed: every lane solves ONE manifold of the warp's pool (lane = pool slot); the corner
-      // masses' velocities travel through shared memory.  Manifolds of the same mass are taken in rank passes,
-      // so each body still sees its constraints in the canonical order (ground is static: bodies are independent).
-      if (man_total > 0) {
+      // contacts, transposed: every lane solves the manifolds of ONE touching corner mass, in rank (polygon) order; the
+      // masses' velocities travel through shared memory.  The ground is static, so different masses are independent and
+      // each body still sees its constraints in the canonical order.
+      if (n_tm > 0) {
         {
           V4<R> t4;
           t4.x = VX[0]; t4.y = VX[1]; t4.z = VX[2]; t4.w = VX[3]; stage[0 * 32 + lane] = t4;
@@ -998,15 +997,15 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
         }
         __syncwarp();
 #pragma unroll 1
-        for (int pass = 0; pass <= man_rank; pass++) {
+        for (int i = lane; i < n_tm; i += 32) {
+          const int mi = tml[i]; // corner mass = owner lane * 4 + k
+          const unsigned slots = massSlots[mi];
+          R vxk = stg[mi], vyk = stg[128 + mi], wk = stg[256 + mi];
 #pragma unroll 1
-          for (int s = lane; s < man_total; s += 32) {
-            const int own = poolO[s];
-            if ((own >> 5) != pass) continue;
+          for (unsigned sl = slots; sl != 0; sl >>= 8) {
+            const int s = (int)(sl & 0xffu) - 1;
             const int meta = poolM[par * S + s];
             const int np = (meta >> 16) & 3;
-            const int mi = (own & 31) * 4 + ((meta >> 14) & 3); // corner mass = owner lane * 4 + k
-            R vxk = stg[mi], vyk = stg[128 + mi], wk = stg[256 + mi];
             R* sp = pool + s * kPoolStride;
             const V2<R> nn = *reinterpret_cast<const V2<R>*>(sp);
             V4<R> imp = ld4(sp + kPI + 4 * par);
@@ -1058,10 +1057,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
             }
             vxk = nx * vn_ + ny * vt_; vyk = ny * vn_ - nx * vt_;
             st4(sp + kPI + 4 * par, imp);
-            stg[mi] = vxk; stg[128 + mi] = vyk; stg[256 + mi] = wk;
           }
-          __syncwarp();
+          stg[mi] = vxk; stg[128 + mi] = vyk; stg[256 + mi] = wk;
         }
+        __syncwarp();
         if (touching) {
           V4<R> t4;
           t4 = stage[0 * 32 + lane]; VX[0] = t4.x; VX[1] = t4.y; VX[2] = t4.z; VX[3] = t4.w;
@@ -1086,7 +1085,6 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
       px0 = spark[12 * 32 + lane]; px1 = spark[13 * 32 + lane]; py0 = spark[14 * 32 + lane]; py1 = spark[15 * 32 + lane];
       pnx = spark[16 * 32 + lane]; pny = spark[17 * 32 + lane];
       ox = spark[18 * 32 + lane]; oy = spark[19 * 32 + lane];
-      rest[0] = spark[20 * 32 + lane]; rest[1] = spark[21 * 32 + lane]; rest[2] = spark[22 * 32 + lane];
     }
 #pragma unroll
     for (int k = 0; k < 4; k++) {
@@ -1114,9 +1112,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
 #pragma unroll 1
       for (int it = 0; it < P.pos_iters; it++) {
         bool ok = true;
-        // contacts, lane = manifold: the masses' poses travel through shared memory (X Y A in the staging area, CS SN in
-        // the spring-bias area, which is dead outside the velocity loop); rank passes keep the manifolds of one mass in order
-        if (man_total > 0) {
+        // contacts, lane = touching mass: the masses' poses travel through shared memory (X Y A in the staging area, CS SN
+        // in the spring-bias area, which is dead outside the velocity loop)
+        if (n_tm > 0) {
           V4<R>* pcs = reinterpret_cast<V4<R>*>(sbias);
           R* pc = sbias;
           {
@@ -1131,14 +1129,15 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
           __syncwarp();
           unsigned mybad = 0;
 #pragma unroll 1
-          for (int pass = 0; pass <= man_rank; pass++) {
+          for (int i = lane; i < n_tm; i += 32) {
+            const int mi = tml[i], ol = mi >> 2;
+            if (!((actm >> ol) & 1u)) continue;
+            const unsigned slots = massSlots[mi];
+            R xk = stg[mi], yk = stg[128 + mi], ak = stg[256 + mi], ck = pc[mi], sk = pc[128 + mi];
 #pragma unroll 1
-            for (int s = lane; s < man_total; s += 32) {
-              const int own = poolO[s];
-              if ((own >> 5) != pass || !((actm >> (own & 31)) & 1u)) continue;
-              const int meta = poolM[par * S + s];
-              const int np = (meta >> 16) & 3, mi = (own & 31) * 4 + ((meta >> 14) & 3);
-              R xk = stg[mi], yk = stg[128 + mi], ak = stg[256 + mi], ck = pc[mi], sk = pc[128 + mi];
+            for (unsigned sl = slots; sl != 0; sl >>= 8) {
+              const int s = (int)(sl & 0xffu) - 1;
+              const int np = (poolM[par * S + s] >> 16) & 3;
               const R* sp = pool + s * kPoolStride;
               const V4<R> pa = ld4(sp), pb = ld4(sp + 4), pl = ld4(sp + kPS + 16);
               const R nx = pa.x, ny = pa.y;
@@ -1147,7 +1146,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
                 const R cpx = q == 0 ? pa.z : pb.y, cpy = q == 0 ? pa.w : pb.z, cdp = q == 0 ? pb.x : pb.w;
                 const R rx = ck * lx - sk * ly, ry = sk * lx + ck * ly;
                 const R sep = nx * (xk + rx - cpx) + ny * (yk + ry - cpy) - cdp;
-                if (sep < -R(3) * K_lin_tol) mybad |= 1u << (own & 31);
+                if (sep < -R(3) * K_lin_tol) mybad |= 1u << ol;
                 R C = K_baum * (sep + K_lin_tol);
                 C = M<R>::min_(C, R(0));
                 C = M<R>::max_(C, -K_max_corr);
@@ -1156,10 +1155,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
                 xk += K_im * nx * l_; yk += K_im * ny * l_;
                 M<R>::rotate(ak, ck, sk, K_ii * rn_ * l_);
               }
-              stg[mi] = xk; stg[128 + mi] = yk; stg[256 + mi] = ak; pc[mi] = ck; pc[128 + mi] = sk;
             }
-            __syncwarp();
+            stg[mi] = xk; stg[128 + mi] = yk; stg[256 + mi] = ak; pc[mi] = ck; pc[128 + mi] = sk;
           }
+          __syncwarp();
           if ((__reduce_or_sync(FULL, mybad) >> lane) & 1u) ok = false;
           if (touching && active) {
             V4<R> t4;
@@ -1421,12 +1420,38 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
       rest[kq] = f >= 0 ? rr - (rr - KC(range_min[kq], P.range_min[kq])) * f : rr + (KC(range_max[kq], P.range_max[kq]) - rr) * -f;
     }
 
+    // ---- energy terms of the kept observations (Outcome.getControlPower / getAreaRatioPower inputs), only when the caller
+    // asked for vsr_result records: per-voxel accumulators live in global memory (L2), nothing is added to the fitness-only path
+    if (P.results != nullptr && step >= P.k_first && step <= P.k_last) {
+      R a2 = 0;
+#pragma unroll
+      for (int i = 0; i < 4; i++) { const int j = (i + 1) & 3; a2 += qx[i] * qy[j] - qx[j] * qy[i]; }
+      const R area = M<R>::abs_(a2) * K_inv_area2;
+      V4<R>* eacc = reinterpret_cast<V4<R>*>(P.energy) + gl;
+      V4<R> e4;
+      if (step == P.k_first) { e4.x = 0; e4.y = 0; e4.z = 0; }
+      else {
+        e4 = *eacc;
+        e4.x += f * f * K_dt; e4.y += M<R>::abs_(area - e4.w); e4.z += M<R>::abs_(area * area - e4.w * e4.w);
+      }
+      e4.w = area;
+      *eacc = e4;
+    }
     // ---- observation: robot centre x at the first / last kept step --------------------------------------
     if (step == P.k_first || step == P.k_last) {
       const double cxv = (double)ox + (double)(R(0.25) * (qx[0] + qx[1] + qx[2] + qx[3]));
       double sum = 0;
       for (int j = 0; j < L; j++) sum += __shfl_sync(FULL, cxv, (base_lane + j) & 31);
       sum /= L;
+      double en0 = 0, en1 = 0, en2 = 0;
+      if (P.results != nullptr && step == P.k_last) { // per-robot sums of the voxel accumulators, in voxel order
+        const V4<R> e4 = reinterpret_cast<const V4<R>*>(P.energy)[gl];
+        for (int j = 0; j < L; j++) {
+          en0 += __shfl_sync(FULL, (double)e4.x, (base_lane + j) & 31);
+          en1 += __shfl_sync(FULL, (double)e4.y, (base_lane + j) & 31);
+          en2 += __shfl_sync(FULL, (double)e4.z, (base_lane + j) & 31);
+        }
+      }
       // K3 result pack: the first observation waits in the fitness slot (global) until the last one arrives
       if (valid && v == 0) {
         if (step == P.k_first) P.fitness[robot] = sum;
@@ -1439,6 +1464,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
             vsr_result r;
             r.velocity = vel; r.distance = dist; r.time = tm; r.first_x = cx_first; r.last_x = sum;
             r.n_steps = P.n_steps; r.k_first = P.k_first; r.k_last = P.k_last; r.contact_overflow = 0;
+            r.control_energy = en0; r.area_ratio_abs = en1; r.area_ratio_sq = en2; r.reserved = 0;
             P.results[robot] = r;
           }
         }

@@ -37,6 +37,19 @@ class Outcome:
     last_x: float
     start_t: float
     end_t: float
+    control_energy: float = 0.0      # sum over kept steps and voxels of f^2 dt                    [U]
+    area_ratio_energy: float = 0.0   # sum over kept steps and voxels of |a_k - a_{k-1}|           [U]
+    area_ratio_energy_sq: float = 0.0  # ... of |a_k^2 - a_{k-1}^2| (the other candidate formula)  [U]
+
+    # detailedOutcomeFunctions (locomotion/NamedFunctions.java:135-137)
+    def get_control_power(self) -> float:
+        return self.control_energy / self.time
+
+    def get_area_ratio_power(self) -> float:
+        return self.area_ratio_energy / self.time
+
+    def get_corrected_efficiency(self) -> float:
+        return self.distance / (1.0 + self.control_energy)
 
     def get_velocity(self) -> float:
         return self.velocity
@@ -147,7 +160,8 @@ class Locomotion:
         genomes = np.stack([self.genome_of(r) for r in robots])
         _, res = ctx.eval(genomes, want_results=True)
         return [Outcome(float(r["velocity"]), float(r["distance"]), float(r["time"]), float(r["first_x"]), float(r["last_x"]),
-                        self.transient_t, self.final_t) for r in res]
+                        self.transient_t, self.final_t, float(r["control_energy"]), float(r["area_ratio_abs"]),
+                        float(r["area_ratio_sq"])) for r in res]
 
     def apply(self, robot: Robot) -> Outcome:
         return self.apply_all([robot])[0]
