@@ -28,7 +28,8 @@ thread_local std::string g_create_error;
 
 struct DeviceState {
   int dev = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaEvent_t ev_copy = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t ev_join = nullptr; // eval_range: this device's slice is back on the primary device
   double *d_tx = nullptr, *d_ty = nullptr;
@@ -557,6 +558,8 @@ int vsr_ctx_create(const vsr_env_desc* env, vsr_ctx** out) {
       return false;
     };
     bool ok = ck(cudaSetDevice(d.dev), "cudaSetDevice") && ck(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking), "cudaStreamCreate") &&
+              ck(cudaStreamCreateWithFlags(&d.copy_stream, cudaStreamNonBlocking), "cudaStreamCreate") &&
+              ck(cudaEventCreateWithFlags(&d.ev_copy, cudaEventDisableTiming), "cudaEventCreate") &&
               ck(cudaEventCreate(&d.ev0), "cudaEventCreate") && ck(cudaEventCreate(&d.ev1), "cudaEventCreate") &&
               ck(cudaEventCreateWithFlags(&d.ev_join, cudaEventDisableTiming), "cudaEventCreate") &&
               ck(cudaMalloc(&d.d_tx, sizeof(double) * c->tx.size()), "cudaMalloc") && ck(cudaMalloc(&d.d_ty, sizeof(double) * c->ty.size()), "cudaMalloc") &&
@@ -579,6 +582,8 @@ void vsr_ctx_destroy(vsr_ctx* c) {
     if (d.ev0) cudaEventDestroy(d.ev0);
     if (d.ev1) cudaEventDestroy(d.ev1);
     if (d.ev_join) cudaEventDestroy(d.ev_join);
+    if (d.ev_copy) cudaEventDestroy(d.ev_copy);
+    if (d.copy_stream) cudaStreamDestroy(d.copy_stream);
     if (d.stream) cudaStreamDestroy(d.stream);
   }
   delete c;
@@ -639,17 +644,38 @@ int vsr_eval(vsr_ctx* ctx, const double* genomes, int32_t n, double* fitness_out
   if (n == 0) return VSR_OK;
   const int G = ctx->kp.genome_len;
   const size_t nd = ctx->devs.size(), per = ((size_t)n + nd - 1) / nd;
-  // shard by contiguous index ranges; one stream per device; no inter-device traffic
+  // page-locked caller buffers (cudaHostAlloc / cudaHostRegister, e.g. a JNI direct buffer registered once) are copied
+  // from directly; pageable ones go through the context's pinned staging buffer
+  bool pinned_in = false;
+  {
+    cudaPointerAttributes pa;
+    if (cudaPointerGetAttributes(&pa, genomes) == cudaSuccess) pinned_in = pa.type == cudaMemoryTypeHost;
+    else cudaGetLastError();
+  }
+  // shard by contiguous index ranges; one stream per device; no inter-device traffic.  A shard larger than kChunk robots
+  // is cut into chunks whose uploads overlap the previous chunk's episodes (copy stream = the device's second stream).
+  constexpr size_t kChunk = 65536;
   for (size_t i = 0; i < nd; i++) {
     DeviceState& d = ctx->devs[i];
     size_t lo = std::min((size_t)n, i * per), hi = std::min((size_t)n, lo + per), cnt = hi - lo;
     if (!cnt) continue;
     int rc = ensure_capacity(ctx, d, cnt);
     if (rc) return rc;
-    std::memcpy(d.h_genomes, genomes + lo * G, cnt * G * sizeof(double));
-    CK(cudaMemcpyAsync(d.d_genomes, d.h_genomes, cnt * G * sizeof(double), cudaMemcpyHostToDevice, d.stream));
-    rc = enqueue(ctx, d, d.d_genomes, cnt, d.d_fitness, results_out ? d.d_results : nullptr, d.stream, nullptr, nullptr, nullptr, 0, i == 0);
-    if (rc) return rc;
+    CK(cudaSetDevice(d.dev));
+    for (size_t c0 = 0; c0 < cnt; c0 += kChunk) {
+      const size_t cn = std::min(kChunk, cnt - c0);
+      const double* src = genomes + (lo + c0) * G;
+      if (!pinned_in) {
+        std::memcpy(d.h_genomes + c0 * G, src, cn * G * sizeof(double));
+        src = d.h_genomes + c0 * G;
+      }
+      CK(cudaMemcpyAsync(d.d_genomes + c0 * G, src, cn * G * sizeof(double), cudaMemcpyHostToDevice, d.copy_stream));
+      CK(cudaEventRecord(d.ev_copy, d.copy_stream));
+      CK(cudaStreamWaitEvent(d.stream, d.ev_copy, 0));
+      rc = enqueue(ctx, d, d.d_genomes + c0 * G, cn, d.d_fitness + c0, results_out ? d.d_results + c0 : nullptr, d.stream, nullptr, nullptr,
+                   nullptr, 0, i == 0 && c0 + cn == cnt);
+      if (rc) return rc;
+    }
     CK(cudaMemcpyAsync(d.h_fitness, d.d_fitness, cnt * sizeof(double), cudaMemcpyDeviceToHost, d.stream));
     if (results_out) CK(cudaMemcpyAsync(d.h_results, d.d_results, cnt * sizeof(vsr_result), cudaMemcpyDeviceToHost, d.stream));
   }
