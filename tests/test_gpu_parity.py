@@ -289,3 +289,26 @@ def test_outcome_energy_terms_match_oracle(F, oracle, cfg):
     from vsrevolution_b200.locomotion import Outcome
     o = Outcome(0.5, 5.0, 10.0, 0.0, 5.0, 1.0, 11.0, control_energy=4.0, area_ratio_energy=2.0)
     assert o.get_control_power() == 0.4 and o.get_area_ratio_power() == 0.2 and o.get_corrected_efficiency() == 1.0
+
+
+@pytest.mark.parametrize("cfg", [1, 3, 4])
+def test_cuda_path_against_committed_golden_vectors(F, oracle, cfg):
+    """tests/golden/config*.npz (frozen oracle output): FP64 kernel vertices within 1e-9 and controls within 1e-9 for the 40
+    recorded steps; FP32 kernel within 1e-4 of the voxel side for the first 10 steps."""
+    import os
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"config{cfg}.npz"))
+    m = oracle.config_model(cfg, final_t=3.0)
+    steps = gold["vertices"].shape[1]
+    for prec in (64, 32):
+        ctx = make_ctx(F, m, prec)
+        for r in range(2):
+            _, tv, _, tc = ctx.trace(gold["genomes"][r], steps)
+            if prec == 64:
+                assert np.abs(tv - gold["vertices"][r]).max() < 1e-9 and np.abs(tc - gold["controls"][r]).max() < 1e-9
+            else:
+                assert np.abs(tv[:10] - gold["vertices"][r][:10]).max() < 1e-4 * 3.0
+        if prec == 64:
+            fit, res = ctx.eval(gold["genomes"], want_results=True)
+            assert (res["k_first"] == gold["k_first"]).all() and (res["k_last"] == gold["k_last"]).all()
+            assert np.abs(res["time"] - gold["time"]).max() < 1e-12
+        ctx.close()

@@ -52,3 +52,58 @@ def test_two_rank_sharded_evaluation_equals_single_rank(n):
     m = O.config_model(1, final_t=1.5)
     g = np.random.default_rng(0).uniform(-1, 1, (n, m.genome_len()))
     assert np.array_equal(full, m.eval_batch(g))
+
+
+def _ga_worker(rank, world, port, n_pop, out_q):
+    """The N>1 generation loop (vsrevolution_b200/solver.py): replicated GA state, sharded evaluation, fitness all-gather.
+    On CPU the GA is oracle/ga.py and the per-rank evaluator a cheap deterministic function; on the GPU box the same exchange
+    runs between vsr_ga_step_begin and vsr_ga_step_end over NCCL."""
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from oracle import ga as OG
+    from vsrevolution_b200.locomotion import shard_range
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    fn = lambda G: np.sin(G).sum(axis=1) - 0.1 * (G * G).sum(axis=1)
+
+    def sharded(G):
+        n = len(G)
+        per = (n + world - 1) // world
+        lo, hi = shard_range(n, rank, world)
+        buf = torch.zeros(per, dtype=torch.float64)
+        buf[: hi - lo] = torch.from_numpy(fn(G[lo:hi]))
+        whole = torch.empty(per * world, dtype=torch.float64)
+        dist.all_gather_into_tensor(whole, buf)
+        return torch.cat([whole[r * per: r * per + (shard_range(n, r, world)[1] - shard_range(n, r, world)[0])] for r in range(world)]).numpy()
+
+    ga = OG.NumGA(n_pop, 12, seed=9)
+    ga.init(sharded)
+    for _ in range(4):
+        ga.step(sharded)
+    if rank == 0:
+        out_q.put((ga.pop.copy(), ga.fit.copy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_pop", [25, 32])
+def test_two_rank_generation_loop_equals_single_rank(n_pop):
+    import torch.multiprocessing as mp
+    from oracle import ga as OG
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_ga_worker, args=(r, 2, port, n_pop, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    pop, fit = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    fn = lambda G: np.sin(G).sum(axis=1) - 0.1 * (G * G).sum(axis=1)
+    ga = OG.NumGA(n_pop, 12, seed=9)
+    ga.init(fn)
+    for _ in range(4):
+        ga.step(fn)
+    assert np.array_equal(pop, ga.pop) and np.array_equal(fit, ga.fit)
