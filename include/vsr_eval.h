@@ -139,6 +139,15 @@ int vsr_eval_device(vsr_ctx* ctx, const double* d_genomes, int32_t n, double* d_
 int vsr_trace(vsr_ctx* ctx, const double* genome, int32_t n_steps, double* vertices_out, double* bodies_out,
               double* ctrl_out, vsr_result* result_out);
 
+/*
+ * Evaluate n robots, each on its OWN terrain: the `-rnd` terrains of Starter.buildLocomotionTask (Starter.java:89-93), where
+ * every evaluation builds `Locomotion.createTerrain(name.replace("-rnd", "-" + random.nextInt(10000)))`.  Robot i runs on the
+ * polyline terrain_x/terrain_y[terrain_off[i] .. terrain_off[i+1]) (HOST arrays; terrain_off has n+1 entries, starts at 0);
+ * its initial placement is recomputed for that polyline.  The context's own terrain only fixes the reference placement.
+ */
+int vsr_eval_terrains(vsr_ctx* ctx, const double* genomes, int32_t n, const double* terrain_x, const double* terrain_y,
+                      const int32_t* terrain_off, double* fitness_out, vsr_result* results_out);
+
 /* timing / accounting of the most recent vsr_eval / vsr_eval_device on device 0 of the context */
 double vsr_last_kernel_ms(vsr_ctx* ctx);    /* CUDA-event duration of the episode kernel; syncs the stream */
 int64_t vsr_kernel_launches(const vsr_ctx* ctx); /* total episode-kernel launches so far */
@@ -168,6 +177,8 @@ int vsr_voxel_cells(const vsr_ctx* ctx, int32_t* cell, int32_t cap);
 int vsr_counts(const vsr_ctx* ctx, int32_t* n_voxels, int32_t* n_springs, int32_t* n_ropes, int32_t* n_welds);
 /* java.util.Random replay (terrain builders): fills out[n] with nextGaussian() of Random(seed) */
 int vsr_java_random_gaussians(int64_t seed, double* out, int32_t n);
+/* ... and with nextInt(bound): the per-evaluation terrain seeds `random.nextInt(10000)` of Starter.java:91 */
+int vsr_java_random_ints(int64_t seed, int32_t bound, int32_t* out, int32_t n);
 
 #ifdef __cplusplus
 }

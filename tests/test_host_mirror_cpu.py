@@ -81,5 +81,21 @@ def test_unsupported_is_loud(V):
     B, L, R, F = V
     with pytest.raises(F.VsrError):
         B.build_mapper("brainHeteroDist<mlp")
-    with pytest.raises(F.VsrError):
-        L.build_locomotion_task("hilly-1-10-rnd", 10.0)
+
+
+def test_rnd_terrain_task_draws_java_seeds(V, oracle):
+    """Starter.java:89-93: `name.replace("-rnd", "-" + random.nextInt(10000))` per evaluation, from the run's java.util.Random."""
+    B, L, R, F = V
+    task = L.build_locomotion_task("hilly-1-10-rnd", 10.0, 1.0, random=L.JavaRandomInts(5))
+    assert isinstance(task, L.RandomTerrainLocomotion)
+    r = oracle.JavaRandom(5)
+    seeds = [r.next_int(10000) for _ in range(5)]
+    got = task.terrains_for(3) + task.terrains_for(2)  # the stream continues across batches
+    for s, (xs, ys) in zip(seeds, got):
+        oxs, oys = oracle.create_terrain("hilly-1-10-%d" % s)
+        assert np.array_equal(xs, oxs) and np.array_equal(ys, oys)
+    assert F.java_random_ints(5, 10000, 5).tolist() == seeds
+    rp = oracle.JavaRandom(-3)
+    assert F.java_random_ints(-3, 16, 4).tolist() == [rp.next_int(16) for _ in range(4)]  # power-of-two bound path
+    with pytest.raises(F.VsrIllegalArgument):
+        L.RandomTerrainLocomotion(10.0, "flat", L.JavaRandomInts(0))

@@ -77,6 +77,7 @@ _SIGS = {
     "vsr_genome_len": (C.c_int, [C.c_void_p]),
     "vsr_n_voxels": (C.c_int, [C.c_void_p]),
     "vsr_eval": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "vsr_eval_terrains": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vsr_eval_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vsr_trace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vsr_last_kernel_ms": (C.c_double, [C.c_void_p]),
@@ -93,6 +94,7 @@ _SIGS = {
     "vsr_voxel_cells": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
     "vsr_counts": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_int32)] * 4),
     "vsr_java_random_gaussians": (C.c_int, [C.c_int64, C.c_void_p, C.c_int32]),
+    "vsr_java_random_ints": (C.c_int, [C.c_int64, C.c_int32, C.c_void_p, C.c_int32]),
 }
 
 # include/vsr_ga.h
@@ -210,6 +212,22 @@ class Context:
         fit = np.empty(g.shape[0], dtype=np.float64)
         res = np.empty(g.shape[0], dtype=RESULT_DTYPE) if want_results else None
         check(lib().vsr_eval(self._h, _ptr(g), g.shape[0], _ptr(fit), _ptr(res)), self._h)
+        return (fit, res) if want_results else fit
+
+    def eval_terrains(self, genomes: np.ndarray, terrains, want_results: bool = False):
+        """One terrain per robot (`-rnd`): terrains = sequence of (xs, ys) polylines, len == number of genomes."""
+        g = np.ascontiguousarray(genomes, dtype=np.float64)
+        if g.ndim != 2 or g.shape[1] != self.genome_len:
+            raise VsrIllegalArgument(VSR_EDIM, f"Wrong number of values: {self.genome_len} expected, {g.shape[-1]} found")
+        if len(terrains) != g.shape[0]:
+            raise VsrIllegalArgument(VSR_EINVAL, f"{g.shape[0]} terrains expected, {len(terrains)} found")
+        off = np.zeros(g.shape[0] + 1, dtype=np.int32)
+        off[1:] = np.cumsum([len(t[0]) for t in terrains])
+        xs = np.ascontiguousarray(np.concatenate([np.asarray(t[0], dtype=np.float64) for t in terrains])) if len(terrains) else np.zeros(0)
+        ys = np.ascontiguousarray(np.concatenate([np.asarray(t[1], dtype=np.float64) for t in terrains])) if len(terrains) else np.zeros(0)
+        fit = np.empty(g.shape[0], dtype=np.float64)
+        res = np.empty(g.shape[0], dtype=RESULT_DTYPE) if want_results else None
+        check(lib().vsr_eval_terrains(self._h, _ptr(g), g.shape[0], _ptr(xs), _ptr(ys), _ptr(off), _ptr(fit), _ptr(res)), self._h)
         return (fit, res) if want_results else fit
 
     def eval_into(self, genomes: np.ndarray, fitness_out: np.ndarray):
@@ -421,6 +439,12 @@ def episode_steps(final_t: float, transient_t: float, dt: float = 1.0 / 60.0):
     v = [C.c_int32() for _ in range(3)]
     check(lib().vsr_episode_steps(final_t, transient_t, dt, *[C.byref(x) for x in v]))
     return tuple(x.value for x in v)
+
+
+def java_random_ints(seed: int, bound: int, n: int) -> np.ndarray:
+    out = np.zeros(n, dtype=np.int32)
+    check(lib().vsr_java_random_ints(seed, bound, _ptr(out), n))
+    return out
 
 
 def java_random_gaussians(seed: int, n: int) -> np.ndarray:

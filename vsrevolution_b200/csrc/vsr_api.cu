@@ -39,6 +39,10 @@ struct DeviceState {
   size_t hist_bytes = 0;
   void* d_energy = nullptr; // per-lane energy accumulators (results mode only)
   size_t energy_bytes = 0;
+  // per-evaluation terrains (vsr_eval_terrains): vertices of all robots of the shard, offsets, ground bottoms, placement shifts
+  double *d_rtx = nullptr, *d_rty = nullptr, *d_rbase = nullptr, *d_rplace = nullptr;
+  int* d_roff = nullptr;
+  size_t rt_vertices = 0, rt_robots = 0;
   double* d_genomes = nullptr;
   double* d_fitness = nullptr;
   vsr_result* d_results = nullptr;
@@ -76,6 +80,7 @@ struct vsr_ctx {
   std::vector<DeviceState> devs;
   std::string err;
   int64_t launches = 0;
+  double place_dx = 0, place_dy = 0; // initial placement on the context's own terrain
 };
 
 namespace {
@@ -93,13 +98,32 @@ int fail(vsr_ctx* c, int code, const std::string& msg) {
       return fail(ctx, VSR_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));               \
   } while (0)
 
-double ground_y_at(const std::vector<double>& tx, const std::vector<double>& ty, double x) {
-  for (size_t i = 1; i < tx.size(); i++)
+double ground_y_at(const double* tx, const double* ty, int n, double x) {
+  for (int i = 1; i < n; i++)
     if (x >= tx[i - 1] && x <= tx[i]) {
       double u = (x - tx[i - 1]) / (tx[i] - tx[i - 1]);
       return ty[i - 1] + u * (ty[i] - ty[i - 1]);
     }
   return -INFINITY;
+}
+
+// Locomotion.apply: translate the robot so that its bounding box starts place_x_gap right of the terrain's second vertex and
+// its lowest voxel is place_y_gap above the ground under that voxel's centre [U]; (dx, dy) is added to the grid positions
+bool placement(const vsr_ctx* ctx, const double* tx, const double* ty, int nt, double* dx_out, double* dy_out) {
+  const vsr_env_desc& e = ctx->env;
+  const double L = e.side_length;
+  double minx = INFINITY;
+  for (int v = 0; v < ctx->n_vox; v++) minx = std::fmin(minx, (ctx->cell_of_vox[v] % ctx->w) * L - L / 2);
+  const double dx = (tx[1] + e.place_x_gap) - minx;
+  double min_gap = INFINITY;
+  for (int v = 0; v < ctx->n_vox; v++) {
+    int cell = ctx->cell_of_vox[v], x = cell % ctx->w, y = cell / ctx->w;
+    double cx = x * L + dx, miny = y * L - L / 2;
+    min_gap = std::fmin(min_gap, miny - ground_y_at(tx, ty, nt, cx));
+  }
+  const double dy = e.place_y_gap - min_gap;
+  *dx_out = dx; *dy_out = dy;
+  return std::isfinite(dy) && std::isfinite(dx);
 }
 
 int sensor_dim(const vsr_sensor_desc& s) {
@@ -201,17 +225,9 @@ int finalize(vsr_ctx* ctx) {
   }
   // Locomotion.apply initial placement
   {
-    double minx = INFINITY;
-    for (int v = 0; v < ctx->n_vox; v++) minx = std::fmin(minx, (ctx->cell_of_vox[v] % ctx->w) * L - L / 2);
-    const double dx = (ctx->tx[1] + e.place_x_gap) - minx;
-    double min_gap = INFINITY;
-    for (int v = 0; v < ctx->n_vox; v++) {
-      int cell = ctx->cell_of_vox[v], x = cell % ctx->w, y = cell / ctx->w;
-      double cx = x * L + dx, miny = y * L - L / 2;
-      min_gap = std::fmin(min_gap, miny - ground_y_at(ctx->tx, ctx->ty, cx));
-    }
-    const double dy = e.place_y_gap - min_gap;
-    if (!std::isfinite(dy)) return fail(ctx, VSR_EINVAL, "robot is placed outside the terrain");
+    double dx, dy;
+    if (!placement(ctx, ctx->tx.data(), ctx->ty.data(), (int)ctx->tx.size(), &dx, &dy)) return fail(ctx, VSR_EINVAL, "robot is placed outside the terrain");
+    ctx->place_dx = dx; ctx->place_dy = dy;
     for (int v = 0; v < ctx->n_vox; v++) {
       int cell = ctx->cell_of_vox[v];
       k.vox_x0[v] = (cell % ctx->w) * L + dx;
@@ -426,7 +442,8 @@ int ensure_energy(vsr_ctx* ctx, DeviceState& d, int grid) {
 
 // enqueue the episode kernel for n robots whose genomes are at d_genomes (device)
 int enqueue(vsr_ctx* ctx, DeviceState& d, const double* d_genomes, size_t n, double* d_fitness, vsr_result* d_results,
-            cudaStream_t st, double* trv, double* trb, double* trc, int trace_steps, bool time_it) {
+            cudaStream_t st, double* trv, double* trb, double* trc, int trace_steps, bool time_it, bool robot_terrains = false,
+            double rt_ymax = 0) {
   if (n == 0) return VSR_OK;
   vsr::KParams k = ctx->kp;
   const int grid = grid_for(ctx, n);
@@ -439,6 +456,7 @@ int enqueue(vsr_ctx* ctx, DeviceState& d, const double* d_genomes, size_t n, dou
   k.energy = d.d_energy;
   k.tx = d.d_tx; k.ty = d.d_ty; k.win_tab = d.d_win; k.hist = d.d_hist; k.noise = d.d_noise;
   k.genomes = d_genomes; k.fitness = d_fitness; k.results = d_results; k.n_robots = (int)n;
+  if (robot_terrains) { k.tx = d.d_rtx; k.ty = d.d_rty; k.toff = d.d_roff; k.tbase = d.d_rbase; k.tplace = d.d_rplace; k.ty_max = rt_ymax; }
   k.tr_vertices = trv; k.tr_bodies = trb; k.tr_ctrl = trc; k.trace_steps = trace_steps;
   if (time_it) CK(cudaEventRecord(d.ev0, st));
   void* args[] = {&k};
@@ -577,6 +595,7 @@ void vsr_ctx_destroy(vsr_ctx* c) {
     cudaSetDevice(d.dev);
     if (d.stream) cudaStreamSynchronize(d.stream);
     cudaFree(d.d_tx); cudaFree(d.d_ty); cudaFree(d.d_win); cudaFree(d.d_hist); cudaFree(d.d_noise); cudaFree(d.d_energy);
+    cudaFree(d.d_rtx); cudaFree(d.d_rty); cudaFree(d.d_rbase); cudaFree(d.d_rplace); cudaFree(d.d_roff);
     cudaFree(d.d_genomes); cudaFree(d.d_fitness); cudaFree(d.d_results);
     cudaFreeHost(d.h_genomes); cudaFreeHost(d.h_fitness); cudaFreeHost(d.h_results);
     if (d.ev0) cudaEventDestroy(d.ev0);
@@ -676,6 +695,78 @@ int vsr_eval(vsr_ctx* ctx, const double* genomes, int32_t n, double* fitness_out
                    nullptr, 0, i == 0 && c0 + cn == cnt);
       if (rc) return rc;
     }
+    CK(cudaMemcpyAsync(d.h_fitness, d.d_fitness, cnt * sizeof(double), cudaMemcpyDeviceToHost, d.stream));
+    if (results_out) CK(cudaMemcpyAsync(d.h_results, d.d_results, cnt * sizeof(vsr_result), cudaMemcpyDeviceToHost, d.stream));
+  }
+  for (size_t i = 0; i < nd; i++) {
+    DeviceState& d = ctx->devs[i];
+    size_t lo = std::min((size_t)n, i * per), hi = std::min((size_t)n, lo + per), cnt = hi - lo;
+    if (!cnt) continue;
+    CK(cudaSetDevice(d.dev));
+    CK(cudaStreamSynchronize(d.stream));
+    std::memcpy(fitness_out + lo, d.h_fitness, cnt * sizeof(double));
+    if (results_out) std::memcpy(results_out + lo, d.h_results, cnt * sizeof(vsr_result));
+  }
+  return VSR_OK;
+}
+
+int vsr_eval_terrains(vsr_ctx* ctx, const double* genomes, int32_t n, const double* terrain_x, const double* terrain_y,
+                      const int32_t* terrain_off, double* fitness_out, vsr_result* results_out) {
+  if (!ctx) return VSR_EINVAL;
+  if (!ctx->ready) return fail(ctx, VSR_ESTATE, "body and controller must be set before vsr_eval_terrains");
+  if (n < 0 || (n > 0 && (!genomes || !fitness_out || !terrain_x || !terrain_y || !terrain_off))) return fail(ctx, VSR_EINVAL, "bad vsr_eval_terrains arguments");
+  if (n == 0) return VSR_OK;
+  const int G = ctx->kp.genome_len;
+  // per robot: polyline checks, bottom of its ground body, placement shift relative to the context's terrain
+  std::vector<double> base((size_t)n), place((size_t)2 * n);
+  double ymax = -INFINITY;
+  if (terrain_off[0] != 0) return fail(ctx, VSR_EINVAL, "terrain_off[0] must be 0");
+  for (int i = 0; i < n; i++) {
+    const int a = terrain_off[i], b = terrain_off[i + 1], nt = b - a;
+    if (nt < 2 || nt > 16383) return fail(ctx, VSR_EINVAL, "every terrain needs 2..16383 vertices");
+    double ymin = INFINITY;
+    for (int j = a; j < b; j++) {
+      if (j > a && !(terrain_x[j] > terrain_x[j - 1])) return fail(ctx, VSR_EINVAL, "terrain xs must be strictly increasing");
+      ymin = std::fmin(ymin, terrain_y[j]); ymax = std::fmax(ymax, terrain_y[j]);
+    }
+    base[i] = ymin - ctx->env.ground_thickness;
+    double dx, dy;
+    if (!placement(ctx, terrain_x + a, terrain_y + a, nt, &dx, &dy)) return fail(ctx, VSR_EINVAL, "robot is placed outside the terrain");
+    place[2 * (size_t)i] = dx - ctx->place_dx; place[2 * (size_t)i + 1] = dy - ctx->place_dy;
+  }
+  const size_t nd = ctx->devs.size(), per = ((size_t)n + nd - 1) / nd;
+  std::vector<int32_t> off;
+  for (size_t i = 0; i < nd; i++) {
+    DeviceState& d = ctx->devs[i];
+    size_t lo = std::min((size_t)n, i * per), hi = std::min((size_t)n, lo + per), cnt = hi - lo;
+    if (!cnt) continue;
+    int rc = ensure_capacity(ctx, d, cnt);
+    if (rc) return rc;
+    CK(cudaSetDevice(d.dev));
+    const size_t v0 = (size_t)terrain_off[lo], nv = (size_t)terrain_off[hi] - v0;
+    if (nv > d.rt_vertices) {
+      cudaFree(d.d_rtx); cudaFree(d.d_rty); d.d_rtx = d.d_rty = nullptr; d.rt_vertices = 0;
+      CK(cudaMalloc(&d.d_rtx, nv * sizeof(double))); CK(cudaMalloc(&d.d_rty, nv * sizeof(double)));
+      d.rt_vertices = nv;
+    }
+    if (cnt > d.rt_robots) {
+      cudaFree(d.d_rbase); cudaFree(d.d_rplace); cudaFree(d.d_roff); d.d_rbase = d.d_rplace = nullptr; d.d_roff = nullptr; d.rt_robots = 0;
+      CK(cudaMalloc(&d.d_rbase, cnt * sizeof(double))); CK(cudaMalloc(&d.d_rplace, 2 * cnt * sizeof(double)));
+      CK(cudaMalloc(&d.d_roff, (cnt + 1) * sizeof(int32_t)));
+      d.rt_robots = cnt;
+    }
+    off.resize(cnt + 1);
+    for (size_t r = 0; r <= cnt; r++) off[r] = terrain_off[lo + r] - (int32_t)v0;
+    // small synchronous uploads (pageable sources); the genomes follow on the stream
+    CK(cudaMemcpy(d.d_rtx, terrain_x + v0, nv * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d.d_rty, terrain_y + v0, nv * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d.d_rbase, base.data() + lo, cnt * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d.d_rplace, place.data() + 2 * lo, 2 * cnt * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d.d_roff, off.data(), (cnt + 1) * sizeof(int32_t), cudaMemcpyHostToDevice));
+    std::memcpy(d.h_genomes, genomes + lo * G, cnt * G * sizeof(double));
+    CK(cudaMemcpyAsync(d.d_genomes, d.h_genomes, cnt * G * sizeof(double), cudaMemcpyHostToDevice, d.stream));
+    rc = enqueue(ctx, d, d.d_genomes, cnt, d.d_fitness, results_out ? d.d_results : nullptr, d.stream, nullptr, nullptr, nullptr, 0, i == 0, true, ymax);
+    if (rc) return rc;
     CK(cudaMemcpyAsync(d.h_fitness, d.d_fitness, cnt * sizeof(double), cudaMemcpyDeviceToHost, d.stream));
     if (results_out) CK(cudaMemcpyAsync(d.h_results, d.d_results, cnt * sizeof(vsr_result), cudaMemcpyDeviceToHost, d.stream));
   }

@@ -85,6 +85,11 @@ struct KParams {
   const double* ty;
   int n_t;
   double base_y, ty_max; // bottom of the ground body; highest terrain vertex
+  // per-evaluation terrains (`-rnd`, Starter.java:89-93): robot i runs on vertices [toff[i], toff[i+1]) of tx / ty, its ground
+  // body ends at tbase[i] and its initial placement is shifted by (tplace[2i], tplace[2i+1]); NULL = one terrain for all
+  const int* toff;
+  const double* tbase;
+  const double* tplace;
   // sensors
   int n_sensors, sens_dim, n_avg, hist_cap;
   SensorK sensors[kMaxSensors];
@@ -459,7 +464,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
   R ox, oy;
   R X[4], Y[4], A[4], CS[4], SN[4], VX[4], VY[4], W[4];
   {
-    const double cx0 = valid ? P.vox_x0[vi] : 0.0, cy0 = valid ? P.vox_y0[vi] : 1.0e4;
+    double cx0 = valid ? P.vox_x0[vi] : 0.0, cy0 = valid ? P.vox_y0[vi] : 1.0e4;
+    if (P.tplace != nullptr && valid) { cx0 += P.tplace[2 * robot]; cy0 += P.tplace[2 * robot + 1]; }
     ox = (R)rint(cx0); oy = (R)rint(cy0);
     const R lx = (R)(cx0 - (double)ox), ly = (R)(cy0 - (double)oy);
     const R off = KC(mass_off, P.side_len / 2 - P.half);
@@ -548,12 +554,15 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
         const R cxl = R(0.25) * (X[0] + X[1] + X[2] + X[3]);
         if (!pk || cxl < px0 || cxl > px1) { // (re)load the polygon under the voxel centre
           const double cxw = oxd + (double)cxl;
+          const int t0 = P.toff ? __ldg(&P.toff[robot]) : 0, tn = P.toff ? __ldg(&P.toff[robot + 1]) - t0 : P.n_t;
+          const double* tx = P.tx + t0;
+          const double* ty = P.ty + t0;
           int kk = kh;
-          while (kk > 1 && __ldg(&P.tx[kk - 1]) > cxw) kk--;
-          while (kk < P.n_t - 1 && __ldg(&P.tx[kk]) <= cxw) kk++;
+          while (kk > 1 && __ldg(&tx[kk - 1]) > cxw) kk--;
+          while (kk < tn - 1 && __ldg(&tx[kk]) <= cxw) kk++;
           kh = kk; pk = kk;
-          px0 = (R)(__ldg(&P.tx[kk - 1]) - oxd); px1 = (R)(__ldg(&P.tx[kk]) - oxd);
-          py0 = (R)(__ldg(&P.ty[kk - 1]) - oyd); py1 = (R)(__ldg(&P.ty[kk]) - oyd);
+          px0 = (R)(__ldg(&tx[kk - 1]) - oxd); px1 = (R)(__ldg(&tx[kk]) - oxd);
+          py0 = (R)(__ldg(&ty[kk - 1]) - oyd); py1 = (R)(__ldg(&ty[kk]) - oyd);
           const R ex = px0 - px1, ey = py0 - py1;
           const R il = M<R>::rsqrt_(ex * ex + ey * ey);
           pnx = ey * il; pny = -ex * il;
@@ -611,14 +620,21 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
       const unsigned prev = massSlots[mi];
       const R ext = K_half * (M<R>::abs_(ck) + M<R>::abs_(sk));
       const bool fast = xk - ext >= qx0 + R(kFastMargin) && xk + ext <= qx1 - R(kFastMargin);
-      double ax0 = 0, ax1 = 0, ay0 = 0;
+      double ax0 = 0, ax1 = 0, ay0 = 0, basey = P.base_y;
+      const double* tx = P.tx;
+      const double* ty = P.ty;
       int kk = pko, kend = pko;
       if (!fast) {
+        int tn = P.n_t;
+        if (P.toff) { // the owner's own terrain
+          const int orobot = gw * P.robots_per_warp + ol / L, t0 = __ldg(&P.toff[orobot]);
+          tn = __ldg(&P.toff[orobot + 1]) - t0; tx += t0; ty += t0; basey = __ldg(&P.tbase[orobot]);
+        }
         ax0 = oxd + (double)(xk - ext); ax1 = oxd + (double)(xk + ext); ay0 = oyd + (double)(yk - ext);
         // smallest polygon index kk (polygon kk spans tx[kk-1]..tx[kk]) with tx[kk] >= ax0
-        while (kk > 1 && __ldg(&P.tx[kk - 1]) >= ax0) kk--;
-        while (kk < P.n_t - 1 && __ldg(&P.tx[kk]) < ax0) kk++;
-        kend = P.n_t - 1;
+        while (kk > 1 && __ldg(&tx[kk - 1]) >= ax0) kk--;
+        while (kk < tn - 1 && __ldg(&tx[kk]) < ax0) kk++;
+        kend = tn - 1;
       }
       int cnt = 0;
       unsigned news = 0;
@@ -630,15 +646,15 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
         if (fast) {
           np = collide_box_top<R>(qx1, qy1, qnx, qny, xk, yk, ck, sk, K_half, nx, ny, px, py, dp, id);
         } else {
-          const double x0 = __ldg(&P.tx[kk - 1]);
+          const double x0 = __ldg(&tx[kk - 1]);
           if (x0 > ax1) break;
-          const double x1 = __ldg(&P.tx[kk]), y0 = __ldg(&P.ty[kk - 1]), y1 = __ldg(&P.ty[kk]);
+          const double x1 = __ldg(&tx[kk]), y0 = __ldg(&ty[kk - 1]), y1 = __ldg(&ty[kk]);
           if (ax1 < x0 || ax0 > x1) continue;
           if (ay0 > fmax(y0, y1)) continue;
           gx0 = (R)(x0 - oxd); gy0 = (R)(y0 - oyd); gx1 = (R)(x1 - oxd); gy1 = (R)(y1 - oyd);
         }
         if (np < 0)
-          np = collide_box_ground<R>(gx0, gy0, gx1, gy1, (R)(P.base_y - oyd), xk, yk, ck, sk, K_half, K_lin_tol, nx, ny, px, py, dp, id);
+          np = collide_box_ground<R>(gx0, gy0, gx1, gy1, (R)(basey - oyd), xk, yk, ck, sk, K_half, K_lin_tol, nx, ny, px, py, dp, id);
         if (!np) continue;
         const int s = atomicAdd(poolCnt, 1);
         if (s >= S) { overflow++; continue; }

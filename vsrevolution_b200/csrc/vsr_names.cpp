@@ -29,6 +29,16 @@ struct JavaRandom {
     seed = (seed * 0x5DEECE66DULL + 0xBULL) & ((1ULL << 48) - 1);
     return (int32_t)((int64_t)seed >> (48 - bits));
   }
+  int32_t next_int(int32_t bound) { // java.util.Random.nextInt(int bound)
+    int32_t r = next(31);
+    const int32_t m = bound - 1;
+    if ((bound & m) == 0) return (int32_t)(((int64_t)bound * (int64_t)r) >> 31);
+    for (int32_t u = r;; u = next(31)) { // Java: `u - (r = u % bound) + m < 0` detects the int overflow
+      r = u % bound;
+      if ((int64_t)u - r + m < (1LL << 31)) break;
+    }
+    return r;
+  }
   double next_double() { return (double)(((int64_t)next(26) << 27) + next(27)) * (1.0 / (double)(1LL << 53)); }
   double next_gaussian() {
     if (have) { have = false; return next_g; }
@@ -78,6 +88,13 @@ int vsr_java_random_gaussians(int64_t seed, double* out, int32_t n) {
   if (!out || n < 0) return VSR_EINVAL;
   JavaRandom r(seed);
   for (int i = 0; i < n; i++) out[i] = r.next_gaussian();
+  return VSR_OK;
+}
+
+int vsr_java_random_ints(int64_t seed, int32_t bound, int32_t* out, int32_t n) {
+  if (!out || n < 0 || bound <= 0) return VSR_EINVAL;
+  JavaRandom r(seed);
+  for (int i = 0; i < n; i++) out[i] = r.next_int(bound);
   return VSR_OK;
 }
 

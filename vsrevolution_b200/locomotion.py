@@ -167,10 +167,50 @@ class Locomotion:
         return self.apply_all([robot])[0]
 
 
-def build_locomotion_task(terrain_name: str, episode_t: float, transient_t: float = 0.0, **kw) -> Locomotion:
-    """Starter.buildLocomotionTask (Starter.java:83-94) for fixed (non `-rnd`) terrains."""
+class JavaRandomInts:
+    """The `random.nextInt(bound)` stream of the run's shared java.util.Random (Starter.java:91), replayed by the library."""
+
+    def __init__(self, seed: int):
+        self.seed, self.used = seed, 0
+
+    def next_ints(self, bound: int, n: int) -> np.ndarray:
+        out = _ffi.java_random_ints(self.seed, bound, self.used + n)[self.used:]
+        self.used += n
+        return out
+
+
+class RandomTerrainLocomotion(Locomotion):
+    """`r -> new Locomotion(T, createTerrain(name.replace("-rnd", "-" + random.nextInt(10000))), settings).apply(r)`
+    (Starter.java:89-93): every evaluation gets its own terrain; the batch goes to the device in one vsr_eval_terrains call.
+    Seeds are drawn in robot order (the reference draws them in thread-completion order, which is not reproducible)."""
+
+    def __init__(self, final_t: float, terrain_name: str, random: JavaRandomInts, settings: Settings | None = None,
+                 transient_t: float = 0.0, **kw):
+        if "-rnd" not in terrain_name:
+            raise _ffi.VsrIllegalArgument(_ffi.VSR_EINVAL, "terrain name without -rnd")
+        self.terrain_name, self.random = terrain_name, random
+        super().__init__(final_t, Locomotion.create_terrain(terrain_name.replace("-rnd", "-0")), settings, transient_t, **kw)
+
+    def terrains_for(self, n: int):
+        return [Locomotion.create_terrain(self.terrain_name.replace("-rnd", "-%d" % s)) for s in self.random.next_ints(10000, n)]
+
+    def apply_all(self, robots: Sequence[Robot]) -> list[Outcome]:
+        if not robots:
+            return []
+        ctx = self._context(robots[0])
+        genomes = np.stack([self.genome_of(r) for r in robots])
+        _, res = ctx.eval_terrains(genomes, self.terrains_for(len(robots)), want_results=True)
+        return [Outcome(float(r["velocity"]), float(r["distance"]), float(r["time"]), float(r["first_x"]), float(r["last_x"]),
+                        self.transient_t, self.final_t, float(r["control_energy"]), float(r["area_ratio_abs"]),
+                        float(r["area_ratio_sq"])) for r in res]
+
+
+def build_locomotion_task(terrain_name: str, episode_t: float, transient_t: float = 0.0, random: JavaRandomInts | None = None,
+                          **kw) -> Locomotion:
+    """Starter.buildLocomotionTask (Starter.java:83-94): one shared Locomotion for fixed terrains, a per-evaluation terrain
+    (`random.nextInt(10000)` as seed) for `-rnd` names."""
     if "-rnd" in terrain_name:
-        raise _ffi.VsrError(_ffi.VSR_EUNSUPPORTED, "per-evaluation random terrains (-rnd) are a 'next' row (SURVEY.md 8f-4)")
+        return RandomTerrainLocomotion(episode_t, terrain_name, random or JavaRandomInts(0), Settings(), transient_t, **kw)
     return Locomotion(episode_t, Locomotion.create_terrain(terrain_name), Settings(), transient_t, **kw)
 
 
@@ -192,6 +232,8 @@ class PopulationEvaluator:
         self.n_voxels = self.ctx.n_voxels
 
     def evaluate(self, genomes: np.ndarray) -> np.ndarray:
+        if isinstance(self.task, RandomTerrainLocomotion):
+            return self.ctx.eval_terrains(genomes, self.task.terrains_for(len(genomes)))
         return self.ctx.eval(genomes)
 
     def kernel_launches(self) -> int:
