@@ -610,8 +610,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
     if (lane == 0) *poolCnt = 0;
     __syncwarp();
 #pragma unroll 1
-    for (int ci = lane; ci < ncand; ci += 32) {
-      const int c = cand[ci], ol = c & 31, k = c >> 5, mi = ol * 4 + k;
+    for (int c0 = 0; c0 < ncand; c0 += 32) { // warp-uniform trip count: the rounds below vote over the whole warp
+      const int ci = c0 + lane;
+      const bool act = ci < ncand;
+      const int c = act ? cand[ci] : 0, ol = c & 31, k = c >> 5, mi = ol * 4 + k;
       const R xk = spark[k * 32 + ol], yk = spark[(4 + k) * 32 + ol], ck = stg[mi], sk = stg[128 + mi];
       const R qx0 = spark[12 * 32 + ol], qx1 = spark[13 * 32 + ol], qy0 = spark[14 * 32 + ol], qy1 = spark[15 * 32 + ol];
       const R qnx = spark[16 * 32 + ol], qny = spark[17 * 32 + ol];
@@ -638,21 +640,37 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
       }
       int cnt = 0;
       unsigned news = 0;
-      for (; kk <= kend && cnt < kMaxMan; kk++) {
+      bool more = act;
+      // Rounds: every lane first walks (cheaply, divergently) to its next polygon that passes the AABB tests, then the warp
+      // re-converges and the narrowphase runs ONCE per round for all lanes that found one (a mass near a polygon boundary
+      // or on narrow steps meets 2-3 polygons; without the re-convergence the narrowphase body was replayed per lane group).
+#pragma unroll 1
+      for (;;) {
+        bool have = false;
+        int kuse = kk;
+        R gx0 = qx0, gy0 = qy0, gx1 = qx1, gy1 = qy1;
+        if (more) {
+          if (fast) { have = true; more = false; }
+          else {
+            while (kk <= kend) {
+              const double x0 = __ldg(&tx[kk - 1]);
+              if (x0 > ax1) { kk = kend + 1; break; }
+              const double x1 = __ldg(&tx[kk]), y0 = __ldg(&ty[kk - 1]), y1 = __ldg(&ty[kk]);
+              const int kc = kk++;
+              if (ax1 < x0 || ax0 > x1 || ay0 > fmax(y0, y1)) continue;
+              have = true; kuse = kc;
+              gx0 = (R)(x0 - oxd); gy0 = (R)(y0 - oyd); gx1 = (R)(x1 - oxd); gy1 = (R)(y1 - oyd);
+              break;
+            }
+            more = have;
+          }
+        }
+        if (!__any_sync(FULL, have)) break;
+        if (!have) continue;
         R nx, ny, px[2], py[2], dp[2];
         int id[2];
         int np = -1;
-        R gx0 = qx0, gy0 = qy0, gx1 = qx1, gy1 = qy1;
-        if (fast) {
-          np = collide_box_top<R>(qx1, qy1, qnx, qny, xk, yk, ck, sk, K_half, nx, ny, px, py, dp, id);
-        } else {
-          const double x0 = __ldg(&tx[kk - 1]);
-          if (x0 > ax1) break;
-          const double x1 = __ldg(&tx[kk]), y0 = __ldg(&ty[kk - 1]), y1 = __ldg(&ty[kk]);
-          if (ax1 < x0 || ax0 > x1) continue;
-          if (ay0 > fmax(y0, y1)) continue;
-          gx0 = (R)(x0 - oxd); gy0 = (R)(y0 - oyd); gx1 = (R)(x1 - oxd); gy1 = (R)(y1 - oyd);
-        }
+        if (fast) np = collide_box_top<R>(qx1, qy1, qnx, qny, xk, yk, ck, sk, K_half, nx, ny, px, py, dp, id);
         if (np < 0)
           np = collide_box_ground<R>(gx0, gy0, gx1, gy1, (R)(basey - oyd), xk, yk, ck, sk, K_half, K_lin_tol, nx, ny, px, py, dp, id);
         if (!np) continue;
@@ -660,7 +678,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
         if (s >= S) { overflow++; continue; }
         R jn0 = 0, jt0 = 0, jn1 = 0, jt1 = 0;
         // warm start from the previous manifold of the same (mass, polygon)
-        const int key = kk | (k << 14);
+        const int key = kuse | (k << 14);
         for (int o = 0; o < kMaxMan; o++) {
           const int os = (int)((prev >> (8 * o)) & 0xffu) - 1;
           if (os < 0) break;
@@ -707,8 +725,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
         poolM[np_ * S + s] = meta;
         news |= (unsigned)(s + 1) << (8 * cnt);
         cnt++;
+        if (cnt >= kMaxMan) more = false;
       }
-      massSlots[mi] = news;
+      if (act) massSlots[mi] = news;
     }
     par ^= 1;
     __syncwarp();
