@@ -350,3 +350,73 @@ def test_per_evaluation_terrains_match_single_terrain_runs(F, oracle):
     with pytest.raises(F.VsrIllegalArgument):
         ctx.eval_terrains(g[:1], [(np.array([0.0, 0.0, 1.0]), np.array([0.0, 0.0, 0.0]))])
     ctx.close()
+
+
+@pytest.mark.parametrize("shape,ctrl,sensors,terrain", [
+    ("box-1x1", "phase", "", "flat"),                       # 1 voxel: 32 robots per warp, no welds
+    ("box-8x4", "phase", "", "hilly-0.5-5-3"),              # 32 voxels: the largest body, one robot per warp
+    ("tripod-5x3", "central", "uniform-r+vxy+t-0", "uphill-10"),  # angle + velocity + touch sensors, sloped terrain
+    ("box-3x5", "dist", "uniform-a+t-0", "downhill-30"),    # tall body, distributed controller, validation terrain (Starter.java:171)
+])
+def test_other_bodies_sensors_and_terrains_track_the_oracle(F, oracle, shape, ctrl, sensors, terrain):
+    """Edge shapes (smallest / largest body), every sensor kind and the remaining terrain families: FP64 kernel vs oracle on the
+    first 30 steps (1e-9), FP32 kernel finite and close on the first 10 steps; ragged batch sizes around the warp packing."""
+    kind = {"phase": oracle.CTRL_PHASE_SIN, "central": oracle.CTRL_MLP_CENTRALIZED, "dist": oracle.CTRL_MLP_DISTRIBUTED_HOMO}[ctrl]
+    m = oracle.Model(shape, terrain, sensors, kind, oracle.default_params(1.5, 0.5))
+    G = m.genome_len()
+    g = np.random.default_rng(11).uniform(-1, 1, (70, G))
+    if kind != oracle.CTRL_PHASE_SIN:
+        # small weights keep the MLP outputs away from +-1: a fully contracted voxel sits exactly on the contraction-limit
+        # knife edge (rope active or not), which flips on 1e-13 differences within a few steps (tools/parity_probe5.py)
+        g *= 0.15
+    c64, c32 = make_ctx(F, m, 64), make_ctx(F, m, 32)
+    assert c64.genome_len == G
+    for r in range(3):
+        _, otv, otb, otc = m.run(g[r], trace_steps=30)
+        _, tv, tb, tc = c64.trace(g[r], 30)
+        assert np.abs(tb - otb).max() < 1e-9 and np.abs(tc - otc).max() < 1e-9, (shape, r)
+        _, tv32, _, _ = c32.trace(g[r], 10)
+        assert np.abs(tv32 - otv[:10]).max() / 3.0 < 1e-4
+    fit = c32.eval(g)
+    assert np.isfinite(fit).all()
+    rpw = 32 // int(m.mask.sum())
+    for n in (1, rpw, rpw + 1, 10 * rpw - 1, 10 * rpw + 1):  # around one warp / one CTA of robots
+        n = min(n, len(g))
+        assert np.array_equal(c32.eval(g[:n]), fit[:n]), (shape, n)
+    c64.close(); c32.close()
+
+
+def test_non_finite_genomes_do_not_hang_or_leak(F, oracle):
+    """NaN / inf genes: the episode still terminates, the fitness of that robot is returned as is (NaN propagates like in the
+    reference, whose comparator decides), and robots sharing its warp are unaffected."""
+    m = oracle.config_model(1, final_t=2.0)
+    ctx = make_ctx(F, m)
+    g = np.random.default_rng(3).uniform(-1, 1, (9, ctx.genome_len))
+    clean = ctx.eval(g)
+    bad = g.copy()
+    bad[1, :] = np.nan
+    bad[4, 3] = np.inf
+    bad[7, 10] = -np.inf
+    out = ctx.eval(bad)
+    ok = [0, 2, 3, 5, 6, 8]
+    assert np.array_equal(out[ok], clean[ok])
+    assert np.isfinite(out[[4, 7]]).all()  # tanh saturates an infinite pre-activation
+    ctx.close()
+
+
+def test_generation_loop_on_a_multi_device_context(F, oracle):
+    """vsr_ga with a context that shards over 2 devices inside one process (peer copies) == the single-device run."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    m = oracle.config_model(1, final_t=2.0)
+    pops = []
+    for devs in ([0], [0, 1]):
+        ctx = make_ctx(F, m, devices=devs)
+        ga = F.GeneticAlgorithm(ctx, 101, seed=6)
+        ga.init()
+        for _ in range(3):
+            ga.step()
+        pops.append(ga.population())
+        ga.close(); ctx.close()
+    assert np.array_equal(pops[0][0], pops[1][0]) and np.array_equal(pops[0][1], pops[1][1])

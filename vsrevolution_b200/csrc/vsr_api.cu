@@ -362,13 +362,15 @@ int finalize(vsr_ctx* ctx) {
   k.smem_warp_stride = (int)o;
   k.sync_mask = 115; // step start, before spring init, before velocity loop, before/after detect (tools/ab_run.sh sweeps)
   if (const char* ev = std::getenv("VSR_SYNC_MASK")) k.sync_mask = std::atoi(ev);
-  // launch shape: 2 CTAs x 5 warps (168 registers, 10 warps/SM) when their shared memory fits an SM; otherwise one CTA of
-  // 8 warps (255 registers) -- e.g. narrow-step terrains with their larger contact pool
-  const size_t smem_sm = 228 * 1024 - 2 * 1024; // 228 KB per SM, 1 KB reserved per resident CTA
+  // launch shape: one CTA of 10 warps (168 registers) when its shared memory fits the 227 KB a CTA may use; otherwise the
+  // 255-register kernel with 8 warps or fewer -- e.g. narrow-step terrains with their larger contact pool, large MLPs
   ctx->shape = kDefaultShape;
-  if (10 * o + 1024 > 227 * 1024 && 8 * o + 1024 <= 227 * 1024) ctx->shape = 2;
+  if (10 * o + 1024 > 227 * 1024) ctx->shape = 2;
   if (const char* ev = std::getenv("VSR_LAUNCH_SHAPE")) ctx->shape = std::max(0, std::min(kNumShapes - 1, std::atoi(ev)));
   ctx->warps = e.precision == 64 ? kWarps64 : kShapes[ctx->shape].warps;
+  // large controllers (weights of every robot of the warp live in shared memory): launch the chosen kernel with fewer warps
+  // per CTA than its launch bound (the kernel indexes by blockDim)
+  while (ctx->warps > 1 && (size_t)ctx->warps * o + 1024 > 227 * 1024) ctx->warps--;
   ctx->kernel = kernel_ptr(e.precision, ctx->kind, ctx->shape, e.scaffolding_mask == 0xF && !std::getenv("VSR_GENERIC_SCAFF"));
   ctx->smem_bytes = o * ctx->warps;
   if (k.n_t > 16383) return fail(ctx, VSR_EUNSUPPORTED, "terrains with more than 16383 vertices are not supported");
