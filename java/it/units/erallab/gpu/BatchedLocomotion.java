@@ -8,7 +8,6 @@ import it.units.erallab.hmsrobots.core.objects.Robot;
 
 import java.util.ArrayList;
 import java.util.List;
-import java.util.concurrent.CompletableFuture;
 import java.util.function.Function;
 
 /**
@@ -19,7 +18,7 @@ import java.util.function.Function;
  * NOT COMPILED IN THE BUILD CONTAINER (no JDK, 2dhmsr/JGEA jars absent). Two ways to use it, both keep JGEA's API:
  *  (1) applyAll(List<Robot>) from a thin evolver subclass that maps the whole population at once (preferred);
  *  (2) apply(Robot) from JGEA's executor threads: calls are micro-batched (flush when `expectedBatch` robots are
- *      waiting or after `maxWaitMillis`), each caller blocks on its future.
+ *      waiting, or by the first waiter whose `maxWaitMillis` expires), each caller blocks until its batch is evaluated.
  */
 public class BatchedLocomotion implements Function<Robot, GpuOutcome>, AutoCloseable {
 
@@ -28,9 +27,6 @@ public class BatchedLocomotion implements Function<Robot, GpuOutcome>, AutoClose
   private final int expectedBatch;
   private final long maxWaitMillis;
   private boolean configured = false;
-  private final List<Robot> pending = new ArrayList<>();
-  private final List<CompletableFuture<GpuOutcome>> futures = new ArrayList<>();
-  private long firstEnqueued = 0;
 
   public BatchedLocomotion(double finalT, double[][] groundProfile, double transientT, int expectedBatch, long maxWaitMillis) {
     this.ctx = VsrEval.create(finalT, transientT, groundProfile[0], groundProfile[1], 32, new int[0]);
@@ -62,35 +58,85 @@ public class BatchedLocomotion implements Function<Robot, GpuOutcome>, AutoClose
     return outcomes;
   }
 
+  /** One open batch: callers append, the filler (or the first waiter whose wait expires) closes and evaluates it. */
+  private static final class Batch {
+    final List<Robot> robots = new ArrayList<>();
+    final long t0 = System.currentTimeMillis();
+    List<GpuOutcome> outcomes;
+    RuntimeException error;
+    boolean done;
+  }
+
+  private Batch open = new Batch();
+  private final Object queueLock = new Object();
+
+  private void flush(Batch batch) {
+    try {
+      batch.outcomes = applyAll(batch.robots); // synchronized: a vsr_ctx is not re-entrant
+    } catch (RuntimeException e) {
+      batch.error = e;
+    }
+    synchronized (batch) {
+      batch.done = true;
+      batch.notifyAll();
+    }
+  }
+
+  /** Same protocol as vsrevolution_b200/locomotion.py:MicroBatchedLocomotion (exercised there by tests/test_host_mirror_cpu.py). */
   @Override
   public GpuOutcome apply(Robot robot) {
-    CompletableFuture<GpuOutcome> future = new CompletableFuture<>();
-    List<Robot> batch = null;
-    List<CompletableFuture<GpuOutcome>> batchFutures = null;
-    synchronized (this) {
-      if (pending.isEmpty()) {
-        firstEnqueued = System.currentTimeMillis();
-      }
-      pending.add(robot);
-      futures.add(future);
-      if (pending.size() >= expectedBatch || System.currentTimeMillis() - firstEnqueued >= maxWaitMillis) {
-        batch = new ArrayList<>(pending);
-        batchFutures = new ArrayList<>(futures);
-        pending.clear();
-        futures.clear();
+    Batch batch;
+    int slot;
+    boolean full;
+    synchronized (queueLock) {
+      batch = open;
+      slot = batch.robots.size();
+      batch.robots.add(robot);
+      full = batch.robots.size() >= expectedBatch;
+      if (full) {
+        open = new Batch();
       }
     }
-    if (batch != null) {
-      try {
-        List<GpuOutcome> outcomes = applyAll(batch);
-        for (int i = 0; i < outcomes.size(); i++) {
-          batchFutures.get(i).complete(outcomes.get(i));
+    if (full) {
+      flush(batch);
+    } else {
+      boolean leader = false;
+      synchronized (batch) {
+        while (!batch.done && !leader) {
+          long left = batch.t0 + maxWaitMillis - System.currentTimeMillis();
+          if (left > 0) {
+            try {
+              batch.wait(left);
+            } catch (InterruptedException e) {
+              Thread.currentThread().interrupt();
+              throw new RuntimeException(e);
+            }
+          } else {
+            synchronized (queueLock) { // timeout: the first waiter that still finds the batch open closes it
+              if (open == batch) {
+                open = new Batch();
+                leader = true;
+              }
+            }
+            if (!leader) {
+              try {
+                batch.wait();
+              } catch (InterruptedException e) {
+                Thread.currentThread().interrupt();
+                throw new RuntimeException(e);
+              }
+            }
+          }
         }
-      } catch (RuntimeException e) {
-        batchFutures.forEach(f -> f.completeExceptionally(e));
+      }
+      if (leader) {
+        flush(batch);
       }
     }
-    return future.join();
+    if (batch.error != null) {
+      throw batch.error;
+    }
+    return batch.outcomes.get(slot);
   }
 
   @Override

@@ -22,8 +22,29 @@ public final class VsrEval {
 
   public static native int genomeLength(long ctx);
 
-  /** vsr_eval: genomes[n*G] row-major -> results[n*5] = {velocity, distance, time, firstX, lastX}. */
+  /** vsr_eval: genomes[n*G] row-major -> results[n*8] = {velocity, distance, time, firstX, lastX, controlEnergy, areaRatioAbs, areaRatioSq}. */
   public static native double[] eval(long ctx, double[] genomes, int n);
+
+  /** vsr_eval_terrains: robot i on the polyline xs/ys[off[i]..off[i+1]) -- the -rnd terrains of Starter.java:89-93. */
+  public static native double[] evalTerrains(long ctx, double[] genomes, int n, double[] terrainXs, double[] terrainYs, int[] terrainOff);
+
+  /** include/vsr_ga.h: the device-resident numGA loop (builder/solver/DoublesStandard.java:41-71); returns the vsr_ga handle. */
+  public static native long gaCreate(long ctx, int nPop, double xOverProb, double tournamentRate, int minNTournament, double sigmaMut,
+                                     long seed, boolean remap);
+
+  public static native void gaInit(long ga);
+
+  public static native void gaStep(long ga);
+
+  /** {fitness, genome[0..G)} of the best individual. */
+  public static native double[] gaBest(long ga, int genomeLength);
+
+  /** {fitness[nPop], genomes[nPop][G]} flattened, best first. */
+  public static native double[] gaPopulation(long ga, int nPop, int genomeLength);
+
+  public static native long gaEvaluations(long ga);
+
+  public static native void gaDestroy(long ga);
 
   public static native void destroy(long ctx);
 }

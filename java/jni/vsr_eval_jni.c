@@ -1,5 +1,6 @@
 /* JNI glue between it.units.erallab.gpu.VsrEval and libvsr_eval.so (include/vsr_eval.h).
- * NOT COMPILED IN THE BUILD CONTAINER (no jni.h).  Build on a JDK host:
+ * NOT COMPILED IN THE BUILD CONTAINER (no JDK): type-checked there against a minimal jni.h stand-in
+ * (tests/jni_stub/jni.h, tests/test_cabi_cpu.py).  Build on a JDK host:
  *   gcc -shared -fPIC -I$JAVA_HOME/include -I$JAVA_HOME/include/linux -I../../include vsr_eval_jni.c \
  *       -L../../vsrevolution_b200 -lvsr_eval -o libvsr_eval_jni.so */
 #include <jni.h>
@@ -7,6 +8,9 @@
 #include <string.h>
 
 #include "vsr_eval.h"
+#include "vsr_ga.h"
+
+static jdoubleArray pack_results(JNIEnv* env, const vsr_result* res, jint n);
 
 static void throw_status(JNIEnv* env, vsr_ctx* ctx, int rc) {
   const char* cls = (rc == VSR_EINVAL || rc == VSR_EDIM) ? "java/lang/IllegalArgumentException" : "java/lang/RuntimeException";
@@ -80,16 +84,109 @@ JNIEXPORT jdoubleArray JNICALL Java_it_units_erallab_gpu_VsrEval_eval(JNIEnv* en
   (*env)->ReleaseDoubleArrayElements(env, genomes, pg, JNI_ABORT);
   jdoubleArray out = NULL;
   if (rc) throw_status(env, ctx, rc);
-  else {
-    out = (*env)->NewDoubleArray(env, n * 8);
-    for (int i = 0; i < n; i++) {
-      jdouble v[8] = {res[i].velocity, res[i].distance, res[i].time, res[i].first_x, res[i].last_x,
-                      res[i].control_energy, res[i].area_ratio_abs, res[i].area_ratio_sq};
-      (*env)->SetDoubleArrayRegion(env, out, i * 8, 8, v);
-    }
-  }
+  else out = pack_results(env, res, n);
   free(fit); free(res);
   return out;
+}
+
+static jdoubleArray pack_results(JNIEnv* env, const vsr_result* res, jint n) {
+  jdoubleArray out = (*env)->NewDoubleArray(env, n * 8);
+  for (int i = 0; i < n; i++) {
+    jdouble v[8] = {res[i].velocity, res[i].distance, res[i].time, res[i].first_x, res[i].last_x,
+                    res[i].control_energy, res[i].area_ratio_abs, res[i].area_ratio_sq};
+    (*env)->SetDoubleArrayRegion(env, out, i * 8, 8, v);
+  }
+  return out;
+}
+
+/* vsr_eval_terrains: one polyline per robot (the -rnd terrains of Starter.buildLocomotionTask, Starter.java:89-93) */
+JNIEXPORT jdoubleArray JNICALL Java_it_units_erallab_gpu_VsrEval_evalTerrains(JNIEnv* env, jclass c, jlong h, jdoubleArray genomes, jint n,
+                                                                              jdoubleArray xs, jdoubleArray ys, jintArray off) {
+  (void)c;
+  vsr_ctx* ctx = (vsr_ctx*)(intptr_t)h;
+  jdouble* pg = (*env)->GetDoubleArrayElements(env, genomes, NULL);
+  jdouble* px = (*env)->GetDoubleArrayElements(env, xs, NULL);
+  jdouble* py = (*env)->GetDoubleArrayElements(env, ys, NULL);
+  jint* po = (*env)->GetIntArrayElements(env, off, NULL);
+  double* fit = (double*)malloc(sizeof(double) * (n ? n : 1));
+  vsr_result* res = (vsr_result*)malloc(sizeof(vsr_result) * (n ? n : 1));
+  int rc = vsr_eval_terrains(ctx, pg, n, px, py, (const int32_t*)po, fit, res);
+  (*env)->ReleaseIntArrayElements(env, off, po, JNI_ABORT);
+  (*env)->ReleaseDoubleArrayElements(env, ys, py, JNI_ABORT);
+  (*env)->ReleaseDoubleArrayElements(env, xs, px, JNI_ABORT);
+  (*env)->ReleaseDoubleArrayElements(env, genomes, pg, JNI_ABORT);
+  jdoubleArray out = NULL;
+  if (rc) throw_status(env, ctx, rc);
+  else out = pack_results(env, res, n);
+  free(fit); free(res);
+  return out;
+}
+
+/* ---- the device-resident numGA loop (include/vsr_ga.h; DoublesStandard.java:41-71) ---- */
+static void throw_ga(JNIEnv* env, vsr_ga* ga, int rc) {
+  const char* cls = (rc == VSR_EINVAL || rc == VSR_EDIM) ? "java/lang/IllegalArgumentException" : "java/lang/RuntimeException";
+  (*env)->ThrowNew(env, (*env)->FindClass(env, cls), ga ? vsr_ga_last_error(ga) : "vsr_ga_create failed");
+}
+
+JNIEXPORT jlong JNICALL Java_it_units_erallab_gpu_VsrEval_gaCreate(JNIEnv* env, jclass c, jlong h, jint nPop, jdouble xOverProb,
+                                                                   jdouble tournamentRate, jint minNTournament, jdouble sigmaMut,
+                                                                   jlong seed, jboolean remap) {
+  (void)c;
+  vsr_ga_desc d;
+  vsr_ga_default(&d);
+  d.n_pop = nPop; d.xover_prob = xOverProb; d.tournament_rate = tournamentRate; d.min_tournament = minNTournament;
+  d.sigma_mut = sigmaMut; d.seed = (uint64_t)seed; d.remap = remap ? 1 : 0;
+  vsr_ga* ga = NULL;
+  int rc = vsr_ga_create((vsr_ctx*)(intptr_t)h, &d, &ga);
+  if (rc) { throw_ga(env, NULL, rc); return 0; }
+  return (jlong)(intptr_t)ga;
+}
+
+JNIEXPORT void JNICALL Java_it_units_erallab_gpu_VsrEval_gaInit(JNIEnv* env, jclass c, jlong g) {
+  (void)c;
+  int rc = vsr_ga_init((vsr_ga*)(intptr_t)g);
+  if (rc) throw_ga(env, (vsr_ga*)(intptr_t)g, rc);
+}
+
+JNIEXPORT void JNICALL Java_it_units_erallab_gpu_VsrEval_gaStep(JNIEnv* env, jclass c, jlong g) {
+  (void)c;
+  int rc = vsr_ga_step((vsr_ga*)(intptr_t)g);
+  if (rc) throw_ga(env, (vsr_ga*)(intptr_t)g, rc);
+}
+
+/* best individual: {fitness, genome[0..G)} */
+JNIEXPORT jdoubleArray JNICALL Java_it_units_erallab_gpu_VsrEval_gaBest(JNIEnv* env, jclass c, jlong g, jint genomeLength) {
+  (void)c;
+  double* buf = (double*)malloc(sizeof(double) * (genomeLength + 1));
+  int rc = vsr_ga_best((vsr_ga*)(intptr_t)g, buf + 1, buf);
+  jdoubleArray out = NULL;
+  if (rc) throw_ga(env, (vsr_ga*)(intptr_t)g, rc);
+  else { out = (*env)->NewDoubleArray(env, genomeLength + 1); (*env)->SetDoubleArrayRegion(env, out, 0, genomeLength + 1, buf); }
+  free(buf);
+  return out;
+}
+
+/* whole population, best first: {fitness[nPop], genomes[nPop][G]} flattened */
+JNIEXPORT jdoubleArray JNICALL Java_it_units_erallab_gpu_VsrEval_gaPopulation(JNIEnv* env, jclass c, jlong g, jint nPop, jint genomeLength) {
+  (void)c;
+  const size_t tot = (size_t)nPop * ((size_t)genomeLength + 1);
+  double* buf = (double*)malloc(sizeof(double) * (tot ? tot : 1));
+  int rc = vsr_ga_population((vsr_ga*)(intptr_t)g, buf + nPop, buf);
+  jdoubleArray out = NULL;
+  if (rc) throw_ga(env, (vsr_ga*)(intptr_t)g, rc);
+  else { out = (*env)->NewDoubleArray(env, (jsize)tot); (*env)->SetDoubleArrayRegion(env, out, 0, (jsize)tot, buf); }
+  free(buf);
+  return out;
+}
+
+JNIEXPORT jlong JNICALL Java_it_units_erallab_gpu_VsrEval_gaEvaluations(JNIEnv* env, jclass c, jlong g) {
+  (void)env; (void)c;
+  return (jlong)vsr_ga_evaluations((vsr_ga*)(intptr_t)g);
+}
+
+JNIEXPORT void JNICALL Java_it_units_erallab_gpu_VsrEval_gaDestroy(JNIEnv* env, jclass c, jlong g) {
+  (void)env; (void)c;
+  vsr_ga_destroy((vsr_ga*)(intptr_t)g);
 }
 
 JNIEXPORT void JNICALL Java_it_units_erallab_gpu_VsrEval_destroy(JNIEnv* env, jclass c, jlong h) { vsr_ctx_destroy((vsr_ctx*)(intptr_t)h); }

@@ -98,3 +98,19 @@ def test_create_rejects_bad_env(F):
     assert b"terrain" in F.lib().vsr_last_error(None)
     assert F.lib().vsr_ctx_create(None, C.byref(h)) == F.VSR_EINVAL
     assert F.lib().vsr_genome_len(None) == F.VSR_EINVAL
+
+
+def test_jni_glue_type_checks_against_the_headers():
+    """java/jni/vsr_eval_jni.c cannot be built here (no JDK), but it must at least type-check against include/*.h: compiled with
+    -fsyntax-only against a minimal jni.h stand-in (tests/jni_stub/jni.h), and every native declared in VsrEval.java has its
+    Java_..._<name> definition in the glue."""
+    import subprocess
+    src = os.path.join(ROOT, "java", "jni", "vsr_eval_jni.c")
+    r = subprocess.run(["gcc", "-fsyntax-only", "-Wall", "-Werror=implicit-function-declaration", "-Werror=incompatible-pointer-types",
+                        "-I" + os.path.join(ROOT, "tests", "jni_stub"), "-I" + os.path.join(ROOT, "include"), src],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    java = open(os.path.join(ROOT, "java", "it", "units", "erallab", "gpu", "VsrEval.java")).read()
+    natives = set(re.findall(r"public static native [\w\[\]]+ (\w+)\(", java))
+    glue = set(re.findall(r"Java_it_units_erallab_gpu_VsrEval_(\w+)\(", open(src).read()))
+    assert natives == glue and len(natives) >= 14

@@ -99,3 +99,45 @@ def test_rnd_terrain_task_draws_java_seeds(V, oracle):
     assert F.java_random_ints(-3, 16, 4).tolist() == [rp.next_int(16) for _ in range(4)]  # power-of-two bound path
     with pytest.raises(F.VsrIllegalArgument):
         L.RandomTerrainLocomotion(10.0, "flat", L.JavaRandomInts(0))
+
+
+def test_micro_batching_keeps_the_one_robot_per_call_contract(V):
+    """SURVEY 8b strategy (1): many threads call apply(robot); one apply_all per batch; timeout flush for a partial batch;
+    every caller gets its own result; an evaluator error reaches every waiter."""
+    import threading
+    B, L, R, F = V
+
+    class FakeTask:  # stands in for Locomotion on a machine without a GPU
+        def __init__(self):
+            self.calls = []
+        def apply_all(self, robots):
+            self.calls.append(len(robots))
+            if any(r == "boom" for r in robots):
+                raise RuntimeError("device failure")
+            return [("outcome", r) for r in robots]
+
+    task = FakeTask()
+    mb = L.MicroBatchedLocomotion(task, expected_batch=16, max_wait_s=0.2)
+    out = {}
+    def call(i):
+        out[i] = mb.apply(i)
+    ts = [threading.Thread(target=call, args=(i,)) for i in range(32)]
+    [t.start() for t in ts]; [t.join() for t in ts]
+    assert sorted(task.calls) == [16, 16] and all(out[i] == ("outcome", i) for i in range(32))
+    # partial batch: flushed by the timeout, once
+    task.calls.clear(); out.clear()
+    ts = [threading.Thread(target=call, args=(i,)) for i in range(5)]
+    [t.start() for t in ts]; [t.join() for t in ts]
+    assert task.calls == [5] and all(out[i] == ("outcome", i) for i in range(5))
+    # errors propagate to every caller of the batch
+    errs = []
+    def call_bad(x):
+        try:
+            mb.apply(x)
+        except RuntimeError as e:
+            errs.append(str(e))
+    ts = [threading.Thread(target=call_bad, args=(x,)) for x in ("a", "boom", "c")]
+    [t.start() for t in ts]; [t.join() for t in ts]
+    assert errs == ["device failure"] * 3
+    with pytest.raises(F.VsrIllegalArgument):
+        L.MicroBatchedLocomotion(task, 0)

@@ -9,6 +9,8 @@ plus `apply_all(robots)`: the whole population in one vsr_eval call (SURVEY.md 8
 """
 from __future__ import annotations
 
+import threading
+import time
 from dataclasses import dataclass
 from typing import Sequence
 
@@ -212,6 +214,62 @@ def build_locomotion_task(terrain_name: str, episode_t: float, transient_t: floa
     if "-rnd" in terrain_name:
         return RandomTerrainLocomotion(episode_t, terrain_name, random or JavaRandomInts(0), Settings(), transient_t, **kw)
     return Locomotion(episode_t, Locomotion.create_terrain(terrain_name), Settings(), transient_t, **kw)
+
+
+class MicroBatchedLocomotion:
+    """Host strategy (1) of SURVEY.md 8b: keep JGEA's one-robot-per-call contract (`qualityFunction.apply(robot)` from the
+    executor's threads, Starter.java:427-436) and batch behind it.  A caller enqueues its robot and blocks; the batch is
+    flushed -- by the caller that fills it, or by the first waiter whose `max_wait_s` expires -- with ONE `apply_all` call
+    (one kernel launch); every caller then returns its own Outcome.  Needs at least `expected_batch` executor threads to
+    fill a batch without waiting for the timeout."""
+
+    class _Batch:
+        def __init__(self):
+            self.robots, self.outcomes, self.error = [], None, None
+            self.done = threading.Event()
+            self.t0 = time.monotonic()
+
+    def __init__(self, task: "Locomotion", expected_batch: int, max_wait_s: float = 0.05):
+        if expected_batch < 1:
+            raise _ffi.VsrIllegalArgument(_ffi.VSR_EINVAL, "expected_batch must be positive")
+        self.task, self.expected_batch, self.max_wait_s = task, expected_batch, max_wait_s
+        self._lock = threading.Lock()
+        self._eval_lock = threading.Lock()  # a vsr_ctx is not re-entrant
+        self._open = self._Batch()
+        self.batches_flushed = 0
+
+    def _flush(self, batch: "_Batch"):
+        try:
+            with self._eval_lock:
+                batch.outcomes = self.task.apply_all(batch.robots)
+        except Exception as e:  # every waiter sees the failure, like an exception thrown by Locomotion.apply
+            batch.error = e
+        self.batches_flushed += 1
+        batch.done.set()
+
+    def apply(self, robot: Robot) -> Outcome:
+        with self._lock:
+            batch = self._open
+            slot = len(batch.robots)
+            batch.robots.append(robot)
+            full = len(batch.robots) >= self.expected_batch
+            if full:
+                self._open = self._Batch()
+        if full:
+            self._flush(batch)
+        else:
+            while not batch.done.wait(max(0.0, batch.t0 + self.max_wait_s - time.monotonic())):
+                with self._lock:  # timeout: the first waiter that still finds the batch open closes and flushes it
+                    leader = self._open is batch
+                    if leader:
+                        self._open = self._Batch()
+                if leader:
+                    self._flush(batch)
+                else:
+                    batch.done.wait()
+        if batch.error is not None:
+            raise batch.error
+        return batch.outcomes[slot]
 
 
 class PopulationEvaluator:
