@@ -379,7 +379,10 @@ template <class R, int CTRL, int WARPS, int MINB, int SCAFF = -1>
 __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __grid_constant__ KParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int gw = blockIdx.x * (blockDim.x >> 5) + warp; // global robot-warp (a CTA may be launched with fewer than WARPS warps)
+  // the 255-register builds (8 and 4 warps) may be launched with fewer warps per CTA than their launch bound, for controllers
+  // whose weights need more shared memory per warp; the 10-warp build is always launched full
+  const int cta_warps = WARPS == 10 ? WARPS : (int)(blockDim.x >> 5);
+  const int gw = blockIdx.x * cta_warps + warp; // global robot-warp
   unsigned char* wsm = smem_raw + (size_t)warp * P.smem_warp_stride;
   R* pool = reinterpret_cast<R*>(wsm + P.off_pool_p);      // [S][kPoolStride]: persist[2][12], solve[20]
   int* poolM = reinterpret_cast<int*>(wsm + P.off_pool_m); // [2][S]
@@ -405,7 +408,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
   const bool valid = lane_used && robot < P.n_robots;
   const int base_lane = rw * L;
   const int gl = gw * 32 + lane; // global lane (history ring column)
-  const int total_lanes = gridDim.x * blockDim.x;
+  const int total_lanes = gridDim.x * cta_warps * 32;
 
   // neighbours as lane ids packed in one register (self when absent, so shuffles stay in range) + validity bits
   const int vi = valid ? v : 0;
