@@ -146,10 +146,29 @@ def run_reference(args, w):
                              "sample": f"{sample} robots of the same workload per step, C port of the reference algorithm "
                                        "(oracle/vsr_oracle.c); the Java reference itself cannot run here (no JVM, 2dhmsr/dyn4j un-vendored)"},
             "e2e": {"value": value, "unit": "voxel-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Libraries (NCCL prints its version banner on stdout) must not break the one-JSON-line contract: everything written to
+    fd 1 during the run goes to stderr; emit() writes the result line to the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
 
 
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -306,7 +325,7 @@ def main():
                                 "hbm": {"achieved_gbs": (n * G * 8 + n * 8) / (kms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                                         "note": "state is register/shared-memory resident; HBM carries genomes in, fitness out"}}
         line["cpu_baseline"] = cpu
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
