@@ -136,3 +136,41 @@ def test_solver_mirror_improves_fitness(ev):
     bests = [e["best.fitness"] for e in log] + [best]
     assert all(b >= a for a, b in zip(bests, bests[1:]))
     assert np.isclose(ev.evaluate(genome[None, :])[0], best, rtol=0, atol=0)  # deterministic re-evaluation of the best
+
+
+def test_large_population_ranking_by_bitonic_sort(ev):
+    """Merged sets above 8192 rows are ranked by a bitonic sort of (key, index) pairs instead of the all-pairs count: same strict
+    total order (higher first, NaN as -inf, -0 == +0, ties towards the lower index), checked against oracle/ga.py:order."""
+    from vsrevolution_b200 import _ffi
+    n, G = 9001, ev.genome_len  # not a power of two: the sort pads to 16384
+    rng = np.random.default_rng(8)
+    fit = rng.normal(size=n).round(2)  # many ties
+    fit[rng.integers(0, n, 40)] = np.nan
+    fit[rng.integers(0, n, 40)] = 0.0
+    fit[rng.integers(0, n, 40)] = -0.0
+    fit[[5, 77]] = np.inf
+    fit[[9, 8000]] = -np.inf
+    genomes = rng.uniform(-1, 1, (n, G))
+    ga = _ffi.GeneticAlgorithm(ev.ctx, n, seed=0)
+    ga.set_population(genomes, fit)
+    o = OG.order(fit)
+    assert np.array_equal(ga.survivors(), o)
+    pop, f = ga.population()
+    assert np.array_equal(pop, genomes[o]) and np.array_equal(f, fit[o], equal_nan=True)
+    ga.close()
+    # and inside a generation (merged set of 2 x 5000 rows), index for index against the oracle
+    n = 5000
+    ga = _ffi.GeneticAlgorithm(ev.ctx, n, seed=21)
+    og = OG.NumGA(n, G, seed=21)
+    ga.init()
+    g0 = og.initial_genomes()
+    og.set_population(g0, ev.evaluate(g0))
+    for gen in (1, 2):
+        ga.step()
+        off, par, off_fit = ga.offspring()
+        assert np.array_equal(par, og.select(gen))
+        origin = og.merge(off, off_fit)
+        assert np.array_equal(ga.survivors(), origin)
+        pop, f = ga.population()
+        assert np.array_equal(f, og.fit) and np.array_equal(pop, og.pop)
+    ga.close()

@@ -101,6 +101,7 @@ __global__ void ga_vary_kernel(GaK p, uint32_t gen, const double* __restrict__ p
 // rank[i] = number of individuals that beat i: higher fitness first, NaN as -inf, ties towards the lower index (a strict
 // total order, so the ranks are a permutation).  Tiled all-pairs count; blockIdx.y splits the opponents.
 constexpr int kRankTile = 2048;
+constexpr int kAllPairsMax = 8192; // larger merged sets are ranked by the bitonic sort below
 __global__ void ga_rank_kernel(const double* __restrict__ fit, int m, int32_t* __restrict__ rank) {
   __shared__ double tile[kRankTile];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -119,6 +120,58 @@ __global__ void ga_rank_kernel(const double* __restrict__ fit, int m, int32_t* _
     c += (fj > fi) || (fj == fi && j < i);
   }
   if (c) atomicAdd(&rank[i], c);
+}
+
+// ---- large populations: ranks by a bitonic sort of (key, index) pairs instead of the all-pairs count (O(m log^2 m)) ----------
+// key = bit pattern that orders doubles descending (best first), NaN as -inf, -0 as +0; padding entries sort last
+__device__ inline uint64_t order_key(double f) {
+  if (!(f == f)) f = -INFINITY;
+  if (f == 0.0) f = 0.0;
+  const uint64_t u = (uint64_t)__double_as_longlong(f);
+  const uint64_t asc = (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+  return ~asc;
+}
+__global__ void ga_keys_kernel(const double* __restrict__ fit, int m, int P, uint64_t* __restrict__ keys, uint32_t* __restrict__ idx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  keys[i] = i < m ? order_key(fit[i]) : ~0ull;
+  idx[i] = (uint32_t)i;
+}
+__device__ inline void cmp_swap(uint64_t& ka, uint32_t& ia, uint64_t& kb, uint32_t& ib, bool up) {
+  const bool a_first = ka < kb || (ka == kb && ia < ib);
+  if (a_first != up) { const uint64_t tk = ka; ka = kb; kb = tk; const uint32_t ti = ia; ia = ib; ib = ti; }
+}
+// one (k, j) step in global memory: thread t owns the pair (i, i | j) with bit j of i clear
+__global__ void ga_bitonic_global(uint64_t* __restrict__ keys, uint32_t* __restrict__ idx, int P, int k, int j) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= P / 2) return;
+  const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j;
+  uint64_t ka = keys[i], kb = keys[l];
+  uint32_t ia = idx[i], ib = idx[l];
+  cmp_swap(ka, ia, kb, ib, (i & k) == 0);
+  keys[i] = ka; keys[l] = kb; idx[i] = ia; idx[l] = ib;
+}
+// all steps j = j0 .. 1 of stage k for a tile of 2048 elements in shared memory (j0 <= 1024)
+constexpr int kSortTile = 2048;
+__global__ void ga_bitonic_shared(uint64_t* __restrict__ keys, uint32_t* __restrict__ idx, int k, int j0) {
+  __shared__ uint64_t sk[kSortTile];
+  __shared__ uint32_t si[kSortTile];
+  const int base = blockIdx.x * kSortTile;
+  for (int e = threadIdx.x; e < kSortTile; e += blockDim.x) { sk[e] = keys[base + e]; si[e] = idx[base + e]; }
+  __syncthreads();
+  for (int j = j0; j > 0; j >>= 1) {
+    const int t = threadIdx.x;
+    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j;
+    cmp_swap(sk[i], si[i], sk[l], si[l], ((base + i) & k) == 0);
+    __syncthreads();
+  }
+  for (int e = threadIdx.x; e < kSortTile; e += blockDim.x) { keys[base + e] = sk[e]; idx[base + e] = si[e]; }
+}
+__global__ void ga_rank_from_sorted(const uint32_t* __restrict__ idx, int m, int P, int32_t* __restrict__ rank) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= P) return;
+  const uint32_t i = idx[r];
+  if (i < (uint32_t)m) rank[i] = r; // padding sorts last, so the first m sorted entries are the real ones
 }
 
 // survivors: row i of the merged set goes to row rank[i] of the next population if rank[i] < n_keep (Last() removes the worst)
@@ -143,6 +196,9 @@ struct vsr_ga {
   double* genomes[2] = {nullptr, nullptr}; // [2 nPop][G]: population rows then offspring rows
   double* fit[2] = {nullptr, nullptr};     // [2 nPop + 8]
   int32_t *parents = nullptr, *rank = nullptr, *origin = nullptr;
+  uint64_t* sort_keys = nullptr; // bitonic sort scratch: next power of two >= 2 nPop entries
+  uint32_t* sort_idx = nullptr;
+  int sort_cap = 0;
   int cur = 0;        // buffer holding the current population
   int off_buf = -1;   // buffer holding the most recent offspring
   int shard_rank = 0, shard_world = 1;
@@ -185,12 +241,31 @@ int eval_pending(vsr_ga* ga, int base, int count, int pending) {
 int truncate_into_next(vsr_ga* ga, int m) {
   const int n = ga->d.n_pop, nxt = ga->cur ^ 1;
   GCK(cudaSetDevice(ga->dev));
-  GCK(cudaMemsetAsync(ga->rank, 0, sizeof(int32_t) * m, ga->st));
-  dim3 grid((m + 255) / 256, (m + kRankTile - 1) / kRankTile);
-  ga_rank_kernel<<<grid, 256, 0, ga->st>>>(ga->fit[ga->cur], m, ga->rank);
+  if (m <= kAllPairsMax) {
+    GCK(cudaMemsetAsync(ga->rank, 0, sizeof(int32_t) * m, ga->st));
+    dim3 grid((m + 255) / 256, (m + kRankTile - 1) / kRankTile);
+    ga_rank_kernel<<<grid, 256, 0, ga->st>>>(ga->fit[ga->cur], m, ga->rank);
+    ga->launches += 1;
+  } else {
+    int P = kSortTile;
+    while (P < m) P <<= 1;
+    ga_keys_kernel<<<(P + 255) / 256, 256, 0, ga->st>>>(ga->fit[ga->cur], m, P, ga->sort_keys, ga->sort_idx);
+    ga->launches += 1;
+    for (int k = 2; k <= P; k <<= 1) {
+      int j = k >> 1;
+      for (; j >= kSortTile; j >>= 1) { // partners farther apart than a tile: one step per launch
+        ga_bitonic_global<<<(P / 2 + 255) / 256, 256, 0, ga->st>>>(ga->sort_keys, ga->sort_idx, P, k, j);
+        ga->launches += 1;
+      }
+      ga_bitonic_shared<<<P / kSortTile, kSortTile / 2, 0, ga->st>>>(ga->sort_keys, ga->sort_idx, k, j);
+      ga->launches += 1;
+    }
+    ga_rank_from_sorted<<<(P + 255) / 256, 256, 0, ga->st>>>(ga->sort_idx, m, P, ga->rank);
+    ga->launches += 1;
+  }
   ga_scatter_kernel<<<m, 64, 0, ga->st>>>(ga->genomes[ga->cur], ga->fit[ga->cur], ga->rank, ga->G, n, ga->genomes[nxt], ga->fit[nxt], ga->origin);
   GCK(cudaGetLastError());
-  ga->launches += 2;
+  ga->launches += 1;
   ga->cur = nxt;
   return VSR_OK;
 }
@@ -238,6 +313,13 @@ int vsr_ga_create(vsr_ctx* ctx, const vsr_ga_desc* d, vsr_ga** out) {
   ok = ok && cudaMalloc(&ga->parents, rows * sizeof(int32_t)) == cudaSuccess;
   ok = ok && cudaMalloc(&ga->rank, rows * sizeof(int32_t)) == cudaSuccess;
   ok = ok && cudaMalloc(&ga->origin, n * sizeof(int32_t)) == cudaSuccess;
+  if (rows > (size_t)kAllPairsMax) {
+    int P = kSortTile;
+    while ((size_t)P < rows) P <<= 1;
+    ga->sort_cap = P;
+    ok = ok && cudaMalloc(&ga->sort_keys, (size_t)P * sizeof(uint64_t)) == cudaSuccess;
+    ok = ok && cudaMalloc(&ga->sort_idx, (size_t)P * sizeof(uint32_t)) == cudaSuccess;
+  }
   if (!ok) { cudaGetLastError(); vsr_ga_destroy(ga); return VSR_ENOMEM; }
   *out = ga;
   return VSR_OK;
@@ -248,7 +330,7 @@ void vsr_ga_destroy(vsr_ga* ga) {
   cudaSetDevice(ga->dev);
   if (ga->st) cudaStreamSynchronize(ga->st);
   for (int b = 0; b < 2; b++) { cudaFree(ga->genomes[b]); cudaFree(ga->fit[b]); }
-  cudaFree(ga->parents); cudaFree(ga->rank); cudaFree(ga->origin);
+  cudaFree(ga->parents); cudaFree(ga->rank); cudaFree(ga->origin); cudaFree(ga->sort_keys); cudaFree(ga->sort_idx);
   delete ga;
 }
 
