@@ -371,7 +371,13 @@ int finalize(vsr_ctx* ctx) {
   // large controllers (weights of every robot of the warp live in shared memory): launch the chosen kernel with fewer warps
   // per CTA than its launch bound (the kernel indexes by blockDim)
   while (ctx->warps > 1 && (size_t)ctx->warps * o + 1024 > 227 * 1024) ctx->warps--;
-  ctx->kernel = kernel_ptr(e.precision, ctx->kind, ctx->shape, e.scaffolding_mask == 0xF && !std::getenv("VSR_GENERIC_SCAFF"));
+  const bool full_scaff = e.scaffolding_mask == 0xF && !std::getenv("VSR_GENERIC_SCAFF");
+  ctx->kernel = kernel_ptr(e.precision, ctx->kind, ctx->shape, full_scaff);
+  // the reference's default robot: one soft-normalised, non-averaged AreaRatio reading per voxel into a centralized MLP
+  if (e.precision == 32 && ctx->shape == 3 && ctx->warps == 10 && full_scaff && ctx->kind == VSR_CTRL_MLP_CENTRALIZED &&
+      ctx->sensors.size() == 1 && ctx->sensors[0].kind == VSR_SENSOR_AREA_RATIO && ctx->sensors[0].soft_norm &&
+      !(ctx->sensors[0].avg_window > 0) && !std::getenv("VSR_GENERIC_SENSORS"))
+    ctx->kernel = vsr_internal::kernel_f32_s3_area();
   ctx->smem_bytes = o * ctx->warps;
   if (k.n_t > 16383) return fail(ctx, VSR_EUNSUPPORTED, "terrains with more than 16383 vertices are not supported");
   if (ctx->smem_bytes > 227 * 1024) return fail(ctx, VSR_EUNSUPPORTED, "controller too large for shared memory");

@@ -24,5 +24,6 @@ VSR_HIDDEN const void* kernel_f32_s0(int ctrl, int full_scaff);
 VSR_HIDDEN const void* kernel_f32_s1(int ctrl, int full_scaff);
 VSR_HIDDEN const void* kernel_f32_s2(int ctrl, int full_scaff);
 VSR_HIDDEN const void* kernel_f32_s3(int ctrl, int full_scaff);
+VSR_HIDDEN const void* kernel_f32_s3_area(void);
 VSR_HIDDEN const void* kernel_f64(int ctrl);
 } // namespace vsr_internal

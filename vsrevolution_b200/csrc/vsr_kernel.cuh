@@ -375,7 +375,8 @@ __device__ __forceinline__ int collide_box_top(R x1, R y1, R pnx, R pny, R bcx, 
 // the episode kernel
 // ------------------------------------------------------------------------------------------------
 // SCAFF >= 0: the scaffolding mask is a compile-time constant (0xF, the Voxel default: no branch per spring); -1: read from P
-template <class R, int CTRL, int WARPS, int MINB, int SCAFF = -1>
+// SENS: 0 = generic sensor loop; 1 = exactly one soft-normalised, non-averaged AreaRatio sensor (optionally Noisy)
+template <class R, int CTRL, int WARPS, int MINB, int SCAFF = -1, int SENS = 0>
 __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __grid_constant__ KParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1321,6 +1322,19 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
       for (int i = 0; i < 8; i++) rd[i] = 0;
       R vang = 0;
       bool have_ang = false;
+      if (SENS == 1) {
+        // specialised build: one soft-normalised AreaRatio reading per voxel (`uniform-a-<sigma>`, the reference default,
+        // Starter.java:152), optionally Noisy -- no sensor loop, none of the velocity / angle / Average code in the stream
+        const SensorK& sk = P.sensors[0];
+        R a2 = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) { const int j = (i + 1) & 3; a2 += qx[i] * qy[j] - qx[j] * qy[i]; }
+        R val = M<R>::abs_(a2) * K_inv_area2;
+        const R vv = (val - (R)sk.dom_min) * (R)sk.dom_inv;
+        val = M<R>::tanh_((vv * R(2) - R(1)) * R(2)) * R(0.5) + R(0.5);
+        if (P.noise) val += (R)__ldg(&P.noise[step]);
+        rd[0] = val;
+      } else {
 #pragma unroll 1
       for (int si = 0; si < P.n_sensors; si++) {
         const SensorK& sk = P.sensors[si];
@@ -1378,6 +1392,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
 #pragma unroll
           for (int z = 0; z < 8; z++) if (z == ri) rd[z] = val;
         }
+      }
       }
       const int D = P.sens_dim, maxN = P.max_neurons;
       if (CTRL == VSR_CTRL_MLP_CENTRALIZED) {

@@ -30,6 +30,8 @@ const void* kernel_f32_s1(int ctrl, int full_scaff) { return pick2<float, 5, 2>(
 const void* kernel_f32_s2(int ctrl, int full_scaff) { return pick2<float, 8, 1>(ctrl, full_scaff); }
 #elif VSR_INST == 3
 const void* kernel_f32_s3(int ctrl, int full_scaff) { return pick2<float, 10, 1>(ctrl, full_scaff); }
+// the reference's default robot (CentralizedSensing MLP over one AreaRatio reading per voxel): sensor loop folded away
+const void* kernel_f32_s3_area(void) { return (const void*)vsr::vsr_episode_kernel<float, VSR_CTRL_MLP_CENTRALIZED, 10, 1, 0xF, 1>; }
 #else
 const void* kernel_f64(int ctrl) { return pick<double, 4, 1, -1>(ctrl); }
 #endif
