@@ -249,6 +249,17 @@ def test_host_mirror_end_to_end(F, oracle):
     assert task.apply(mapper(g[2])).sub_outcome(1.0, T).get_velocity() == fit[2]
     m = oracle.config_model(1, final_t=T)
     assert np.abs(fit - m.eval_batch(g)).max() < 3e-2  # 2 s window after the first FP32-vs-FP64 solver flips
+    # Starter.validate (Starter.java:122-135): the same robots on the validation terrains (default `flat,downhill-30`, :171)
+    from vsrevolution_b200.locomotion import validate
+    robots = [mapper(row) for row in g]
+    vflat = validate(robots, "flat", "identity", 0, T, 1.0)
+    assert [v.outcome.get_velocity() for v in vflat] == fit.tolist() and vflat[0].terrain_name == "flat" and vflat[0].seed == 0
+    vdown = validate(robots, "downhill-30", "identity", 0, T, 1.0)
+    assert np.mean([v.outcome.get_velocity() for v in vdown]) > np.mean(fit) + 0.5  # everybody slides down a 30 degree slope
+    vrnd = validate(robots, "hilly-1-10-rnd", "identity", 3, T, 1.0)
+    assert len({round(v.outcome.get_velocity(), 9) for v in vrnd}) == len(robots)
+    with pytest.raises(F.VsrError):
+        validate(robots, "flat", "broken-0.5", 0, T, 1.0)
 
 
 def test_multi_device_sharding_is_exact(F, oracle):

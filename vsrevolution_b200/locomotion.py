@@ -216,6 +216,27 @@ def build_locomotion_task(terrain_name: str, episode_t: float, transient_t: floa
     return Locomotion(episode_t, Locomotion.create_terrain(terrain_name), Settings(), transient_t, **kw)
 
 
+@dataclass
+class ValidationOutcome:
+    """Starter.ValidationOutcome (locomotion/Starter.java:78-80)."""
+    terrain_name: str
+    transformation_name: str
+    seed: int
+    outcome: Outcome
+
+
+def validate(robots: Sequence[Robot], terrain_name: str, transformation_name: str, seed: int, episode_time: float,
+             transient_time: float, **kw) -> list[ValidationOutcome]:
+    """Starter.validate (locomotion/Starter.java:122-135) for a batch of robots: re-evaluation on a validation terrain
+    (defaults `flat,downhill-30`, :171) with `new Random(seed)` feeding the `-rnd` terrain seeds.  Only the `identity`
+    transformation (the Starter default, :153) is built; robots of one call share body and controller structure."""
+    if transformation_name != "identity":
+        raise _ffi.VsrError(_ffi.VSR_EUNSUPPORTED, f"robot transformation {transformation_name!r} is outside the hot path")
+    task = build_locomotion_task(terrain_name, episode_time, transient_time, random=JavaRandomInts(seed), **kw)
+    return [ValidationOutcome(terrain_name, transformation_name, seed, o.sub_outcome(transient_time, episode_time))
+            for o in task.apply_all(robots)]
+
+
 class MicroBatchedLocomotion:
     """Host strategy (1) of SURVEY.md 8b: keep JGEA's one-robot-per-call contract (`qualityFunction.apply(robot)` from the
     executor's threads, Starter.java:427-436) and batch behind it.  A caller enqueues its robot and blocks; the batch is
