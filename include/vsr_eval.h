@@ -79,7 +79,20 @@ typedef struct {
 /* ---- controllers: CentralizedSensing (builder/robot/BrainCentralized.java:42-45), PhaseSin
  *      (builder/robot/BrainPhaseValues.java:47-50), homogeneous DistributedSensing
  *      (builder/robot/BrainHomoDistributed.java:76-87) ----------------------------------------- */
-typedef enum { VSR_CTRL_PHASE_SIN = 0, VSR_CTRL_MLP_CENTRALIZED = 1, VSR_CTRL_MLP_DISTRIBUTED_HOMO = 2 } vsr_ctrl_kind;
+/*      MLP_DISTRIBUTED_HETERO: DistributedSensing with one MLP per voxel (builder/robot/BrainHeteroDistributed.java:76-83);
+ *      the genome row is the voxels' weight vectors concatenated in grid order, as builder/misc/FunctionsGrid.java:31-46
+ *      slices it (`brainHeteroDist<funsGrid`); every voxel has the same sensors, so layers[] is shared and
+ *      G = n_voxels * vsr_mlp_count_weights(layers).
+ *      TIME_SIN: TimeFunctions of per-voxel sinusoids t -> amplitude * sin(2 pi frequency t + phase)
+ *      (builder/robot/BodyBrainSinusoidal.java:87-119) on the fixed body of the context; the genome row is
+ *      (frequency, phase, amplitude) per voxel in grid order, G = 3 * n_voxels (freq / amp arguments ignored). */
+typedef enum {
+  VSR_CTRL_PHASE_SIN = 0,
+  VSR_CTRL_MLP_CENTRALIZED = 1,
+  VSR_CTRL_MLP_DISTRIBUTED_HOMO = 2,
+  VSR_CTRL_MLP_DISTRIBUTED_HETERO = 3,
+  VSR_CTRL_TIME_SIN = 4
+} vsr_ctrl_kind;
 
 /* ---- per-robot result: the Outcome getters the host reads (locomotion/NamedFunctions.java:68-70) */
 typedef struct {
@@ -110,7 +123,7 @@ const char* vsr_last_error(const vsr_ctx* ctx); /* ctx may be NULL: error of the
  * Replaces RobotUtils.buildSensorizingFunction(cfg).apply(RobotUtils.buildShape(shape)) (Starter.java:402-406). */
 int vsr_body_set(vsr_ctx* ctx, int32_t w, int32_t h, const uint8_t* mask, const vsr_sensor_desc* sensors, int32_t n_sensors);
 
-/* controller: layers[] = MLP neurons per layer incl. input and output (ignored for PHASE_SIN) */
+/* controller: layers[] = MLP neurons per layer incl. input and output (ignored for PHASE_SIN / TIME_SIN) */
 int vsr_controller_set(vsr_ctx* ctx, vsr_ctrl_kind kind, const int32_t* layers, int32_t n_layers, int32_t signals,
                        double freq, double amp, int32_t mlp_input_activation);
 

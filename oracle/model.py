@@ -249,7 +249,7 @@ class VoResult(C.Structure):
         [(n, C.c_double) for n in ("control_energy", "area_ratio_abs", "area_ratio_sq")]
 
 
-CTRL_PHASE_SIN, CTRL_MLP_CENTRALIZED, CTRL_MLP_DISTRIBUTED_HOMO = 0, 1, 2
+CTRL_PHASE_SIN, CTRL_MLP_CENTRALIZED, CTRL_MLP_DISTRIBUTED_HOMO, CTRL_MLP_DISTRIBUTED_HETERO, CTRL_TIME_SIN = 0, 1, 2, 3, 4
 
 _lib = None
 
@@ -315,11 +315,11 @@ class Model:
         c.input_activation = self.input_activation
         if self.ctrl_kind == CTRL_MLP_CENTRALIZED:
             n_in, n_out = nv * dim, nv
-        elif self.ctrl_kind == CTRL_MLP_DISTRIBUTED_HOMO:
+        elif self.ctrl_kind in (CTRL_MLP_DISTRIBUTED_HOMO, CTRL_MLP_DISTRIBUTED_HETERO):
             n_in, n_out = dim + 4 * self.signals, 1 + 4 * self.signals
         else:
             n_in = n_out = 0
-        if self.ctrl_kind != CTRL_PHASE_SIN:
+        if self.ctrl_kind not in (CTRL_PHASE_SIN, CTRL_TIME_SIN):
             neurons = [n_in] + inner_neurons(n_in, n_out, self.ratio, self.n_inner) + [n_out]
             c.n_layers = len(neurons)
             for i, n in enumerate(neurons):

@@ -1051,6 +1051,10 @@ int vo_genome_len(int w, int h, const uint8_t* mask, const vo_sensor* sensors, i
     case VO_CTRL_MLP_DISTRIBUTED_HOMO:
       if (ctrl->layers[0] != dim + 4 * ctrl->signals || ctrl->layers[ctrl->n_layers - 1] != 1 + 4 * ctrl->signals) return -2;
       return mlp_n_weights(ctrl);
+    case VO_CTRL_MLP_DISTRIBUTED_HETERO:
+      if (ctrl->layers[0] != dim + 4 * ctrl->signals || ctrl->layers[ctrl->n_layers - 1] != 1 + 4 * ctrl->signals) return -2;
+      return nv * mlp_n_weights(ctrl);
+    case VO_CTRL_TIME_SIN: return 3 * nv;
   }
   return -1;
 }
@@ -1165,7 +1169,8 @@ int vo_run(const vo_params* p, int w, int h, const uint8_t* mask,
   S.hist_t = (double*)calloc(S.hist_cap, sizeof(double));
   S.hist_v = (double*)calloc((size_t)S.hist_cap * W->n_vox * D, sizeof(double));
   /* distributed controller signal buffers */
-  int sig = ctrl->kind == VO_CTRL_MLP_DISTRIBUTED_HOMO ? ctrl->signals : 0;
+  int sig = (ctrl->kind == VO_CTRL_MLP_DISTRIBUTED_HOMO || ctrl->kind == VO_CTRL_MLP_DISTRIBUTED_HETERO) ? ctrl->signals : 0;
+  const int w_stride = ctrl->kind == VO_CTRL_MLP_DISTRIBUTED_HETERO ? mlp_n_weights(ctrl) : 0; /* per-voxel weight block */
   double* last_sig = (double*)calloc((size_t)W->n_vox * 4 * (sig > 0 ? sig : 1), sizeof(double));
   double* cur_sig = (double*)calloc((size_t)W->n_vox * 4 * (sig > 0 ? sig : 1), sizeof(double));
 
@@ -1191,7 +1196,12 @@ int vo_run(const vo_params* p, int w, int h, const uint8_t* mask,
         mlp_apply(ctrl, genome, in, o);
         for (int v = 0; v < W->n_vox; v++) apply_control(W, v, o[v]);
       } break;
-      case VO_CTRL_MLP_DISTRIBUTED_HOMO: {
+      case VO_CTRL_TIME_SIN: /* TimeFunctions: per-voxel (frequency, phase, amplitude) */
+        for (int v = 0; v < W->n_vox; v++)
+          apply_control(W, v, genome[3 * v + 2] * sin(2.0 * M_PI * genome[3 * v] * t + genome[3 * v + 1]));
+        break;
+      case VO_CTRL_MLP_DISTRIBUTED_HOMO:
+      case VO_CTRL_MLP_DISTRIBUTED_HETERO: {
         /* Dir: N(0,-1) E(1,0) S(0,1) W(-1,0); index N0 E1 S2 W3; input from neighbour's opposite side */
         static const int DX[4] = {0, 1, 0, -1}, DY[4] = {-1, 0, 1, 0}, OPP[4] = {2, 3, 0, 1};
         for (int v = 0; v < W->n_vox; v++) {
@@ -1202,7 +1212,7 @@ int vo_run(const vo_params* p, int w, int h, const uint8_t* mask,
             int nb = (ax >= 0 && ax < w && ay >= 0 && ay < h) ? W->vox_of_cell[ay * w + ax] : -1;
             for (int s = 0; s < sig; s++) in[ni++] = nb >= 0 ? last_sig[(nb * 4 + OPP[d]) * sig + s] : 0.0;
           }
-          mlp_apply(ctrl, genome, in, o);
+          mlp_apply(ctrl, genome + (size_t)v * w_stride, in, o);
           apply_control(W, v, o[0]);
           for (int i = 0; i < 4 * sig; i++) cur_sig[v * 4 * sig + i] = o[1 + i];
         }

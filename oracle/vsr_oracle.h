@@ -76,7 +76,12 @@ typedef struct {
   double noise_sigma; /* >0: Noisy(sensor, sigma, seed 0): + nextGaussian()*sigma*|domain| per reading per step */
 } vo_sensor;
 
-enum { VO_CTRL_PHASE_SIN = 0, VO_CTRL_MLP_CENTRALIZED = 1, VO_CTRL_MLP_DISTRIBUTED_HOMO = 2 };
+/* DISTRIBUTED_HETERO: one MLP per voxel, genome = the voxels' weight vectors concatenated in grid order
+ * (brainHeteroDist<funsGrid: builder/robot/BrainHeteroDistributed.java:76-83, builder/misc/FunctionsGrid.java:31-46).
+ * TIME_SIN: TimeFunctions of per-voxel sinusoids, genome = (frequency, phase, amplitude) per voxel in grid order
+ * (builder/robot/BodyBrainSinusoidal.java:87-119: t -> amplitude * sin(2 pi freq t + phase)). */
+enum { VO_CTRL_PHASE_SIN = 0, VO_CTRL_MLP_CENTRALIZED = 1, VO_CTRL_MLP_DISTRIBUTED_HOMO = 2,
+       VO_CTRL_MLP_DISTRIBUTED_HETERO = 3, VO_CTRL_TIME_SIN = 4 };
 
 typedef struct {
   int    kind;

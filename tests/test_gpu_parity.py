@@ -39,7 +39,7 @@ def make_ctx(F, m, precision=32, devices=None, gravity=None):
     sens = [F.SensorDesc(s.kind, s.axes, s.rotated, s.soft_norm, s.dom_min, s.dom_max, s.avg_window, s.noise_sigma) for s in m.sensors]
     ctx.body_set(m.mask, sens)
     layers = [m.ctrl.layers[i] for i in range(m.ctrl.n_layers)]
-    ctx.controller_set(m.ctrl_kind, layers, m.signals if m.ctrl_kind == 2 else 0, m.freq, m.amp, m.input_activation)
+    ctx.controller_set(m.ctrl_kind, layers, m.signals if m.ctrl_kind in (2, 3) else 0, m.freq, m.amp, m.input_activation)
     return ctx
 
 
@@ -368,15 +368,24 @@ def test_per_evaluation_terrains_match_single_terrain_runs(F, oracle):
     ("box-8x4", "phase", "", "hilly-0.5-5-3"),              # 32 voxels: the largest body, one robot per warp
     ("tripod-5x3", "central", "uniform-r+vxy+t-0", "uphill-10"),  # angle + velocity + touch sensors, sloped terrain
     ("box-3x5", "dist", "uniform-a+t-0", "downhill-30"),    # tall body, distributed controller, validation terrain (Starter.java:171)
+    ("comb-7x2", "hetero", "uniform-t+vxy+a-0", "flat"),    # brainHeteroDist<funsGrid: one MLP per voxel (BrainHeteroDistributed.java:76-83)
+    ("biped-4x3", "hetero", "uniform-a-0", "hilly-1-10-0"),
+    ("biped-4x3", "timesin", "", "flat"),                   # TimeFunctions sinusoids (BodyBrainSinusoidal.java:87-119)
+    ("worm-8x2", "timesin", "", "hilly-1-10-0"),
 ])
 def test_other_bodies_sensors_and_terrains_track_the_oracle(F, oracle, shape, ctrl, sensors, terrain):
     """Edge shapes (smallest / largest body), every sensor kind and the remaining terrain families: FP64 kernel vs oracle on the
     first 30 steps (1e-9), FP32 kernel finite and close on the first 10 steps; ragged batch sizes around the warp packing."""
-    kind = {"phase": oracle.CTRL_PHASE_SIN, "central": oracle.CTRL_MLP_CENTRALIZED, "dist": oracle.CTRL_MLP_DISTRIBUTED_HOMO}[ctrl]
+    kind = {"phase": oracle.CTRL_PHASE_SIN, "central": oracle.CTRL_MLP_CENTRALIZED, "dist": oracle.CTRL_MLP_DISTRIBUTED_HOMO,
+            "hetero": oracle.CTRL_MLP_DISTRIBUTED_HETERO, "timesin": oracle.CTRL_TIME_SIN}[ctrl]
     m = oracle.Model(shape, terrain, sensors, kind, oracle.default_params(1.5, 0.5))
     G = m.genome_len()
     g = np.random.default_rng(11).uniform(-1, 1, (70, G))
-    if kind != oracle.CTRL_PHASE_SIN:
+    if kind == oracle.CTRL_TIME_SIN:
+        # the decode of bodyBrainSin (BodyBrainSinusoidal.java:96-113): frequency in [0.5, 2], phase in [0, pi], amplitude in [0, 1]
+        g = g.reshape(70, -1, 3)
+        g = np.stack([0.5 + 1.5 * (g[..., 0] + 1) / 2, np.pi * (g[..., 1] + 1) / 2, (g[..., 2] + 1) / 2], axis=-1).reshape(70, G)
+    elif kind != oracle.CTRL_PHASE_SIN:
         # small weights keep the MLP outputs away from +-1: a fully contracted voxel sits exactly on the contraction-limit
         # knife edge (rope active or not), which flips on 1e-13 differences within a few steps (tools/parity_probe5.py)
         g *= 0.15
@@ -431,3 +440,53 @@ def test_generation_loop_on_a_multi_device_context(F, oracle):
         pops.append(ga.population())
         ga.close(); ctx.close()
     assert np.array_equal(pops[0][0], pops[1][0]) and np.array_equal(pops[0][1], pops[1][1])
+
+
+def test_new_controller_kinds_reduce_to_the_old_ones_on_the_device(F, oracle):
+    """Same reductions as tests/test_oracle_known_answers.py, through the C ABI on the FP32 kernel: per-voxel weights that are all
+    equal == the homogeneous brain, TimeFunctions sinusoids with one frequency / amplitude == PhaseSin.  Bit-identical."""
+    p = oracle.default_params(3.0, 0.5)
+    homo = oracle.Model("comb-7x2", "steppy-0.25-1-0", "uniform-t+vxy+a-0", oracle.CTRL_MLP_DISTRIBUTED_HOMO, p)
+    het = oracle.Model("comb-7x2", "steppy-0.25-1-0", "uniform-t+vxy+a-0", oracle.CTRL_MLP_DISTRIBUTED_HETERO, p)
+    g = np.random.default_rng(0).uniform(-1, 1, (37, 75))
+    c1, c2 = make_ctx(F, homo), make_ctx(F, het)
+    assert c2.genome_len == 825
+    a, b = c1.eval(g), c2.eval(np.tile(g, (1, 11)))
+    assert np.isfinite(a).all() and np.array_equal(a, b)
+    g2 = np.tile(g, (1, 11))
+    g2[:, 5 * 75:6 * 75] *= -1
+    assert not np.array_equal(c2.eval(g2), a)
+    c1.close(); c2.close()
+    ph = oracle.Model("worm-8x2", "hilly-1-10-0", "", oracle.CTRL_PHASE_SIN, p, freq=1.3, amp=0.8)
+    ts = oracle.Model("worm-8x2", "hilly-1-10-0", "", oracle.CTRL_TIME_SIN, p)
+    phases = np.random.default_rng(1).uniform(-1, 1, (41, 16))
+    triples = np.stack([np.full((41, 16), 1.3), phases, np.full((41, 16), 0.8)], axis=-1).reshape(41, 48)
+    c1, c2 = make_ctx(F, ph), make_ctx(F, ts)
+    assert c2.genome_len == 48
+    assert np.array_equal(c1.eval(phases), c2.eval(triples))
+    c1.close(); c2.close()
+
+
+def test_host_transforming_mappers_through_the_population_evaluator(F, oracle):
+    """brainPhaseFun<mlp (host evaluates the phase function once per voxel, device runs PhaseSin) and bodyBrainSin<dirNumGrid
+    (body from the genome: robots grouped by morphology, one launch per distinct body) against the oracle run on the robots the
+    mappers build."""
+    from vsrevolution_b200 import locomotion as L
+    ev = L.population_evaluator("biped-4x3", "", "brainPhaseFun;f=1<mlp;r=0.65;nIL=1", "flat", 3.0, 0.5)
+    assert not ev.direct and ev.genome_len == 9
+    g = np.random.default_rng(2).uniform(-1, 1, (12, 9))
+    fit = ev.evaluate(g)
+    m = oracle.Model("biped-4x3", "flat", "", oracle.CTRL_PHASE_SIN, oracle.default_params(3.0, 0.5), freq=1.0, amp=1.0)
+    phases = np.stack([L.Locomotion.genome_of(ev._build(row)) for row in g])
+    ref = m.eval_batch(phases)
+    assert np.isfinite(fit).all() and np.median(np.abs(fit - ref)) < 2e-3, (fit, ref)
+    ev2 = L.population_evaluator("biped-4x3", "", "bodyBrainSin;p=50<dirNumGrid", "flat", 3.0, 0.5)
+    assert not ev2.direct and ev2.genome_len == 36
+    g2 = np.random.default_rng(3).uniform(-1, 1, (10, 36))
+    fit2 = ev2.evaluate(g2)
+    assert np.isfinite(fit2).all() and len(ev2.task._ctxs) >= 2   # several morphologies -> several contexts
+    # every robot evaluated alone gives the same value as inside its group
+    for i in (0, 4, 9):
+        assert ev2.task.apply(ev2._build(g2[i])).get_velocity() == fit2[i]
+    direct = L.population_evaluator("comb-7x2", "uniform-t+vxy+a-0", "brainHeteroDist;s=1<funsGrid", "flat", 2.0, 0.5)
+    assert direct.direct and direct.genome_len == 825

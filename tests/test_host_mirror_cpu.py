@@ -80,7 +80,152 @@ def test_shard_range_partitions(V):
 def test_unsupported_is_loud(V):
     B, L, R, F = V
     with pytest.raises(F.VsrError):
-        B.build_mapper("brainHeteroDist<mlp")
+        B.build_mapper("brainAutoPoses;nP=4")  # PosesController: outside the hot path
+    with pytest.raises(F.VsrError):
+        B.build_mapper("sensorBrainCentralized")
+
+
+def test_brain_hetero_distributed_functions_grid(V):
+    """brainHeteroDist<funsGrid (BrainHeteroDistributed.java:36-83, FunctionsGrid.java:31-46): the flat genome is sliced into one
+    MLP per non-null voxel in Grid iteration order; the device genome is the same vector."""
+    B, L, R, F = V
+    t = _target(R, "comb-7x2", "uniform-t+vxy+a-0")
+    mapper = B.build_mapper("brainHeteroDist;s=1<funsGrid")
+    assert len(mapper.example_for(t)) == 11 * 75
+    g = np.linspace(-1, 1, 825)
+    robot = mapper.build_for(t)(g)
+    c = robot.get_controller()
+    fs = c.get_functions()
+    assert isinstance(c, R.DistributedSensing) and c.signals == 1
+    # comb-7x2: full top row (y = 1), even-x bottom row (y = 0); iteration = bottom row first
+    assert fs.get(1, 0) is None and np.array_equal(fs.get(0, 0).get_params(), g[:75]) and np.array_equal(fs.get(2, 0).get_params(), g[75:150])
+    assert np.array_equal(fs.get(0, 1).get_params(), g[4 * 75:5 * 75])
+    assert np.array_equal(L.Locomotion.genome_of(robot), g)
+    # a functions grid of the wrong size / arity gives the reference's messages
+    bf = B.BrainHeteroDistributed().build({"s": "1"}).build_for(t)
+    with pytest.raises(ValueError, match="Wrong size of functions grid: 7x2 expected, 3x2 found"):
+        bf(R.Grid(3, 2, R.RealFunction(8, 5)))
+    with pytest.raises(ValueError, match=r"Wrong number of function input args at \(0,0\): 8 expected, 7 found"):
+        bf(R.Grid(7, 2, R.RealFunction(7, 5)))
+    with pytest.raises(ValueError, match=r"Wrong number of function output args at \(0,0\): 5 expected, 4 found"):
+        bf(R.Grid(7, 2, R.RealFunction(8, 4)))
+
+
+def test_brain_phase_function_divides_both_coordinates_by_the_width(V, oracle):
+    """brainPhaseFun<mlp (BrainPhaseFunction.java:36-43): phase(x, y) = f(0, [x / w, y / w])[0] for every cell."""
+    B, L, R, F = V
+    t = _target(R, "biped-4x3", "")
+    mapper = B.build_mapper("brainPhaseFun;f=0.5;a=0.9<mlp;r=0.65;nIL=1")
+    G = len(mapper.example_for(t))
+    assert G == 9  # 2-2-1: innerNeurons(2, 1, 0.65, 1) = [max(round(2 * 0.65), 2)]... evaluated by the C library
+    w = np.random.default_rng(4).uniform(-1, 1, G)
+    robot = mapper.build_for(t)(w)
+    c = robot.get_controller()
+    assert (c.frequency, c.amplitude) == (0.5, 0.9)
+    mlp = R.MultiLayerPerceptron("tanh", 2, F.mlp_inner_neurons(2, 1, 0.65, 1), 1, w)
+    for (x, y) in ((0, 0), (3, 0), (1, 0), (2, 2)):
+        assert c.phases.get(x, y) == mlp.apply([x / 4, y / 4])[0]   # y / 4, not y / 3; (1, 0) is not a voxel but still has a phase
+    dev = L.Locomotion.genome_of(robot)
+    assert len(dev) == 10 and dev[1] == c.phases.get(3, 0) and dev[2] == c.phases.get(0, 1)
+    with pytest.raises(ValueError, match="Wrong number of function input args: 2 expected, 3 found"):
+        B.BrainPhaseFunction().build({}).build_for(t)(R.RealFunction(3, 1))
+
+
+def test_host_mlp_apply_is_the_oracle_mlp(V, oracle):
+    """MultiLayerPerceptron.apply on the host == the oracle's controller arithmetic: a 1x1 robot whose centralized MLP maps its
+    area-ratio reading to the control value; first-step control from the oracle trace vs the host evaluation."""
+    B, L, R, F = V
+    m = oracle.Model("box-1x1", "flat", "uniform-a-0", oracle.CTRL_MLP_CENTRALIZED, oracle.default_params(0.5, 0.0), n_inner=1)
+    G = m.genome_len()
+    g = np.random.default_rng(8).uniform(-1, 1, G)
+    _, _, _, tc = m.run(g, trace_steps=1)
+    layers = [m.ctrl.layers[i] for i in range(m.ctrl.n_layers)]
+    mlp = R.MultiLayerPerceptron("tanh", layers[0], layers[1:-1], layers[-1], g)
+    # the reading at step 1: soft-normalised area ratio of the (still almost undeformed) voxel; recover it by inverting nothing --
+    # evaluate the MLP over a sweep and check the oracle's control value is attained at a reading close to the rest value
+    xs = np.linspace(0.45, 0.55, 20001)
+    ys = np.array([mlp.apply([x])[0] for x in xs[::200]])
+    assert ys.min() - 1e-6 <= tc[0, 0] <= ys.max() + 1e-6
+
+
+def test_direct_numbers_grid_is_column_major(V):
+    B, L, R, F = V
+    grid = R.Grid(3, 2, lambda x, y: [0.0, 0.0])
+    out = B.DirectNumbersGrid().build({}).build_for(grid)(list(range(12)))
+    assert out.get(0, 0) == [0, 1] and out.get(0, 1) == [2, 3] and out.get(1, 0) == [4, 5] and out.get(2, 1) == [10, 11]
+    with pytest.raises(ValueError, match="Wrong number of values: 12 expected, 11 found"):
+        B.DirectNumbersGrid().build({}).build_for(grid)(list(range(11)))
+
+
+def test_percentile_is_commons_math_legacy(V):
+    B, *_ = V
+    # documented examples of the LEGACY estimator: pos = p (n + 1) / 100
+    assert B.percentile_legacy([1, 2, 3, 4, 5], 50) == 3.0
+    assert B.percentile_legacy([1, 2, 3, 4], 50) == 2.5
+    assert B.percentile_legacy([4, 1, 3, 2], 25) == 1.25
+    assert B.percentile_legacy([1, 2, 3, 4], 99) == 4.0
+    assert B.percentile_legacy([7.0], 30) == 7.0
+    # the Starter's default p = 0.5 is half a PERCENT: on any grid below 199 cells the threshold is the minimum
+    assert B.percentile_legacy(list(range(12)), 0.5) == 0.0
+
+
+def test_body_brain_sinusoidal(V):
+    """bodyBrainSin<dirNumGrid (BodyBrainSinusoidal.java:36-124): with the default p the whole grid becomes the body; with p = 50
+    the upper half by body value, largest connected component, cropped; frequencies / phases decoded from clipped genes."""
+    B, L, R, F = V
+    t = _target(R, "biped-4x3", "")
+    mapper = B.build_mapper("bodyBrainSin<dirNumGrid")
+    G = len(mapper.example_for(t))
+    assert G == 4 * 3 * 3
+    vals = np.zeros((4, 3, 3))  # [x][y][(body, frequency, phase)] in dirNumGrid's column-major order
+    vals[..., 0] = np.arange(12).reshape(4, 3)
+    vals[..., 1] = -1.0
+    vals[..., 2] = 3.0  # clipped to 1
+    vals[1, 2, 1] = 0.0
+    robot = mapper.build_for(t)(vals.reshape(-1))
+    assert robot.voxels.mask().all() and robot.voxels.w == 4 and robot.voxels.h == 3
+    fns = robot.get_controller().get_functions()
+    assert fns.get(0, 0) == R.Sinusoid(0.5, np.pi, 1.0) and fns.get(1, 2) == R.Sinusoid(1.25, np.pi, 1.0)
+    dev = L.Locomotion.genome_of(robot).reshape(12, 3)
+    assert np.array_equal(dev[1 + 2 * 4], [1.25, np.pi, 1.0])  # grid order: y * w + x
+    half = B.build_mapper("bodyBrainSin;p=50<dirNumGrid").build_for(t)(vals.reshape(-1))
+    # body values 0..11 column-major: threshold = 5.5 -> x = 2, 3 columns (values 6..11) survive, cropped to 2x3
+    assert half.voxels.w == 2 and half.voxels.h == 3 and half.voxels.mask().all()
+    with pytest.raises(ValueError, match="Wrong grid size: 4x3 expected, 3x3 found"):
+        B.BodyBrainSinusoidal().build({}).build_for(t)(R.Grid(3, 3, lambda x, y: [0.0] * 3))
+    with pytest.raises(ValueError, match="Wrong number of values in grid at 0,0: 3 expected, 2 found"):
+        B.BodyBrainSinusoidal().build({}).build_for(t)(R.Grid(4, 3, lambda x, y: [0.0] * 2))
+
+
+def test_apply_all_groups_robots_by_morphology(V):
+    """Mixed populations (body-evolving mappers): one device batch per distinct (body, sensors, controller structure), results
+    returned in the callers' order.  Runs without a GPU against stand-in contexts."""
+    B, L, R, F = V
+    t = _target(R, "biped-4x3", "")
+    full = B.build_mapper("bodyBrainSin<dirNumGrid").build_for(t)
+    half = B.build_mapper("bodyBrainSin;p=50<dirNumGrid").build_for(t)
+    rng = np.random.default_rng(0)
+    robots = [(full if i % 3 else half)(rng.uniform(-1, 1, 36)) for i in range(7)]
+
+    class FakeCtx:
+        def __init__(self, nv):
+            self.nv, self.calls = nv, []
+        def eval(self, genomes, want_results=False):
+            self.calls.append(genomes.shape)
+            res = np.zeros(len(genomes), dtype=F.RESULT_DTYPE)
+            res["velocity"] = genomes[:, 0] + 100 * self.nv
+            res["time"] = 1.0
+            return res["velocity"].copy(), res
+
+    task = L.Locomotion(5.0, ([0.0, 10.0], [0.0, 0.0]))
+    fakes = {}
+    task._context = lambda r: fakes.setdefault(int(r.voxels.mask().sum()), FakeCtx(int(r.voxels.mask().sum())))
+    out = task.apply_all(robots)
+    assert sorted(fakes) == sorted({int(r.voxels.mask().sum()) for r in robots}) and len(fakes) >= 2
+    assert all(len(c.calls) == 1 for c in fakes.values())
+    for r, o in zip(robots, out):
+        nv = int(r.voxels.mask().sum())
+        assert o.get_velocity() == L.Locomotion.genome_of(r)[0] + 100 * nv
 
 
 def test_rnd_terrain_task_draws_java_seeds(V, oracle):

@@ -175,3 +175,25 @@ def test_noisy_sensor_adds_first_gaussians_of_random_0(oracle):
         # step 1 is exact; later steps feed back through the controlled area, so only the first is a closed form
         if k == 0:
             assert abs(noisy_reading - clean_reading - gs[0] * 0.05) < 1e-12
+
+
+def test_new_controller_kinds_reduce_to_the_old_ones(oracle):
+    """DISTRIBUTED_HETERO with the same weights in every voxel == DISTRIBUTED_HOMO (BrainHeteroDistributed.java:76-83 installs one
+    function per voxel into the same DistributedSensing); TIME_SIN with one frequency / amplitude == PhaseSin
+    (BodyBrainSinusoidal.java:115 vs PhaseSin's a*sin(2 pi f t + phi)).  Bit-identical: same arithmetic, same order."""
+    p = oracle.default_params(2.0, 0.5)
+    homo = oracle.Model("comb-7x2", "flat", "uniform-t+vxy+a-0", oracle.CTRL_MLP_DISTRIBUTED_HOMO, p)
+    het = oracle.Model("comb-7x2", "flat", "uniform-t+vxy+a-0", oracle.CTRL_MLP_DISTRIBUTED_HETERO, p)
+    assert homo.genome_len() == 75 and het.genome_len() == 11 * 75
+    g = np.random.default_rng(0).uniform(-1, 1, (3, 75))
+    assert np.array_equal(homo.eval_batch(g), het.eval_batch(np.tile(g, (1, 11))))
+    # and it is really per voxel: changing one voxel's weights changes the outcome
+    g2 = np.tile(g, (1, 11))
+    g2[:, 5 * 75:6 * 75] *= -1
+    assert not np.array_equal(het.eval_batch(g2), homo.eval_batch(g))
+    ph = oracle.Model("biped-4x3", "flat", "", oracle.CTRL_PHASE_SIN, p, freq=1.3, amp=0.8)
+    ts = oracle.Model("biped-4x3", "flat", "", oracle.CTRL_TIME_SIN, p)
+    assert ts.genome_len() == 30
+    phases = np.random.default_rng(1).uniform(-1, 1, (3, 10))
+    triples = np.stack([np.full((3, 10), 1.3), phases, np.full((3, 10), 0.8)], axis=-1).reshape(3, 30)
+    assert np.array_equal(ph.eval_batch(phases), ts.eval_batch(triples))

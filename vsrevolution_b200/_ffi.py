@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("VSR_LIB") or os.path.join(_HERE, "libvsr_eval.so")  # VSR_LIB: A/B builds (tools/)
 
 VSR_OK, VSR_EINVAL, VSR_ECUDA, VSR_ENOMEM, VSR_EDIM, VSR_EUNSUPPORTED, VSR_ESTATE = 0, -1, -2, -3, -4, -5, -6
-CTRL_PHASE_SIN, CTRL_MLP_CENTRALIZED, CTRL_MLP_DISTRIBUTED_HOMO = 0, 1, 2
+CTRL_PHASE_SIN, CTRL_MLP_CENTRALIZED, CTRL_MLP_DISTRIBUTED_HOMO, CTRL_MLP_DISTRIBUTED_HETERO, CTRL_TIME_SIN = 0, 1, 2, 3, 4
 SENSOR_AREA_RATIO, SENSOR_TOUCH, SENSOR_VELOCITY, SENSOR_ANGLE = 0, 1, 2, 3
 
 

@@ -136,13 +136,22 @@ int genome_len_of(const vsr_ctx* c) {
   int dim = 0;
   for (auto& s : c->sensors) dim += sensor_dim(s);
   if (c->kind == VSR_CTRL_PHASE_SIN) return c->n_vox;
+  if (c->kind == VSR_CTRL_TIME_SIN) return 3 * c->n_vox;
   int n_in = c->layers.front(), n_out = c->layers.back();
   if (c->kind == VSR_CTRL_MLP_CENTRALIZED) {
     if (n_in != c->n_vox * dim || n_out != c->n_vox) return VSR_EDIM;
   } else {
     if (n_in != dim + 4 * c->signals || n_out != 1 + 4 * c->signals) return VSR_EDIM;
   }
-  return vsr_mlp_count_weights(c->layers.data(), (int)c->layers.size());
+  const int nw = vsr_mlp_count_weights(c->layers.data(), (int)c->layers.size());
+  return c->kind == VSR_CTRL_MLP_DISTRIBUTED_HETERO ? c->n_vox * nw : nw;
+}
+
+// the episode kernel is instantiated for three controller families; the two extra kinds run inside them
+bool is_sin(vsr_ctrl_kind k) { return k == VSR_CTRL_PHASE_SIN || k == VSR_CTRL_TIME_SIN; }
+bool is_dist(vsr_ctrl_kind k) { return k == VSR_CTRL_MLP_DISTRIBUTED_HOMO || k == VSR_CTRL_MLP_DISTRIBUTED_HETERO; }
+int kernel_ctrl(vsr_ctrl_kind k) {
+  return is_sin(k) ? VSR_CTRL_PHASE_SIN : (is_dist(k) ? VSR_CTRL_MLP_DISTRIBUTED_HOMO : VSR_CTRL_MLP_CENTRALIZED);
 }
 
 size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
@@ -305,7 +314,10 @@ int finalize(vsr_ctx* ctx) {
     }
   }
   // controller
-  k.ctrl_kind = ctx->kind; k.signals = ctx->signals; k.in_act = ctx->in_act; k.freq = ctx->freq; k.amp = ctx->amp;
+  k.ctrl_kind = kernel_ctrl(ctx->kind);
+  k.w_stride = ctx->kind == VSR_CTRL_MLP_DISTRIBUTED_HETERO ? glen / ctx->n_vox : 0;
+  k.time_sin = ctx->kind == VSR_CTRL_TIME_SIN ? 1 : 0;
+  k.signals = ctx->signals; k.in_act = ctx->in_act; k.freq = ctx->freq; k.amp = ctx->amp;
   k.genome_len = glen;
   k.n_layers = (int)ctx->layers.size();
   k.max_neurons = 1;
@@ -334,13 +346,13 @@ int finalize(vsr_ctx* ctx) {
   // phases of a step: one region, sized for the larger
   size_t act_bytes = 0;
   if (ctx->kind == VSR_CTRL_MLP_CENTRALIZED) act_bytes = (size_t)k.robots_per_warp * 2 * k.max_neurons * rs;
-  if (ctx->kind == VSR_CTRL_MLP_DISTRIBUTED_HOMO) act_bytes = (size_t)2 * k.max_neurons * 32 * rs;
+  if (is_dist(ctx->kind)) act_bytes = (size_t)2 * k.max_neurons * 32 * rs;
   k.off_stage = (int)o; k.off_act = (int)o;
   o = align16(o + std::max((size_t)3 * 32 * 4 * rs, act_bytes));
   k.off_w = (int)o;
-  if (ctx->kind != VSR_CTRL_PHASE_SIN) o = align16(o + (size_t)k.robots_per_warp * glen * rs);
+  if (!is_sin(ctx->kind)) o = align16(o + (size_t)k.robots_per_warp * glen * rs);
   k.off_sig = (int)o;
-  if (ctx->kind == VSR_CTRL_MLP_DISTRIBUTED_HOMO) o = align16(o + (size_t)2 * 32 * 4 * std::max(1, k.signals) * rs);
+  if (is_dist(ctx->kind)) o = align16(o + (size_t)2 * 32 * 4 * std::max(1, k.signals) * rs);
   o = (o + 31) & ~size_t(31); // also staged as V4 rows by the position phase
   k.off_bias = (int)o;
   o = align16(o + (size_t)18 * 32 * rs);
@@ -372,7 +384,7 @@ int finalize(vsr_ctx* ctx) {
   // per CTA than its launch bound (the kernel indexes by blockDim)
   while (ctx->warps > 1 && (size_t)ctx->warps * o + 1024 > 227 * 1024) ctx->warps--;
   const bool full_scaff = e.scaffolding_mask == 0xF && !std::getenv("VSR_GENERIC_SCAFF");
-  ctx->kernel = kernel_ptr(e.precision, ctx->kind, ctx->shape, full_scaff);
+  ctx->kernel = kernel_ptr(e.precision, kernel_ctrl(ctx->kind), ctx->shape, full_scaff);
   // the reference's default robot: one soft-normalised, non-averaged AreaRatio reading per voxel into a centralized MLP
   if (e.precision == 32 && ctx->shape == 3 && ctx->warps == 10 && full_scaff && ctx->kind == VSR_CTRL_MLP_CENTRALIZED &&
       ctx->sensors.size() == 1 && ctx->sensors[0].kind == VSR_SENSOR_AREA_RATIO && ctx->sensors[0].soft_norm &&
@@ -646,16 +658,17 @@ int vsr_body_set(vsr_ctx* ctx, int32_t w, int32_t h, const uint8_t* mask, const 
 int vsr_controller_set(vsr_ctx* ctx, vsr_ctrl_kind kind, const int32_t* layers, int32_t n_layers, int32_t signals, double freq,
                        double amp, int32_t in_act) {
   if (!ctx) return VSR_EINVAL;
-  if (kind != VSR_CTRL_PHASE_SIN) {
+  if ((int)kind < 0 || (int)kind > VSR_CTRL_TIME_SIN) return fail(ctx, VSR_EINVAL, "unknown controller kind");
+  if (!is_sin(kind)) {
     if (!layers || n_layers < 2 || n_layers > vsr::kMaxLayers) return fail(ctx, VSR_EINVAL, "MLP needs 2..8 layers");
     for (int i = 0; i < n_layers; i++)
       if (layers[i] <= 0 || layers[i] > 255) return fail(ctx, VSR_EUNSUPPORTED, "layer size must be in 1..255");
-    if (kind == VSR_CTRL_MLP_DISTRIBUTED_HOMO && (signals < 0 || signals > 4)) return fail(ctx, VSR_EUNSUPPORTED, "signals must be in 0..4");
+    if (is_dist(kind) && (signals < 0 || signals > 4)) return fail(ctx, VSR_EUNSUPPORTED, "signals must be in 0..4");
   }
   ctx->kind = kind;
   ctx->layers.clear();
-  if (kind != VSR_CTRL_PHASE_SIN) ctx->layers.assign(layers, layers + n_layers);
-  ctx->signals = kind == VSR_CTRL_MLP_DISTRIBUTED_HOMO ? signals : 0;
+  if (!is_sin(kind)) ctx->layers.assign(layers, layers + n_layers);
+  ctx->signals = is_dist(kind) ? signals : 0;
   ctx->freq = freq; ctx->amp = amp; ctx->in_act = in_act ? 1 : 0;
   ctx->has_ctrl = true;
   return finalize(ctx);

@@ -98,6 +98,8 @@ struct KParams {
   void* hist;             // R[hist_cap][n_avg][total_lanes] ring of raw readings
   // controller
   int ctrl_kind, n_layers, layers[kMaxLayers], signals, in_act, genome_len, max_neurons;
+  int w_stride; // heterogeneous DistributedSensing: weights of voxel v start at v * w_stride inside the robot's row (0 = one shared MLP)
+  int time_sin; // PHASE_SIN kernel running TimeFunctions sinusoids: genome row = (frequency, phase, amplitude) per voxel
   double freq, amp;
   // episode
   int n_steps, k_first, k_last;
@@ -496,7 +498,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
   // ---- controller state --------------------------------------------------------------------------
   R phase = 0;
   if (CTRL == VSR_CTRL_PHASE_SIN) {
-    if (valid) phase = (R)P.genomes[(size_t)robot * P.genome_len + v];
+    if (valid && !P.time_sin) phase = (R)P.genomes[(size_t)robot * P.genome_len + v];
   } else {
     // K2 genome upload: the warp's robots are consecutive rows -> one contiguous range of doubles,
     // read with 128-bit loads (double2) after a scalar head for 16-byte alignment.
@@ -1314,7 +1316,14 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
     }
     R f = 0;
     if (CTRL == VSR_CTRL_PHASE_SIN) {
-      f = M<R>::phase_sin(P.amp, P.freq, t, phase);
+      if (P.time_sin) {
+        // TimeFunctions of per-voxel sinusoids (BodyBrainSinusoidal.java:87-119): the triple is re-read once per step (L1/L2)
+        if (valid) {
+          const double* g3 = P.genomes + (size_t)robot * P.genome_len + 3 * v;
+          f = M<R>::phase_sin(__ldg(g3 + 2), __ldg(g3), t, (R)__ldg(g3 + 1));
+        }
+      } else
+        f = M<R>::phase_sin(P.amp, P.freq, t, phase);
     } else {
       // sensor readings of this voxel
       R rd[8];
@@ -1425,7 +1434,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
       } else { // homogeneous DistributedSensing: every voxel runs the same MLP on its own inputs
         const int sg = P.signals;
         R* a0 = act; // [2][maxN][32]
-        const R* w_ = wts + (size_t)(lane_used ? rw : 0) * P.genome_len;
+        const R* w_ = wts + (size_t)(lane_used ? rw : 0) * P.genome_len + (size_t)(lane_used ? v : 0) * P.w_stride;
         const R* sin_ = sig + (size_t)sig_par * 32 * 4 * sg;
         R* sout = sig + (size_t)(sig_par ^ 1) * 32 * 4 * sg;
         int ni = 0;

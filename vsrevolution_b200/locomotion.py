@@ -18,7 +18,8 @@ import numpy as np
 
 from . import _ffi
 from .builder import build_mapper
-from .robot import CentralizedSensing, DistributedSensing, MultiLayerPerceptron, PhaseSin, Robot, RobotUtils
+from .robot import (CentralizedSensing, DistributedSensing, MultiLayerPerceptron, PhaseSin, Robot, RobotUtils, Sinusoid,
+                    TimeFunctions)
 
 
 @dataclass
@@ -109,8 +110,15 @@ class Locomotion:
         elif isinstance(c, CentralizedSensing):
             ckey = ("central", tuple(self._mlp(c.function).neurons))
         elif isinstance(c, DistributedSensing):
-            f = next(f for f in c.get_functions().values() if f is not None)
-            ckey = ("dist", c.signals, tuple(self._mlp(f).neurons))
+            fs = [f for f in c.get_functions().values() if f is not None]
+            neurons = tuple(self._mlp(fs[0]).neurons)
+            if any(tuple(self._mlp(f).neurons) != neurons for f in fs[1:]):
+                raise _ffi.VsrError(_ffi.VSR_EUNSUPPORTED, "per-voxel MLPs of different sizes are outside this build")
+            ckey = ("hetero" if self._is_hetero(fs) else "dist", c.signals, neurons)
+        elif isinstance(c, TimeFunctions):
+            if any(not isinstance(c.get_functions().get(e.key.x, e.key.y), Sinusoid) for e in body if e.value is not None):
+                raise _ffi.VsrError(_ffi.VSR_EUNSUPPORTED, "TimeFunctions: only Sinusoid entries run on the device")
+            ckey = ("timesin",)
         else:
             raise _ffi.VsrError(_ffi.VSR_EUNSUPPORTED, f"controller {type(c).__name__} is outside the hot path")
         key = (mask.tobytes(), mask.shape, skey, ckey)
@@ -130,10 +138,19 @@ class Locomotion:
                 ctx.controller_set(_ffi.CTRL_PHASE_SIN, (), 0, c.frequency, c.amplitude)
             elif ckey[0] == "central":
                 ctx.controller_set(_ffi.CTRL_MLP_CENTRALIZED, ckey[1])
+            elif ckey[0] == "timesin":
+                ctx.controller_set(_ffi.CTRL_TIME_SIN)
             else:
-                ctx.controller_set(_ffi.CTRL_MLP_DISTRIBUTED_HOMO, ckey[2], c.signals)
+                kind = _ffi.CTRL_MLP_DISTRIBUTED_HETERO if ckey[0] == "hetero" else _ffi.CTRL_MLP_DISTRIBUTED_HOMO
+                ctx.controller_set(kind, ckey[2], c.signals)
             self._ctxs[key] = ctx
         return ctx
+
+    @staticmethod
+    def _is_hetero(fs) -> bool:
+        """A DistributedSensing whose voxels do not all share one function (BrainHeteroDistributed) needs per-voxel weights."""
+        w0 = Locomotion._mlp(fs[0]).get_params()
+        return any(f is not fs[0] and not np.array_equal(Locomotion._mlp(f).get_params(), w0) for f in fs[1:])
 
     @staticmethod
     def _mlp(f) -> MultiLayerPerceptron:
@@ -146,24 +163,45 @@ class Locomotion:
         """Flatten the controller parameters in the order the kernel expects (== the mappers' genome order)."""
         c = robot.get_controller()
         if isinstance(c, PhaseSin):
-            return np.array([p for p in c.phases.values() if p is not None], dtype=np.float64)
+            # the phases of the voxels only: brainPhaseFun fills every cell of the grid, voxel or not (BrainPhaseFunction.java:36-43)
+            return np.array([c.phases.get(e.key.x, e.key.y) for e in robot.get_voxels() if e.value is not None], dtype=np.float64)
         if isinstance(c, CentralizedSensing):
             return Locomotion._mlp(c.function).get_params()
+        if isinstance(c, TimeFunctions):
+            body = robot.get_voxels()
+            return np.array([[s.frequency, s.phase, s.amplitude] for s in
+                             (c.get_functions().get(e.key.x, e.key.y) for e in body if e.value is not None)],
+                            dtype=np.float64).reshape(-1)
         fs = [f for f in c.get_functions().values() if f is not None]
-        w0 = Locomotion._mlp(fs[0]).get_params()
-        if any(f is not fs[0] and not np.array_equal(Locomotion._mlp(f).get_params(), w0) for f in fs[1:]):
-            raise _ffi.VsrError(_ffi.VSR_EUNSUPPORTED, "heterogeneous DistributedSensing is outside this build")
-        return w0
+        if Locomotion._is_hetero(fs):
+            return np.concatenate([Locomotion._mlp(f).get_params() for f in fs])  # grid order == FunctionsGrid's slicing order
+        return Locomotion._mlp(fs[0]).get_params()
+
+    def _outcomes(self, res) -> list[Outcome]:
+        return [Outcome(float(r["velocity"]), float(r["distance"]), float(r["time"]), float(r["first_x"]), float(r["last_x"]),
+                        self.transient_t, self.final_t, float(r["control_energy"]), float(r["area_ratio_abs"]),
+                        float(r["area_ratio_sq"])) for r in res]
+
+    def _groups(self, robots: Sequence[Robot]) -> list[tuple[_ffi.Context, list[int]]]:
+        """Robots grouped by device context (body, sensors, controller structure), first-appearance order.  A population of one
+        morphology is one group = one launch; mappers that also evolve the body (bodyBrainSin) give one launch per distinct
+        body (and a homogeneous distributed brain lands in another group than a heterogeneous one)."""
+        groups: dict[int, tuple[_ffi.Context, list[int]]] = {}
+        for i, r in enumerate(robots):
+            ctx = self._context(r)
+            groups.setdefault(id(ctx), (ctx, []))[1].append(i)
+        return list(groups.values())
 
     def apply_all(self, robots: Sequence[Robot]) -> list[Outcome]:
         if not robots:
             return []
-        ctx = self._context(robots[0])
-        genomes = np.stack([self.genome_of(r) for r in robots])
-        _, res = ctx.eval(genomes, want_results=True)
-        return [Outcome(float(r["velocity"]), float(r["distance"]), float(r["time"]), float(r["first_x"]), float(r["last_x"]),
-                        self.transient_t, self.final_t, float(r["control_energy"]), float(r["area_ratio_abs"]),
-                        float(r["area_ratio_sq"])) for r in res]
+        out: list = [None] * len(robots)
+        for ctx, idx in self._groups(robots):
+            genomes = np.stack([self.genome_of(robots[i]) for i in idx])
+            _, res = ctx.eval(genomes, want_results=True)
+            for i, o in zip(idx, self._outcomes(res)):
+                out[i] = o
+        return out
 
     def apply(self, robot: Robot) -> Outcome:
         return self.apply_all([robot])[0]
@@ -199,12 +237,14 @@ class RandomTerrainLocomotion(Locomotion):
     def apply_all(self, robots: Sequence[Robot]) -> list[Outcome]:
         if not robots:
             return []
-        ctx = self._context(robots[0])
-        genomes = np.stack([self.genome_of(r) for r in robots])
-        _, res = ctx.eval_terrains(genomes, self.terrains_for(len(robots)), want_results=True)
-        return [Outcome(float(r["velocity"]), float(r["distance"]), float(r["time"]), float(r["first_x"]), float(r["last_x"]),
-                        self.transient_t, self.final_t, float(r["control_energy"]), float(r["area_ratio_abs"]),
-                        float(r["area_ratio_sq"])) for r in res]
+        terrains = self.terrains_for(len(robots))  # seeds are drawn in robot order, before any grouping
+        out: list = [None] * len(robots)
+        for ctx, idx in self._groups(robots):
+            genomes = np.stack([self.genome_of(robots[i]) for i in idx])
+            _, res = ctx.eval_terrains(genomes, [terrains[i] for i in idx], want_results=True)
+            for i, o in zip(idx, self._outcomes(res)):
+                out[i] = o
+        return out
 
 
 def build_locomotion_task(terrain_name: str, episode_t: float, transient_t: float = 0.0, random: JavaRandomInts | None = None,
@@ -295,7 +335,10 @@ class MicroBatchedLocomotion:
 
 class PopulationEvaluator:
     """genome matrix -> fitness vector for one (shape, sensors, mapper, terrain): what a batching JGEA evolver calls
-    once per generation.  The genome layout IS the mapper's layout, so rows go to the device untouched."""
+    once per generation.  For the mappers whose genome IS the controller parameter vector (brainCentralized<mlp,
+    brainPhaseVals, brainHomoDist<mlp, brainHeteroDist<funsGrid) rows go to the device untouched (`direct`); the mappers that
+    transform the genome on the host (brainPhaseFun<mlp, bodyBrainSin<dirNumGrid ...) are applied row by row and the
+    robots go through `apply_all`, which groups them by morphology."""
 
     def __init__(self, shape: str, sensor_config: str, mapper: str, terrain: str, episode_t: float, transient_t: float,
                  precision: int = 32, devices: Sequence[int] | None = None):
@@ -304,13 +347,19 @@ class PopulationEvaluator:
         self.target = Robot(None, body)
         self.mapper = build_mapper(mapper)
         self.genome_len = len(self.mapper.example_for(self.target))
-        proto = self.mapper.build_for(self.target)(np.zeros(self.genome_len))
+        self._build = self.mapper.build_for(self.target)
+        # direct <=> a probe genome comes back unchanged as the device genome of the robot it builds (distinct values, so a
+        # heterogeneous brain is recognised as such)
+        probe = np.linspace(-0.5, 0.5, self.genome_len)
+        proto = self._build(probe)
         self.ctx = self.task._context(proto)
-        if self.ctx.genome_len != self.genome_len:
-            raise _ffi.VsrIllegalArgument(_ffi.VSR_EDIM, f"mapper genome length {self.genome_len} != device {self.ctx.genome_len}")
+        dev = Locomotion.genome_of(proto)
+        self.direct = self.ctx.genome_len == self.genome_len and np.array_equal(dev, probe)
         self.n_voxels = self.ctx.n_voxels
 
     def evaluate(self, genomes: np.ndarray) -> np.ndarray:
+        if not self.direct:
+            return np.array([o.get_velocity() for o in self.task.apply_all([self._build(g) for g in np.asarray(genomes)])])
         if isinstance(self.task, RandomTerrainLocomotion):
             return self.ctx.eval_terrains(genomes, self.task.terrains_for(len(genomes)))
         return self.ctx.eval(genomes)

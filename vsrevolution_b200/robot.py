@@ -7,7 +7,9 @@ Mirrors (names and argument meaning) of, as used by the reference:
   Robot(controller, voxels) ...core.objects.Robot                           (builder/robot/BrainCentralized.java:42-45)
   PhaseSin(f, a, phases)    ...core.controllers.PhaseSin                    (builder/robot/BrainPhaseValues.java:47-50)
   CentralizedSensing        ...core.controllers.CentralizedSensing          (builder/robot/BrainCentralized.java:28-43)
-  DistributedSensing        ...core.controllers.DistributedSensing          (builder/robot/BrainHomoDistributed.java:76-82)
+  DistributedSensing        ...core.controllers.DistributedSensing          (builder/robot/BrainHomoDistributed.java:76-82,
+                                                                             builder/robot/BrainHeteroDistributed.java:76-83)
+  TimeFunctions             ...core.controllers.TimeFunctions               (builder/robot/BodyBrainSinusoidal.java:87-119)
   MultiLayerPerceptron      ...core.controllers.MultiLayerPerceptron        (builder/function/MLP.java:63-69)
   RealFunction.build        ...core.controllers.RealFunction                (builder/robot/BrainCentralized.java:52-56)
   RobotUtils.buildShape / buildSensorizingFunction                          (locomotion/Starter.java:402-406)
@@ -142,6 +144,29 @@ class MultiLayerPerceptron(TimedRealFunction):
     def get_params(self) -> np.ndarray:
         return self.weights
 
+    def apply(self, t_or_input, input_=None, input_activation: bool = True) -> np.ndarray:
+        """`function.apply(t, in)` / `function.apply(in)` on the host, in double: used by the mappers that evaluate a function
+        once per voxel at build time (BrainPhaseFunction.java:37-43, FunctionNumbersGrid.java:50-54), never per step.  Same
+        arithmetic as the oracle's mlp_apply (weights layer -> to-neuron -> (bias, from-neurons...), tanh on every layer)."""
+        x = np.asarray(t_or_input if input_ is None else input_, dtype=np.float64)
+        if len(x) != self.neurons[0]:
+            raise _ffi.VsrIllegalArgument(_ffi.VSR_EDIM, f"Expected input length is {self.neurons[0]}: found {len(x)}")
+        if input_activation:
+            x = np.tanh(x)
+        o = 0
+        for l in range(1, len(self.neurons)):
+            nf, nt = self.neurons[l - 1], self.neurons[l]
+            w = self.weights[o:o + nt * (nf + 1)].reshape(nt, nf + 1)
+            y = np.empty(nt)
+            for j in range(nt):  # same summation order as the oracle: bias, then the from-neurons in order
+                acc = w[j, 0]
+                for k in range(nf):
+                    acc += x[k] * w[j, 1 + k]
+                y[j] = np.tanh(acc)
+            x = y
+            o += nt * (nf + 1)
+        return x
+
 
 # ---- controllers ---------------------------------------------------------------------------------------
 class Controller:
@@ -153,6 +178,26 @@ class Controller:
 class PhaseSin(Controller):
     def __init__(self, frequency: float, amplitude: float, phases: Grid):
         self.frequency, self.amplitude, self.phases = frequency, amplitude, phases
+
+
+@dataclass(frozen=True)
+class Sinusoid:
+    """`t -> amplitude * Math.sin(2 * Math.PI * freq * t + phase)` (BodyBrainSinusoidal.java:115): the only time function the
+    reference builds for TimeFunctions; kept as data so that the device can evaluate it."""
+    frequency: float
+    phase: float
+    amplitude: float
+
+    def __call__(self, t: float) -> float:
+        return self.amplitude * float(np.sin(2 * np.pi * self.frequency * t + self.phase))
+
+
+class TimeFunctions(Controller):
+    def __init__(self, functions: Grid):
+        self.functions = functions
+
+    def get_functions(self) -> Grid:
+        return self.functions
 
 
 class CentralizedSensing(Controller):
