@@ -490,3 +490,18 @@ def test_host_transforming_mappers_through_the_population_evaluator(F, oracle):
         assert ev2.task.apply(ev2._build(g2[i])).get_velocity() == fit2[i]
     direct = L.population_evaluator("comb-7x2", "uniform-t+vxy+a-0", "brainHeteroDist;s=1<funsGrid", "flat", 2.0, 0.5)
     assert direct.direct and direct.genome_len == 825
+
+
+def test_live_contexts_sharing_a_kernel_instantiation(F, oracle):
+    """Several contexts alive at once (one per morphology) launch the same kernel function with different shared-memory footprints:
+    creating the smaller one must not shrink the function's dynamic shared-memory opt-in under the larger one."""
+    p = oracle.default_params(1.0, 0.5)
+    big = oracle.Model("worm-8x2", "flat", "", oracle.CTRL_PHASE_SIN, p)
+    small = oracle.Model("box-1x1", "flat", "", oracle.CTRL_PHASE_SIN, p)
+    cb = make_ctx(F, big)
+    gb = np.random.default_rng(0).uniform(-1, 1, (5, 16))
+    first = cb.eval(gb)
+    cs = make_ctx(F, small)
+    assert np.isfinite(cs.eval(np.zeros((3, 1)))).all()
+    assert np.array_equal(cb.eval(gb), first)
+    cs.close(); cb.close()

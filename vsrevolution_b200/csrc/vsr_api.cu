@@ -396,7 +396,9 @@ int finalize(vsr_ctx* ctx) {
   // per-device uploads
   for (auto& d : ctx->devs) {
     CK(cudaSetDevice(d.dev));
-    CK(cudaFuncSetAttribute(ctx->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_bytes));
+    // the attribute belongs to the kernel function, not to this context: several live contexts (one per morphology) share an
+    // instantiation, so always opt in to the CTA maximum instead of this context's own footprint
+    CK(cudaFuncSetAttribute(ctx->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     if (d.d_win) { cudaFree(d.d_win); d.d_win = nullptr; }
     CK(cudaMalloc(&d.d_win, ctx->win_tab.size()));
     CK(cudaMemcpy(d.d_win, ctx->win_tab.data(), ctx->win_tab.size(), cudaMemcpyHostToDevice));
