@@ -49,12 +49,29 @@ typedef struct {
   double init_min, init_max; /* UniformDoubleFactory(-1, 1)                                                      */
   uint64_t seed;
   int32_t remap;           /* `remap`: re-evaluate the parents every generation (DoublesStandard.java:45); 0 = false */
+  /* which JGEA solver the loop restates: VSR_SOLVER_NUM_GA (above) or VSR_SOLVER_ES, the reference's `ES` =
+   * new SimpleES(0.35, 0.4) (locomotion/Starter.java:179) -> builder/solver/SimpleES.java:41-49 ->
+   * JGEA SimpleEvolutionaryStrategy(mapper, UniformDoubleFactory(-1, 1) genotypes, nPop, stop,
+   *                                 nOfParents = round(nPop * parentsRate), nOfElites = 1, sigma, remap).
+   * One ES generation: the population is sorted; means[j] = mean of gene j over the best n_parents; the next population is the
+   * n_elites best individuals, kept with their fitness (re-evaluated if remap), plus nPop - n_elites offspring
+   * means + sigma_mut * N(0, 1) per gene; non-overlapping (the rest of the old population is dropped).  xover_prob,
+   * tournament_rate and min_tournament are ignored.  JGEA 2.0.1 is un-vendored: semantics [U], as for numGA.                */
+  int32_t solver;
+  int32_t n_parents;       /* ES: nOfParents = (int) Math.round(nPop * parentsRate), SimpleES.java:46                     */
+  int32_t n_elites;        /* ES: nOfElites = 1, SimpleES.java:47                                                          */
 } vsr_ga_desc;
+
+enum { VSR_SOLVER_NUM_GA = 0, VSR_SOLVER_ES = 1 };
 
 typedef struct vsr_ga vsr_ga;
 
 int vsr_ga_default(vsr_ga_desc* d);            /* numGA constants; n_pop = 0 (caller sets), seed 0                */
 int vsr_ga_tournament_size(const vsr_ga_desc* d); /* max(minNTournament, ceil(nPop * tournamentRate))             */
+/* ES constants of Starter.java:179 for a population of n_pop: sigma 0.35, n_parents = round(0.4 n_pop), n_elites = 1 */
+int vsr_es_default(vsr_ga_desc* d, int32_t n_pop);
+/* ES only: the means of the most recent generation step ([G] doubles, HOST buffer)                                  */
+int vsr_ga_means(vsr_ga* ga, double* means_out);
 
 /* ctx must be ready (body + controller set); the GA borrows it (destroy the GA first). */
 int vsr_ga_create(vsr_ctx* ctx, const vsr_ga_desc* d, vsr_ga** out);
@@ -86,7 +103,8 @@ int vsr_ga_population(vsr_ga* ga, double* genomes_out /* [nPop][G] or NULL */, d
  * parents[i][1] = -1 for mutation-only), fitness [nPop]; any pointer may be NULL                                   */
 int vsr_ga_offspring(vsr_ga* ga, double* genomes_out, int32_t* parents_out, double* fitness_out);
 /* where the current population came from: origin[r] = row of the merged set (rows 0..nPop-1 = previous population, rows
- * nPop..2nPop-1 = offspring) that now sits at rank r; after init / set_population: the row of the unsorted input      */
+ * nPop..2nPop-1 = offspring) that now sits at rank r; after init / set_population: the row of the unsorted input.
+ * ES: the row of the new generation (rows 0..n_elites-1 = the elites, then the offspring in draw order)               */
 int vsr_ga_survivors(vsr_ga* ga, int32_t* origin_out /* [nPop] */);
 /* overwrite the population (HOST [nPop][G] genomes, [nPop] fitness values; sorted internally): resume / tests       */
 int vsr_ga_set_population(vsr_ga* ga, const double* genomes, const double* fitness);

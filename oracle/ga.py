@@ -133,3 +133,55 @@ class NumGA:
     def init(self, fitness_fn):
         g = self.initial_genomes()
         return self.set_population(g, fitness_fn(g))
+
+
+class SimpleES:
+    """The solver the reference names ``ES``: ``new SimpleES(0.35, 0.4)`` (locomotion/Starter.java:179), built in
+    builder/solver/SimpleES.java:41-49 as a JGEA ``SimpleEvolutionaryStrategy(mapper, UniformDoubleFactory(-1, 1) genotypes, nPop,
+    stop, nOfParents = round(nPop * parentsRate), nOfElites = 1, sigma, remap)``.  One generation [U: JGEA 2.0.1 is un-vendored]:
+    sort; means = gene-wise mean of the best nOfParents; next population = the nOfElites best (fitness kept, or re-evaluated with
+    remap) + (nPop - nOfElites) offspring ``means + N(0, 1) * sigma``.  Draws: Philox stream S_MUT at (generation, offspring, gene)."""
+
+    def __init__(self, n_pop: int, genome_len: int, seed: int = 0, sigma: float = 0.35, parents_rate: float = 0.4,
+                 n_elites: int = 1, init_range=(-1.0, 1.0), remap: bool = False):
+        self.n, self.G = n_pop, genome_len
+        self.key = (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+        self.sigma, self.rng, self.remap = sigma, init_range, remap
+        self.n_parents = int(math.floor(n_pop * parents_rate + 0.5))  # (int) Math.round(...)
+        self.n_elites = n_elites
+        self.gen = -1
+        self.pop = self.fit = self.means = None
+
+    initial_genomes = NumGA.initial_genomes
+    set_population = NumGA.set_population
+
+    def init(self, fitness_fn):
+        g = self.initial_genomes()
+        return self.set_population(g, fitness_fn(g))
+
+    def sample(self, gen: int):
+        """(means, next-generation genomes [n][G]: elites first, then the offspring in draw order)"""
+        s = np.zeros(self.G)
+        for i in range(self.n_parents):  # rank order, like the device's es_means_kernel
+            s = s + self.pop[i]
+        means = s / float(self.n_parents)
+        e = self.n_elites
+        i = np.arange(self.n - e)[:, None]
+        g = np.arange(self.G)[None, :]
+        r = philox4x32(self.key, (gen, i, S_MUT, g))
+        u1 = u53(r[0], r[1]) + 1.0 / 9007199254740992.0
+        u2 = u53(r[2], r[3])
+        z = np.sqrt(-2.0 * np.log(u1)) * np.cos(6.283185307179586 * u2)
+        return means, np.concatenate([self.pop[:e], means[None, :] + self.sigma * z])
+
+    def step(self, fitness_fn):
+        self.means, nxt = self.sample(self.gen + 1)
+        e = self.n_elites
+        if self.remap:
+            f = fitness_fn(nxt)
+        else:
+            f = np.concatenate([self.fit[:e], fitness_fn(nxt[e:])])
+        o = order(f)
+        self.pop, self.fit = nxt[o], f[o]
+        self.gen += 1
+        return o

@@ -174,3 +174,47 @@ def test_large_population_ranking_by_bitonic_sort(ev):
         pop, f = ga.population()
         assert np.array_equal(f, og.fit) and np.array_equal(pop, og.pop)
     ga.close()
+
+
+@pytest.mark.parametrize("remap", [False, True])
+def test_es_generation_loop_matches_oracle(ev, remap):
+    """`ES` = SimpleES(0.35, 0.4) (Starter.java:179; builder/solver/SimpleES.java:41-49) on the device vs oracle/ga.py: means bit
+    for bit (same summation order), offspring genes to 1e-12 (device libm Gaussian), elites / ranks exact."""
+    from vsrevolution_b200 import _ffi
+    n, G = 50, ev.genome_len
+    ga = _ffi.GeneticAlgorithm(ev.ctx, n, seed=5, remap=remap, solver=_ffi.SOLVER_ES)
+    og = OG.SimpleES(n, G, seed=5, remap=remap)
+    assert ga.desc.n_parents == og.n_parents == 20 and ga.desc.n_elites == 1 and ga.desc.sigma_mut == 0.35
+    ga.init()
+    g0 = og.initial_genomes()
+    og.set_population(g0, ev.evaluate(g0))
+    pop, fit = ga.population()
+    assert np.array_equal(pop, og.pop) and np.array_equal(fit, og.fit)
+    for gen in range(1, 4):
+        ga.step()
+        means, nxt = og.sample(gen)
+        assert np.array_equal(ga.means(), means)
+        off, par, off_fit = ga.offspring()        # rows of the new generation: the elite, then the offspring
+        assert np.array_equal(off[:1], og.pop[:1]) and np.abs(off - nxt).max() < 1e-12 and (par == -1).all()
+        if not remap:
+            assert off_fit[0] == og.fit[0]        # the elite keeps its fitness
+        o = OG.order(off_fit)
+        og.pop, og.fit, og.gen = off[o], off_fit[o], gen
+        pop, fit = ga.population()
+        assert np.array_equal(ga.survivors(), o)
+        assert np.array_equal(pop, og.pop) and np.array_equal(fit, og.fit) and np.all(np.diff(fit) <= 0)
+    assert ga.evaluations == n + 3 * (n if remap else n - 1)
+    if not remap:  # elitism: the best fitness never decreases
+        assert fit[0] >= ev.evaluate(g0).max()
+    ga.close()
+    with pytest.raises(_ffi.VsrIllegalArgument):
+        _ffi.GeneticAlgorithm(ev.ctx, n, solver=_ffi.SOLVER_ES, n_parents=n + 1)
+
+
+def test_es_solver_mirror_improves(ev):
+    from vsrevolution_b200 import solver as S
+    loop = S.es().build({"nPop": "64", "nEval": "400"}).build(ev, seed=2)
+    seen = []
+    best_g, best_f = loop.solve(listener=lambda d: seen.append(d["best.fitness"]))
+    assert len(seen) >= 5 and all(b >= a for a, b in zip(seen, seen[1:])) and best_f >= seen[0]
+    assert loop.ga.evaluations >= 400 and len(best_g) == ev.genome_len

@@ -97,7 +97,7 @@ def test_ga_library_exports_every_declared_symbol():
     if not os.path.exists(_ffi.LIB_PATH):
         g.build()
     hdr = open(os.path.join(ROOT, "include", "vsr_ga.h")).read()
-    declared = set(re.findall(r"\b(vsr_ga_[a-z0-9_]+)\s*\(", hdr))
+    declared = set(re.findall(r"\b(vsr_(?:ga|es)_[a-z0-9_]+)\s*\(", hdr))
     lib = C.CDLL(_ffi.LIB_PATH)
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in vsr_ga.h but not exported"
@@ -109,6 +109,14 @@ def test_ga_library_exports_every_declared_symbol():
     for n in (1, 10, 41, 61, 100, 4096, 1 << 18):
         d.n_pop = n
         assert _ffi.lib().vsr_ga_tournament_size(d) == OG.tournament_size(n)
+    # `ES` constants (Starter.java:179; SimpleES.java:46-47): nOfParents = (int) Math.round(nPop * 0.4), one elite
+    for n, npar in ((9, 4), (25, 10), (30, 12), (100, 40), (4096, 1638)):
+        assert _ffi.lib().vsr_es_default(d, n) == 0
+        assert (d.solver, d.n_pop, d.n_parents, d.n_elites, d.sigma_mut) == (_ffi.SOLVER_ES, n, npar, 1, 0.35)
+        assert OG.SimpleES(n, 3).n_parents == npar
+    from vsrevolution_b200.solver import SimpleES, es
+    eb = es().build({"nPop": "30", "nEval": "300", "remap": "true"})
+    assert (eb.n_pop, eb.n_eval, eb.remap, eb.outer.sigma, eb.outer.parents_rate) == (30, 300, True, 0.35, 0.4)
     # the mirror of the builder parses the same parameter names
     from vsrevolution_b200.solver import DoublesStandard, num_ga
     import pytest
@@ -116,3 +124,38 @@ def test_ga_library_exports_every_declared_symbol():
     assert (b.n_pop, b.n_eval, b.remap) == (100, 1000, False)
     with pytest.raises(_ffi.VsrIllegalArgument):
         DoublesStandard(0.75, 0.05, 3, 0.35).build({"nPop": "100"})
+
+
+def test_simple_es_semantics():
+    """oracle/ga.py SimpleES = JGEA SimpleEvolutionaryStrategy as builder/solver/SimpleES.java:41-49 configures it: parents = best
+    round(0.4 nPop), one elite kept with its fitness, nPop - 1 offspring around the parents' mean, non-overlapping."""
+    from oracle import ga as OG
+    n, G = 30, 7
+    es = OG.SimpleES(n, G, seed=3)
+    assert es.n_parents == 12 and es.n_elites == 1
+    assert OG.SimpleES(25, G).n_parents == 10 and OG.SimpleES(9, G).n_parents == 4   # Math.round(3.6) = 4, round half up
+    sphere = lambda g: -np.sum((g - 0.3) ** 2, axis=1)
+    calls = []
+    def fit(g):
+        calls.append(len(g))
+        return sphere(g)
+    es.init(fit)
+    assert calls == [n] and np.all(np.diff(es.fit) <= 0)
+    best0, elite0 = es.fit[0], es.pop[0].copy()
+    parents_mean = es.pop[:12].mean(axis=0)
+    es.step(fit)
+    assert calls == [n, n - 1]                       # the elite is not re-evaluated
+    assert np.allclose(es.means, parents_mean, atol=1e-15)
+    assert es.fit[0] >= best0 and any(np.array_equal(row, elite0) for row in es.pop)
+    # offspring are centred on the means with std sigma
+    for _ in range(30):
+        es.step(fit)
+    assert es.fit[0] > -0.2 and es.fit[0] >= best0       # settles around the optimum (constant sigma: no further)
+    m, nxt = es.sample(es.gen + 1)
+    z = (nxt[1:] - m) / es.sigma
+    assert abs(z.mean()) < 0.2 and 0.8 < z.std() < 1.2
+    # remap re-evaluates the elite too
+    es2 = OG.SimpleES(n, G, seed=3, remap=True)
+    calls.clear()
+    es2.init(fit); es2.step(fit)
+    assert calls == [n, n]

@@ -61,7 +61,11 @@ class VsrIllegalArgument(VsrError, ValueError):
 class GaDesc(C.Structure):
     _fields_ = [("n_pop", C.c_int32), ("xover_prob", C.c_double), ("tournament_rate", C.c_double),
                 ("min_tournament", C.c_int32), ("sigma_mut", C.c_double), ("init_min", C.c_double),
-                ("init_max", C.c_double), ("seed", C.c_uint64), ("remap", C.c_int32)]
+                ("init_max", C.c_double), ("seed", C.c_uint64), ("remap", C.c_int32), ("solver", C.c_int32),
+                ("n_parents", C.c_int32), ("n_elites", C.c_int32)]
+
+
+SOLVER_NUM_GA, SOLVER_ES = 0, 1
 
 
 _lib = None
@@ -101,6 +105,8 @@ _SIGS = {
 _GA_SIGS = {
     "vsr_ga_default": (C.c_int, [C.POINTER(GaDesc)]),
     "vsr_ga_tournament_size": (C.c_int, [C.POINTER(GaDesc)]),
+    "vsr_es_default": (C.c_int, [C.POINTER(GaDesc), C.c_int32]),
+    "vsr_ga_means": (C.c_int, [C.c_void_p, C.c_void_p]),
     "vsr_ga_create": (C.c_int, [C.c_void_p, C.POINTER(GaDesc), C.POINTER(C.c_void_p)]),
     "vsr_ga_destroy": (None, [C.c_void_p]),
     "vsr_ga_last_error": (C.c_char_p, [C.c_void_p]),
@@ -282,11 +288,16 @@ class Context:
 class GeneticAlgorithm:
     """Thin RAII wrapper of vsr_ga (include/vsr_ga.h): the device-resident `numGA` generation loop."""
 
-    def __init__(self, ctx: Context, n_pop: int, seed: int = 0, remap: bool = False, **params):
+    def __init__(self, ctx: Context, n_pop: int, seed: int = 0, remap: bool = False, solver: int = SOLVER_NUM_GA, **params):
         self._h = C.c_void_p()
         self.ctx = ctx  # the GA borrows the context: keep it alive
         d = GaDesc()
-        check(lib().vsr_ga_default(C.byref(d)))
+        if solver == SOLVER_ES:  # `ES` = SimpleES(0.35, 0.4) defaults for this population size (Starter.java:179)
+            rc = lib().vsr_es_default(C.byref(d), n_pop)
+            if rc < 0:
+                raise VsrIllegalArgument(rc, "bad ES parameters")
+        else:
+            check(lib().vsr_ga_default(C.byref(d)))
         d.n_pop, d.seed, d.remap = n_pop, seed, int(remap)
         for k, v in params.items():
             if not hasattr(d, k):
@@ -370,6 +381,11 @@ class GeneticAlgorithm:
         p = np.empty((self.n_pop, 2), dtype=np.int32)
         self._ck(lib().vsr_ga_offspring(self._h, _ptr(g), _ptr(p), _ptr(f)))
         return g, p, f
+
+    def means(self) -> np.ndarray:
+        m = np.empty(self.genome_len)
+        self._ck(lib().vsr_ga_means(self._h, _ptr(m)))
+        return m
 
     def survivors(self) -> np.ndarray:
         o = np.empty(self.n_pop, dtype=np.int32)

@@ -98,6 +98,34 @@ __global__ void ga_vary_kernel(GaK p, uint32_t gen, const double* __restrict__ p
   off[idx] = pop[(size_t)src * p.G + g] + p.sigma * z;
 }
 
+// ---- ES (JGEA SimpleEvolutionaryStrategy; builder/solver/SimpleES.java:41-49) ---------------------------------------------------
+// means[g] = mean of gene g over the best n_par individuals (the population is sorted: rows 0..n_par-1), summed in rank order so
+// that the result does not depend on the launch geometry (and oracle/ga.py reproduces it bit for bit)
+__global__ void es_means_kernel(const double* __restrict__ pop, int G, int n_par, double* __restrict__ means) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G) return;
+  double s = 0;
+  for (int i = 0; i < n_par; i++) s += pop[(size_t)i * G + g];
+  means[g] = s / (double)n_par;
+}
+// next generation, rows [0, n_elites) = the elites (genome and fitness), rows [n_elites, n_pop) = means + sigma * N(0, 1)
+__global__ void es_sample_kernel(GaK p, uint32_t gen, int n_elites, const double* __restrict__ pop, const double* __restrict__ pop_fit,
+                                 const double* __restrict__ means, double* __restrict__ nxt, double* __restrict__ nxt_fit) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x, total = (size_t)p.n_pop * p.G;
+  if (idx >= total) return;
+  const uint32_t i = (uint32_t)(idx / p.G), g = (uint32_t)(idx % p.G);
+  if ((int)i < n_elites) {
+    nxt[idx] = pop[idx];
+    if (g == 0) nxt_fit[i] = pop_fit[i];
+    return;
+  }
+  const U4 r = philox(p.k0, p.k1, gen, i - (uint32_t)n_elites, S_MUT, g);
+  const double u1 = u53(r.x, r.y) + (1.0 / 9007199254740992.0); // (0, 1]
+  const double u2 = u53(r.z, r.w);
+  const double z = sqrt(-2.0 * log(u1)) * cos(6.283185307179586 * u2);
+  nxt[idx] = means[g] + p.sigma * z;
+}
+
 // rank[i] = number of individuals that beat i: higher fitness first, NaN as -inf, ties towards the lower index (a strict
 // total order, so the ranks are a permutation).  Tiled all-pairs count; blockIdx.y splits the opponents.
 constexpr int kRankTile = 2048;
@@ -196,6 +224,7 @@ struct vsr_ga {
   double* genomes[2] = {nullptr, nullptr}; // [2 nPop][G]: population rows then offspring rows
   double* fit[2] = {nullptr, nullptr};     // [2 nPop + 8]
   int32_t *parents = nullptr, *rank = nullptr, *origin = nullptr;
+  double* means = nullptr; // ES: [G]
   uint64_t* sort_keys = nullptr; // bitonic sort scratch: next power of two >= 2 nPop entries
   uint32_t* sort_idx = nullptr;
   int sort_cap = 0;
@@ -237,19 +266,21 @@ int eval_pending(vsr_ga* ga, int base, int count, int pending) {
   return VSR_OK;
 }
 
-// rank the first m rows of buffer `cur`, keep the best n_pop in the other buffer, swap
-int truncate_into_next(vsr_ga* ga, int m) {
+// rank rows [base, base + m) of buffer `cur`, keep the best n_pop in the other buffer, swap
+int truncate_into_next(vsr_ga* ga, int m, int base = 0) {
   const int n = ga->d.n_pop, nxt = ga->cur ^ 1;
+  const double* src_fit = ga->fit[ga->cur] + base;
+  const double* src_gen = ga->genomes[ga->cur] + (size_t)base * ga->G;
   GCK(cudaSetDevice(ga->dev));
   if (m <= kAllPairsMax) {
     GCK(cudaMemsetAsync(ga->rank, 0, sizeof(int32_t) * m, ga->st));
     dim3 grid((m + 255) / 256, (m + kRankTile - 1) / kRankTile);
-    ga_rank_kernel<<<grid, 256, 0, ga->st>>>(ga->fit[ga->cur], m, ga->rank);
+    ga_rank_kernel<<<grid, 256, 0, ga->st>>>(src_fit, m, ga->rank);
     ga->launches += 1;
   } else {
     int P = kSortTile;
     while (P < m) P <<= 1;
-    ga_keys_kernel<<<(P + 255) / 256, 256, 0, ga->st>>>(ga->fit[ga->cur], m, P, ga->sort_keys, ga->sort_idx);
+    ga_keys_kernel<<<(P + 255) / 256, 256, 0, ga->st>>>(src_fit, m, P, ga->sort_keys, ga->sort_idx);
     ga->launches += 1;
     for (int k = 2; k <= P; k <<= 1) {
       int j = k >> 1;
@@ -263,7 +294,7 @@ int truncate_into_next(vsr_ga* ga, int m) {
     ga_rank_from_sorted<<<(P + 255) / 256, 256, 0, ga->st>>>(ga->sort_idx, m, P, ga->rank);
     ga->launches += 1;
   }
-  ga_scatter_kernel<<<m, 64, 0, ga->st>>>(ga->genomes[ga->cur], ga->fit[ga->cur], ga->rank, ga->G, n, ga->genomes[nxt], ga->fit[nxt], ga->origin);
+  ga_scatter_kernel<<<m, 64, 0, ga->st>>>(src_gen, src_fit, ga->rank, ga->G, n, ga->genomes[nxt], ga->fit[nxt], ga->origin);
   GCK(cudaGetLastError());
   ga->launches += 1;
   ga->cur = nxt;
@@ -282,6 +313,18 @@ int vsr_ga_default(vsr_ga_desc* d) {
   return VSR_OK;
 }
 
+int vsr_es_default(vsr_ga_desc* d, int32_t n_pop) {
+  if (!d || n_pop <= 0) return VSR_EINVAL;
+  std::memset(d, 0, sizeof(*d));
+  d->solver = VSR_SOLVER_ES; d->n_pop = n_pop;
+  d->sigma_mut = 0.35;                                       // Starter.java:179: new SimpleES(0.35, 0.4)
+  d->n_parents = (int32_t)std::floor(n_pop * 0.4 + 0.5);     // (int) Math.round(nPop * parentsRate), SimpleES.java:46
+  d->n_elites = 1;                                           // SimpleES.java:47
+  d->init_min = -1.0; d->init_max = 1.0;                     // SimpleES.java:43
+  d->min_tournament = 1;
+  return VSR_OK;
+}
+
 int vsr_ga_tournament_size(const vsr_ga_desc* d) {
   if (!d || d->n_pop <= 0) return VSR_EINVAL;
   return std::max(d->min_tournament, (int)std::ceil((double)d->n_pop * d->tournament_rate)); // DoublesStandard.java:65
@@ -293,6 +336,9 @@ int vsr_ga_create(vsr_ctx* ctx, const vsr_ga_desc* d, vsr_ga** out) {
   if (!vsr_internal::ready(ctx)) return VSR_ESTATE;
   if (d->n_pop <= 0 || d->n_pop > (1 << 22) || !(d->xover_prob >= 0 && d->xover_prob <= 1) || !(d->tournament_rate >= 0) ||
       d->min_tournament < 1 || !(d->sigma_mut >= 0) || !(d->init_max >= d->init_min))
+    return VSR_EINVAL;
+  if (d->solver != VSR_SOLVER_NUM_GA && d->solver != VSR_SOLVER_ES) return VSR_EINVAL;
+  if (d->solver == VSR_SOLVER_ES && (d->n_parents < 1 || d->n_parents > d->n_pop || d->n_elites < 0 || d->n_elites >= d->n_pop))
     return VSR_EINVAL;
   vsr_ga* ga = new (std::nothrow) vsr_ga();
   if (!ga) return VSR_ENOMEM;
@@ -313,6 +359,8 @@ int vsr_ga_create(vsr_ctx* ctx, const vsr_ga_desc* d, vsr_ga** out) {
   ok = ok && cudaMalloc(&ga->parents, rows * sizeof(int32_t)) == cudaSuccess;
   ok = ok && cudaMalloc(&ga->rank, rows * sizeof(int32_t)) == cudaSuccess;
   ok = ok && cudaMalloc(&ga->origin, n * sizeof(int32_t)) == cudaSuccess;
+  ok = ok && cudaMemset(ga->parents, 0xFF, rows * sizeof(int32_t)) == cudaSuccess; // ES: no parent indices (-1)
+  ok = ok && cudaMalloc(&ga->means, (size_t)ga->G * sizeof(double)) == cudaSuccess;
   if (rows > (size_t)kAllPairsMax) {
     int P = kSortTile;
     while ((size_t)P < rows) P <<= 1;
@@ -330,7 +378,7 @@ void vsr_ga_destroy(vsr_ga* ga) {
   cudaSetDevice(ga->dev);
   if (ga->st) cudaStreamSynchronize(ga->st);
   for (int b = 0; b < 2; b++) { cudaFree(ga->genomes[b]); cudaFree(ga->fit[b]); }
-  cudaFree(ga->parents); cudaFree(ga->rank); cudaFree(ga->origin); cudaFree(ga->sort_keys); cudaFree(ga->sort_idx);
+  cudaFree(ga->parents); cudaFree(ga->rank); cudaFree(ga->origin); cudaFree(ga->means); cudaFree(ga->sort_keys); cudaFree(ga->sort_idx);
   delete ga;
 }
 
@@ -380,6 +428,16 @@ int vsr_ga_step_begin(vsr_ga* ga) {
   const size_t total = (size_t)n * ga->G;
   double* pop = ga->genomes[ga->cur];
   double* off = pop + total;
+  if (ga->d.solver == VSR_SOLVER_ES) {
+    const int e = ga->d.n_elites;
+    es_means_kernel<<<(ga->G + 63) / 64, 64, 0, ga->st>>>(pop, ga->G, ga->d.n_parents, ga->means);
+    es_sample_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ga->st>>>(ga->k, gen, e, pop, ga->fit[ga->cur], ga->means, off, ga->fit[ga->cur] + n);
+    GCK(cudaGetLastError());
+    ga->launches += 2;
+    ga->off_buf = ga->cur;
+    // the elites keep their fitness unless remap (SimpleEvolutionaryStrategy.update: map(offspringGenotypes, elites, ...))
+    return ga->d.remap ? eval_pending(ga, n, n, 2) : eval_pending(ga, n + e, n - e, 2);
+  }
   ga_select_kernel<<<(2 * n + 127) / 128, 128, 0, ga->st>>>(ga->k, gen, ga->parents);
   ga_vary_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ga->st>>>(ga->k, gen, pop, ga->parents, off);
   GCK(cudaGetLastError());
@@ -391,7 +449,8 @@ int vsr_ga_step_begin(vsr_ga* ga) {
 int vsr_ga_step_end(vsr_ga* ga) {
   if (!ga) return VSR_EINVAL;
   if (ga->pending != 2) return gfail(ga, VSR_ESTATE, "vsr_ga_step_end without vsr_ga_step_begin");
-  int rc = truncate_into_next(ga, 2 * ga->d.n_pop);
+  const int n = ga->d.n_pop;
+  int rc = ga->d.solver == VSR_SOLVER_ES ? truncate_into_next(ga, n, n) : truncate_into_next(ga, 2 * n);
   if (rc) return rc;
   ga->evals += ga->pend_count;
   ga->pending = 0; ga->gen++;
@@ -452,6 +511,15 @@ int vsr_ga_offspring(vsr_ga* ga, double* genomes_out, int32_t* parents_out, doub
   if (genomes_out) GCK(cudaMemcpyAsync(genomes_out, ga->genomes[ga->off_buf] + n * ga->G, n * ga->G * sizeof(double), cudaMemcpyDeviceToHost, ga->st));
   if (parents_out) GCK(cudaMemcpyAsync(parents_out, ga->parents, 2 * n * sizeof(int32_t), cudaMemcpyDeviceToHost, ga->st));
   if (fitness_out) GCK(cudaMemcpyAsync(fitness_out, ga->fit[ga->off_buf] + n, n * sizeof(double), cudaMemcpyDeviceToHost, ga->st));
+  GCK(cudaStreamSynchronize(ga->st));
+  return VSR_OK;
+}
+
+int vsr_ga_means(vsr_ga* ga, double* means_out) {
+  if (!ga || !means_out) return VSR_EINVAL;
+  if (ga->d.solver != VSR_SOLVER_ES || ga->gen < 1) return gfail(ga, VSR_ESTATE, "no ES generation step yet");
+  GCK(cudaSetDevice(ga->dev));
+  GCK(cudaMemcpyAsync(means_out, ga->means, (size_t)ga->G * sizeof(double), cudaMemcpyDeviceToHost, ga->st));
   GCK(cudaStreamSynchronize(ga->st));
   return VSR_OK;
 }

@@ -29,12 +29,20 @@ class _DeviceDoubles:
 class GenerationLoop:
     """StandardEvolver(..., overlapping=true, remap) restated on the device; stop condition nOfFitnessEvaluations(nEval)."""
 
-    def __init__(self, evaluator: PopulationEvaluator, n_pop: int, n_eval: int, x_over_prob: float, tournament_rate: float,
-                 min_n_tournament: int, sigma_mut: float, remap: bool = False, seed: int = 0, process_group=None):
+    def __init__(self, evaluator: PopulationEvaluator, n_pop: int, n_eval: int, x_over_prob: float = 0.75,
+                 tournament_rate: float = 0.05, min_n_tournament: int = 3, sigma_mut: float = 0.35, remap: bool = False,
+                 seed: int = 0, process_group=None, es: dict | None = None):
         self.evaluator = evaluator
         self.n_pop, self.n_eval = n_pop, n_eval
-        self.ga = _ffi.GeneticAlgorithm(evaluator.ctx, n_pop, seed=seed, remap=remap, xover_prob=x_over_prob,
-                                        tournament_rate=tournament_rate, min_tournament=min_n_tournament, sigma_mut=sigma_mut)
+        if not getattr(evaluator, "direct", True):
+            raise _ffi.VsrError(_ffi.VSR_EUNSUPPORTED, "the device-resident loop needs a mapper whose genome is the controller "
+                                "parameter vector; host-transforming mappers go through PopulationEvaluator.evaluate")
+        if es is not None:  # SimpleEvolutionaryStrategy(..., nOfParents, nOfElites, sigma, remap)
+            self.ga = _ffi.GeneticAlgorithm(evaluator.ctx, n_pop, seed=seed, remap=remap, solver=_ffi.SOLVER_ES,
+                                            sigma_mut=es["sigma"], n_parents=es["n_parents"], n_elites=es["n_elites"])
+        else:
+            self.ga = _ffi.GeneticAlgorithm(evaluator.ctx, n_pop, seed=seed, remap=remap, xover_prob=x_over_prob,
+                                            tournament_rate=tournament_rate, min_tournament=min_n_tournament, sigma_mut=sigma_mut)
         self.pg = process_group
         self.world = 1
         if process_group is not None:
@@ -101,6 +109,36 @@ class DoublesStandard:
         if str(params.get("diversity", "false")).lower() == "true":
             raise _ffi.VsrError(_ffi.VSR_EUNSUPPORTED, "StandardWithEnforcedDiversityEvolver is outside the hot path (SURVEY.md 8)")
         return _SolverBuilder(self, n_pop, n_eval, str(params.get("remap", "false")).lower() == "true")
+
+
+class _ESBuilder:
+    def __init__(self, outer: "SimpleES", n_pop: int, n_eval: int, remap: bool):
+        self.outer, self.n_pop, self.n_eval, self.remap = outer, n_pop, n_eval, remap
+
+    def build(self, evaluator: PopulationEvaluator, seed: int = 0, process_group=None) -> GenerationLoop:
+        n_parents = int(np.floor(self.n_pop * self.outer.parents_rate + 0.5))  # (int) Math.round(nPop * parentsRate)
+        return GenerationLoop(evaluator, self.n_pop, self.n_eval, remap=self.remap, seed=seed, process_group=process_group,
+                              es={"sigma": self.outer.sigma, "n_parents": n_parents, "n_elites": 1})
+
+
+class SimpleES:
+    """builder/solver/SimpleES.java: (sigma, parentsRate); `build(params)` reads nPop, nEval, remap (:31-33) and builds a JGEA
+    SimpleEvolutionaryStrategy with nOfParents = round(nPop * parentsRate), nOfElites = 1 (:41-49)."""
+
+    def __init__(self, sigma: float, parents_rate: float):
+        self.sigma, self.parents_rate = sigma, parents_rate
+
+    def build(self, params: dict) -> _ESBuilder:
+        try:
+            n_pop, n_eval = int(params["nPop"]), int(params["nEval"])
+        except KeyError as e:
+            raise _ffi.VsrIllegalArgument(_ffi.VSR_EINVAL, f"missing solver parameter {e.args[0]}")
+        return _ESBuilder(self, n_pop, n_eval, str(params.get("remap", "false")).lower() == "true")
+
+
+def es() -> SimpleES:
+    """`ES` (locomotion/Starter.java:179)."""
+    return SimpleES(0.35, 0.4)
 
 
 def num_ga() -> DoublesStandard:
