@@ -160,7 +160,12 @@ public class BatchedLocomotion implements Function<Robot, GpuOutcome>, AutoClose
         throw new UnsupportedOperationException("phases: Grid values in iteration order, nulls skipped");
       }
       if (c instanceof DistributedSensing ds) {
-        return ((MultiLayerPerceptron) ds.getFunctions().values().stream().filter(f -> f != null).findFirst().orElseThrow()).getParams();
+        // kind 2 (brainHomoDist): the shared weights once; kind 3 (brainHeteroDist): every voxel's weights, Grid iteration order
+        // (== FunctionsGrid's slicing order, builder/misc/FunctionsGrid.java:31-46)
+        List<double[]> ws = ds.getFunctions().values().stream().filter(f -> f != null)
+            .map(f -> ((MultiLayerPerceptron) f).getParams()).toList();
+        boolean homo = ws.stream().allMatch(w -> java.util.Arrays.equals(w, ws.get(0)));
+        return homo ? ws.get(0) : ws.stream().flatMapToDouble(java.util.Arrays::stream).toArray();
       }
       throw new IllegalArgumentException("Unsupported controller " + c.getClass().getSimpleName());
     }

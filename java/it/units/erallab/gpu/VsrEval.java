@@ -17,7 +17,9 @@ public final class VsrEval {
   /** vsr_body_set: mask[y*w+x], y = 0 bottom row; sensors flattened as {kind, axes, rotated, softNorm} ints + {min, max, window, sigma} doubles. */
   public static native void setBody(long ctx, int w, int h, byte[] mask, int[] sensorInts, double[] sensorDoubles);
 
-  /** vsr_controller_set: kind 0 PhaseSin, 1 CentralizedSensing MLP, 2 homogeneous DistributedSensing MLP. */
+  /** vsr_controller_set: kind 0 PhaseSin, 1 CentralizedSensing MLP, 2 homogeneous DistributedSensing MLP, 3 heterogeneous
+   *  DistributedSensing (one MLP per voxel, weights concatenated in Grid order), 4 TimeFunctions of per-voxel sinusoids
+   *  ((frequency, phase, amplitude) per voxel). */
   public static native void setController(long ctx, int kind, int[] layers, int signals, double freq, double amp, boolean inputActivation);
 
   public static native int genomeLength(long ctx);

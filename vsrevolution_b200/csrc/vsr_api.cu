@@ -382,6 +382,8 @@ int finalize(vsr_ctx* ctx) {
   ctx->warps = e.precision == 64 ? kWarps64 : kShapes[ctx->shape].warps;
   // large controllers (weights of every robot of the warp live in shared memory): launch the chosen kernel with fewer warps
   // per CTA than its launch bound (the kernel indexes by blockDim)
+  // (the 10-warp build folds its warp count at compile time, so a forced shape 3 that does not fit falls back to shape 2)
+  if (e.precision != 64 && ctx->shape == 3 && 10 * o + 1024 > 227 * 1024) { ctx->shape = 2; ctx->warps = kShapes[2].warps; }
   while (ctx->warps > 1 && (size_t)ctx->warps * o + 1024 > 227 * 1024) ctx->warps--;
   const bool full_scaff = e.scaffolding_mask == 0xF && !std::getenv("VSR_GENERIC_SCAFF");
   ctx->kernel = kernel_ptr(e.precision, kernel_ctrl(ctx->kind), ctx->shape, full_scaff);
