@@ -162,6 +162,16 @@ int vsr_eval_terrains(vsr_ctx* ctx, const double* genomes, int32_t n, const doub
                       const int32_t* terrain_off, double* fitness_out, vsr_result* results_out);
 
 /* timing / accounting of the most recent vsr_eval / vsr_eval_device on device 0 of the context */
+/*
+ * vsr_eval plus the robot-centre trajectory: centers_out [n][K][2] doubles = (x, y) of the robot centre (mean of the voxel
+ * polygon centres, the point Outcome.getDistance / getVelocity measure) at each of the K = k_last - k_first + 1 kept observations
+ * (vsr_episode_steps gives k_first / k_last).  These series are the inputs of Outcome.getCenterXVelocitySpectrum /
+ * getCenterYVelocitySpectrum / getCenterXPositionSpectrum (locomotion/NamedFunctions.java:139-162), for the whole population in one
+ * launch; the full per-step polygons of ONE robot (posture, footprints, video: NamedFunctions.java:163-189, VideoMaker.java:129-133)
+ * come from vsr_trace.  Costs two extra warp reductions per kept step, only in this entry point.
+ */
+int vsr_eval_centers(vsr_ctx* ctx, const double* genomes, int32_t n, double* fitness_out, vsr_result* results_out, double* centers_out);
+
 double vsr_last_kernel_ms(vsr_ctx* ctx);    /* CUDA-event duration of the episode kernel; syncs the stream */
 int64_t vsr_kernel_launches(const vsr_ctx* ctx); /* total episode-kernel launches so far */
 int vsr_kernel_info(const vsr_ctx* ctx, int32_t* regs_per_thread, int32_t* smem_bytes, int32_t* threads_per_cta,

@@ -505,3 +505,28 @@ def test_live_contexts_sharing_a_kernel_instantiation(F, oracle):
     assert np.isfinite(cs.eval(np.zeros((3, 1)))).all()
     assert np.array_equal(cb.eval(gb), first)
     cs.close(); cb.close()
+
+
+def test_centre_trajectories_match_the_oracle_trace(F, oracle):
+    """vsr_eval_centers: the (x, y) of the robot centre at every kept observation == the centre of the oracle's traced polygons
+    (FP64 kernel 1e-9 while both follow the same trajectory, FP32 1e-4 on the first steps); first / last entries are the
+    first_x / last_x of vsr_result; the fitness is the one vsr_eval returns."""
+    m = oracle.config_model(3, final_t=2.0)
+    m.params.transient_t = 0.5
+    g = np.random.default_rng(1).uniform(-1, 1, (7, m.genome_len()))
+    n_steps, k_first, k_last = F.episode_steps(2.0, 0.5)
+    for prec, tol in ((64, 1e-9), (32, 1e-4)):
+        ctx = make_ctx(F, m, prec)
+        fit, res, cen = ctx.eval_centers(g)
+        assert cen.shape == (7, k_last - k_first + 1, 2)
+        assert np.array_equal(fit, ctx.eval(g))
+        assert np.array_equal(cen[:, 0, 0], res["first_x"]) and np.array_equal(cen[:, -1, 0], res["last_x"])
+        for r in (0, 3, 6):
+            _, tv, _, _ = m.run(g[r], trace_steps=k_first + 25)
+            ref = tv.mean(axis=2).mean(axis=1)[k_first - 1:]        # [steps][2]: mean over voxels of the mean of the 4 vertices
+            assert np.abs(cen[r, :len(ref)] - ref).max() < tol, (prec, r, np.abs(cen[r, :len(ref)] - ref).max())
+        ctx.close()
+    from vsrevolution_b200 import locomotion as L
+    ev = L.population_evaluator("worm-8x2", "", "brainPhaseVals;f=1", "hilly-1-10-0", 2.0, 0.5)
+    outs = ev.task.apply_all_observed([ev._build(row) for row in g[:3]])
+    assert outs[1].centers.shape == (k_last - k_first + 1, 2) and len(outs[1].get_center_x_velocity_spectrum(0.0, 4.0, 8)) == 8

@@ -286,3 +286,20 @@ def test_micro_batching_keeps_the_one_robot_per_call_contract(V):
     assert errs == ["device failure"] * 3
     with pytest.raises(F.VsrIllegalArgument):
         L.MicroBatchedLocomotion(task, 0)
+
+
+def test_outcome_quantized_spectrum(V):
+    """The centre spectra of detailedOutcomeFunctions (NamedFunctions.java:139-162) on a synthetic trajectory: a 2.25 Hz oscillation
+    of the centre velocity lands in the bin that holds it; without recorded centres the getters fail loudly."""
+    B, L, R, F = V
+    dt = 1 / 60.0
+    t = np.arange(1, 541) * dt
+    x = 0.5 * t + 0.02 * np.sin(2 * np.pi * 2.25 * t)
+    y = 1.0 + 0.01 * np.sin(2 * np.pi * 3.25 * t)
+    o = L.Outcome(0.5, 4.5, 9.0, 0.0, 4.5, 1.0, 10.0, centers=np.stack([x, y], axis=1), dt=dt)
+    sx = o.get_center_x_velocity_spectrum(0.0, 4.0, 8)   # Starter.java:139-141: [0, 4] Hz, spectrumSize bins
+    sy = o.get_center_y_velocity_spectrum(0.0, 4.0, 8)
+    assert len(sx) == 8 and int(np.argmax(sx[1:])) + 1 == 4 and int(np.argmax(sy)) == 6   # 2.25 Hz -> bin [2, 2.5), 3.25 Hz -> bin [3, 3.5)
+    assert int(np.argmax(o.get_center_x_position_spectrum(0.0, 4.0, 8))) == 0             # the drift dominates the position spectrum
+    with pytest.raises(F.VsrError):
+        L.Outcome(0.5, 4.5, 9.0, 0.0, 4.5, 1.0, 10.0).get_center_x_velocity_spectrum(0, 4, 8)

@@ -81,6 +81,7 @@ _SIGS = {
     "vsr_genome_len": (C.c_int, [C.c_void_p]),
     "vsr_n_voxels": (C.c_int, [C.c_void_p]),
     "vsr_eval": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "vsr_eval_centers": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vsr_eval_terrains": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vsr_eval_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vsr_trace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -219,6 +220,18 @@ class Context:
         res = np.empty(g.shape[0], dtype=RESULT_DTYPE) if want_results else None
         check(lib().vsr_eval(self._h, _ptr(g), g.shape[0], _ptr(fit), _ptr(res)), self._h)
         return (fit, res) if want_results else fit
+
+    def eval_centers(self, genomes: np.ndarray):
+        """(fitness [n], results [n], centers [n][K][2]): vsr_eval plus the robot-centre (x, y) at every kept observation."""
+        g = np.ascontiguousarray(genomes, dtype=np.float64)
+        if g.ndim != 2 or g.shape[1] != self.genome_len:
+            raise VsrIllegalArgument(VSR_EDIM, f"Wrong number of values: {self.genome_len} expected, {g.shape[-1]} found")
+        n_steps, k_first, k_last = episode_steps(self.env.final_t, self.env.transient_t, self.env.dt)
+        fit = np.empty(g.shape[0], dtype=np.float64)
+        res = np.empty(g.shape[0], dtype=RESULT_DTYPE)
+        cen = np.empty((g.shape[0], k_last - k_first + 1, 2), dtype=np.float64)
+        check(lib().vsr_eval_centers(self._h, _ptr(g), g.shape[0], _ptr(fit), _ptr(res), _ptr(cen)), self._h)
+        return fit, res, cen
 
     def eval_terrains(self, genomes: np.ndarray, terrains, want_results: bool = False):
         """One terrain per robot (`-rnd`): terrains = sequence of (xs, ys) polylines, len == number of genomes."""

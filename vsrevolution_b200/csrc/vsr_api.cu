@@ -50,6 +50,9 @@ struct DeviceState {
   double* h_fitness = nullptr;
   vsr_result* h_results = nullptr;
   size_t cap = 0; // robots the buffers hold
+  double* d_centers = nullptr; // vsr_eval_centers: [robots of the shard][kept observations][2]
+  size_t centers_bytes = 0;
+  double* cur_centers = nullptr; // non-null only while vsr_eval_centers enqueues
   bool timed = false;
 };
 
@@ -480,6 +483,7 @@ int enqueue(vsr_ctx* ctx, DeviceState& d, const double* d_genomes, size_t n, dou
   k.energy = d.d_energy;
   k.tx = d.d_tx; k.ty = d.d_ty; k.win_tab = d.d_win; k.hist = d.d_hist; k.noise = d.d_noise;
   k.genomes = d_genomes; k.fitness = d_fitness; k.results = d_results; k.n_robots = (int)n;
+  k.centers = d.cur_centers;
   if (robot_terrains) { k.tx = d.d_rtx; k.ty = d.d_rty; k.toff = d.d_roff; k.tbase = d.d_rbase; k.tplace = d.d_rplace; k.ty_max = rt_ymax; }
   k.tr_vertices = trv; k.tr_bodies = trb; k.tr_ctrl = trc; k.trace_steps = trace_steps;
   if (time_it) CK(cudaEventRecord(d.ev0, st));
@@ -620,7 +624,7 @@ void vsr_ctx_destroy(vsr_ctx* c) {
     if (d.stream) cudaStreamSynchronize(d.stream);
     cudaFree(d.d_tx); cudaFree(d.d_ty); cudaFree(d.d_win); cudaFree(d.d_hist); cudaFree(d.d_noise); cudaFree(d.d_energy);
     cudaFree(d.d_rtx); cudaFree(d.d_rty); cudaFree(d.d_rbase); cudaFree(d.d_rplace); cudaFree(d.d_roff);
-    cudaFree(d.d_genomes); cudaFree(d.d_fitness); cudaFree(d.d_results);
+    cudaFree(d.d_genomes); cudaFree(d.d_fitness); cudaFree(d.d_results); cudaFree(d.d_centers);
     cudaFreeHost(d.h_genomes); cudaFreeHost(d.h_fitness); cudaFreeHost(d.h_results);
     if (d.ev0) cudaEventDestroy(d.ev0);
     if (d.ev1) cudaEventDestroy(d.ev1);
@@ -731,6 +735,48 @@ int vsr_eval(vsr_ctx* ctx, const double* genomes, int32_t n, double* fitness_out
     CK(cudaStreamSynchronize(d.stream));
     std::memcpy(fitness_out + lo, d.h_fitness, cnt * sizeof(double));
     if (results_out) std::memcpy(results_out + lo, d.h_results, cnt * sizeof(vsr_result));
+  }
+  return VSR_OK;
+}
+
+int vsr_eval_centers(vsr_ctx* ctx, const double* genomes, int32_t n, double* fitness_out, vsr_result* results_out, double* centers_out) {
+  if (!ctx) return VSR_EINVAL;
+  if (!ctx->ready) return fail(ctx, VSR_ESTATE, "body and controller must be set before vsr_eval_centers");
+  if (n < 0 || (n > 0 && (!genomes || !fitness_out || !centers_out))) return fail(ctx, VSR_EINVAL, "bad vsr_eval_centers arguments");
+  if (n == 0) return VSR_OK;
+  const size_t G = (size_t)ctx->kp.genome_len, kept = (size_t)(ctx->kp.k_last - ctx->kp.k_first + 1);
+  const size_t nd = ctx->devs.size(), per = ((size_t)n + nd - 1) / nd;
+  for (size_t i = 0; i < nd; i++) {
+    DeviceState& d = ctx->devs[i];
+    const size_t lo = std::min((size_t)n, i * per), hi = std::min((size_t)n, lo + per), cnt = hi - lo;
+    if (!cnt) continue;
+    int rc = ensure_capacity(ctx, d, cnt);
+    if (rc) return rc;
+    CK(cudaSetDevice(d.dev));
+    const size_t bytes = cnt * kept * 2 * sizeof(double);
+    if (bytes > d.centers_bytes) {
+      cudaFree(d.d_centers); d.d_centers = nullptr; d.centers_bytes = 0;
+      if (cudaMalloc(&d.d_centers, bytes) != cudaSuccess) { cudaGetLastError(); return fail(ctx, VSR_ENOMEM, "centre trajectories do not fit the device"); }
+      d.centers_bytes = bytes;
+    }
+    std::memcpy(d.h_genomes, genomes + lo * G, cnt * G * sizeof(double));
+    CK(cudaMemcpyAsync(d.d_genomes, d.h_genomes, cnt * G * sizeof(double), cudaMemcpyHostToDevice, d.stream));
+    d.cur_centers = d.d_centers;
+    rc = enqueue(ctx, d, d.d_genomes, cnt, d.d_fitness, results_out ? d.d_results : nullptr, d.stream, nullptr, nullptr, nullptr, 0, i == 0);
+    d.cur_centers = nullptr;
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(d.h_fitness, d.d_fitness, cnt * sizeof(double), cudaMemcpyDeviceToHost, d.stream));
+    if (results_out) CK(cudaMemcpyAsync(d.h_results, d.d_results, cnt * sizeof(vsr_result), cudaMemcpyDeviceToHost, d.stream));
+  }
+  for (size_t i = 0; i < nd; i++) {
+    DeviceState& d = ctx->devs[i];
+    const size_t lo = std::min((size_t)n, i * per), hi = std::min((size_t)n, lo + per), cnt = hi - lo;
+    if (!cnt) continue;
+    CK(cudaSetDevice(d.dev));
+    CK(cudaStreamSynchronize(d.stream));
+    std::memcpy(fitness_out + lo, d.h_fitness, cnt * sizeof(double));
+    if (results_out) std::memcpy(results_out + lo, d.h_results, cnt * sizeof(vsr_result));
+    CK(cudaMemcpy(centers_out + lo * kept * 2, d.d_centers, cnt * kept * 2 * sizeof(double), cudaMemcpyDeviceToHost));
   }
   return VSR_OK;
 }

@@ -108,6 +108,7 @@ struct KParams {
   const double* genomes;
   double* fitness;
   vsr_result* results;
+  double* centers;       // optional [n_robots][k_last - k_first + 1][2]: robot centre (x, y) at every kept observation (vsr_eval_centers)
   void* energy;          // V4<R>[total lanes]: per-voxel energy accumulators (sum f^2 dt, sum |da|, sum |d(a^2)|, last a); used only with results
   int n_robots;
   // trace (robot 0 only)
@@ -1500,11 +1501,21 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
       *eacc = e4;
     }
     // ---- observation: robot centre x at the first / last kept step --------------------------------------
-    if (step == P.k_first || step == P.k_last) {
+    const bool obs_all = P.centers != nullptr && step >= P.k_first && step <= P.k_last;
+    if (step == P.k_first || step == P.k_last || obs_all) {
       const double cxv = (double)ox + (double)(R(0.25) * (qx[0] + qx[1] + qx[2] + qx[3]));
       double sum = 0;
       for (int j = 0; j < L; j++) sum += __shfl_sync(FULL, cxv, (base_lane + j) & 31);
       sum /= L;
+      if (obs_all) { // centre trajectory of the kept observations (inputs of Outcome's centre spectra, NamedFunctions.java:139-172)
+        const double cyv = (double)oy + (double)(R(0.25) * (qy[0] + qy[1] + qy[2] + qy[3]));
+        double sumy = 0;
+        for (int j = 0; j < L; j++) sumy += __shfl_sync(FULL, cyv, (base_lane + j) & 31);
+        if (valid && v == 0) {
+          double* c = P.centers + ((size_t)robot * (size_t)(P.k_last - P.k_first + 1) + (size_t)(step - P.k_first)) * 2;
+          c[0] = sum; c[1] = sumy / L;
+        }
+      }
       double en0 = 0, en1 = 0, en2 = 0;
       if (P.results != nullptr && step == P.k_last) { // per-robot sums of the voxel accumulators, in voxel order
         const V4<R> e4 = reinterpret_cast<const V4<R>*>(P.energy)[gl];

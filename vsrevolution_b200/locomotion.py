@@ -43,6 +43,41 @@ class Outcome:
     control_energy: float = 0.0      # sum over kept steps and voxels of f^2 dt                    [U]
     area_ratio_energy: float = 0.0   # sum over kept steps and voxels of |a_k - a_{k-1}|           [U]
     area_ratio_energy_sq: float = 0.0  # ... of |a_k^2 - a_{k-1}^2| (the other candidate formula)  [U]
+    centers: np.ndarray | None = None  # [K][2] robot centre (x, y) at the kept observations (apply_all_observed only)
+    dt: float = 1.0 / 60.0
+
+    # centre spectra of detailedOutcomeFunctions (locomotion/NamedFunctions.java:139-162).  2dhmsr's BehaviorUtils is un-vendored:
+    # the definition below is the documented one [U] -- magnitude of the FFT of the series zero-padded to a power of two
+    # (commons-math FastFourierTransformer only accepts those), frequencies i / (N dt), averaged inside nBins equal bins of
+    # [minF, maxF]; bins without a frequency sample are 0.
+    @staticmethod
+    def quantized_spectrum(signal: np.ndarray, dt: float, min_f: float, max_f: float, n_bins: int) -> np.ndarray:
+        n = 1
+        while n < len(signal):
+            n *= 2
+        mag = np.abs(np.fft.fft(np.concatenate([signal, np.zeros(n - len(signal))])))[: n // 2 + 1]
+        f = np.arange(n // 2 + 1) / (n * dt)
+        out = np.zeros(n_bins)
+        edges = np.linspace(min_f, max_f, n_bins + 1)
+        for b in range(n_bins):
+            sel = (f >= edges[b]) & ((f < edges[b + 1]) if b + 1 < n_bins else (f <= edges[b + 1]))
+            if sel.any():
+                out[b] = mag[sel].mean()
+        return out
+
+    def _need_centers(self) -> np.ndarray:
+        if self.centers is None:
+            raise _ffi.VsrError(_ffi.VSR_ESTATE, "centre trajectories were not recorded: use Locomotion.apply_all_observed")
+        return self.centers
+
+    def get_center_x_position_spectrum(self, min_f: float, max_f: float, n_bins: int) -> np.ndarray:
+        return self.quantized_spectrum(self._need_centers()[:, 0], self.dt, min_f, max_f, n_bins)
+
+    def get_center_x_velocity_spectrum(self, min_f: float, max_f: float, n_bins: int) -> np.ndarray:
+        return self.quantized_spectrum(np.diff(self._need_centers()[:, 0]) / self.dt, self.dt, min_f, max_f, n_bins)
+
+    def get_center_y_velocity_spectrum(self, min_f: float, max_f: float, n_bins: int) -> np.ndarray:
+        return self.quantized_spectrum(np.diff(self._need_centers()[:, 1]) / self.dt, self.dt, min_f, max_f, n_bins)
 
     # detailedOutcomeFunctions (locomotion/NamedFunctions.java:135-137)
     def get_control_power(self) -> float:
@@ -200,6 +235,20 @@ class Locomotion:
             genomes = np.stack([self.genome_of(robots[i]) for i in idx])
             _, res = ctx.eval(genomes, want_results=True)
             for i, o in zip(idx, self._outcomes(res)):
+                out[i] = o
+        return out
+
+    def apply_all_observed(self, robots: Sequence[Robot]) -> list[Outcome]:
+        """apply_all that also keeps every robot's centre trajectory over the kept observations (vsr_eval_centers): what
+        `detailedOutcomeFunctions` needs for the centre spectra, for the whole population in one launch per morphology."""
+        if not robots:
+            return []
+        out: list = [None] * len(robots)
+        for ctx, idx in self._groups(robots):
+            genomes = np.stack([self.genome_of(robots[i]) for i in idx])
+            _, res, cen = ctx.eval_centers(genomes)
+            for j, (i, o) in enumerate(zip(idx, self._outcomes(res))):
+                o.centers, o.dt = cen[j], self.settings.step_frequency
                 out[i] = o
         return out
 
