@@ -395,7 +395,7 @@ int finalize(vsr_ctx* ctx) {
       ctx->sensors.size() == 1 && ctx->sensors[0].kind == VSR_SENSOR_AREA_RATIO && ctx->sensors[0].soft_norm &&
       !(ctx->sensors[0].avg_window > 0) && !std::getenv("VSR_GENERIC_SENSORS"))
     ctx->kernel = vsr_internal::kernel_f32_s3_area();
-  ctx->smem_bytes = o * ctx->warps;
+  ctx->smem_bytes = o * ctx->warps + 128; // + the CTA's phase counters (bounded-skew alignment)
   if (k.n_t > 16383) return fail(ctx, VSR_EUNSUPPORTED, "terrains with more than 16383 vertices are not supported");
   if (ctx->smem_bytes > 227 * 1024) return fail(ctx, VSR_EUNSUPPORTED, "controller too large for shared memory");
   // per-device uploads

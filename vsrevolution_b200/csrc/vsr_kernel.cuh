@@ -47,6 +47,9 @@ constexpr int kPoolStride = 36;
 #define VSR_SYNC_MASK_DEFAULT 115
 #endif
 constexpr int kSyncMaskDefault = VSR_SYNC_MASK_DEFAULT;
+#ifndef VSR_SOFT_SYNC
+#define VSR_SOFT_SYNC 0 // > 0: bounded-skew phase alignment (warps may run this many boundaries ahead); 0: __syncthreads
+#endif
 
 struct SensorK {
   int kind, axes, rotated, soft_norm;
@@ -760,10 +763,33 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
   detect(); // World.step's first-step detect()
 
   double t = 0.0;
+#if VSR_SOFT_SYNC > 0
+  volatile int* sphase = reinterpret_cast<volatile int*>(smem_raw + (size_t)cta_warps * P.smem_warp_stride); // [cta_warps] boundaries passed
+  int my_phase = 0;
+  if (lane == 0) sphase[warp] = 0;
+  __syncthreads();
+#endif
   // =================================================================================================
 #pragma unroll 1
   for (int step = 1; step <= P.n_steps; step++) {
+#if VSR_SOFT_SYNC > 0
+    // bounded-skew alignment: a warp may run at most VSR_SOFT_SYNC phase boundaries ahead of the slowest warp of its CTA, so the
+    // warps still share (almost) one instruction stream, but a warp that needs extra position iterations or narrowphase rounds in
+    // one step no longer stalls the other nine: the slack is paid back when another warp straggles.  Pure timing: no data crosses
+    // warps, so the volatile counters need no fence.
+#define PHASE_SYNC(bit)                                                                     \
+    if ((SCAFF >= 0 ? kSyncMaskDefault : P.sync_mask) & (bit)) {                              \
+      my_phase++;                                                                           \
+      __syncwarp();                                                                         \
+      if (lane == 0) sphase[warp] = my_phase;                                               \
+      for (;;) {                                                                            \
+        const int p_ = lane < cta_warps ? sphase[lane] : 0x7fffffff;                        \
+        if (__reduce_min_sync(FULL, p_) >= my_phase - VSR_SOFT_SYNC) break;                 \
+      }                                                                                     \
+    }
+#else
 #define PHASE_SYNC(bit) if ((SCAFF >= 0 ? kSyncMaskDefault : P.sync_mask) & (bit)) __syncthreads(); /* re-align the CTA's warps: shared instruction stream */
+#endif
     PHASE_SYNC(1)
     t += P.dt;
     // ---- integrate velocities: gravity, then damping ---------------------------------------------
