@@ -19,9 +19,30 @@ SEEDS = {1: 0, 3: 1, 4: 2}
 STEPS, T = 40, 3.0
 
 
-def build(cfg: int) -> dict:
-    m = O.config_model(cfg, final_t=T)
-    g = np.random.default_rng(SEEDS[cfg]).uniform(-1, 1, (2, m.genome_len()))
+# the controller kinds added after the BASELINE configs: name -> (model, genome transform)
+def extra_model(name: str):
+    if name == "hetero":  # brainHeteroDist<funsGrid on config 4's robot and terrain
+        return O.Model("comb-7x2", "steppy-0.25-1-0", "uniform-t+vxy+a-0", O.CTRL_MLP_DISTRIBUTED_HETERO, O.default_params(T), signals=1)
+    if name == "timesin":  # TimeFunctions sinusoids on config 3's robot and terrain
+        return O.Model("worm-8x2", "hilly-1-10-0", "", O.CTRL_TIME_SIN, O.default_params(T))
+    raise ValueError(name)
+
+
+def extra_genomes(name: str, m) -> np.ndarray:
+    g = np.random.default_rng({"hetero": 7, "timesin": 8}[name]).uniform(-1, 1, (2, m.genome_len()))
+    if name == "timesin":  # the decode of bodyBrainSin: frequency in [0.5, 2], phase in [0, pi], amplitude in [0, 1]
+        g = g.reshape(2, -1, 3)
+        g = np.stack([0.5 + 1.5 * (g[..., 0] + 1) / 2, np.pi * (g[..., 1] + 1) / 2, (g[..., 2] + 1) / 2], axis=-1).reshape(2, -1)
+    return g
+
+
+def build(cfg) -> dict:
+    if isinstance(cfg, str):
+        m = extra_model(cfg)
+        g = extra_genomes(cfg, m)
+    else:
+        m = O.config_model(cfg, final_t=T)
+        g = np.random.default_rng(SEEDS[cfg]).uniform(-1, 1, (2, m.genome_len()))
     tv, tc = [], []
     for r in range(2):
         _, v, _, c = m.run(g[r], trace_steps=STEPS)
@@ -34,6 +55,10 @@ def build(cfg: int) -> dict:
 
 
 if __name__ == "__main__":
-    for cfg in SEEDS:
-        np.savez_compressed(os.path.join(HERE, f"config{cfg}.npz"), **build(cfg))
-        print("wrote config%d.npz" % cfg)
+    only = sys.argv[1:]
+    for cfg in list(SEEDS) + ["hetero", "timesin"]:
+        name = cfg if isinstance(cfg, str) else f"config{cfg}"
+        if only and name not in only:
+            continue
+        np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **build(cfg))
+        print("wrote %s.npz" % name)

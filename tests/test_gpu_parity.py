@@ -325,6 +325,28 @@ def test_cuda_path_against_committed_golden_vectors(F, oracle, cfg):
         ctx.close()
 
 
+@pytest.mark.parametrize("name", ["hetero", "timesin"])
+def test_cuda_path_against_golden_vectors_of_the_later_controller_kinds(F, oracle, name):
+    """tests/golden/{hetero,timesin}.npz: FP64 kernel 1e-9 on the 40 recorded steps, FP32 kernel 1e-4 of the voxel side on the first 10."""
+    import importlib.util, os
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(here, "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    gold = np.load(os.path.join(here, "golden", f"{name}.npz"))
+    m = mg.extra_model(name)
+    steps = gold["vertices"].shape[1]
+    for prec in (64, 32):
+        ctx = make_ctx(F, m, prec)
+        for r in range(2):
+            _, tv, _, tc = ctx.trace(gold["genomes"][r], steps)
+            if prec == 64:
+                assert np.abs(tv - gold["vertices"][r]).max() < 1e-9 and np.abs(tc - gold["controls"][r]).max() < 1e-9
+            else:
+                assert np.abs(tv[:10] - gold["vertices"][r][:10]).max() < 1e-4 * 3.0
+        ctx.close()
+
+
 def test_per_evaluation_terrains_match_single_terrain_runs(F, oracle):
     """vsr_eval_terrains (`-rnd` terrains, Starter.java:89-93): robot i on terrain i in ONE launch == robot i evaluated alone in a
     context built on terrain i (bit-identical, FP32), and the FP64 kernel tracks the oracle run on that terrain."""
