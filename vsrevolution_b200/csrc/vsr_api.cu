@@ -334,8 +334,11 @@ int finalize(vsr_ctx* ctx) {
   double min_seg = INFINITY;
   for (size_t i = 1; i < ctx->tx.size(); i++) min_seg = std::fmin(min_seg, ctx->tx[i] - ctx->tx[i - 1]);
   const bool narrow = min_seg < 2.0 * m;
+  // Small bodies need more than 6/5 per voxel: whichever side of a w x h body lies on the ground, up to max(w, h) voxels rest on
+  // two corner masses each, plus two polygon-boundary doubles (a 1x1 robot: 4 manifolds for 1 voxel, 32 robots per warp).
+  const int resting = k.robots_per_warp * std::min(2 * std::max(ctx->w, ctx->h) + 2, 4 * ctx->n_vox);
   int S = narrow ? std::max(16, std::min(96, k.robots_per_warp * ctx->n_vox * 2))
-                 : std::max(16, std::min(64, k.robots_per_warp * ctx->n_vox * 6 / 5));
+                 : std::max(16, std::min(254, std::max(std::min(64, k.robots_per_warp * ctx->n_vox * 6 / 5), resting)));
   if (const char* ev = std::getenv("VSR_POOL_SLOTS")) S = std::max(8, std::min(255, std::atoi(ev)));
   k.pool_slots = S;
   size_t o = 0;
