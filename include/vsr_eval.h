@@ -174,6 +174,9 @@ int vsr_eval_centers(vsr_ctx* ctx, const double* genomes, int32_t n, double* fit
 
 double vsr_last_kernel_ms(vsr_ctx* ctx);    /* CUDA-event duration of the episode kernel; syncs the stream */
 int64_t vsr_kernel_launches(const vsr_ctx* ctx); /* total episode-kernel launches so far */
+/* warps whose contact pool overflowed, over every launch of this context so far (0 = every fitness value is reliable; also counts the
+ * fitness-only and generation-loop launches, which have no vsr_result to carry contact_overflow); synchronises the streams */
+int64_t vsr_contact_overflows(vsr_ctx* ctx);
 int vsr_kernel_info(const vsr_ctx* ctx, int32_t* regs_per_thread, int32_t* smem_bytes, int32_t* threads_per_cta,
                     int32_t* robots_per_warp, int32_t* ctas_per_sm);
 

@@ -563,3 +563,23 @@ def test_centre_trajectories_match_the_oracle_trace(F, oracle):
     ev = L.population_evaluator("worm-8x2", "", "brainPhaseVals;f=1", "hilly-1-10-0", 2.0, 0.5)
     outs = ev.task.apply_all_observed([ev._build(row) for row in g[:3]])
     assert outs[1].centers.shape == (k_last - k_first + 1, 2) and len(outs[1].get_center_x_velocity_spectrum(0.0, 4.0, 8)) == 8
+
+
+def test_contact_pool_overflow_is_never_silent(F, oracle, monkeypatch):
+    """vsr_contact_overflows counts the warps whose contact pool overflowed in ANY launch of the context (fitness-only and generation-
+    loop launches have no vsr_result to carry the flag): 0 for the shipped pool sizes, > 0 when the pool is forced too small."""
+    m = oracle.config_model(1, final_t=1.5)
+    g = np.random.default_rng(0).uniform(-1, 1, (64, m.genome_len()))
+    ctx = make_ctx(F, m)
+    ctx.eval(g)
+    assert ctx.contact_overflows() == 0
+    ctx.close()
+    monkeypatch.setenv("VSR_POOL_SLOTS", "8")   # 3 bipeds on 8 slots: every warp overflows as soon as the robots land
+    small = make_ctx(F, m)
+    monkeypatch.delenv("VSR_POOL_SLOTS")
+    fit, res = small.eval(g, want_results=True)
+    n_warps = (64 + 2) // 3
+    assert 0 < small.contact_overflows() <= n_warps and (res["contact_overflow"] > 0).any()
+    small.eval(g)                                 # fitness-only launch: still counted
+    assert small.contact_overflows() > n_warps // 2
+    small.close()

@@ -87,6 +87,7 @@ _SIGS = {
     "vsr_trace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vsr_last_kernel_ms": (C.c_double, [C.c_void_p]),
     "vsr_kernel_launches": (C.c_int64, [C.c_void_p]),
+    "vsr_contact_overflows": (C.c_int64, [C.c_void_p]),
     "vsr_kernel_info": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_int32)] * 5),
     "vsr_shape_mask": (C.c_int, [C.c_char_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_void_p, C.c_int32]),
     "vsr_terrain": (C.c_int, [C.c_char_p, C.c_void_p, C.c_void_p, C.c_int32]),
@@ -220,6 +221,9 @@ class Context:
         res = np.empty(g.shape[0], dtype=RESULT_DTYPE) if want_results else None
         check(lib().vsr_eval(self._h, _ptr(g), g.shape[0], _ptr(fit), _ptr(res)), self._h)
         return (fit, res) if want_results else fit
+
+    def contact_overflows(self) -> int:
+        return check(lib().vsr_contact_overflows(self._h), self._h)
 
     def eval_centers(self, genomes: np.ndarray):
         """(fitness [n], results [n], centers [n][K][2]): vsr_eval plus the robot-centre (x, y) at every kept observation."""

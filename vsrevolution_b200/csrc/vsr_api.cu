@@ -50,6 +50,7 @@ struct DeviceState {
   double* h_fitness = nullptr;
   vsr_result* h_results = nullptr;
   size_t cap = 0; // robots the buffers hold
+  int* d_ovf = nullptr;        // warps whose contact pool overflowed, accumulated over all launches (vsr_contact_overflows)
   double* d_centers = nullptr; // vsr_eval_centers: [robots of the shard][kept observations][2]
   size_t centers_bytes = 0;
   double* cur_centers = nullptr; // non-null only while vsr_eval_centers enqueues
@@ -487,6 +488,7 @@ int enqueue(vsr_ctx* ctx, DeviceState& d, const double* d_genomes, size_t n, dou
   k.tx = d.d_tx; k.ty = d.d_ty; k.win_tab = d.d_win; k.hist = d.d_hist; k.noise = d.d_noise;
   k.genomes = d_genomes; k.fitness = d_fitness; k.results = d_results; k.n_robots = (int)n;
   k.centers = d.cur_centers;
+  k.overflow_count = d.d_ovf;
   if (robot_terrains) { k.tx = d.d_rtx; k.ty = d.d_rty; k.toff = d.d_roff; k.tbase = d.d_rbase; k.tplace = d.d_rplace; k.ty_max = rt_ymax; }
   k.tr_vertices = trv; k.tr_bodies = trb; k.tr_ctrl = trc; k.trace_steps = trace_steps;
   if (time_it) CK(cudaEventRecord(d.ev0, st));
@@ -613,7 +615,8 @@ int vsr_ctx_create(const vsr_env_desc* env, vsr_ctx** out) {
               ck(cudaEventCreateWithFlags(&d.ev_join, cudaEventDisableTiming), "cudaEventCreate") &&
               ck(cudaMalloc(&d.d_tx, sizeof(double) * c->tx.size()), "cudaMalloc") && ck(cudaMalloc(&d.d_ty, sizeof(double) * c->ty.size()), "cudaMalloc") &&
               ck(cudaMemcpy(d.d_tx, c->tx.data(), sizeof(double) * c->tx.size(), cudaMemcpyHostToDevice), "cudaMemcpy") &&
-              ck(cudaMemcpy(d.d_ty, c->ty.data(), sizeof(double) * c->ty.size(), cudaMemcpyHostToDevice), "cudaMemcpy");
+              ck(cudaMemcpy(d.d_ty, c->ty.data(), sizeof(double) * c->ty.size(), cudaMemcpyHostToDevice), "cudaMemcpy") &&
+              ck(cudaMalloc(&d.d_ovf, sizeof(int)), "cudaMalloc") && ck(cudaMemset(d.d_ovf, 0, sizeof(int)), "cudaMemset");
     if (!ok) { vsr_ctx_destroy(c); return VSR_ECUDA; }
   }
   *out = c;
@@ -627,7 +630,7 @@ void vsr_ctx_destroy(vsr_ctx* c) {
     if (d.stream) cudaStreamSynchronize(d.stream);
     cudaFree(d.d_tx); cudaFree(d.d_ty); cudaFree(d.d_win); cudaFree(d.d_hist); cudaFree(d.d_noise); cudaFree(d.d_energy);
     cudaFree(d.d_rtx); cudaFree(d.d_rty); cudaFree(d.d_rbase); cudaFree(d.d_rplace); cudaFree(d.d_roff);
-    cudaFree(d.d_genomes); cudaFree(d.d_fitness); cudaFree(d.d_results); cudaFree(d.d_centers);
+    cudaFree(d.d_genomes); cudaFree(d.d_fitness); cudaFree(d.d_results); cudaFree(d.d_centers); cudaFree(d.d_ovf);
     cudaFreeHost(d.h_genomes); cudaFreeHost(d.h_fitness); cudaFreeHost(d.h_results);
     if (d.ev0) cudaEventDestroy(d.ev0);
     if (d.ev1) cudaEventDestroy(d.ev1);
@@ -907,6 +910,19 @@ double vsr_last_kernel_ms(vsr_ctx* ctx) {
 }
 
 int64_t vsr_kernel_launches(const vsr_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int64_t vsr_contact_overflows(vsr_ctx* ctx) {
+  if (!ctx) return VSR_EINVAL;
+  int64_t total = 0;
+  for (auto& d : ctx->devs) {
+    int v = 0;
+    CK(cudaSetDevice(d.dev));
+    CK(cudaStreamSynchronize(d.stream));
+    CK(cudaMemcpy(&v, d.d_ovf, sizeof(int), cudaMemcpyDeviceToHost));
+    total += v;
+  }
+  return total;
+}
 
 int vsr_kernel_info(const vsr_ctx* ctx_c, int32_t* regs, int32_t* smem, int32_t* threads, int32_t* rpw, int32_t* ctas_per_sm) {
   vsr_ctx* ctx = const_cast<vsr_ctx*>(ctx_c);

@@ -111,6 +111,7 @@ struct KParams {
   const double* genomes;
   double* fitness;
   vsr_result* results;
+  int* overflow_count;   // device counter: += 1 per warp whose contact pool overflowed (checked by the host even when no vsr_result is requested)
   double* centers;       // optional [n_robots][k_last - k_first + 1][2]: robot centre (x, y) at every kept observation (vsr_eval_centers)
   void* energy;          // V4<R>[total lanes]: per-voxel energy accumulators (sum f^2 dt, sum |da|, sum |d(a^2)|, last a); used only with results
   int n_robots;
@@ -1591,6 +1592,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
   // ---- epilogue: contact-pool overflow count (fitness / result were written at step k_last) ---------------
   const int ovf = __reduce_add_sync(FULL, overflow);
   if (valid && v == 0 && P.results && ovf) P.results[robot].contact_overflow = ovf;
+  if (ovf && lane == 0 && P.overflow_count) atomicAdd(P.overflow_count, 1);
 #undef WELD_APPLY
 #undef WELD_SOLVE
 #undef ln_s
