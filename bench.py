@@ -278,6 +278,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, e2e_ms, ga_ms = t.tolist()
     fit_ok = bool(np.isfinite(host_fit).all()) and bool(torch.isfinite(d_fit).all().item())
+    overflows = int(ev.ctx.contact_overflows())  # this rank's warps whose contact pool overflowed in any launch above (0 = reliable)
 
     if rank == 0:
         units = world * n * nv * n_steps * args.steps  # voxel-steps over all ranks and steps
@@ -292,7 +293,7 @@ def main():
                 "evals_per_sec": value / (nv * n_steps),
                 "e2e": {"value": e2e, "unit": "voxel-steps/s", "h2d_bytes_per_step": n * G * 8, "d2h_bytes_per_step": n * 8,
                         "evals_per_sec": e2e / (nv * n_steps), "ms_per_step": e2e_ms / args.steps},
-                "gpu_launches": int(launches), "clocks": clocks, "fitness_finite": fit_ok}
+                "gpu_launches": int(launches), "clocks": clocks, "fitness_finite": fit_ok, "contact_pool_overflows": overflows}
         if ga_info:
             per_gen = ga_ms / args.ga_generations
             ga_info.update({"ms_per_generation": per_gen, "evals_per_sec": ga_info["n_pop"] / (per_gen * 1e-3),
