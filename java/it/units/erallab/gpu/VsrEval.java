@@ -34,6 +34,12 @@ public final class VsrEval {
   public static native long gaCreate(long ctx, int nPop, double xOverProb, double tournamentRate, int minNTournament, double sigmaMut,
                                      long seed, boolean remap);
 
+  /** The solver ES (builder/solver/SimpleES.java:41-49: nParents = round(nPop * parentsRate), nElites = 1) on the same loop. */
+  public static native long esCreate(long ctx, int nPop, int nParents, int nElites, double sigma, long seed, boolean remap);
+
+  /** Warps whose contact pool overflowed in any launch so far; 0 = every fitness value is reliable. */
+  public static native long contactOverflows(long ctx);
+
   public static native void gaInit(long ga);
 
   public static native void gaStep(long ga);

@@ -142,6 +142,25 @@ JNIEXPORT jlong JNICALL Java_it_units_erallab_gpu_VsrEval_gaCreate(JNIEnv* env, 
   return (jlong)(intptr_t)ga;
 }
 
+/* the solver `ES` = new SimpleES(sigma, parentsRate) (builder/solver/SimpleES.java:41-49) on the same loop */
+JNIEXPORT jlong JNICALL Java_it_units_erallab_gpu_VsrEval_esCreate(JNIEnv* env, jclass c, jlong h, jint nPop, jint nParents, jint nElites,
+                                                                   jdouble sigma, jlong seed, jboolean remap) {
+  (void)c;
+  vsr_ga_desc d;
+  if (vsr_es_default(&d, nPop)) { throw_ga(env, NULL, VSR_EINVAL); return 0; }
+  d.n_parents = nParents; d.n_elites = nElites; d.sigma_mut = sigma; d.seed = (uint64_t)seed; d.remap = remap ? 1 : 0;
+  vsr_ga* ga = NULL;
+  int rc = vsr_ga_create((vsr_ctx*)(intptr_t)h, &d, &ga);
+  if (rc) { throw_ga(env, NULL, rc); return 0; }
+  return (jlong)(intptr_t)ga;
+}
+
+/* warps whose contact pool overflowed in any launch of the context so far (0 = every fitness value is reliable) */
+JNIEXPORT jlong JNICALL Java_it_units_erallab_gpu_VsrEval_contactOverflows(JNIEnv* env, jclass c, jlong h) {
+  (void)env; (void)c;
+  return (jlong)vsr_contact_overflows((vsr_ctx*)(intptr_t)h);
+}
+
 JNIEXPORT void JNICALL Java_it_units_erallab_gpu_VsrEval_gaInit(JNIEnv* env, jclass c, jlong g) {
   (void)c;
   int rc = vsr_ga_init((vsr_ga*)(intptr_t)g);
