@@ -620,9 +620,6 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
     }
     if (lane == 0) *poolCnt = 0;
     __syncwarp();
-#ifdef VSR_SYNC16_LATE
-    __syncthreads(); // experiment: the pre-detect alignment barrier after the broadphase, so that it overlaps position-phase stragglers
-#endif
 #pragma unroll 1
     for (int c0 = 0; c0 < ncand; c0 += 32) { // warp-uniform trip count: the rounds below vote over the whole warp
       const int ci = c0 + lane;
@@ -1186,11 +1183,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
         bool ok = true;
         // contacts, lane = touching mass: the masses' poses travel through shared memory (X Y A in the staging area, CS SN
         // in the spring-bias area, which is dead outside the velocity loop)
-#ifdef VSR_POS_SKIP
-        if (n_tm > 0 && __any_sync(FULL, active && touching)) { // experiment: no active robot of the warp touches the ground -> skip
-#else
         if (n_tm > 0) {
-#endif
           V4<R>* pcs = reinterpret_cast<V4<R>*>(sbias);
           R* pc = sbias;
           {
@@ -1333,9 +1326,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
       }
     }
     // ---- detect for the next step / touch sensors -----------------------------------------------------
-#ifndef VSR_SYNC16_LATE
     PHASE_SYNC(16)
-#endif
     detect();
     PHASE_SYNC(32)
 
