@@ -583,3 +583,18 @@ def test_contact_pool_overflow_is_never_silent(F, oracle, monkeypatch):
     small.eval(g)                                 # fitness-only launch: still counted
     assert small.contact_overflows() > n_warps // 2
     small.close()
+
+
+@pytest.mark.parametrize("cfg,n", [(2, 4000), (3, 2500), (4, 2500)])
+def test_launch_shape_does_not_change_the_result(F, oracle, cfg, n):
+    """Sub-wave batches run the 255-register build spread over every SM, full waves the 10-warp build (launch plan): a
+    robot's fitness is bit-identical in a one-robot call, a sub-wave batch and a full-wave batch."""
+    m = oracle.config_model(cfg, final_t=1.5)
+    g = np.random.default_rng(cfg).uniform(-1, 1, (n, m.genome_len()))
+    ctx = make_ctx(F, m)
+    whole = ctx.eval(g)
+    assert np.isfinite(whole).all() and ctx.contact_overflows() == 0
+    assert np.array_equal(ctx.eval(g[:300]), whole[:300])
+    for i in (0, 7, n - 1):
+        assert ctx.eval(g[i:i + 1])[0] == whole[i]
+    ctx.close()

@@ -79,6 +79,12 @@ struct vsr_ctx {
   std::vector<uint8_t> win_tab;
   std::vector<double> noise_tab; // Noisy sensors: [sens_dim][n_steps+1]
   size_t smem_bytes = 0;
+  // sub-wave batches (fewer robot-warps than fill the 10-warp kernel's wave): the 255-register build launched with just enough warps
+  // per CTA to spread the batch over every SM (tools/latency_probe.sh: 1.2-1.5x lower episode latency below ~3500 bipeds)
+  const void* kernel_lat = nullptr;
+  int warps_lat = 0;        // most warps per CTA the latency kernel may get (shared memory / launch bound)
+  size_t smem_warp = 0;     // shared-memory bytes per warp
+  int n_sm = 148;
   int shape = kDefaultShape, warps = 4;
   const void* kernel = nullptr;
   std::vector<DeviceState> devs;
@@ -392,6 +398,8 @@ int finalize(vsr_ctx* ctx) {
   // (the 10-warp build folds its warp count at compile time, so a forced shape 3 that does not fit falls back to shape 2)
   if (e.precision != 64 && ctx->shape == 3 && 10 * o + 1024 > 227 * 1024) { ctx->shape = 2; ctx->warps = kShapes[2].warps; }
   while (ctx->warps > 1 && (size_t)ctx->warps * o + 1024 > 227 * 1024) ctx->warps--;
+  if (const char* ev = std::getenv("VSR_WARPS")) // tuning: fewer warps per CTA (the 255-register builds index by blockDim)
+    if (e.precision != 64 && ctx->shape != 3) ctx->warps = std::max(1, std::min(ctx->warps, std::atoi(ev)));
   const bool full_scaff = e.scaffolding_mask == 0xF && !std::getenv("VSR_GENERIC_SCAFF");
   ctx->kernel = kernel_ptr(e.precision, kernel_ctrl(ctx->kind), ctx->shape, full_scaff);
   // the reference's default robot: one soft-normalised, non-averaged AreaRatio reading per voxel into a centralized MLP
@@ -400,6 +408,19 @@ int finalize(vsr_ctx* ctx) {
       !(ctx->sensors[0].avg_window > 0) && !std::getenv("VSR_GENERIC_SENSORS"))
     ctx->kernel = vsr_internal::kernel_f32_s3_area();
   ctx->smem_bytes = o * ctx->warps + 128; // + the CTA's phase counters (bounded-skew alignment)
+  ctx->smem_warp = o;
+  ctx->kernel_lat = nullptr; ctx->warps_lat = 0;
+  if (e.precision == 32 && !std::getenv("VSR_LAUNCH_SHAPE") && !std::getenv("VSR_WARPS") && !std::getenv("VSR_NO_LATENCY_SHAPE")) {
+    if (ctx->shape == 3) { // default wave kernel = 10 warps at 168 registers; latency kernel = the 8-warp build at 255
+      ctx->kernel_lat = ctx->kernel == vsr_internal::kernel_f32_s3_area() ? vsr_internal::kernel_f32_s2_area()
+                                                                          : kernel_ptr(32, kernel_ctrl(ctx->kind), 2, full_scaff);
+      ctx->warps_lat = kShapes[2].warps;
+      while (ctx->warps_lat > 1 && (size_t)ctx->warps_lat * o + 1024 > 227 * 1024) ctx->warps_lat--;
+    } else if (ctx->shape == 2) { // already the flexible 255-register build: only the warp count varies
+      ctx->kernel_lat = ctx->kernel;
+      ctx->warps_lat = ctx->warps;
+    }
+  }
   if (k.n_t > 16383) return fail(ctx, VSR_EUNSUPPORTED, "terrains with more than 16383 vertices are not supported");
   if (ctx->smem_bytes > 227 * 1024) return fail(ctx, VSR_EUNSUPPORTED, "controller too large for shared memory");
   // per-device uploads
@@ -408,6 +429,9 @@ int finalize(vsr_ctx* ctx) {
     // the attribute belongs to the kernel function, not to this context: several live contexts (one per morphology) share an
     // instantiation, so always opt in to the CTA maximum instead of this context's own footprint
     CK(cudaFuncSetAttribute(ctx->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    if (ctx->kernel_lat) CK(cudaFuncSetAttribute(ctx->kernel_lat, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    int n_sm = 0;
+    if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, d.dev) == cudaSuccess && n_sm > 0) ctx->n_sm = n_sm;
     if (d.d_win) { cudaFree(d.d_win); d.d_win = nullptr; }
     CK(cudaMalloc(&d.d_win, ctx->win_tab.size()));
     CK(cudaMemcpy(d.d_win, ctx->win_tab.data(), ctx->win_tab.size(), cudaMemcpyHostToDevice));
@@ -439,17 +463,27 @@ int ensure_capacity(vsr_ctx* ctx, DeviceState& d, size_t n) {
   return VSR_OK;
 }
 
-int grid_for(const vsr_ctx* ctx, size_t n) {
+// launch shape of one batch: kernel, warps per CTA, grid
+struct LaunchPlan { const void* kernel; int warps, grid; size_t smem; };
+LaunchPlan plan_for(const vsr_ctx* ctx, size_t n) {
   const vsr::KParams& k = ctx->kp;
-  const size_t per_cta = (size_t)ctx->warps * k.robots_per_warp;
-  return (int)((n + per_cta - 1) / per_cta);
+  const size_t robot_warps = (n + k.robots_per_warp - 1) / k.robots_per_warp;
+  LaunchPlan p{ctx->kernel, ctx->warps, (int)((robot_warps + ctx->warps - 1) / ctx->warps), ctx->smem_bytes};
+  // a batch that the latency kernel can hold in one wave (<= warps_lat warps on every SM) is spread evenly over the SMs
+  if (ctx->kernel_lat && robot_warps <= (size_t)ctx->warps_lat * ctx->n_sm) {
+    p.kernel = ctx->kernel_lat;
+    p.warps = (int)std::max<size_t>(1, (robot_warps + ctx->n_sm - 1) / ctx->n_sm);
+    p.grid = (int)((robot_warps + p.warps - 1) / p.warps);
+    p.smem = ctx->smem_warp * p.warps + 128;
+  }
+  return p;
 }
 
-int ensure_hist(vsr_ctx* ctx, DeviceState& d, int grid) {
+int ensure_hist(vsr_ctx* ctx, DeviceState& d, int cta_warps_total) {
   const vsr::KParams& k = ctx->kp;
   if (!k.n_avg) return VSR_OK;
   const size_t rs = ctx->env.precision == 64 ? 8 : 4;
-  size_t bytes = (size_t)k.hist_cap * k.n_avg * grid * ctx->warps * 32 * rs;
+  size_t bytes = (size_t)k.hist_cap * k.n_avg * cta_warps_total * 32 * rs;
   if (bytes > d.hist_bytes) {
     if (d.d_hist) cudaFree(d.d_hist);
     d.hist_bytes = 0;
@@ -459,9 +493,9 @@ int ensure_hist(vsr_ctx* ctx, DeviceState& d, int grid) {
   return VSR_OK;
 }
 
-int ensure_energy(vsr_ctx* ctx, DeviceState& d, int grid) {
+int ensure_energy(vsr_ctx* ctx, DeviceState& d, int cta_warps_total) {
   const size_t rs = ctx->env.precision == 64 ? 8 : 4;
-  const size_t bytes = (size_t)grid * ctx->warps * 32 * 4 * rs;
+  const size_t bytes = (size_t)cta_warps_total * 32 * 4 * rs;
   if (bytes > d.energy_bytes) {
     if (d.d_energy) cudaFree(d.d_energy);
     d.energy_bytes = 0;
@@ -477,11 +511,14 @@ int enqueue(vsr_ctx* ctx, DeviceState& d, const double* d_genomes, size_t n, dou
             double rt_ymax = 0) {
   if (n == 0) return VSR_OK;
   vsr::KParams k = ctx->kp;
-  const int grid = grid_for(ctx, n);
-  int rc = ensure_hist(ctx, d, grid);
+  // traces (robot 0 only, parity tests) always use the context's default kernel
+  const LaunchPlan lp = trace_steps > 0 ? LaunchPlan{ctx->kernel, ctx->warps, (int)((((n + k.robots_per_warp - 1) / k.robots_per_warp) + ctx->warps - 1) / ctx->warps), ctx->smem_bytes}
+                                        : plan_for(ctx, n);
+  const int grid = lp.grid;
+  int rc = ensure_hist(ctx, d, grid * lp.warps);
   if (rc) return rc;
   if (d_results) {
-    rc = ensure_energy(ctx, d, grid);
+    rc = ensure_energy(ctx, d, grid * lp.warps);
     if (rc) return rc;
   }
   k.energy = d.d_energy;
@@ -493,7 +530,7 @@ int enqueue(vsr_ctx* ctx, DeviceState& d, const double* d_genomes, size_t n, dou
   k.tr_vertices = trv; k.tr_bodies = trb; k.tr_ctrl = trc; k.trace_steps = trace_steps;
   if (time_it) CK(cudaEventRecord(d.ev0, st));
   void* args[] = {&k};
-  CK(cudaLaunchKernel(ctx->kernel, dim3(grid), dim3(ctx->warps * 32), args, ctx->smem_bytes, st));
+  CK(cudaLaunchKernel(lp.kernel, dim3(grid), dim3(lp.warps * 32), args, lp.smem, st));
   CK(cudaGetLastError());
   if (time_it) { CK(cudaEventRecord(d.ev1, st)); d.timed = true; }
   ctx->launches++;

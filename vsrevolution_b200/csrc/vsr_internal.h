@@ -25,5 +25,6 @@ VSR_HIDDEN const void* kernel_f32_s1(int ctrl, int full_scaff);
 VSR_HIDDEN const void* kernel_f32_s2(int ctrl, int full_scaff);
 VSR_HIDDEN const void* kernel_f32_s3(int ctrl, int full_scaff);
 VSR_HIDDEN const void* kernel_f32_s3_area(void);
+VSR_HIDDEN const void* kernel_f32_s2_area(void);
 VSR_HIDDEN const void* kernel_f64(int ctrl);
 } // namespace vsr_internal

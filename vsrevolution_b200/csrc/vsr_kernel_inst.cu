@@ -28,6 +28,8 @@ const void* kernel_f32_s0(int ctrl, int full_scaff) { return pick2<float, 4, 2>(
 const void* kernel_f32_s1(int ctrl, int full_scaff) { return pick2<float, 5, 2>(ctrl, full_scaff); }
 #elif VSR_INST == 2
 const void* kernel_f32_s2(int ctrl, int full_scaff) { return pick2<float, 8, 1>(ctrl, full_scaff); }
+// the sub-wave (latency) partner of kernel_f32_s3_area: same specialisation, so a robot gets the same bits in either launch shape
+const void* kernel_f32_s2_area(void) { return (const void*)vsr::vsr_episode_kernel<float, VSR_CTRL_MLP_CENTRALIZED, 8, 1, 0xF, 1>; }
 #elif VSR_INST == 3
 const void* kernel_f32_s3(int ctrl, int full_scaff) { return pick2<float, 10, 1>(ctrl, full_scaff); }
 // the reference's default robot (CentralizedSensing MLP over one AreaRatio reading per voxel): sensor loop folded away
