@@ -177,6 +177,8 @@ int64_t vsr_kernel_launches(const vsr_ctx* ctx); /* total episode-kernel launche
 /* warps whose contact pool overflowed, over every launch of this context so far (0 = every fitness value is reliable; also counts the
  * fitness-only and generation-loop launches, which have no vsr_result to carry contact_overflow); synchronises the streams */
 int64_t vsr_contact_overflows(vsr_ctx* ctx);
+/* launch shape of the most recent episode-kernel launch (before any launch: the full-wave default).  Batches that need at most 8
+ * robot-warps per SM run the 255-register build spread over every SM, larger ones the 10-warp build; results are bit-identical. */
 int vsr_kernel_info(const vsr_ctx* ctx, int32_t* regs_per_thread, int32_t* smem_bytes, int32_t* threads_per_cta,
                     int32_t* robots_per_warp, int32_t* ctas_per_sm);
 

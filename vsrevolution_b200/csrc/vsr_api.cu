@@ -85,6 +85,9 @@ struct vsr_ctx {
   int warps_lat = 0;        // most warps per CTA the latency kernel may get (shared memory / launch bound)
   size_t smem_warp = 0;     // shared-memory bytes per warp
   int n_sm = 148;
+  const void* last_kernel = nullptr; // launch shape of the most recent episode-kernel launch (vsr_kernel_info)
+  int last_warps = 0;
+  size_t last_smem = 0;
   int shape = kDefaultShape, warps = 4;
   const void* kernel = nullptr;
   std::vector<DeviceState> devs;
@@ -409,7 +412,7 @@ int finalize(vsr_ctx* ctx) {
     ctx->kernel = vsr_internal::kernel_f32_s3_area();
   ctx->smem_bytes = o * ctx->warps + 128; // + the CTA's phase counters (bounded-skew alignment)
   ctx->smem_warp = o;
-  ctx->kernel_lat = nullptr; ctx->warps_lat = 0;
+  ctx->kernel_lat = nullptr; ctx->warps_lat = 0; ctx->last_kernel = nullptr;
   if (e.precision == 32 && !std::getenv("VSR_LAUNCH_SHAPE") && !std::getenv("VSR_WARPS") && !std::getenv("VSR_NO_LATENCY_SHAPE")) {
     if (ctx->shape == 3) { // default wave kernel = 10 warps at 168 registers; latency kernel = the 8-warp build at 255
       ctx->kernel_lat = ctx->kernel == vsr_internal::kernel_f32_s3_area() ? vsr_internal::kernel_f32_s2_area()
@@ -531,6 +534,7 @@ int enqueue(vsr_ctx* ctx, DeviceState& d, const double* d_genomes, size_t n, dou
   if (time_it) CK(cudaEventRecord(d.ev0, st));
   void* args[] = {&k};
   CK(cudaLaunchKernel(lp.kernel, dim3(grid), dim3(lp.warps * 32), args, lp.smem, st));
+  ctx->last_kernel = lp.kernel; ctx->last_warps = lp.warps; ctx->last_smem = lp.smem;
   CK(cudaGetLastError());
   if (time_it) { CK(cudaEventRecord(d.ev1, st)); d.timed = true; }
   ctx->launches++;
@@ -966,13 +970,17 @@ int vsr_kernel_info(const vsr_ctx* ctx_c, int32_t* regs, int32_t* smem, int32_t*
   if (!ctx) return VSR_EINVAL;
   if (!ctx->ready) return fail(ctx, VSR_ESTATE, "body and controller must be set first");
   CK(cudaSetDevice(ctx->devs[0].dev));
+  // the shape of the most recent launch (sub-wave batches use another build and warp count), else the full-wave default
+  const void* kern = ctx->last_kernel ? ctx->last_kernel : ctx->kernel;
+  const int warps = ctx->last_kernel ? ctx->last_warps : ctx->warps;
+  const size_t sm = ctx->last_kernel ? ctx->last_smem : ctx->smem_bytes;
   cudaFuncAttributes a;
-  CK(cudaFuncGetAttributes(&a, ctx->kernel));
+  CK(cudaFuncGetAttributes(&a, kern));
   int nb = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ctx->kernel, ctx->warps * 32, ctx->smem_bytes));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, warps * 32, sm));
   if (regs) *regs = a.numRegs;
-  if (smem) *smem = (int)ctx->smem_bytes;
-  if (threads) *threads = ctx->warps * 32;
+  if (smem) *smem = (int)sm;
+  if (threads) *threads = warps * 32;
   if (rpw) *rpw = ctx->kp.robots_per_warp;
   if (ctas_per_sm) *ctas_per_sm = nb;
   return VSR_OK;
