@@ -197,3 +197,52 @@ def test_new_controller_kinds_reduce_to_the_old_ones(oracle):
     phases = np.random.default_rng(1).uniform(-1, 1, (3, 10))
     triples = np.stack([np.full((3, 10), 1.3), phases, np.full((3, 10), 0.8)], axis=-1).reshape(3, 30)
     assert np.array_equal(ph.eval_batch(phases), ts.eval_batch(triples))
+
+
+def test_sliding_on_a_slope_is_coulomb_plus_damping(oracle):
+    """A 1x1 robot on `downhill-30` (Starter.java:171's validation terrain; the polyline drops 1980 sin(30 deg) over 1980, i.e. an
+    incline of atan(1/2)): with mu = sqrt(f_voxel f_ground) < tan(theta) the centre of mass slides down the slope with
+    v' = (v + g (sin theta - mu cos theta) dt)(1 - dt d) -- kinetic Coulomb friction on an inclined polygon plus dyn4j's linear damping
+    form -- and with the default friction (mu = 4.47) it sticks.  Pins the contact normal / tangent of inclined ground polygons."""
+    dt = 1 / 60.0
+    for f_voxel in (0.05, 0.2):
+        p = oracle.default_params(5.0, 0.5)
+        p.voxel_friction = f_voxel
+        m = oracle.Model("box-1x1", "downhill-30", "", oracle.CTRL_PHASE_SIN, p, amp=0.0)
+        th = math.atan2(m.ty[1] - m.ty[2], m.tx[2] - m.tx[1])
+        assert abs(math.tan(th) - 0.5) < 1e-12
+        _, _, tb, _ = m.run(np.zeros(1), trace_steps=300)
+        vel = tb[:, :, 3:5].mean(axis=1)
+        along = vel[:, 0] * math.cos(th) - vel[:, 1] * math.sin(th)
+        normal = vel[:, 0] * math.sin(th) + vel[:, 1] * math.cos(th)
+        mu = math.sqrt(f_voxel * 0.2)
+        a = 9.8 * (math.sin(th) - mu * math.cos(th))
+        k0 = 120                                     # landed and settled
+        v, rec = along[k0], []
+        for _k in range(k0, 300):
+            rec.append(v)
+            v = (v + a * dt) * (1 - dt * 1.0)
+        assert np.abs(along[k0:] - np.array(rec)).max() < 1e-6 * abs(rec[-1])
+        assert np.abs(normal[k0:]).max() < 1e-5      # it stays on the slope
+        assert abs(along[-1] - a * (1 - dt)) < 0.03 * a   # close to the terminal velocity a dt (1 - dt d) / (dt d)
+    p = oracle.default_params(5.0, 0.5)              # default friction: static
+    m = oracle.Model("box-1x1", "downhill-30", "", oracle.CTRL_PHASE_SIN, p, amp=0.0)
+    _, _, tb, _ = m.run(np.zeros(1), trace_steps=300)
+    assert np.abs(tb[-1, :, 3:5]).max() < 1e-6 and np.abs(tb[-1, :, :2] - tb[-60, :, :2]).max() < 1e-5
+
+
+def test_welds_keep_neighbouring_voxels_rigidly_attached(oracle):
+    """Robot.assemble() welds the facing corner masses of neighbouring voxels: in the frame of body1 the partner stays at its initial
+    offset (one mass side = 0.9 apart, same angle) within the position solver's tolerances (0.005, 2 deg) -- at rest and while the
+    voxels are actuated in opposition."""
+    for amp in (0.0, 1.0):
+        p = oracle.default_params(4.0, 0.5)
+        m = oracle.Model("box-2x1", "flat", "", oracle.CTRL_PHASE_SIN, p, amp=amp, freq=1.0)
+        _, _, tb, _ = m.run(np.array([0.0, math.pi]), trace_steps=240)
+        for a, b in ((1 * 4 + 0, 0 * 4 + 1), (1 * 4 + 3, 0 * 4 + 2)):   # voxel 1's NW / SW on voxel 0's NE / SE
+            d = tb[:, a, :3] - tb[:, b, :3]
+            assert np.allclose(d[0], [0.9, 0.0, 0.0], atol=1e-12)
+            ang = -tb[:, b, 2]
+            rx = np.cos(ang) * d[:, 0] - np.sin(ang) * d[:, 1]
+            ry = np.sin(ang) * d[:, 0] + np.cos(ang) * d[:, 1]
+            assert np.hypot(rx - 0.9, ry).max() < 0.005 and np.abs(d[:, 2]).max() < math.radians(2.0)
