@@ -598,3 +598,28 @@ def test_launch_shape_does_not_change_the_result(F, oracle, cfg, n):
     for i in (0, 7, n - 1):
         assert ctx.eval(g[i:i + 1])[0] == whole[i]
     ctx.close()
+
+
+@pytest.mark.parametrize("prec", [32, 64])
+def test_kernel_sliding_on_a_slope_is_coulomb_plus_damping(F, oracle, prec):
+    """The closed-form check of tests/test_oracle_known_answers.py applied to the CUDA kernels themselves (no oracle in the loop): a 1x1
+    robot with mu = 0.1 on the `downhill-30` incline slides with v' = (v + g (sin theta - mu cos theta) dt)(1 - dt d)."""
+    import math
+    tx, ty = oracle.create_terrain("downhill-30")
+    e = F.env_default()
+    e.final_t, e.transient_t, e.precision, e.voxel_friction = 5.0, 0.5, prec, 0.05
+    ctx = F.Context(e, tx, ty)
+    ctx.body_set(np.ones((1, 1), dtype=np.uint8), [])
+    ctx.controller_set(F.CTRL_PHASE_SIN, (), 0, 1.0, 0.0)
+    _, _, tb, _ = ctx.trace(np.zeros(1), 300)
+    th = math.atan2(ty[1] - ty[2], tx[2] - tx[1])
+    vel = tb[:, :, 3:5].mean(axis=1)
+    along = vel[:, 0] * math.cos(th) - vel[:, 1] * math.sin(th)
+    a, dt, k0 = 9.8 * (math.sin(th) - math.sqrt(0.05 * 0.2) * math.cos(th)), 1 / 60.0, 120
+    v, rec = along[k0], []
+    for _k in range(k0, 300):
+        rec.append(v)
+        v = (v + a * dt) * (1 - dt)
+    err = np.abs(along[k0:] - np.array(rec)).max() / abs(rec[-1])
+    assert err < (1e-6 if prec == 64 else 2e-4), err
+    ctx.close()
