@@ -54,7 +54,7 @@ def test_two_rank_sharded_evaluation_equals_single_rank(n):
     assert np.array_equal(full, m.eval_batch(g))
 
 
-def _ga_worker(rank, world, port, n_pop, out_q):
+def _ga_worker(rank, world, port, n_pop, out_q, solver="ga"):
     """The N>1 generation loop (vsrevolution_b200/solver.py): replicated GA state, sharded evaluation, fitness all-gather.
     On CPU the GA is oracle/ga.py and the per-rank evaluator a cheap deterministic function; on the GPU box the same exchange
     runs between vsr_ga_step_begin and vsr_ga_step_end over NCCL."""
@@ -77,24 +77,24 @@ def _ga_worker(rank, world, port, n_pop, out_q):
         dist.all_gather_into_tensor(whole, buf)
         return torch.cat([whole[r * per: r * per + (shard_range(n, r, world)[1] - shard_range(n, r, world)[0])] for r in range(world)]).numpy()
 
-    ga = OG.NumGA(n_pop, 12, seed=9)
+    ga = OG.NumGA(n_pop, 12, seed=9) if solver == "ga" else OG.SimpleES(n_pop, 12, seed=9)
     ga.init(sharded)
     for _ in range(4):
-        ga.step(sharded)
+        ga.step(sharded)  # ES evaluates n_pop - 1 offspring: an odd count split over the ranks
     if rank == 0:
         out_q.put((ga.pop.copy(), ga.fit.copy()))
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_pop", [25, 32])
-def test_two_rank_generation_loop_equals_single_rank(n_pop):
+@pytest.mark.parametrize("n_pop,solver", [(25, "ga"), (32, "ga"), (25, "es"), (32, "es")])
+def test_two_rank_generation_loop_equals_single_rank(n_pop, solver):
     import torch.multiprocessing as mp
     from oracle import ga as OG
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_ga_worker, args=(r, 2, port, n_pop, q)) for r in range(2)]
+    procs = [ctx.Process(target=_ga_worker, args=(r, 2, port, n_pop, q, solver)) for r in range(2)]
     for p in procs:
         p.start()
     pop, fit = q.get(timeout=120)
@@ -102,7 +102,7 @@ def test_two_rank_generation_loop_equals_single_rank(n_pop):
         p.join(timeout=60)
         assert p.exitcode == 0
     fn = lambda G: np.sin(G).sum(axis=1) - 0.1 * (G * G).sum(axis=1)
-    ga = OG.NumGA(n_pop, 12, seed=9)
+    ga = OG.NumGA(n_pop, 12, seed=9) if solver == "ga" else OG.SimpleES(n_pop, 12, seed=9)
     ga.init(fn)
     for _ in range(4):
         ga.step(fn)
