@@ -369,7 +369,7 @@ def test_per_evaluation_terrains_match_single_terrain_runs(F, oracle):
                 _, otv, _, _ = mi.run(g[i], trace_steps=40)
                 _, tv, _, _ = ci.trace(g[i], 40)
                 # placement + free fall (the robot lands after ~27 steps) to rounding.  Landing on a terrain VERTEX is a
-                # knife edge of the narrowphase (reference-face choice, 1- vs 2-point manifold): tools/parity_probe4.py shows
+                # knife edge of the narrowphase (reference-face choice, 1- vs 2-point manifold): tests/tools/parity_probe4.py shows
                 # rounding differences of 1e-13 growing ~1000x per step there, so after the landing the bound is loose
                 assert np.abs(tv[:25] - otv[:25]).max() < 1e-10, (names[i], float(np.abs(tv[:25] - otv[:25]).max()))
                 assert np.abs(tv - otv).max() < 5e-2, (names[i], float(np.abs(tv - otv).max()))
@@ -410,7 +410,7 @@ def test_other_bodies_sensors_and_terrains_track_the_oracle(F, oracle, shape, ct
         g = np.stack([0.5 + 1.5 * (g[..., 0] + 1) / 2, np.pi * (g[..., 1] + 1) / 2, (g[..., 2] + 1) / 2], axis=-1).reshape(70, G)
     elif kind != oracle.CTRL_PHASE_SIN:
         # small weights keep the MLP outputs away from +-1: a fully contracted voxel sits exactly on the contraction-limit
-        # knife edge (rope active or not), which flips on 1e-13 differences within a few steps (tools/parity_probe5.py)
+        # knife edge (rope active or not), which flips on 1e-13 differences within a few steps (tests/tools/parity_probe5.py)
         g *= 0.15
     c64, c32 = make_ctx(F, m, 64), make_ctx(F, m, 32)
     assert c64.genome_len == G

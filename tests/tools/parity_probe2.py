@@ -3,7 +3,9 @@ import numpy as np
 sys.path.insert(0, ".")
 from oracle import model as O
 from vsrevolution_b200 import _ffi as F
-from tools.parity_probe import make_ctx
+import os
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from parity_probe import make_ctx
 np.set_printoptions(precision=3, linewidth=200)
 T = 5.0
 for cfg, seed in ((1, 0), (3, 1)):

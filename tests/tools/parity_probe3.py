@@ -2,7 +2,9 @@ import sys
 import numpy as np
 sys.path.insert(0, ".")
 from oracle import model as O
-from tools.parity_probe import make_ctx
+import os
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from parity_probe import make_ctx
 T = 5.0
 for cfg, seed, robots in ((1, 0, (5, 6, 7)), (3, 1, (0, 1, 2)), (4, 2, (0, 1))):
     m = O.config_model(cfg, final_t=T)

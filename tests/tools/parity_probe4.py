@@ -3,7 +3,9 @@ import sys
 import numpy as np
 sys.path.insert(0, ".")
 from oracle import model as O
-from tools.parity_probe import make_ctx
+import os
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from parity_probe import make_ctx
 names = sys.argv[1:] or ["hilly-1-10-42", "hilly-1-10-5"]
 g = np.random.default_rng(4).uniform(-1, 1, (8, 16))
 idx = {"hilly-1-10-5": 4, "hilly-1-10-42": 5}

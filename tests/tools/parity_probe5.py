@@ -3,7 +3,9 @@ import sys
 import numpy as np
 sys.path.insert(0, ".")
 from oracle import model as O
-from tools.parity_probe import make_ctx
+import os
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from parity_probe import make_ctx
 shape, ctrl, sensors, terrain = sys.argv[1:5]
 kind = {"phase": O.CTRL_PHASE_SIN, "central": O.CTRL_MLP_CENTRALIZED, "dist": O.CTRL_MLP_DISTRIBUTED_HOMO}[ctrl]
 m = O.Model(shape, terrain, sensors, kind, O.default_params(1.5, 0.5))

@@ -5,7 +5,9 @@ import json, sys, time
 import numpy as np
 sys.path.insert(0, ".")
 from oracle import model as O
-from tools.parity_probe import make_ctx
+import os
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from parity_probe import make_ctx
 
 SIDE = 3.0
 out = {"tolerance": "max over voxel vertices of |cuda - oracle| <= 1e-4 * voxel side (3.0)", "first_steps": {}, "population": {}}
