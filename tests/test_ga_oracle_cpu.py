@@ -124,6 +124,9 @@ def test_ga_library_exports_every_declared_symbol():
     assert (b.n_pop, b.n_eval, b.remap) == (100, 1000, False)
     with pytest.raises(_ffi.VsrIllegalArgument):
         DoublesStandard(0.75, 0.05, 3, 0.35).build({"nPop": "100"})
+    # diversity=true (StandardWithEnforcedDiversityEvolver) is accepted: with a Gaussian mutation on every offspring its re-draw never fires
+    bd = num_ga().build({"nPop": "10", "nEval": "100", "diversity": "true", "remap": "true"})
+    assert (bd.n_pop, bd.n_eval, bd.remap) == (10, 100, True)
 
 
 def test_simple_es_semantics():

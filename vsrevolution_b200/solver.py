@@ -106,8 +106,10 @@ class DoublesStandard:
             n_pop, n_eval = int(params["nPop"]), int(params["nEval"])
         except KeyError as e:  # Integer.parseInt(null) -> NumberFormatException in the reference
             raise _ffi.VsrIllegalArgument(_ffi.VSR_EINVAL, f"missing solver parameter {e.args[0]}")
-        if str(params.get("diversity", "false")).lower() == "true":
-            raise _ffi.VsrError(_ffi.VSR_EUNSUPPORTED, "StandardWithEnforcedDiversityEvolver is outside the hot path (SURVEY.md 8)")
+        # `diversity=true` builds a StandardWithEnforcedDiversityEvolver (DoublesStandard.java:72-87): an offspring whose genotype
+        # already exists in the population is re-drawn, at most 100 times.  Every offspring of this solver went through
+        # GaussianMutation (both operators end with it, :54-57), so a duplicate of an existing List<Double> has probability zero and
+        # the re-draw never triggers: the enforced-diversity loop is the standard loop, and the same device loop serves both.
         return _SolverBuilder(self, n_pop, n_eval, str(params.get("remap", "false")).lower() == "true")
 
 
