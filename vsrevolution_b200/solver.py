@@ -80,6 +80,10 @@ class GenerationLoop:
             if listener is not None:
                 listener({"iterations": self.ga.generation, "evals": self.ga.evaluations, "best.fitness": self.ga.best_fitness()})
             self.step()
+        overflows = self.evaluator.ctx.contact_overflows()
+        if overflows:  # never silent: some fitness values of this run came from a warp whose contact pool was full
+            import warnings
+            warnings.warn(f"{overflows} warp launches overflowed the contact pool; fitness values of those robots are unreliable")
         return self.ga.best()
 
 
