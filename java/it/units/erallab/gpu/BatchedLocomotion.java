@@ -5,6 +5,17 @@ import it.units.erallab.hmsrobots.core.controllers.DistributedSensing;
 import it.units.erallab.hmsrobots.core.controllers.MultiLayerPerceptron;
 import it.units.erallab.hmsrobots.core.controllers.PhaseSin;
 import it.units.erallab.hmsrobots.core.objects.Robot;
+import it.units.erallab.hmsrobots.core.objects.Voxel;
+import it.units.erallab.hmsrobots.core.sensors.Angle;
+import it.units.erallab.hmsrobots.core.sensors.AreaRatio;
+import it.units.erallab.hmsrobots.core.sensors.Average;
+import it.units.erallab.hmsrobots.core.sensors.CompositeSensor;
+import it.units.erallab.hmsrobots.core.sensors.Noisy;
+import it.units.erallab.hmsrobots.core.sensors.Sensor;
+import it.units.erallab.hmsrobots.core.sensors.SoftNormalization;
+import it.units.erallab.hmsrobots.core.sensors.Touch;
+import it.units.erallab.hmsrobots.core.sensors.Velocity;
+import it.units.erallab.hmsrobots.util.Grid;
 
 import java.util.ArrayList;
 import java.util.List;
@@ -146,9 +157,80 @@ public class BatchedLocomotion implements Function<Robot, GpuOutcome>, AutoClose
 
   /** Flattens the 2dhmsr objects into the plain arrays of the C ABI (the only place that touches Grid iteration order). */
   static final class RobotFlattener {
+    /**
+     * vsr_body_set + vsr_controller_set from the first robot of the run. Written against the 2dhmsr 1.12.1 API as recalled
+     * (accessor names marked [U] must be checked against the jar): Grid.getW/getH/get(x, y), Voxel.getSensors(),
+     * CompositeSensor.getSensor(), Sensor.getDomains() (DoubleRange min()/max()), Average.getInterval() [U], Noisy.getSigma() [U],
+     * Velocity.isRotated()/getAxes() [U], MultiLayerPerceptron.getNeurons() (int[] incl. input and output layer),
+     * PhaseSin.getFrequency()/getAmplitude() [U], DistributedSensing.getSignals() [U].
+     */
     static void configure(long ctx, Robot robot) {
-      // body mask in y*w+x order, per-voxel sensor list (uniform), controller structure: see INTEGRATION.md section 3
-      throw new UnsupportedOperationException("written against the 2dhmsr 1.12.1 API; compile with the jars to finish");
+      Grid<Voxel> body = robot.getVoxels();
+      int w = body.getW(), h = body.getH();
+      byte[] mask = new byte[w * h];
+      Voxel first = null;
+      for (int y = 0; y < h; y++) {
+        for (int x = 0; x < w; x++) {
+          Voxel v = body.get(x, y);
+          mask[y * w + x] = (byte) (v == null ? 0 : 1); // y = 0 is the bottom row, as in Grid
+          if (v != null && first == null) {
+            first = v;
+          }
+        }
+      }
+      if (first == null) {
+        throw new IllegalArgumentException("Target robot has no voxels");
+      }
+      // the uniform per-voxel sensor list (buildSensorizingFunction("uniform-...")), wrappers peeled from the outside in
+      List<Sensor> sensors = first.getSensors();
+      int[] si = new int[4 * sensors.size()];
+      double[] sd = new double[4 * sensors.size()];
+      for (int i = 0; i < sensors.size(); i++) {
+        Sensor s = sensors.get(i);
+        double window = 0, sigma = 0;
+        boolean softNorm = false;
+        while (s instanceof CompositeSensor cs) {
+          if (s instanceof Noisy n) {
+            sigma = n.getSigma();
+          } else if (s instanceof SoftNormalization) {
+            softNorm = true;
+          } else if (s instanceof Average a) {
+            window = a.getInterval();
+          } else {
+            throw new IllegalArgumentException("Unsupported sensor wrapper " + s.getClass().getSimpleName());
+          }
+          s = cs.getSensor();
+        }
+        int kind, axes = 0, rotated = 0;
+        if (s instanceof AreaRatio) {
+          kind = 0;
+        } else if (s instanceof Touch) {
+          kind = 1;
+        } else if (s instanceof Velocity vel) {
+          kind = 2;
+          axes = (vel.getAxes().contains(Velocity.Axis.X) ? 1 : 0) | (vel.getAxes().contains(Velocity.Axis.Y) ? 2 : 0);
+          rotated = vel.isRotated() ? 1 : 0;
+        } else if (s instanceof Angle) {
+          kind = 3;
+        } else {
+          throw new IllegalArgumentException("Unsupported sensor " + s.getClass().getSimpleName());
+        }
+        si[4 * i] = kind; si[4 * i + 1] = axes; si[4 * i + 2] = rotated; si[4 * i + 3] = softNorm ? 1 : 0;
+        sd[4 * i] = s.getDomains()[0].min(); sd[4 * i + 1] = s.getDomains()[0].max(); sd[4 * i + 2] = window; sd[4 * i + 3] = sigma;
+      }
+      VsrEval.setBody(ctx, w, h, mask, si, sd);
+      Object c = robot.getController();
+      if (c instanceof PhaseSin ps) {
+        VsrEval.setController(ctx, 0, new int[0], 0, ps.getFrequency(), ps.getAmplitude(), true);
+      } else if (c instanceof CentralizedSensing cs) {
+        VsrEval.setController(ctx, 1, ((MultiLayerPerceptron) cs.getFunction()).getNeurons(), 0, 1d, 1d, true);
+      } else if (c instanceof DistributedSensing ds) {
+        List<MultiLayerPerceptron> fs = ds.getFunctions().values().stream().filter(f -> f != null).map(f -> (MultiLayerPerceptron) f).toList();
+        boolean homo = fs.stream().allMatch(f -> java.util.Arrays.equals(f.getParams(), fs.get(0).getParams()));
+        VsrEval.setController(ctx, homo ? 2 : 3, fs.get(0).getNeurons(), ds.getSignals(), 1d, 1d, true);
+      } else {
+        throw new IllegalArgumentException("Unsupported controller " + c.getClass().getSimpleName());
+      }
     }
 
     static double[] parameters(Robot robot) {
@@ -156,8 +238,10 @@ public class BatchedLocomotion implements Function<Robot, GpuOutcome>, AutoClose
       if (c instanceof CentralizedSensing cs) {
         return ((MultiLayerPerceptron) cs.getFunction()).getParams();
       }
-      if (c instanceof PhaseSin) {
-        throw new UnsupportedOperationException("phases: Grid values in iteration order, nulls skipped");
+      if (c instanceof PhaseSin ps) {
+        // the phases of the voxels in Grid iteration order (brainPhaseFun fills the non-voxel cells too: skip them by the body)
+        Grid<Voxel> body = robot.getVoxels();
+        return body.stream().filter(e -> e.value() != null).mapToDouble(e -> ps.getPhases().get(e.key().x(), e.key().y())).toArray();
       }
       if (c instanceof DistributedSensing ds) {
         // kind 2 (brainHomoDist): the shared weights once; kind 3 (brainHeteroDist): every voxel's weights, Grid iteration order
