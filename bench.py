@@ -13,7 +13,13 @@ GPU gets its own R robots); timing is max over ranks.
 `roofline`: FP32-issue roofline of the episode kernel: algorithmic flops from the ORACLE's
            operation tallies, live CUDA-event kernel time.
 `cpu_baseline`: the CPU oracle (C port of the reference algorithm, "port") on the host cores, bounded sample.
-`--impl reference`: times that CPU port alone (the Java reference cannot run here: no JVM, deps un-vendored).
+`--impl reference`: times that CPU port alone on the SAME config (one full population batch per step when the host cores
+           finish K of them within ~4.5 minutes, else the largest sample that does); it first probes for a JVM and the
+           reference jars (`java_reference` key) -- the Java reference cannot run in the build image (no JVM, deps un-vendored).
+`parity`  : a 64-robot sample of the workload evaluated by the CUDA path and by the oracle, outside the timed region.
+`other_configs`: one timed launch each of BASELINE configs 3 and 4 at full size (N=1 only).
+`multi_device_exact` (N>1): rank 0 also drives ONE context over all N devices (in-process sharding with peer copies) and checks
+           it bit for bit against a single-device context.
 """
 from __future__ import annotations
 
@@ -124,27 +130,85 @@ def peak_fp32_tflops():
     return 148 * 128 * 2 * mhz * 1e6 / 1e12, peaks.get("hbm_gbs", 6650.0), ("measured" if peaks else "fallback")
 
 
+def probe_java_reference() -> dict:
+    """SURVEY.md 8c-4 / BASELINE.md section 3: the only true parity pin is the real `new Locomotion(...).apply(robot)`
+    (locomotion/Starter.java:87-93) of 2dhmsr 1.12.1.  Look for a JVM and the jars; never read /root/reference at run time."""
+    import glob
+    import shutil
+    java = shutil.which("java")
+    javac = shutil.which("javac")
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    jars = sorted(glob.glob(os.path.join(ref_dir, "**", "*.jar"), recursive=True))
+    info = {"java": None, "javac": bool(javac), "jars": [os.path.relpath(j, ROOT) for j in jars][:8]}
+    if java:
+        try:
+            r = subprocess.run([java, "-version"], capture_output=True, text=True, timeout=20)
+            info["java"] = (r.stderr or r.stdout).strip().splitlines()[0] if (r.stderr or r.stdout).strip() else "present"
+        except Exception as e:  # a broken launcher counts as absent
+            info["java"] = None
+            info["error"] = repr(e)
+    need = [n for n, ok in (("JVM", info["java"]), ("javac", javac),
+                            ("2dhmsr jar under baseline/_ref", any("TwoDimHighlyModularSoftRobots" in j or "2dhmsr" in j.lower() for j in jars))) if not ok]
+    if need:
+        info["status"] = "unavailable: missing " + ", ".join(need)
+        return info
+    # everything is there: run the committed harness (java/harness/DumpLocomotion.java) on the golden genomes; it writes
+    # tests/golden/ref_*.npz-compatible CSVs that tests/tools/import_reference_traces.py turns into fixtures
+    try:
+        out = os.path.join(ROOT, "gpurun_out", "java_ref")
+        os.makedirs(out, exist_ok=True)
+        cp = os.pathsep.join(jars + [out])
+        subprocess.check_call([javac, "-cp", cp, "-d", out, os.path.join(ROOT, "java", "harness", "DumpLocomotion.java")], timeout=300)
+        subprocess.check_call([java, "-cp", cp, "DumpLocomotion", os.path.join(ROOT, "tests", "golden"), out], timeout=1800)
+        info["status"] = "ran: traces under gpurun_out/java_ref (import with tests/tools/import_reference_traces.py)"
+    except Exception as e:
+        info["status"] = "unavailable: harness failed: " + repr(e)[:200]
+    return info
+
+
+def shared_config(w, robots, n_steps, nv, G):
+    """The `config` object both arms print (so that the driver's same-config check compares like with like)."""
+    return {"workload": w["name"], "robots_per_gpu": robots, "physics_steps": n_steps, "voxels": nv, "genome_len": G,
+            "l2": "GPU arm: 256 MiB device write between timed iterations (inputs 5 MB << L2); CPU arm: not applicable"}
+
+
 def run_reference(args, w):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from oracle import model as O
     threads = os.cpu_count() or 1
-    sample = args.ref_sample
-    for _ in range(args.warmup):
-        cpu_port(w, max(threads, sample // 8), threads)
+    java = probe_java_reference()
+    m = O.config_model(w["oracle_cfg"], final_t=w["T"])
+    G = m.genome_len()
+    # size the step: the full population batch of the GPU arm if K of them fit the time budget, else the largest sample that does
+    probe_n = max(threads, min(args.robots, 8 * threads))
+    _, _, steps, nv, probe_dt = cpu_port(w, probe_n, threads)
+    per_robot = probe_dt / probe_n
+    budget_s = float(os.environ.get("VSR_REF_BUDGET_S", "270"))
+    sample = args.robots if args.ref_sample <= 0 else args.ref_sample
+    fit_n = int(budget_s / max(1, args.steps) / per_robot)
+    if sample > fit_n:
+        sample = max(threads, (fit_n // threads) * threads)
+    for _ in range(args.warmup):  # warm-up passes only page the library in and spin the pool up: small batches
+        cpu_port(w, probe_n, threads)
     vals, tot = [], 0.0
     for _ in range(args.steps):
         v, flops, steps, nv, dt = cpu_port(w, sample, threads)
         vals.append(v); tot += dt
     value = float(np.mean(vals))
+    full = sample == args.robots
     line = {"impl": "reference", "metric": "voxel-steps/sec", "value": value, "unit": "voxel-steps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": w["name"], "robots_per_step": sample, "physics_steps": steps, "voxels": nv},
+            "config": shared_config(w, args.robots, steps, nv, G),
             "evals_per_sec": value / (nv * steps),
+            "java_reference": java["status"], "java_probe": java,
             "cpu_baseline": {"value": value, "unit": "voxel-steps/s", "cores": threads, "kind": "port",
-                             "sample": f"{sample} robots of the same workload per step, C port of the reference algorithm "
-                                       "(oracle/vsr_oracle.c); the Java reference itself cannot run here (no JVM, 2dhmsr/dyn4j un-vendored)"},
+                             "sample": (f"the full {sample}-robot batch of the workload per step" if full else
+                                        f"{sample} of the workload's {args.robots} robots per step (what {threads} cores finish in the time budget)")
+                                       + ", C port of the reference algorithm (oracle/vsr_oracle.c, PARITY UNPINNED); the Java "
+                                         "reference itself cannot run here (no JVM, 2dhmsr/dyn4j un-vendored): " + java["status"]},
             "e2e": {"value": value, "unit": "voxel-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -167,6 +231,85 @@ def emit(line: dict):
     os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
 
 
+def spearman(a, b):
+    ra, rb = np.argsort(np.argsort(a)), np.argsort(np.argsort(b))
+    return float(np.corrcoef(ra, rb)[0, 1])
+
+
+def parity_block(ev, w, n=64):
+    """Driver-visible parity evidence, OUTSIDE the timed region: the same `n` seeded robots of the workload through the CUDA
+    path (vsr_eval) and through the oracle (checker only), full-length episodes; plus how many leading steps the FP32 kernel's
+    voxel vertices stay within 1e-4 of the voxel side of the oracle's for the first 4 robots."""
+    from oracle import model as O
+    m = O.config_model(w["oracle_cfg"], final_t=w["T"])
+    g = np.random.default_rng(w["seed"] + 77).uniform(-1, 1, (n, m.genome_len()))
+    ref = m.eval_batch(g, n_threads=os.cpu_count() or 1)
+    fit = ev.evaluate(g)
+    d = np.abs(fit - ref)
+    lead = []
+    steps = 120
+    for r in range(4):
+        _, otv, _, _ = m.run(g[r], trace_steps=steps)
+        _, tv, _, _ = ev.ctx.trace(g[r], steps)
+        err = np.abs(tv - otv).reshape(steps, -1).max(axis=1) / 3.0
+        bad = np.nonzero(err > 1e-4)[0]
+        lead.append(int(bad[0]) if len(bad) else steps)
+    return {"robots": n, "checker": "oracle/vsr_oracle.c (C restatement, double) -- PARITY UNPINNED against 2dhmsr itself",
+            "spearman": spearman(fit, ref), "median_abs_dfitness": float(np.median(d)), "max_abs_dfitness": float(d.max()),
+            "frac_within_1e-3": float((d < 1e-3).mean()), "fitness_std": float(ref.std()),
+            "leading_steps_within_1e-4_of_voxel_side": lead, "tolerance": "north_star: 1e-4 relative over the first N steps; "
+            "fitness statistically (the model has knife-edge discontinuities, DESIGN.md 6)"}
+
+
+def other_config(wk, robots, dev, torch):
+    """One warm-up and ONE timed launch of another BASELINE config at full size (device-resident genomes, CUDA events)."""
+    from vsrevolution_b200.locomotion import population_evaluator
+    from vsrevolution_b200 import _ffi
+    w = WORKLOADS[wk]
+    ev = population_evaluator(w["shape"], w["sensors"], w["mapper"], w["terrain"], w["T"], 1.0, devices=[dev.index])
+    n_steps = _ffi.episode_steps(w["T"], 1.0)[0]
+    g = torch.from_numpy(np.random.default_rng(w["seed"]).uniform(-1, 1, (robots, ev.genome_len))).to(dev)
+    fit = torch.empty(robots, dtype=torch.float64, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    ev.ctx.eval_device(g.data_ptr(), min(robots, 2048), fit.data_ptr(), 0, st)  # warm-up: a sub-wave batch pages the kernel in
+    torch.cuda.synchronize()
+    ev.ctx.eval_device(g.data_ptr(), robots, fit.data_ptr(), 0, st)
+    ms = ev.ctx.last_kernel_ms()
+    torch.cuda.synchronize()
+    ok = bool(torch.isfinite(fit).all().item())
+    out = {"workload": w["name"], "robots": robots, "physics_steps": n_steps, "voxels": ev.n_voxels, "kernel_ms": ms,
+           "voxel_steps_per_sec": robots * ev.n_voxels * n_steps / (ms * 1e-3), "evals_per_sec": robots / (ms * 1e-3),
+           "fitness_finite": ok, "contact_pool_overflows": int(ev.ctx.contact_overflows()), "kernel": ev.ctx.kernel_info()}
+    ev.ctx.close()
+    return out
+
+
+def multi_device_check(w, world):
+    """Rank 0 drives ONE context over all `world` devices (in-process sharding, peer copies in the generation loop) and compares
+    it bit for bit with a single-device context: 101 robots (ragged over the devices), short episodes."""
+    from vsrevolution_b200.locomotion import population_evaluator
+    from vsrevolution_b200 import _ffi
+    one = population_evaluator(w["shape"], w["sensors"], w["mapper"], w["terrain"], 3.0, 1.0, devices=[0])
+    many = population_evaluator(w["shape"], w["sensors"], w["mapper"], w["terrain"], 3.0, 1.0, devices=list(range(world)))
+    g = np.random.default_rng(5).uniform(-1, 1, (101, one.genome_len))
+    a, b = one.evaluate(g), many.evaluate(g)
+    exact = bool(np.array_equal(a, b)) and bool(np.isfinite(a).all())
+    # the generation loop on the multi-device context (peer copies of genomes out and fitness back) against the single-device loop
+    ga1 = _ffi.GeneticAlgorithm(one.ctx, 96, seed=4)
+    gan = _ffi.GeneticAlgorithm(many.ctx, 96, seed=4)
+    for ga in (ga1, gan):
+        ga.init()
+        ga.step()
+    p1, f1 = ga1.population()
+    pn, fn = gan.population()
+    exact_ga = bool(np.array_equal(p1, pn)) and bool(np.array_equal(f1, fn))
+    ga1.close(); gan.close()
+    launches = int(many.kernel_launches())
+    one.ctx.close(); many.ctx.close()
+    return {"devices": world, "robots": 101, "eval_bit_identical": exact, "generation_loop_bit_identical": exact_ga,
+            "episode_kernel_launches": launches}
+
+
 def main():
     quiet_stdout()
     ap = argparse.ArgumentParser()
@@ -176,9 +319,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--robots", type=int, default=4096, help="robots per GPU per step")
     ap.add_argument("--workload", type=int, default=2, choices=sorted(WORKLOADS))
-    ap.add_argument("--ref-sample", type=int, default=1024)
+    ap.add_argument("--ref-sample", type=int, default=0, help="robots per reference step; 0 = the GPU arm's batch (--robots)")
     ap.add_argument("--cpu-sample", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the 64-robot parity block")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the one-launch timings of configs 3 and 4 (N=1 only)")
     ap.add_argument("--ga-generations", type=int, default=3,
                     help="also time this many generations of the device-resident numGA loop (config 5); 0 = skip")
     args = ap.parse_args()
@@ -280,6 +425,16 @@ def main():
     fit_ok = bool(np.isfinite(host_fit).all()) and bool(torch.isfinite(d_fit).all().item())
     overflows = int(ev.ctx.contact_overflows())  # this rank's warps whose contact pool overflowed in any launch above (0 = reliable)
 
+    kinfo = ev.ctx.kernel_info()  # launch shape of the timed launches (before the extra blocks below launch anything else)
+    # ---- outside the timed region: parity sample, the other configs (N=1), the in-process multi-device path (N>1) -------
+    parity = others = multi = None
+    if rank == 0:
+        if not args.no_parity:
+            parity = parity_block(ev, w)
+        if world > 1:
+            multi = multi_device_check(w, world)
+        elif not args.no_other_configs:
+            others = [other_config(3, 65536, dev, torch), other_config(4, 16384, dev, torch)]
     if rank == 0:
         units = world * n * nv * n_steps * args.steps  # voxel-steps over all ranks and steps
         value = units / (dev_ms * 1e-3)
@@ -287,9 +442,9 @@ def main():
         line = {"metric": "voxel-steps/sec", "value": value, "unit": "voxel-steps/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": w["name"], "robots_per_gpu": n, "physics_steps": n_steps, "voxels": nv,
-                           "genome_len": G, "parallelism": f"robots sharded by index over {world} GPU(s), no collective",
-                           "l2": "256 MiB device write between timed iterations", "kernel": ev.ctx.kernel_info()},
+                "config": shared_config(w, n, n_steps, nv, G),
+                "parallelism": f"robots sharded by index over {world} GPU(s), one process per GPU, no collective on the data path",
+                "kernel": kinfo,
                 "evals_per_sec": value / (nv * n_steps),
                 "e2e": {"value": e2e, "unit": "voxel-steps/s", "h2d_bytes_per_step": n * G * 8, "d2h_bytes_per_step": n * 8,
                         "evals_per_sec": e2e / (nv * n_steps), "ms_per_step": e2e_ms / args.steps},
@@ -312,7 +467,6 @@ def main():
             cpu = {"value": v, "unit": "voxel-steps/s", "cores": threads, "kind": "port",
                    "sample": f"{args.cpu_sample} robots of the same workload ({cdt:.1f} s wall), oracle/vsr_oracle.c double precision"}
         kms = float(np.mean(kernel_ms))
-        kinfo = ev.ctx.kernel_info()
         if flops_per_robot:
             ach = flops_per_robot * n / (kms * 1e-3) / 1e12
             sust = (clocks or {}).get("sm_mhz") or None
@@ -326,6 +480,12 @@ def main():
                                 "hbm": {"achieved_gbs": (n * G * 8 + n * 8) / (kms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                                         "note": "state is register/shared-memory resident; HBM carries genomes in, fitness out"}}
         line["cpu_baseline"] = cpu
+        if parity:
+            line["parity"] = parity
+        if others:
+            line["other_configs"] = others
+        if multi:
+            line["multi_device_exact"] = multi
         emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -111,6 +111,9 @@ int vsr_ga_set_population(vsr_ga* ga, const double* genomes, const double* fitne
 int64_t vsr_ga_generation(const vsr_ga* ga);   /* generations completed (0 after init)                            */
 int64_t vsr_ga_evaluations(const vsr_ga* ga);  /* fitness evaluations so far (JGEA nOfFitnessEvaluations), whole job */
 int64_t vsr_ga_kernel_launches(const vsr_ga* ga); /* GA kernels launched so far (episode kernels are counted by the ctx) */
+/* sizes of the read-out buffers, from the native handle (a binding must not trust caller-supplied sizes) */
+int32_t vsr_ga_n_pop(const vsr_ga* ga);
+int32_t vsr_ga_genome_len(const vsr_ga* ga);
 
 #ifdef __cplusplus
 }

@@ -17,11 +17,28 @@ static void throw_status(JNIEnv* env, vsr_ctx* ctx, int rc) {
   (*env)->ThrowNew(env, (*env)->FindClass(env, cls), vsr_last_error(ctx));
 }
 
+static int throw_iae(JNIEnv* env, const char* msg) {
+  (*env)->ThrowNew(env, (*env)->FindClass(env, "java/lang/IllegalArgumentException"), msg);
+  return 1;
+}
+/* every length that reaches native code is checked against the Java arrays first: a wrong `n` must raise
+ * IllegalArgumentException, never read out of bounds */
+static int bad_batch(JNIEnv* env, vsr_ctx* ctx, jdoubleArray genomes, jint n) {
+  if (!ctx) return throw_iae(env, "null context handle");
+  if (!genomes || n < 0) return throw_iae(env, "genomes is null or n is negative");
+  const int g = vsr_genome_len(ctx);
+  if (g < 0) { throw_status(env, ctx, g); return 1; }
+  if ((jlong)(*env)->GetArrayLength(env, genomes) < (jlong)n * (jlong)g) return throw_iae(env, "genomes.length < n * genomeLength");
+  return 0;
+}
+
 JNIEXPORT jlong JNICALL Java_it_units_erallab_gpu_VsrEval_create(JNIEnv* env, jclass c, jdouble finalT, jdouble transientT,
                                                                  jdoubleArray xs, jdoubleArray ys, jint precision, jintArray devices) {
   vsr_env_desc e;
   vsr_env_default(&e);
   e.final_t = finalT; e.transient_t = transientT; e.precision = precision;
+  if (!xs || !ys || !devices) { throw_iae(env, "xs, ys and devices must not be null"); return 0; }
+  if ((*env)->GetArrayLength(env, xs) != (*env)->GetArrayLength(env, ys)) { throw_iae(env, "xs.length != ys.length"); return 0; }
   jsize n = (*env)->GetArrayLength(env, xs);
   jdouble* px = (*env)->GetDoubleArrayElements(env, xs, NULL);
   jdouble* py = (*env)->GetDoubleArrayElements(env, ys, NULL);
@@ -42,6 +59,11 @@ JNIEXPORT jlong JNICALL Java_it_units_erallab_gpu_VsrEval_create(JNIEnv* env, jc
 JNIEXPORT void JNICALL Java_it_units_erallab_gpu_VsrEval_setBody(JNIEnv* env, jclass c, jlong h, jint w, jint hh, jbyteArray mask,
                                                                  jintArray si, jdoubleArray sd) {
   vsr_ctx* ctx = (vsr_ctx*)(intptr_t)h;
+  if (!ctx || !mask || !si || !sd) { throw_iae(env, "null argument"); return; }
+  if (w <= 0 || hh <= 0 || (jlong)(*env)->GetArrayLength(env, mask) < (jlong)w * hh) { throw_iae(env, "mask.length < w * h"); return; }
+  if ((*env)->GetArrayLength(env, si) % 4 || (*env)->GetArrayLength(env, sd) != (*env)->GetArrayLength(env, si)) {
+    throw_iae(env, "sensor arrays must hold 4 ints and 4 doubles per sensor"); return;
+  }
   jsize ns = (*env)->GetArrayLength(env, si) / 4;
   jbyte* pm = (*env)->GetByteArrayElements(env, mask, NULL);
   jint* pi = (*env)->GetIntArrayElements(env, si, NULL);
@@ -62,6 +84,7 @@ JNIEXPORT void JNICALL Java_it_units_erallab_gpu_VsrEval_setBody(JNIEnv* env, jc
 JNIEXPORT void JNICALL Java_it_units_erallab_gpu_VsrEval_setController(JNIEnv* env, jclass c, jlong h, jint kind, jintArray layers,
                                                                        jint signals, jdouble freq, jdouble amp, jboolean inAct) {
   vsr_ctx* ctx = (vsr_ctx*)(intptr_t)h;
+  if (!ctx || !layers) { throw_iae(env, "null argument"); return; }
   jsize nl = (*env)->GetArrayLength(env, layers);
   jint* pl = (*env)->GetIntArrayElements(env, layers, NULL);
   int rc = vsr_controller_set(ctx, (vsr_ctrl_kind)kind, (const int32_t*)pl, nl, signals, freq, amp, inAct ? 1 : 0);
@@ -77,6 +100,7 @@ JNIEXPORT jint JNICALL Java_it_units_erallab_gpu_VsrEval_genomeLength(JNIEnv* en
 
 JNIEXPORT jdoubleArray JNICALL Java_it_units_erallab_gpu_VsrEval_eval(JNIEnv* env, jclass c, jlong h, jdoubleArray genomes, jint n) {
   vsr_ctx* ctx = (vsr_ctx*)(intptr_t)h;
+  if (bad_batch(env, ctx, genomes, n)) return NULL;
   jdouble* pg = (*env)->GetDoubleArrayElements(env, genomes, NULL);
   double* fit = (double*)malloc(sizeof(double) * (n ? n : 1));
   vsr_result* res = (vsr_result*)malloc(sizeof(vsr_result) * (n ? n : 1));
@@ -104,6 +128,20 @@ JNIEXPORT jdoubleArray JNICALL Java_it_units_erallab_gpu_VsrEval_evalTerrains(JN
                                                                               jdoubleArray xs, jdoubleArray ys, jintArray off) {
   (void)c;
   vsr_ctx* ctx = (vsr_ctx*)(intptr_t)h;
+  if (bad_batch(env, ctx, genomes, n)) return NULL;
+  if (!xs || !ys || !off) { throw_iae(env, "terrain arrays must not be null"); return NULL; }
+  if ((*env)->GetArrayLength(env, off) < n + 1) { throw_iae(env, "off.length < n + 1"); return NULL; }
+  {
+    /* off[] itself is caller data: its last entry bounds the reads of xs / ys */
+    jint last = 0;
+    jint* po_ = (*env)->GetIntArrayElements(env, off, NULL);
+    for (jint i = 0; i <= n; i++) if (po_[i] < 0 || (i > 0 && po_[i] < po_[i - 1])) last = -1;
+    if (last == 0) last = po_[n];
+    (*env)->ReleaseIntArrayElements(env, off, po_, JNI_ABORT);
+    if (last < 0 || (*env)->GetArrayLength(env, xs) < last || (*env)->GetArrayLength(env, ys) < last) {
+      throw_iae(env, "off must be non-decreasing and off[n] <= xs.length, ys.length"); return NULL;
+    }
+  }
   jdouble* pg = (*env)->GetDoubleArrayElements(env, genomes, NULL);
   jdouble* px = (*env)->GetDoubleArrayElements(env, xs, NULL);
   jdouble* py = (*env)->GetDoubleArrayElements(env, ys, NULL);
@@ -174,8 +212,11 @@ JNIEXPORT void JNICALL Java_it_units_erallab_gpu_VsrEval_gaStep(JNIEnv* env, jcl
 }
 
 /* best individual: {fitness, genome[0..G)} */
-JNIEXPORT jdoubleArray JNICALL Java_it_units_erallab_gpu_VsrEval_gaBest(JNIEnv* env, jclass c, jlong g, jint genomeLength) {
-  (void)c;
+JNIEXPORT jdoubleArray JNICALL Java_it_units_erallab_gpu_VsrEval_gaBest(JNIEnv* env, jclass c, jlong g, jint genomeLengthHint) {
+  (void)c; (void)genomeLengthHint;
+  if (!g) { throw_iae(env, "null solver handle"); return NULL; }
+  const jint genomeLength = vsr_ga_genome_len((vsr_ga*)(intptr_t)g); /* buffer sizes come from the native handle, not from Java */
+  if (genomeLength < 0) { throw_ga(env, (vsr_ga*)(intptr_t)g, genomeLength); return NULL; }
   double* buf = (double*)malloc(sizeof(double) * (genomeLength + 1));
   int rc = vsr_ga_best((vsr_ga*)(intptr_t)g, buf + 1, buf);
   jdoubleArray out = NULL;
@@ -186,8 +227,11 @@ JNIEXPORT jdoubleArray JNICALL Java_it_units_erallab_gpu_VsrEval_gaBest(JNIEnv* 
 }
 
 /* whole population, best first: {fitness[nPop], genomes[nPop][G]} flattened */
-JNIEXPORT jdoubleArray JNICALL Java_it_units_erallab_gpu_VsrEval_gaPopulation(JNIEnv* env, jclass c, jlong g, jint nPop, jint genomeLength) {
-  (void)c;
+JNIEXPORT jdoubleArray JNICALL Java_it_units_erallab_gpu_VsrEval_gaPopulation(JNIEnv* env, jclass c, jlong g, jint nPopHint, jint genomeLengthHint) {
+  (void)c; (void)nPopHint; (void)genomeLengthHint;
+  if (!g) { throw_iae(env, "null solver handle"); return NULL; }
+  const jint nPop = vsr_ga_n_pop((vsr_ga*)(intptr_t)g), genomeLength = vsr_ga_genome_len((vsr_ga*)(intptr_t)g);
+  if (nPop < 0 || genomeLength < 0) { throw_ga(env, (vsr_ga*)(intptr_t)g, VSR_EINVAL); return NULL; }
   const size_t tot = (size_t)nPop * ((size_t)genomeLength + 1);
   double* buf = (double*)malloc(sizeof(double) * (tot ? tot : 1));
   int rc = vsr_ga_population((vsr_ga*)(intptr_t)g, buf + nPop, buf);

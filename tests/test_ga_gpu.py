@@ -218,3 +218,35 @@ def test_es_solver_mirror_improves(ev):
     best_g, best_f = loop.solve(listener=lambda d: seen.append(d["best.fitness"]))
     assert len(seen) >= 5 and all(b >= a for a, b in zip(seen, seen[1:])) and best_f >= seen[0]
     assert loop.ga.evaluations >= 400 and len(best_g) == ev.genome_len
+
+
+def test_generation_loop_rejects_per_evaluation_terrains():
+    """Starter.java:89-93 draws a terrain seed per evaluation for `-rnd` names; the device loop has one terrain per context, so it must
+    refuse instead of silently evaluating every individual on seed 0."""
+    from vsrevolution_b200 import _ffi
+    from vsrevolution_b200.locomotion import population_evaluator
+    from vsrevolution_b200.solver import num_ga
+    rnd = population_evaluator("biped-4x3", "uniform-a-0", "brainCentralized<mlp;r=0.65;nIL=1", "hilly-1-10-rnd", 2.0, 0.5)
+    with pytest.raises(_ffi.VsrError) as ei:
+        num_ga().build({"nPop": "32", "nEval": "64"}).build(rnd)
+    assert ei.value.code == _ffi.VSR_EUNSUPPORTED
+    assert np.isfinite(rnd.evaluate(np.zeros((4, rnd.genome_len)))).all()   # the batched path still serves -rnd
+
+
+def test_overflowing_robots_rank_last_in_the_generation_loop(monkeypatch):
+    """A robot whose warp dropped a manifold gets NaN (vsr_kernel.cuh epilogue); NaN ranks last, so the loop cannot select on it."""
+    from vsrevolution_b200 import _ffi
+    from vsrevolution_b200.locomotion import population_evaluator
+    monkeypatch.setenv("VSR_POOL_SLOTS", "8")
+    small = population_evaluator("biped-4x3", "uniform-a-0", "brainCentralized<mlp;r=0.65;nIL=1", "flat", 1.5, 0.5)
+    monkeypatch.delenv("VSR_POOL_SLOTS")
+    ga = _ffi.GeneticAlgorithm(small.ctx, 48, seed=3)
+    ga.init()
+    ga.step()
+    _, fit = ga.population()
+    assert small.ctx.contact_overflows() > 0
+    nan = np.isnan(fit)
+    assert nan.any()
+    first_nan = int(np.argmax(nan))
+    assert nan[first_nan:].all() and not nan[:first_nan].any()              # sorted best-first, every NaN behind every number
+    ga.close()

@@ -142,6 +142,13 @@ def test_edge_cases_and_errors(F, oracle):
         ctx.body_set(big, [])
     assert ei.value.code == F.VSR_EUNSUPPORTED
     ctx.close()
+    # a window [transient_t, final_t) holding ONE observation has distance 0 over time 0: rejected, not NaN for every robot
+    m1 = oracle.config_model(1, final_t=2.0)
+    m1.params.transient_t = 1.995
+    n_steps, k_first, k_last = F.episode_steps(2.0, m1.params.transient_t)
+    assert k_first == k_last
+    with pytest.raises(F.VsrIllegalArgument):
+        make_ctx(F, m1)
 
 
 def test_zero_gravity_zero_amplitude_robot_does_not_move(F, oracle):
@@ -580,7 +587,11 @@ def test_contact_pool_overflow_is_never_silent(F, oracle, monkeypatch):
     fit, res = small.eval(g, want_results=True)
     n_warps = (64 + 2) // 3
     assert 0 < small.contact_overflows() <= n_warps and (res["contact_overflow"] > 0).any()
-    small.eval(g)                                 # fitness-only launch: still counted
+    # a robot that lost ground contacts never returns a rankable fitness: NaN (ranks last), finite diagnostics in vsr_result
+    bad = res["contact_overflow"] > 0
+    assert np.isnan(fit[bad]).all() and np.isfinite(fit[~bad]).all() and np.isfinite(res["velocity"]).all()
+    fit2 = small.eval(g)                          # fitness-only launch: still counted, still NaN
+    assert np.array_equal(np.isnan(fit2), bad)
     assert small.contact_overflows() > n_warps // 2
     small.close()
 

@@ -130,6 +130,8 @@ _GA_SIGS = {
     "vsr_ga_generation": (C.c_int64, [C.c_void_p]),
     "vsr_ga_evaluations": (C.c_int64, [C.c_void_p]),
     "vsr_ga_kernel_launches": (C.c_int64, [C.c_void_p]),
+    "vsr_ga_n_pop": (C.c_int32, [C.c_void_p]),
+    "vsr_ga_genome_len": (C.c_int32, [C.c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGS)

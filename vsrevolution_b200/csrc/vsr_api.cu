@@ -264,6 +264,8 @@ int finalize(vsr_ctx* ctx) {
   int rc = vsr_episode_steps(e.final_t, e.transient_t, e.dt, &ns, &kf, &kl);
   if (rc) return fail(ctx, rc, "bad episode times");
   if (!kf) return fail(ctx, VSR_EINVAL, "no observation falls inside [transient_t, final_t)");
+  // a single kept observation has distance 0 over time 0: Outcome.getVelocity() would be 0/0
+  if (kf == kl) return fail(ctx, VSR_EINVAL, "only one observation falls inside [transient_t, final_t): velocity is undefined");
   k.n_steps = ns; k.k_first = kf; k.k_last = kl;
   {
     volatile double t = 0.0;

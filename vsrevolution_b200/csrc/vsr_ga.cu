@@ -551,5 +551,7 @@ int vsr_ga_set_population(vsr_ga* ga, const double* genomes, const double* fitne
 int64_t vsr_ga_generation(const vsr_ga* ga) { return ga ? ga->gen : -1; }
 int64_t vsr_ga_evaluations(const vsr_ga* ga) { return ga ? ga->evals : 0; }
 int64_t vsr_ga_kernel_launches(const vsr_ga* ga) { return ga ? ga->launches : 0; }
+int32_t vsr_ga_n_pop(const vsr_ga* ga) { return ga ? ga->d.n_pop : VSR_EINVAL; }
+int32_t vsr_ga_genome_len(const vsr_ga* ga) { return ga ? ga->G : VSR_EINVAL; }
 
 } // extern "C"

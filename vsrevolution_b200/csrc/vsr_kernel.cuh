@@ -1590,8 +1590,14 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
   } // steps
 
   // ---- epilogue: contact-pool overflow count (fitness / result were written at step k_last) ---------------
+  // A dropped manifold means missing ground contact for the rest of the episode: the robots of such a warp get a NaN fitness
+  // (NaN ranks last in the generation loop and in the host comparator), so a solver can never select on an unreliable value;
+  // vsr_result keeps the finite numbers next to contact_overflow for diagnosis.
   const int ovf = __reduce_add_sync(FULL, overflow);
-  if (valid && v == 0 && P.results && ovf) P.results[robot].contact_overflow = ovf;
+  if (valid && v == 0 && ovf) {
+    P.fitness[robot] = __longlong_as_double(0x7ff8000000000000LL);
+    if (P.results) P.results[robot].contact_overflow = ovf;
+  }
   if (ovf && lane == 0 && P.overflow_count) atomicAdd(P.overflow_count, 1);
 #undef WELD_APPLY
 #undef WELD_SOLVE

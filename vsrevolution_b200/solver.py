@@ -37,6 +37,12 @@ class GenerationLoop:
         if not getattr(evaluator, "direct", True):
             raise _ffi.VsrError(_ffi.VSR_EUNSUPPORTED, "the device-resident loop needs a mapper whose genome is the controller "
                                 "parameter vector; host-transforming mappers go through PopulationEvaluator.evaluate")
+        from .locomotion import RandomTerrainLocomotion
+        if isinstance(evaluator.task, RandomTerrainLocomotion):
+            # Starter.java:89-93 draws one terrain seed per evaluation; the device loop evaluates on the context's one terrain, so
+            # running it here would silently turn `-rnd` into `-0` for every individual of every generation
+            raise _ffi.VsrError(_ffi.VSR_EUNSUPPORTED, "per-evaluation (-rnd) terrains are not available inside the device-resident "
+                                "generation loop; evaluate with PopulationEvaluator.evaluate (vsr_eval_terrains) or use a fixed terrain")
         if es is not None:  # SimpleEvolutionaryStrategy(..., nOfParents, nOfElites, sigma, remap)
             self.ga = _ffi.GeneticAlgorithm(evaluator.ctx, n_pop, seed=seed, remap=remap, solver=_ffi.SOLVER_ES,
                                             sigma_mut=es["sigma"], n_parents=es["n_parents"], n_elites=es["n_elites"])
