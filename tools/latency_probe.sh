@@ -8,7 +8,7 @@ import sys,json
 for l in sys.stdin:
     try: d=json.loads(l)
     except Exception: print(l.strip()[:200]); continue
-    k=d['config']['kernel']
+    k=d['kernel']
     print('ms/step %7.2f  value %.3e  regs %d thr %d ctas/sm %d' % (d['ms_per_step'], d['value'], k['regs_per_thread'], k['threads_per_cta'], k['ctas_per_sm']))
 "
   done

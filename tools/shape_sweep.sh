@@ -11,7 +11,7 @@ import sys,json
 for l in sys.stdin:
     try: d=json.loads(l)
     except Exception: print(l.strip()[:200]); continue
-    k=d['config']['kernel']
+    k=d['kernel']
     print('value %.3e  ms/step %7.1f  regs %d ctas/sm %d thr %d smem %d' % (d['value'], d['ms_per_step'], k['regs_per_thread'], k['ctas_per_sm'], k['threads_per_cta'], k['smem_bytes']))
 "
     done

@@ -132,15 +132,29 @@ struct KParams {
 // sincos / tanh (all within a few ulp); the FP64 build uses the precise libm calls.
 // ------------------------------------------------------------------------------------------------
 template <class R> struct M;
+// A/B switches for the FP32 approximations (profiles/r2_fp32_approx_ab.md: which one ends step-wise tracking of the oracle first):
+//   -DVSR_IEEE_DIV      correctly rounded reciprocal / reciprocal square root instead of the MUFU approximations
+//   -DVSR_LIBM_SINCOS   CUDA libm sincosf instead of the Cody-Waite polynomials
+//   -DVSR_NO_SMALL_ROTATE  every position-solver rotation re-evaluates sin / cos of the angle (no small-angle update)
+//   -DVSR_LIBM_TANH     tanhf instead of ex2.approx + rcp.approx
 template <> struct M<float> {
+#ifdef VSR_IEEE_DIV
+  static __device__ __forceinline__ float rcp(float x) { return __frcp_rn(x); }
+  static __device__ __forceinline__ float rsqrt_(float x) { return __frcp_rn(__fsqrt_rn(x)); }
+#else
   static __device__ __forceinline__ float rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
   static __device__ __forceinline__ float rsqrt_(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+#endif
   static __device__ __forceinline__ float abs_(float x) { return fabsf(x); }
   static __device__ __forceinline__ float max_(float a, float b) { return fmaxf(a, b); }
   static __device__ __forceinline__ float min_(float a, float b) { return fminf(a, b); }
   static __device__ __forceinline__ float rint_(float a) { return rintf(a); }
   // Cody-Waite reduction by pi/2 + minimax polynomials on [-pi/4, pi/4]; |a| < ~1e5
   static __device__ __forceinline__ void sincos_(float a, float* sn, float* cs) {
+#ifdef VSR_LIBM_SINCOS
+    sincosf(a, sn, cs);
+    return;
+#endif
     const float k = rintf(a * 0.636619772367581343f);
     float r = fmaf(k, -1.57079625129699707031f, a);
     r = fmaf(k, -7.54978941586159635335e-08f, r);
@@ -161,6 +175,10 @@ template <> struct M<float> {
   // rotate (c,s) by a small angle d (position-solver corrections); falls back to the full evaluation
   static __device__ __forceinline__ void rotate(float& a, float& c, float& s, float d) {
     a += d;
+#ifdef VSR_NO_SMALL_ROTATE
+    sincos_(a, &s, &c);
+    return;
+#endif
     if (fabsf(d) < 0.125f) {
       const float d2 = d * d;
       const float sd = d * fmaf(d2, fmaf(d2, 8.33333333e-3f, -1.66666667e-1f), 1.0f);
@@ -173,6 +191,9 @@ template <> struct M<float> {
     }
   }
   static __device__ __forceinline__ float tanh_(float x) {
+#ifdef VSR_LIBM_TANH
+    return tanhf(x);
+#endif
     // 1 - 2/(e^{2x}+1); ex2.approx + rcp.approx, abs error ~2e-7
     const float xc = fminf(fmaxf(x, -15.f), 15.f);
     float e;
@@ -239,8 +260,15 @@ __device__ __forceinline__ void opaque(double& x) { asm volatile("" : "+d"(x)); 
 // narrowphase: corner-mass box vs one ground polygon (SAT + reference-face clipping)
 // ground polygon CCW: V0=(x0,base) V1=(x1,base) V2=(x1,y1) V3=(x0,y0); box centre (bcx,bcy), half side hh
 // ------------------------------------------------------------------------------------------------
+// -DVSR_NARROW_NOINLINE: the general narrowphase as a real function (flat / wide terrains take collide_box_top; this body then leaves
+// the step's instruction stream)
+#ifdef VSR_NARROW_NOINLINE
+#define VSR_NARROW_INLINE __noinline__
+#else
+#define VSR_NARROW_INLINE __forceinline__
+#endif
 template <class R>
-__device__ __forceinline__ int collide_box_ground(R x0, R y0, R x1, R y1, R base, R bcx, R bcy, R c, R s, R hh, R lin_tol,
+__device__ VSR_NARROW_INLINE int collide_box_ground(R x0, R y0, R x1, R y1, R base, R bcx, R bcy, R c, R s, R hh, R lin_tol,
                                                   R& onx, R& ony, R* opx, R* opy, R* odepth, int* oid) {
   const R hc = hh * c, hs = hh * s;
   const R bx[4] = {bcx - hc + hs, bcx + hc + hs, bcx + hc - hs, bcx - hc - hs};
