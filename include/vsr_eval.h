@@ -161,6 +161,57 @@ int vsr_trace(vsr_ctx* ctx, const double* genome, int32_t n_steps, double* verti
 int vsr_eval_terrains(vsr_ctx* ctx, const double* genomes, int32_t n, const double* terrain_x, const double* terrain_y,
                       const int32_t* terrain_off, double* fitness_out, vsr_result* results_out);
 
+/*
+ * The general batched call: vsr_eval plus, each optional,
+ *   - per-robot terrains (as vsr_eval_terrains);
+ *   - the robot transformation `broken-<ratio>-<seed>` of RobotUtils.buildRobotTransformation(transformationName, random)
+ *     (Starter.java:126,428; `identity` is the default, :153): frozen_masks[i] bit v = voxel v (grid order) of robot i was replaced by a
+ *     BreakableVoxel whose ACTUATOR is FROZEN from t = 0 -- it applies the last force before freezing, i.e. none; sensors keep working.
+ *     Which voxels break is decided on the host (`random.nextDouble() > ratio ? v : broken`, one nextInt() consumed per broken voxel):
+ *     vsr_broken_masks replays it;
+ *   - the per-observation summaries behind the Outcome getters the reference logs: Outcome.getAveragePosture(n) (Starter.java:180-190:
+ *     the feature vector `numSpeciated` clusters on; NamedFunctions.java:356), Outcome.getFootprintsSpectra(n, ...)
+ *     (NamedFunctions.java:179-180 n = 4, :392 n = 3) and the centre trajectory with the angle of the central voxel
+ *     (getCenterXVelocitySpectrum / getCenterYVelocitySpectrum / getCenterAngleSpectrum, NamedFunctions.java:139-172), for the whole
+ *     population in one launch.  K = k_last - k_first + 1 kept observations (vsr_episode_steps).  The 2dhmsr BehaviorUtils
+ *     definitions are recalled [U] and restated in oracle/vsr_oracle.c (vo_extras).
+ * All pointers are HOST memory, caller-owned; NULL / 0 = not requested.  Observation requests run the observation build of the
+ * episode kernel (8 warps per CTA at 255 registers); fitness values are those of vsr_eval.
+ */
+typedef struct {
+  const uint32_t* frozen_masks;     /* [n] or NULL */
+  const double* terrain_x;          /* per-robot terrains: all three or none */
+  const double* terrain_y;
+  const int32_t* terrain_off;       /* [n + 1] */
+  int32_t posture_n;                /* 0, or grid side 1..8 */
+  int32_t footprint_n[2];           /* 0, or segments 1..8 (two requests: the reference asks for 3 and for 4) */
+  uint8_t* posture_out;             /* [n][posture_n * posture_n], index y * n + x, y = 0 bottom row, 1 = cell set on average */
+  uint8_t* footprints_out[2];       /* [n][K], bit s = segment s touches the ground at that observation */
+  double* centers_out;              /* [n][K][3] = robot centre x, y, angle of the central voxel */
+} vsr_eval_opts;
+int vsr_eval_ex(vsr_ctx* ctx, const double* genomes, int32_t n, const vsr_eval_opts* opts, double* fitness_out, vsr_result* results_out);
+/*
+ * Stage the per-robot inputs of vsr_eval_opts (frozen masks and / or per-robot terrains; no observation requests) for the
+ * device-resident paths -- vsr_eval_device and the generation loop of vsr_ga.h: entry i applies to robot i of every following batch
+ * (a batch may evaluate fewer than n robots, never more) until the next call; n = 0 or opts = NULL clears.  The data is copied.
+ * This is how `-rnd` terrains (Starter.java:89-93) and robot transformations (Starter.java:427-429) reach the generation loop: the
+ * host draws the seeds / masks of a generation, stages them, then runs the generation.
+ */
+int vsr_stage_eval_opts(vsr_ctx* ctx, int32_t n, const vsr_eval_opts* opts);
+/* `broken-<ratio>-<seed>` replayed for n robots of this context's body, in robot order, from ONE java.util.Random(seed) shared by
+ * the run (RobotUtils.buildRobotTransformation creates it once; with seed `rnd` the caller passes the run's shared seed and the
+ * number of values already drawn is *not* tracked here): per voxel in grid order nextDouble() > ratio keeps the voxel, else the voxel
+ * breaks and one nextInt() (the BreakableVoxel's own seed) is consumed.  masks_out [n]. */
+int vsr_broken_masks(const vsr_ctx* ctx, double ratio, int64_t seed, int32_t n, uint32_t* masks_out);
+/* the same on a running stream: *lcg_state is the raw 48-bit state of the shared java.util.Random -- (seed ^ 0x5DEECE66D) & (2^48 - 1)
+ * right after `new Random(seed)` -- and is advanced, so consecutive batches (generations) continue where the last one stopped */
+int vsr_broken_masks_stream(const vsr_ctx* ctx, double ratio, uint64_t* lcg_state, int32_t n, uint32_t* masks_out);
+/* RobotUtils.buildRobotTransformation(name, random): parses `identity` (kind 0) and `broken-<ratio>-<seed|rnd>` (kind 1);
+ * `breakable-...` (malfunctions triggered during the episode) returns VSR_EUNSUPPORTED, anything else VSR_EINVAL */
+int vsr_robot_transformation(const char* name, int32_t* kind, double* ratio, int64_t* seed, int32_t* seed_is_rnd);
+/* index (voxel order) of BehaviorUtils.getCentralElement of the body: the voxel whose angle centers_out[..][2] records */
+int vsr_central_voxel(const vsr_ctx* ctx);
+
 /* timing / accounting of the most recent vsr_eval / vsr_eval_device on device 0 of the context */
 /*
  * vsr_eval plus the robot-centre trajectory: centers_out [n][K][2] doubles = (x, y) of the robot centre (mean of the voxel

@@ -249,6 +249,11 @@ class VoResult(C.Structure):
         [(n, C.c_double) for n in ("control_energy", "area_ratio_abs", "area_ratio_sq")]
 
 
+class VoExtras(C.Structure):
+    _fields_ = [("frozen_mask", C.c_uint32), ("posture_n", C.c_int), ("posture_out", C.c_void_p), ("posture_counts", C.c_void_p),
+                ("footprint_n", C.c_int * 2), ("footprints_out", C.c_void_p * 2), ("centers_out", C.c_void_p)]
+
+
 CTRL_PHASE_SIN, CTRL_MLP_CENTRALIZED, CTRL_MLP_DISTRIBUTED_HOMO, CTRL_MLP_DISTRIBUTED_HETERO, CTRL_TIME_SIN = 0, 1, 2, 3, 4
 
 _lib = None
@@ -270,6 +275,8 @@ def lib():
         _lib.vo_default_params.argtypes = [C.POINTER(VoParams)]
         _lib.vo_genome_len.restype = C.c_int
         _lib.vo_run.restype = C.c_int
+        _lib.vo_run_ex.restype = C.c_int
+        _lib.vo_central_voxel.restype = C.c_int
         _lib.vo_eval_batch.restype = C.c_int
     return _lib
 
@@ -362,6 +369,39 @@ class Model:
         if rc:
             raise RuntimeError(f"vo_run failed: {rc}")
         return res, tv, tb, tc
+
+    def run_ex(self, genome: np.ndarray, frozen_mask: int = 0, posture_n: int = 0, footprint_n=(0, 0), centers: bool = False):
+        """One episode with the extras of vo_run_ex: returns (result, dict with posture [n*n] uint8, posture_counts, footprints
+        (two uint8 [K] arrays or None), centers [K][3] or None)."""
+        g = np.ascontiguousarray(genome, dtype=np.float64)
+        _, kf, kl = episode_steps(self.params.final_t, self.params.transient_t, self.params.dt)
+        K = kl - kf + 1
+        ex = VoExtras()
+        ex.frozen_mask, ex.posture_n = frozen_mask, posture_n
+        post = np.zeros(max(1, posture_n * posture_n), dtype=np.uint8)
+        cnt = np.zeros(max(1, posture_n * posture_n), dtype=np.int32)
+        ex.posture_out, ex.posture_counts = post.ctypes.data, cnt.ctypes.data
+        fps = [None, None]
+        for q in range(2):
+            ex.footprint_n[q] = footprint_n[q]
+            if footprint_n[q]:
+                fps[q] = np.zeros(K, dtype=np.uint8)
+                ex.footprints_out[q] = fps[q].ctypes.data
+        cen = np.zeros((K, 3)) if centers else None
+        if centers:
+            ex.centers_out = cen.ctypes.data
+        res = VoResult()
+        ptr = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
+        rc = lib().vo_run_ex(C.byref(self.params), self.w, self.h, ptr(self.mask), self._sensor_array(), len(self.sensors),
+                             C.byref(self.ctrl), ptr(self.tx), ptr(self.ty), len(self.tx), ptr(g), len(g),
+                             0, None, None, None, C.byref(ex), C.byref(res))
+        if rc:
+            raise RuntimeError(f"vo_run_ex failed: {rc}")
+        return res, {"posture": post[:posture_n * posture_n], "posture_counts": cnt[:posture_n * posture_n], "footprints": fps,
+                     "centers": cen, "kept": K}
+
+    def central_voxel(self) -> int:
+        return lib().vo_central_voxel(self.w, self.h, self.mask.ctypes.data_as(C.c_void_p))
 
     def eval_batch(self, genomes: np.ndarray, n_threads: int = 1, want_results: bool = False):
         g = np.ascontiguousarray(genomes, dtype=np.float64)

@@ -103,6 +103,7 @@ typedef struct {
   int* n_man;    /* [n_bodies] */
   /* control */
   double* ctrl_f; /* [n_vox] last applied control */
+  uint32_t frozen; /* bit v: actuator of voxel v frozen at 0 (vo_extras.frozen_mask) */
   vo_result* tally;
 } World;
 
@@ -1061,6 +1062,7 @@ int vo_genome_len(int w, int h, const uint8_t* mask, const vo_sensor* sensors, i
 
 /* Voxel.applyForce(f), ForceMethod.DISTANCE */
 static void apply_control(World* W, int v, double f) {
+  if ((W->frozen >> v) & 1u) f = 0.0; /* BreakableVoxel, ACTUATOR FROZEN since t = 0: the last applied force (0) is applied instead */
   if (fabs(f) > 1.0) f = f > 0 ? 1.0 : -1.0;
   W->ctrl_f[v] = f;
   for (int i = 0; i < W->n_joints; i++) {
@@ -1108,14 +1110,130 @@ static void world_free(World* W) {
   free(W->tx); free(W->ty); free(W->man); free(W->n_man); free(W->ctrl_f);
 }
 
+/* ------------------------------------------------------------------------------------------- */
+/* per-observation summaries (BehaviorUtils [U]; see vo_extras in the header)                    */
+/* ------------------------------------------------------------------------------------------- */
+int vo_central_voxel(int w, int h, const uint8_t* mask) {
+  double mx = 0, my = 0;
+  int n = 0;
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w; x++)
+      if (mask[y * w + x]) { mx += x; my += y; n++; }
+  if (!n) return -1;
+  mx /= n; my /= n;
+  double best = INFINITY;
+  int bi = -1, v = 0;
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w; x++)
+      if (mask[y * w + x]) {
+        double d = (x - mx) * (x - mx) + (y - my) * (y - my);
+        if (d < best) { best = d; bi = v; } /* first minimum in grid iteration order */
+        v++;
+      }
+  return bi;
+}
+
+/* crossing-number point-in-polygon test (what java.awt Path2D.contains decides for a simple polygon) */
+static int quad_contains(const double q[4][2], double px, double py) {
+  int in = 0;
+  for (int i = 0, j = 3; i < 4; j = i++) {
+    const double xi = q[i][0], yi = q[i][1], xj = q[j][0], yj = q[j][1];
+    if (((yi > py) != (yj > py)) && (px < (xj - xi) * (py - yi) / (yj - yi) + xi)) in = !in;
+  }
+  return in;
+}
+
+/* BehaviorUtils.computePosture(polies, n): cells of the squared bounding box whose centre lies inside a voxel polygon */
+static uint64_t posture_mask(const World* W, int n) {
+  double minx = INFINITY, miny = INFINITY, maxx = -INFINITY, maxy = -INFINITY;
+  for (int v = 0; v < W->n_vox; v++) {
+    double q[4][2];
+    voxel_vertices(W, v, q);
+    for (int k = 0; k < 4; k++) {
+      minx = fmin(minx, q[k][0]); maxx = fmax(maxx, q[k][0]);
+      miny = fmin(miny, q[k][1]); maxy = fmax(maxy, q[k][1]);
+    }
+  }
+  /* adjust the box to make it squared (centred) */
+  const double wdt = maxx - minx, hgt = maxy - miny;
+  if (hgt < wdt) { const double d = wdt - hgt; miny -= d / 2; maxy += d / 2; }
+  else if (hgt > wdt) { const double d = hgt - wdt; minx -= d / 2; maxx += d / 2; }
+  const double side = maxx - minx;
+  uint64_t m = 0;
+  for (int v = 0; v < W->n_vox; v++) {
+    double q[4][2];
+    voxel_vertices(W, v, q);
+    for (int iy = 0; iy < n; iy++)
+      for (int ix = 0; ix < n; ix++) {
+        const double px = minx + (ix + 0.5) / n * side, py = miny + (iy + 0.5) / n * side;
+        if (quad_contains(q, px, py)) m |= 1ULL << (iy * n + ix);
+      }
+  }
+  return m;
+}
+
+/* BehaviorUtils.computeFootprint(polies, n) */
+static uint8_t footprint_mask(const World* W, int n) {
+  double rmin = INFINITY, rmax = -INFINITY;
+  for (int v = 0; v < W->n_vox; v++) {
+    double q[4][2];
+    voxel_vertices(W, v, q);
+    for (int k = 0; k < 4; k++) { rmin = fmin(rmin, q[k][0]); rmax = fmax(rmax, q[k][0]); }
+  }
+  uint8_t m = 0;
+  for (int v = 0; v < W->n_vox; v++) {
+    int touch = 0;
+    for (int k = 0; k < 4; k++) touch |= W->n_man[v * 4 + k] > 0;
+    if (!touch) continue;
+    double q[4][2];
+    voxel_vertices(W, v, q);
+    double cmin = INFINITY, cmax = -INFINITY;
+    for (int k = 0; k < 4; k++) { cmin = fmin(cmin, q[k][0]); cmax = fmax(cmax, q[k][0]); }
+    const int i0 = (int)floor((cmin - rmin) / (rmax - rmin) * (double)(n - 1) + 0.5); /* Math.round */
+    int i1 = (int)floor((cmax - rmin) / (rmax - rmin) * (double)(n - 1) + 0.5);
+    if (i1 > n - 1) i1 = n - 1;
+    for (int x = i0 < 0 ? 0 : i0; x <= i1; x++) m |= (uint8_t)(1u << x);
+  }
+  return m;
+}
+
+/* VoxelPoly.getAngle(): mean direction of the polygon's upper (NW -> NE) and lower (SW -> SE) sides */
+static double voxel_poly_angle(const World* W, int v) {
+  double q[4][2];
+  voxel_vertices(W, v, q);
+  return (atan2(q[1][1] - q[0][1], q[1][0] - q[0][0]) + atan2(q[2][1] - q[3][1], q[2][0] - q[3][0])) / 2.0;
+}
+
+static double robot_center_y(const World* W) {
+  double s = 0;
+  for (int v = 0; v < W->n_vox; v++) {
+    double q[4][2];
+    voxel_vertices(W, v, q);
+    s += (q[0][1] + q[1][1] + q[2][1] + q[3][1]) / 4.0;
+  }
+  return s / W->n_vox;
+}
+
 int vo_run(const vo_params* p, int w, int h, const uint8_t* mask,
            const vo_sensor* sensors, int n_sensors, const vo_ctrl* ctrl,
            const double* terrain_x, const double* terrain_y, int n_terrain,
            const double* genome, int genome_len,
            int trace_steps, double* trace_vertices, double* trace_bodies, double* trace_ctrl,
            vo_result* out) {
+  return vo_run_ex(p, w, h, mask, sensors, n_sensors, ctrl, terrain_x, terrain_y, n_terrain, genome, genome_len, trace_steps,
+                   trace_vertices, trace_bodies, trace_ctrl, NULL, out);
+}
+
+int vo_run_ex(const vo_params* p, int w, int h, const uint8_t* mask,
+              const vo_sensor* sensors, int n_sensors, const vo_ctrl* ctrl,
+              const double* terrain_x, const double* terrain_y, int n_terrain,
+              const double* genome, int genome_len,
+              int trace_steps, double* trace_vertices, double* trace_bodies, double* trace_ctrl,
+              const vo_extras* ex, vo_result* out) {
   if (!p || !mask || !ctrl || !out || w <= 0 || h <= 0 || n_terrain < 2) return -1;
   if (n_sensors > 8) return -3;
+  if (ex && (ex->posture_n < 0 || ex->posture_n > 8 || ex->footprint_n[0] < 0 || ex->footprint_n[0] > 8 || ex->footprint_n[1] < 0 ||
+             ex->footprint_n[1] > 8)) return -6;
   int glen = vo_genome_len(w, h, mask, sensors, n_sensors, ctrl);
   if (glen < 0) return glen;
   if (glen != genome_len) return -4;
@@ -1124,6 +1242,7 @@ int vo_run(const vo_params* p, int w, int h, const uint8_t* mask,
   memset(W, 0, sizeof(*W));
   W->p = *p;
   W->tally = out;
+  W->frozen = ex ? ex->frozen_mask : 0u;
   derive(W);
   W->w = w; W->h = h;
   int ns, nr, nw;
@@ -1180,6 +1299,8 @@ int vo_run(const vo_params* p, int w, int h, const uint8_t* mask,
   double in[256], o[256];
   double* last_area = (double*)calloc((size_t)W->n_vox, sizeof(double));
   out->control_energy = out->area_ratio_abs = out->area_ratio_sq = 0.0;
+  int post_cnt[64] = {0}, n_kept = 0;
+  const int central = vo_central_voxel(w, h, mask);
   while (t < p->final_t) {
     t += p->dt;
     k++;
@@ -1234,6 +1355,20 @@ int vo_run(const vo_params* p, int w, int h, const uint8_t* mask,
       }
       if (!have_first) { have_first = 1; first_t = t; first_x = cx; out->k_first = k; }
       last_t = t; last_x = cx; out->k_last = k;
+      if (ex) {
+        if (ex->posture_n > 0) {
+          const uint64_t pm = posture_mask(W, ex->posture_n);
+          for (int c = 0; c < ex->posture_n * ex->posture_n; c++) post_cnt[c] += (int)((pm >> c) & 1ULL);
+        }
+        for (int q = 0; q < 2; q++)
+          if (ex->footprint_n[q] > 0 && ex->footprints_out[q]) ex->footprints_out[q][n_kept] = footprint_mask(W, ex->footprint_n[q]);
+        if (ex->centers_out) {
+          ex->centers_out[3 * (size_t)n_kept] = cx;
+          ex->centers_out[3 * (size_t)n_kept + 1] = robot_center_y(W);
+          ex->centers_out[3 * (size_t)n_kept + 2] = voxel_poly_angle(W, central);
+        }
+      }
+      n_kept++;
     }
     if (k <= trace_steps) {
       if (trace_vertices)
@@ -1258,6 +1393,11 @@ int vo_run(const vo_params* p, int w, int h, const uint8_t* mask,
   out->distance = last_x - first_x;
   out->time = last_t - first_t;
   out->velocity = out->distance / out->time;
+  if (ex && ex->posture_n > 0)
+    for (int c = 0; c < ex->posture_n * ex->posture_n; c++) {
+      if (ex->posture_out) ex->posture_out[c] = (uint8_t)(2 * post_cnt[c] > n_kept); /* average over the observations > 0.5 */
+      if (ex->posture_counts) ex->posture_counts[c] = post_cnt[c];
+    }
   free(S.off); free(S.readings); free(S.hist_t); free(S.hist_v); free(last_sig); free(cur_sig); free(last_area);
   world_free(W);
   return 0;

@@ -110,6 +110,28 @@ typedef struct {
   double control_energy, area_ratio_abs, area_ratio_sq;
 } vo_result;
 
+/* Optional extras of one episode (vo_run_ex): the robot transformation `broken-<ratio>-<seed>` and the per-observation
+ * summaries behind the Outcome getters the host logs ([U]: 2dhmsr RobotUtils.buildRobotTransformation, BehaviorUtils):
+ *   frozen_mask   bit v = voxel v is a BreakableVoxel whose ACTUATOR is FROZEN from t = 0 (trigger TIME >= 0, restore time
+ *                 infinite): applyForce(f) applies the last force before freezing, i.e. 0 -- the voxel is passive, its sensors work
+ *   posture       Outcome.getAveragePosture(n) (Starter.java:180-190, NamedFunctions.java:356): per kept observation the voxel
+ *                 polygons are rasterised on the n x n grid of the squared bounding box (cell centre inside any polygon);
+ *                 average posture = cells set in MORE than half of the observations; [y*n + x], y = 0 bottom
+ *   footprints    BehaviorUtils.computeFootprint(polies, n) behind Outcome.getFootprintsSpectra(n, ...) (NamedFunctions.java:179-180,
+ *                 392): x-range of every ground-touching voxel polygon mapped on n segments of the robot's x-extent with
+ *                 round((x - min) / (max - min) * (n - 1)); one byte per kept observation, bit s = segment s
+ *   centers       per kept observation: robot centre x, y and the angle of the central voxel (getCentralElement: the voxel closest to
+ *                 the mean grid position) -- inputs of getCenterX/YVelocitySpectrum and getCenterAngleSpectrum */
+typedef struct {
+  uint32_t frozen_mask;
+  int      posture_n;        /* 0 = off, else 1..8 */
+  uint8_t* posture_out;      /* [posture_n * posture_n] */
+  int32_t* posture_counts;   /* optional [posture_n * posture_n]: observations in which the cell was set */
+  int      footprint_n[2];   /* 0 = off, else 1..8 */
+  uint8_t* footprints_out[2]; /* [kept observations] each */
+  double*  centers_out;      /* optional [kept observations][3] */
+} vo_extras;
+
 void vo_default_params(vo_params* p);
 
 /* counts: voxels, springs, ropes, welds for a mask (w*h, row-major y*w+x, y=0 bottom) */
@@ -132,6 +154,15 @@ int vo_run(const vo_params* p, int w, int h, const uint8_t* mask,
            const double* genome, int genome_len,
            int trace_steps, double* trace_vertices, double* trace_bodies, double* trace_ctrl,
            vo_result* out);
+
+int vo_run_ex(const vo_params* p, int w, int h, const uint8_t* mask,
+              const vo_sensor* sensors, int n_sensors, const vo_ctrl* ctrl,
+              const double* terrain_x, const double* terrain_y, int n_terrain,
+              const double* genome, int genome_len,
+              int trace_steps, double* trace_vertices, double* trace_bodies, double* trace_ctrl,
+              const vo_extras* extras, vo_result* out);
+/* index (in voxel order) of BehaviorUtils.getCentralElement of the body grid */
+int vo_central_voxel(int w, int h, const uint8_t* mask);
 
 /* Evaluate n genomes ([n][genome_len] row-major) on n_threads host threads; velocity -> fitness_out[n]. */
 int vo_eval_batch(const vo_params* p, int w, int h, const uint8_t* mask,

@@ -220,17 +220,36 @@ def test_es_solver_mirror_improves(ev):
     assert loop.ga.evaluations >= 400 and len(best_g) == ev.genome_len
 
 
-def test_generation_loop_rejects_per_evaluation_terrains():
-    """Starter.java:89-93 draws a terrain seed per evaluation for `-rnd` names; the device loop has one terrain per context, so it must
-    refuse instead of silently evaluating every individual on seed 0."""
+def test_generation_loop_draws_per_evaluation_terrains_and_transformations():
+    """Starter.java:89-93 draws a terrain seed per evaluation for `-rnd` names and Starter.java:427-429 applies the robot
+    transformation per evaluation: the device loop stages them per batch (vsr_stage_eval_opts) instead of silently evaluating every
+    individual on seed 0 / untransformed.  The loop's fitness of an offspring == that robot evaluated alone on its
+    terrain with its frozen mask."""
     from vsrevolution_b200 import _ffi
     from vsrevolution_b200.locomotion import population_evaluator
     from vsrevolution_b200.solver import num_ga
-    rnd = population_evaluator("biped-4x3", "uniform-a-0", "brainCentralized<mlp;r=0.65;nIL=1", "hilly-1-10-rnd", 2.0, 0.5)
-    with pytest.raises(_ffi.VsrError) as ei:
-        num_ga().build({"nPop": "32", "nEval": "64"}).build(rnd)
-    assert ei.value.code == _ffi.VSR_EUNSUPPORTED
-    assert np.isfinite(rnd.evaluate(np.zeros((4, rnd.genome_len)))).all()   # the batched path still serves -rnd
+    kw = dict(transformation="broken-0.3-7")
+    ev = population_evaluator("biped-4x3", "uniform-a-0", "brainCentralized<mlp;r=0.65;nIL=1", "hilly-1-10-rnd", 2.0, 0.5, **kw)
+    twin = population_evaluator("biped-4x3", "uniform-a-0", "brainCentralized<mlp;r=0.65;nIL=1", "hilly-1-10-rnd", 2.0, 0.5, **kw)
+    assert ev.has_per_evaluation_inputs
+    n = 48
+    loop = num_ga().build({"nPop": str(n), "nEval": str(3 * n)}).build(ev, seed=5)
+    loop.init()
+    frozen0, terrains0 = twin.per_evaluation_inputs(n)          # the same draws, replayed: generation 0
+    loop.step()
+    frozen1, terrains1 = twin.per_evaluation_inputs(n)          # generation 1 continues both streams
+    assert frozen0.any() and not np.array_equal(frozen0, frozen1)
+    assert not np.array_equal(terrains0[0][1], terrains1[0][1]) and not np.array_equal(terrains1[0][1], terrains1[1][1])
+    g, _, f = loop.ga.offspring()
+    ref = twin.ctx.eval_ex(g, frozen_masks=frozen1, terrains=terrains1)[0]
+    assert np.array_equal(f, ref)
+    plain = twin.ctx.eval(g)                                       # ... and NOT what the context's own terrain / intact robots give
+    assert (plain != f).mean() > 0.9
+    # ES stages n - n_elites entries per generation
+    from vsrevolution_b200.solver import es
+    loop2 = es().build({"nPop": "32", "nEval": "96"}).build(ev, seed=1)
+    loop2.solve()
+    assert np.isfinite(loop2.ga.best()[1])
 
 
 def test_overflowing_robots_rank_last_in_the_generation_loop(monkeypatch):

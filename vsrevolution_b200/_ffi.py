@@ -48,6 +48,13 @@ RESULT_DTYPE = np.dtype([("velocity", "f8"), ("distance", "f8"), ("time", "f8"),
 assert RESULT_DTYPE.itemsize == C.sizeof(Result)
 
 
+class EvalOpts(C.Structure):
+    """vsr_eval_opts (include/vsr_eval.h)."""
+    _fields_ = [("frozen_masks", C.c_void_p), ("terrain_x", C.c_void_p), ("terrain_y", C.c_void_p), ("terrain_off", C.c_void_p),
+                ("posture_n", C.c_int32), ("footprint_n", C.c_int32 * 2), ("posture_out", C.c_void_p),
+                ("footprints_out", C.c_void_p * 2), ("centers_out", C.c_void_p)]
+
+
 class VsrError(RuntimeError):
     def __init__(self, code: int, message: str):
         super().__init__(f"libvsr_eval error {code}: {message}")
@@ -84,6 +91,12 @@ _SIGS = {
     "vsr_eval_centers": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vsr_eval_terrains": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vsr_eval_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vsr_eval_ex": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(EvalOpts), C.c_void_p, C.c_void_p]),
+    "vsr_stage_eval_opts": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(EvalOpts)]),
+    "vsr_broken_masks": (C.c_int, [C.c_void_p, C.c_double, C.c_int64, C.c_int32, C.c_void_p]),
+    "vsr_broken_masks_stream": (C.c_int, [C.c_void_p, C.c_double, C.POINTER(C.c_uint64), C.c_int32, C.c_void_p]),
+    "vsr_robot_transformation": (C.c_int, [C.c_char_p, C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
+    "vsr_central_voxel": (C.c_int, [C.c_void_p]),
     "vsr_trace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vsr_last_kernel_ms": (C.c_double, [C.c_void_p]),
     "vsr_kernel_launches": (C.c_int64, [C.c_void_p]),
@@ -254,6 +267,91 @@ class Context:
         res = np.empty(g.shape[0], dtype=RESULT_DTYPE) if want_results else None
         check(lib().vsr_eval_terrains(self._h, _ptr(g), g.shape[0], _ptr(xs), _ptr(ys), _ptr(off), _ptr(fit), _ptr(res)), self._h)
         return (fit, res) if want_results else fit
+
+    def eval_ex(self, genomes: np.ndarray, frozen_masks=None, terrains=None, posture_n: int = 0, footprint_n=(0, 0),
+                centers: bool = False):
+        """vsr_eval_ex: (fitness [n], results [n], extras) with extras = {"posture": [n][p*p] uint8 or None, "footprints": [two [n][K]
+        uint8 arrays or None], "centers": [n][K][3] or None}.  frozen_masks: [n] uint32 (robot transformation `broken-...`);
+        terrains: per-robot (xs, ys) polylines as in eval_terrains."""
+        g = np.ascontiguousarray(genomes, dtype=np.float64)
+        if g.ndim != 2 or g.shape[1] != self.genome_len:
+            raise VsrIllegalArgument(VSR_EDIM, f"Wrong number of values: {self.genome_len} expected, {g.shape[-1]} found")
+        n = g.shape[0]
+        _, k_first, k_last = episode_steps(self.env.final_t, self.env.transient_t, self.env.dt)
+        K = k_last - k_first + 1
+        o = EvalOpts()
+        keep = []
+        if frozen_masks is not None:
+            fm = np.ascontiguousarray(frozen_masks, dtype=np.uint32)
+            if fm.shape != (n,):
+                raise VsrIllegalArgument(VSR_EINVAL, f"{n} frozen masks expected, {fm.shape} found")
+            keep.append(fm); o.frozen_masks = fm.ctypes.data
+        if terrains is not None:
+            if len(terrains) != n:
+                raise VsrIllegalArgument(VSR_EINVAL, f"{n} terrains expected, {len(terrains)} found")
+            off = np.zeros(n + 1, dtype=np.int32)
+            off[1:] = np.cumsum([len(t[0]) for t in terrains])
+            xs = np.ascontiguousarray(np.concatenate([np.asarray(t[0], dtype=np.float64) for t in terrains])) if n else np.zeros(1)
+            ys = np.ascontiguousarray(np.concatenate([np.asarray(t[1], dtype=np.float64) for t in terrains])) if n else np.zeros(1)
+            keep += [off, xs, ys]
+            o.terrain_x, o.terrain_y, o.terrain_off = xs.ctypes.data, ys.ctypes.data, off.ctypes.data
+        post = fps = cen = None
+        if posture_n:
+            post = np.zeros((n, posture_n * posture_n), dtype=np.uint8)
+            o.posture_n, o.posture_out = posture_n, post.ctypes.data
+        fps = [None, None]
+        for q in range(2):
+            if footprint_n[q]:
+                fps[q] = np.zeros((n, K), dtype=np.uint8)
+                o.footprint_n[q] = footprint_n[q]
+                o.footprints_out[q] = fps[q].ctypes.data
+        if centers:
+            cen = np.zeros((n, K, 3), dtype=np.float64)
+            o.centers_out = cen.ctypes.data
+        fit = np.empty(n, dtype=np.float64)
+        res = np.empty(n, dtype=RESULT_DTYPE)
+        check(lib().vsr_eval_ex(self._h, _ptr(g), n, C.byref(o), _ptr(fit), _ptr(res)), self._h)
+        return fit, res, {"posture": post, "footprints": fps, "centers": cen, "kept": K}
+
+    def stage_eval_opts(self, n: int, frozen_masks=None, terrains=None):
+        """vsr_stage_eval_opts: per-robot inputs of the next device-resident batches (eval_device, generation loop); n = 0 clears."""
+        if n == 0 or (frozen_masks is None and terrains is None):
+            check(lib().vsr_stage_eval_opts(self._h, 0, None), self._h)
+            return
+        o = EvalOpts()
+        keep = []
+        if frozen_masks is not None:
+            fm = np.ascontiguousarray(frozen_masks, dtype=np.uint32)
+            if fm.shape != (n,):
+                raise VsrIllegalArgument(VSR_EINVAL, f"{n} frozen masks expected, {fm.shape} found")
+            keep.append(fm); o.frozen_masks = fm.ctypes.data
+        if terrains is not None:
+            if len(terrains) != n:
+                raise VsrIllegalArgument(VSR_EINVAL, f"{n} terrains expected, {len(terrains)} found")
+            off = np.zeros(n + 1, dtype=np.int32)
+            off[1:] = np.cumsum([len(t[0]) for t in terrains])
+            xs = np.ascontiguousarray(np.concatenate([np.asarray(t[0], dtype=np.float64) for t in terrains]))
+            ys = np.ascontiguousarray(np.concatenate([np.asarray(t[1], dtype=np.float64) for t in terrains]))
+            keep += [off, xs, ys]
+            o.terrain_x, o.terrain_y, o.terrain_off = xs.ctypes.data, ys.ctypes.data, off.ctypes.data
+        check(lib().vsr_stage_eval_opts(self._h, n, C.byref(o)), self._h)
+
+    def broken_masks(self, ratio: float, seed: int, n: int) -> np.ndarray:
+        out = np.zeros(n, dtype=np.uint32)
+        check(lib().vsr_broken_masks(self._h, ratio, seed, n, _ptr(out)), self._h)
+        return out
+
+    def broken_masks_stream(self, ratio: float, state: "JavaRandomState", n: int) -> np.ndarray:
+        """broken_masks on a running java.util.Random (state.value is advanced)."""
+        out = np.zeros(n, dtype=np.uint32)
+        st = C.c_uint64(state.value)
+        check(lib().vsr_broken_masks_stream(self._h, ratio, C.byref(st), n, _ptr(out)), self._h)
+        state.value = st.value
+        return out
+
+    @property
+    def central_voxel(self) -> int:
+        return check(lib().vsr_central_voxel(self._h), self._h)
 
     def eval_into(self, genomes: np.ndarray, fitness_out: np.ndarray):
         """Zero-allocation variant for timing loops: genomes [n][G] float64 C-contiguous, fitness_out [n]."""
@@ -474,6 +572,35 @@ def episode_steps(final_t: float, transient_t: float, dt: float = 1.0 / 60.0):
     v = [C.c_int32() for _ in range(3)]
     check(lib().vsr_episode_steps(final_t, transient_t, dt, *[C.byref(x) for x in v]))
     return tuple(x.value for x in v)
+
+
+class JavaRandomState:
+    """Raw 48-bit LCG state of a java.util.Random shared by a run (`new Random(seed)`), advanced by the library calls that draw from it."""
+
+    def __init__(self, seed: int):
+        self.value = (seed ^ 0x5DEECE66D) & ((1 << 48) - 1)
+
+    def _next(self, bits: int) -> int:
+        self.value = (self.value * 0x5DEECE66D + 0xB) & ((1 << 48) - 1)
+        v = self.value >> (48 - bits)
+        return v - (1 << bits) if bits == 32 and v >= 1 << 31 else v
+
+    def next_double(self) -> float:
+        return ((self._next(26) << 27) + self._next(27)) * (1.0 / (1 << 53))
+
+    def next_int(self) -> int:
+        return self._next(32)
+
+
+def robot_transformation(name: str):
+    """RobotUtils.buildRobotTransformation name -> ("identity",) | ("broken", ratio, seed or None for `rnd`)."""
+    kind, ratio, seed, rnd = C.c_int32(), C.c_double(), C.c_int64(), C.c_int32()
+    rc = lib().vsr_robot_transformation(name.encode(), C.byref(kind), C.byref(ratio), C.byref(seed), C.byref(rnd))
+    if rc == VSR_EUNSUPPORTED:
+        raise VsrError(rc, f"robot transformation {name!r} is outside this build (malfunctions triggered during the episode)")
+    if rc:
+        raise VsrIllegalArgument(rc, f"Unknown transformation name: {name}")
+    return ("identity",) if kind.value == 0 else ("broken", ratio.value, None if rnd.value else seed.value)
 
 
 def java_random_ints(seed: int, bound: int, n: int) -> np.ndarray:

@@ -55,9 +55,42 @@ struct DeviceState {
   size_t centers_bytes = 0;
   double* cur_centers = nullptr; // non-null only while vsr_eval_centers enqueues
   bool timed = false;
+  // vsr_eval_ex: robot transformations and per-observation summaries
+  uint32_t* d_frozen = nullptr; size_t frozen_cap = 0;
+  unsigned int* d_post = nullptr; size_t post_cap = 0;       // [robots][64] posture counters
+  uint8_t* d_fp[2] = {nullptr, nullptr}; size_t fp_bytes[2] = {0, 0}; // [robots][K]
+  double* d_cen3 = nullptr; size_t cen3_bytes = 0;           // [robots][K][3]
+  bool obs_attr = false; // dynamic shared-memory opt-in of the observation kernel done on this device
+};
+
+// what one launch carries besides genomes -> fitness (vsr_eval_ex / vsr_eval_terrains)
+struct LaunchExtras {
+  bool robot_terrains = false;
+  double rt_ymax = 0;
+  const uint32_t* d_frozen = nullptr;
+  bool obs = false;
+  int post_n = 0, fp_n[2] = {0, 0};
+  unsigned int* d_post = nullptr;
+  uint8_t* d_fp[2] = {nullptr, nullptr};
+  double* d_cen3 = nullptr;
 };
 
 } // namespace
+
+// validated host-side view of the per-robot inputs of one batch (vsr_eval_ex: the caller's arrays; vsr_stage_eval_opts: owned copies)
+struct HostExtras {
+  int n = 0;
+  const uint32_t* frozen = nullptr;
+  const double *tx = nullptr, *ty = nullptr;
+  const int32_t* off = nullptr;
+  std::vector<double> base, place; // per robot: bottom of its ground body; placement shift relative to the context's terrain
+  double ymax = 0;
+  // owned storage (staging only)
+  std::vector<uint32_t> o_frozen;
+  std::vector<double> o_tx, o_ty;
+  std::vector<int32_t> o_off;
+  void clear() { *this = HostExtras(); }
+};
 
 struct vsr_ctx {
   vsr_env_desc env;
@@ -94,6 +127,8 @@ struct vsr_ctx {
   std::string err;
   int64_t launches = 0;
   double place_dx = 0, place_dy = 0; // initial placement on the context's own terrain
+  int central_vox = 0;               // BehaviorUtils.getCentralElement of the body grid (voxel order)
+  HostExtras staged;                 // vsr_stage_eval_opts: per-robot inputs of the next device-resident batches (n = 0: none)
 };
 
 namespace {
@@ -244,6 +279,16 @@ int finalize(vsr_ctx* ctx) {
       return (int8_t)ctx->vox_of_cell[ay * ctx->w + ax];
     };
     k.nb_l[v] = nb(x - 1, y); k.nb_r[v] = nb(x + 1, y); k.nb_d[v] = nb(x, y - 1); k.nb_u[v] = nb(x, y + 1);
+  }
+  { // BehaviorUtils.getCentralElement [U]: the voxel closest to the mean grid position, first minimum in grid order
+    double mx = 0, my = 0;
+    for (int v = 0; v < ctx->n_vox; v++) { mx += ctx->cell_of_vox[v] % ctx->w; my += ctx->cell_of_vox[v] / ctx->w; }
+    mx /= ctx->n_vox; my /= ctx->n_vox;
+    double best = INFINITY;
+    for (int v = 0; v < ctx->n_vox; v++) {
+      const double ddx = ctx->cell_of_vox[v] % ctx->w - mx, ddy = ctx->cell_of_vox[v] / ctx->w - my, dd = ddx * ddx + ddy * ddy;
+      if (dd < best) { best = dd; ctx->central_vox = v; }
+    }
   }
   // Locomotion.apply initial placement
   {
@@ -512,13 +557,26 @@ int ensure_energy(vsr_ctx* ctx, DeviceState& d, int cta_warps_total) {
 
 // enqueue the episode kernel for n robots whose genomes are at d_genomes (device)
 int enqueue(vsr_ctx* ctx, DeviceState& d, const double* d_genomes, size_t n, double* d_fitness, vsr_result* d_results,
-            cudaStream_t st, double* trv, double* trb, double* trc, int trace_steps, bool time_it, bool robot_terrains = false,
-            double rt_ymax = 0) {
+            cudaStream_t st, double* trv, double* trb, double* trc, int trace_steps, bool time_it, const LaunchExtras* x = nullptr) {
   if (n == 0) return VSR_OK;
   vsr::KParams k = ctx->kp;
   // traces (robot 0 only, parity tests) always use the context's default kernel
-  const LaunchPlan lp = trace_steps > 0 ? LaunchPlan{ctx->kernel, ctx->warps, (int)((((n + k.robots_per_warp - 1) / k.robots_per_warp) + ctx->warps - 1) / ctx->warps), ctx->smem_bytes}
-                                        : plan_for(ctx, n);
+  LaunchPlan lp = trace_steps > 0 ? LaunchPlan{ctx->kernel, ctx->warps, (int)((((n + k.robots_per_warp - 1) / k.robots_per_warp) + ctx->warps - 1) / ctx->warps), ctx->smem_bytes}
+                                  : plan_for(ctx, n);
+  if (x && x->obs) {
+    // the observation build: FP32 = the flexible 8-warp shape at 255 registers, FP64 = the parity build's shape; spread over the SMs
+    const size_t robot_warps = (n + k.robots_per_warp - 1) / k.robots_per_warp;
+    int maxw = ctx->env.precision == 64 ? kWarps64 : 8;
+    while (maxw > 1 && (size_t)maxw * ctx->smem_warp + 1024 > 227 * 1024) maxw--;
+    lp.kernel = vsr_internal::kernel_obs(ctx->env.precision, kernel_ctrl(ctx->kind));
+    lp.warps = (int)std::min<size_t>((size_t)maxw, std::max<size_t>(1, (robot_warps + ctx->n_sm - 1) / ctx->n_sm));
+    lp.grid = (int)((robot_warps + lp.warps - 1) / lp.warps);
+    lp.smem = ctx->smem_warp * lp.warps + 128;
+    if (!d.obs_attr) {
+      CK(cudaFuncSetAttribute(lp.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      d.obs_attr = true;
+    }
+  }
   const int grid = lp.grid;
   int rc = ensure_hist(ctx, d, grid * lp.warps);
   if (rc) return rc;
@@ -531,7 +589,14 @@ int enqueue(vsr_ctx* ctx, DeviceState& d, const double* d_genomes, size_t n, dou
   k.genomes = d_genomes; k.fitness = d_fitness; k.results = d_results; k.n_robots = (int)n;
   k.centers = d.cur_centers;
   k.overflow_count = d.d_ovf;
-  if (robot_terrains) { k.tx = d.d_rtx; k.ty = d.d_rty; k.toff = d.d_roff; k.tbase = d.d_rbase; k.tplace = d.d_rplace; k.ty_max = rt_ymax; }
+  if (x && x->robot_terrains) { k.tx = d.d_rtx; k.ty = d.d_rty; k.toff = d.d_roff; k.tbase = d.d_rbase; k.tplace = d.d_rplace; k.ty_max = x->rt_ymax; }
+  if (x) {
+    k.frozen = x->d_frozen;
+    if (x->obs) {
+      k.post_n = x->post_n; k.fp_n0 = x->fp_n[0]; k.fp_n1 = x->fp_n[1]; k.central_vox = ctx->central_vox;
+      k.post_cnt = x->d_post; k.footprints0 = x->d_fp[0]; k.footprints1 = x->d_fp[1]; k.centers3 = x->d_cen3;
+    }
+  }
   k.tr_vertices = trv; k.tr_bodies = trb; k.tr_ctrl = trc; k.trace_steps = trace_steps;
   if (time_it) CK(cudaEventRecord(d.ev0, st));
   void* args[] = {&k};
@@ -540,6 +605,77 @@ int enqueue(vsr_ctx* ctx, DeviceState& d, const double* d_genomes, size_t n, dou
   CK(cudaGetLastError());
   if (time_it) { CK(cudaEventRecord(d.ev1, st)); d.timed = true; }
   ctx->launches++;
+  return VSR_OK;
+}
+
+// validate the per-robot inputs of a batch of n robots and derive what the kernel needs per robot (ground bottom, placement shift)
+int build_host_extras(vsr_ctx* ctx, int n, const vsr_eval_opts& o, HostExtras& h) {
+  h.clear();
+  h.n = n;
+  const bool terrains = o.terrain_x || o.terrain_y || o.terrain_off;
+  if (terrains && (!o.terrain_x || !o.terrain_y || !o.terrain_off)) return fail(ctx, VSR_EINVAL, "per-robot terrains need terrain_x, terrain_y and terrain_off");
+  if (o.frozen_masks) {
+    if (ctx->n_vox < 32)
+      for (int i = 0; i < n; i++)
+        if (o.frozen_masks[i] >> ctx->n_vox) return fail(ctx, VSR_EINVAL, "frozen mask names a voxel the body does not have");
+    h.frozen = o.frozen_masks;
+  }
+  if (terrains) {
+    h.base.resize((size_t)n); h.place.resize((size_t)2 * n);
+    h.ymax = -INFINITY;
+    if (n > 0 && o.terrain_off[0] != 0) return fail(ctx, VSR_EINVAL, "terrain_off[0] must be 0");
+    for (int i = 0; i < n; i++) {
+      const int a = o.terrain_off[i], b = o.terrain_off[i + 1], nt = b - a;
+      if (nt < 2 || nt > 16383) return fail(ctx, VSR_EINVAL, "every terrain needs 2..16383 vertices");
+      double ymin = INFINITY;
+      for (int j = a; j < b; j++) {
+        if (j > a && !(o.terrain_x[j] > o.terrain_x[j - 1])) return fail(ctx, VSR_EINVAL, "terrain xs must be strictly increasing");
+        ymin = std::fmin(ymin, o.terrain_y[j]); h.ymax = std::fmax(h.ymax, o.terrain_y[j]);
+      }
+      h.base[i] = ymin - ctx->env.ground_thickness;
+      double dx, dy;
+      if (!placement(ctx, o.terrain_x + a, o.terrain_y + a, nt, &dx, &dy)) return fail(ctx, VSR_EINVAL, "robot is placed outside the terrain");
+      h.place[2 * (size_t)i] = dx - ctx->place_dx; h.place[2 * (size_t)i + 1] = dy - ctx->place_dy;
+    }
+    h.tx = o.terrain_x; h.ty = o.terrain_y; h.off = o.terrain_off;
+  }
+  return VSR_OK;
+}
+
+// upload robots [lo, hi) of the batch's per-robot inputs to device d and point the launch at them (small synchronous copies)
+int upload_extras(vsr_ctx* ctx, DeviceState& d, const HostExtras& h, size_t lo, size_t hi, LaunchExtras& x) {
+  const size_t cnt = hi - lo;
+  if (h.tx) {
+    const size_t v0 = (size_t)h.off[lo], nv = (size_t)h.off[hi] - v0;
+    if (nv > d.rt_vertices) {
+      cudaFree(d.d_rtx); cudaFree(d.d_rty); d.d_rtx = d.d_rty = nullptr; d.rt_vertices = 0;
+      CK(cudaMalloc(&d.d_rtx, nv * sizeof(double))); CK(cudaMalloc(&d.d_rty, nv * sizeof(double)));
+      d.rt_vertices = nv;
+    }
+    if (cnt > d.rt_robots) {
+      cudaFree(d.d_rbase); cudaFree(d.d_rplace); cudaFree(d.d_roff); d.d_rbase = d.d_rplace = nullptr; d.d_roff = nullptr; d.rt_robots = 0;
+      CK(cudaMalloc(&d.d_rbase, cnt * sizeof(double))); CK(cudaMalloc(&d.d_rplace, 2 * cnt * sizeof(double)));
+      CK(cudaMalloc(&d.d_roff, (cnt + 1) * sizeof(int32_t)));
+      d.rt_robots = cnt;
+    }
+    std::vector<int32_t> off(cnt + 1);
+    for (size_t r = 0; r <= cnt; r++) off[r] = h.off[lo + r] - (int32_t)v0;
+    CK(cudaMemcpy(d.d_rtx, h.tx + v0, nv * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d.d_rty, h.ty + v0, nv * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d.d_rbase, h.base.data() + lo, cnt * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d.d_rplace, h.place.data() + 2 * lo, 2 * cnt * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d.d_roff, off.data(), (cnt + 1) * sizeof(int32_t), cudaMemcpyHostToDevice));
+    x.robot_terrains = true; x.rt_ymax = h.ymax;
+  }
+  if (h.frozen) {
+    if (cnt > d.frozen_cap) {
+      cudaFree(d.d_frozen); d.d_frozen = nullptr; d.frozen_cap = 0;
+      CK(cudaMalloc(&d.d_frozen, cnt * sizeof(uint32_t)));
+      d.frozen_cap = cnt;
+    }
+    CK(cudaMemcpy(d.d_frozen, h.frozen + lo, cnt * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    x.d_frozen = d.d_frozen;
+  }
   return VSR_OK;
 }
 
@@ -557,6 +693,9 @@ int eval_range(vsr_ctx* ctx, const double* d_genomes, size_t lo, size_t hi, doub
   if (hi <= lo) return VSR_OK;
   const size_t G = (size_t)ctx->kp.genome_len, nd = ctx->devs.size(), cnt = hi - lo, per = (cnt + nd - 1) / nd;
   DeviceState& d0 = ctx->devs[0];
+  // per-robot inputs staged for this batch (vsr_stage_eval_opts): robot i of the batch uses entry i
+  const HostExtras* hx = ctx->staged.n > 0 ? &ctx->staged : nullptr;
+  if (hx && hi > (size_t)hx->n) return fail(ctx, VSR_EINVAL, "the staged per-robot inputs cover fewer robots than the batch evaluates");
   cudaEvent_t fork = nullptr;
   if (nd > 1) {
     // the genomes are produced on `st`: the other devices' streams wait for them
@@ -573,7 +712,9 @@ int eval_range(vsr_ctx* ctx, const double* d_genomes, size_t lo, size_t hi, doub
     CK(cudaSetDevice(d.dev));
     CK(cudaStreamWaitEvent(d.stream, fork, 0));
     CK(cudaMemcpyPeerAsync(d.d_genomes, d.dev, d_genomes + a * G, d0.dev, (b - a) * G * sizeof(double), d.stream));
-    rc = enqueue(ctx, d, d.d_genomes, b - a, d.d_fitness, nullptr, d.stream, nullptr, nullptr, nullptr, 0, false);
+    LaunchExtras x;
+    if (hx) { rc = upload_extras(ctx, d, *hx, a, b, x); if (rc) return rc; }
+    rc = enqueue(ctx, d, d.d_genomes, b - a, d.d_fitness, nullptr, d.stream, nullptr, nullptr, nullptr, 0, false, hx ? &x : nullptr);
     if (rc) return rc;
     CK(cudaMemcpyPeerAsync(d_fitness + a, d0.dev, d.d_fitness, d.dev, (b - a) * sizeof(double), d.stream));
     CK(cudaEventRecord(d.ev_join, d.stream));
@@ -581,7 +722,9 @@ int eval_range(vsr_ctx* ctx, const double* d_genomes, size_t lo, size_t hi, doub
   CK(cudaSetDevice(d0.dev));
   {
     const size_t b = std::min(hi, lo + per);
-    int rc = enqueue(ctx, d0, d_genomes + lo * G, b - lo, d_fitness + lo, nullptr, st, nullptr, nullptr, nullptr, 0, true);
+    LaunchExtras x;
+    if (hx) { int rc = upload_extras(ctx, d0, *hx, lo, b, x); if (rc) return rc; }
+    int rc = enqueue(ctx, d0, d_genomes + lo * G, b - lo, d_fitness + lo, nullptr, st, nullptr, nullptr, nullptr, 0, true, hx ? &x : nullptr);
     if (rc) return rc;
   }
   for (size_t i = 1; i < nd; i++) {
@@ -674,6 +817,7 @@ void vsr_ctx_destroy(vsr_ctx* c) {
     cudaFree(d.d_tx); cudaFree(d.d_ty); cudaFree(d.d_win); cudaFree(d.d_hist); cudaFree(d.d_noise); cudaFree(d.d_energy);
     cudaFree(d.d_rtx); cudaFree(d.d_rty); cudaFree(d.d_rbase); cudaFree(d.d_rplace); cudaFree(d.d_roff);
     cudaFree(d.d_genomes); cudaFree(d.d_fitness); cudaFree(d.d_results); cudaFree(d.d_centers); cudaFree(d.d_ovf);
+    cudaFree(d.d_frozen); cudaFree(d.d_post); cudaFree(d.d_fp[0]); cudaFree(d.d_fp[1]); cudaFree(d.d_cen3);
     cudaFreeHost(d.h_genomes); cudaFreeHost(d.h_fitness); cudaFreeHost(d.h_results);
     if (d.ev0) cudaEventDestroy(d.ev0);
     if (d.ev1) cudaEventDestroy(d.ev1);
@@ -833,29 +977,36 @@ int vsr_eval_centers(vsr_ctx* ctx, const double* genomes, int32_t n, double* fit
 int vsr_eval_terrains(vsr_ctx* ctx, const double* genomes, int32_t n, const double* terrain_x, const double* terrain_y,
                       const int32_t* terrain_off, double* fitness_out, vsr_result* results_out) {
   if (!ctx) return VSR_EINVAL;
-  if (!ctx->ready) return fail(ctx, VSR_ESTATE, "body and controller must be set before vsr_eval_terrains");
-  if (n < 0 || (n > 0 && (!genomes || !fitness_out || !terrain_x || !terrain_y || !terrain_off))) return fail(ctx, VSR_EINVAL, "bad vsr_eval_terrains arguments");
+  if (n > 0 && (!terrain_x || !terrain_y || !terrain_off)) return fail(ctx, VSR_EINVAL, "bad vsr_eval_terrains arguments");
+  vsr_eval_opts o;
+  std::memset(&o, 0, sizeof(o));
+  o.terrain_x = terrain_x; o.terrain_y = terrain_y; o.terrain_off = terrain_off;
+  return vsr_eval_ex(ctx, genomes, n, &o, fitness_out, results_out);
+}
+
+int vsr_eval_ex(vsr_ctx* ctx, const double* genomes, int32_t n, const vsr_eval_opts* opts, double* fitness_out, vsr_result* results_out) {
+  if (!ctx) return VSR_EINVAL;
+  if (!ctx->ready) return fail(ctx, VSR_ESTATE, "body and controller must be set before vsr_eval_ex");
+  if (n < 0 || (n > 0 && (!genomes || !fitness_out))) return fail(ctx, VSR_EINVAL, "bad vsr_eval_ex arguments");
+  vsr_eval_opts none;
+  std::memset(&none, 0, sizeof(none));
+  const vsr_eval_opts& o = opts ? *opts : none;
+  if (o.posture_n < 0 || o.posture_n > 8) return fail(ctx, VSR_EUNSUPPORTED, "posture grids of side 1..8 are supported");
+  for (int q = 0; q < 2; q++)
+    if (o.footprint_n[q] < 0 || o.footprint_n[q] > 8) return fail(ctx, VSR_EUNSUPPORTED, "footprints of 1..8 segments are supported");
+  if ((o.posture_n > 0) != (o.posture_out != nullptr)) return fail(ctx, VSR_EINVAL, "posture_n and posture_out go together");
+  for (int q = 0; q < 2; q++)
+    if ((o.footprint_n[q] > 0) != (o.footprints_out[q] != nullptr)) return fail(ctx, VSR_EINVAL, "footprint_n and footprints_out go together");
   if (n == 0) return VSR_OK;
+  const bool obs = o.posture_n > 0 || o.footprint_n[0] > 0 || o.footprint_n[1] > 0 || o.centers_out != nullptr;
   const int G = ctx->kp.genome_len;
-  // per robot: polyline checks, bottom of its ground body, placement shift relative to the context's terrain
-  std::vector<double> base((size_t)n), place((size_t)2 * n);
-  double ymax = -INFINITY;
-  if (terrain_off[0] != 0) return fail(ctx, VSR_EINVAL, "terrain_off[0] must be 0");
-  for (int i = 0; i < n; i++) {
-    const int a = terrain_off[i], b = terrain_off[i + 1], nt = b - a;
-    if (nt < 2 || nt > 16383) return fail(ctx, VSR_EINVAL, "every terrain needs 2..16383 vertices");
-    double ymin = INFINITY;
-    for (int j = a; j < b; j++) {
-      if (j > a && !(terrain_x[j] > terrain_x[j - 1])) return fail(ctx, VSR_EINVAL, "terrain xs must be strictly increasing");
-      ymin = std::fmin(ymin, terrain_y[j]); ymax = std::fmax(ymax, terrain_y[j]);
-    }
-    base[i] = ymin - ctx->env.ground_thickness;
-    double dx, dy;
-    if (!placement(ctx, terrain_x + a, terrain_y + a, nt, &dx, &dy)) return fail(ctx, VSR_EINVAL, "robot is placed outside the terrain");
-    place[2 * (size_t)i] = dx - ctx->place_dx; place[2 * (size_t)i + 1] = dy - ctx->place_dy;
+  const size_t K = (size_t)(ctx->kp.k_last - ctx->kp.k_first + 1), P2 = (size_t)o.posture_n * o.posture_n;
+  HostExtras hx;
+  {
+    int rc = build_host_extras(ctx, n, o, hx);
+    if (rc) return rc;
   }
   const size_t nd = ctx->devs.size(), per = ((size_t)n + nd - 1) / nd;
-  std::vector<int32_t> off;
   for (size_t i = 0; i < nd; i++) {
     DeviceState& d = ctx->devs[i];
     size_t lo = std::min((size_t)n, i * per), hi = std::min((size_t)n, lo + per), cnt = hi - lo;
@@ -863,33 +1014,47 @@ int vsr_eval_terrains(vsr_ctx* ctx, const double* genomes, int32_t n, const doub
     int rc = ensure_capacity(ctx, d, cnt);
     if (rc) return rc;
     CK(cudaSetDevice(d.dev));
-    const size_t v0 = (size_t)terrain_off[lo], nv = (size_t)terrain_off[hi] - v0;
-    if (nv > d.rt_vertices) {
-      cudaFree(d.d_rtx); cudaFree(d.d_rty); d.d_rtx = d.d_rty = nullptr; d.rt_vertices = 0;
-      CK(cudaMalloc(&d.d_rtx, nv * sizeof(double))); CK(cudaMalloc(&d.d_rty, nv * sizeof(double)));
-      d.rt_vertices = nv;
+    LaunchExtras x;
+    rc = upload_extras(ctx, d, hx, lo, hi, x);
+    if (rc) return rc;
+    if (obs) {
+      x.obs = true; x.post_n = o.posture_n; x.fp_n[0] = o.footprint_n[0]; x.fp_n[1] = o.footprint_n[1];
+      if (o.posture_n > 0) {
+        if (cnt > d.post_cap) {
+          cudaFree(d.d_post); d.d_post = nullptr; d.post_cap = 0;
+          CK(cudaMalloc(&d.d_post, cnt * 64 * sizeof(unsigned int)));
+          d.post_cap = cnt;
+        }
+        CK(cudaMemsetAsync(d.d_post, 0, cnt * 64 * sizeof(unsigned int), d.stream));
+        x.d_post = d.d_post;
+      }
+      for (int q = 0; q < 2; q++)
+        if (o.footprint_n[q] > 0) {
+          if (cnt * K > d.fp_bytes[q]) {
+            cudaFree(d.d_fp[q]); d.d_fp[q] = nullptr; d.fp_bytes[q] = 0;
+            if (cudaMalloc(&d.d_fp[q], cnt * K) != cudaSuccess) { cudaGetLastError(); return fail(ctx, VSR_ENOMEM, "footprint series do not fit the device"); }
+            d.fp_bytes[q] = cnt * K;
+          }
+          x.d_fp[q] = d.d_fp[q];
+        }
+      if (o.centers_out) {
+        const size_t bytes = cnt * K * 3 * sizeof(double);
+        if (bytes > d.cen3_bytes) {
+          cudaFree(d.d_cen3); d.d_cen3 = nullptr; d.cen3_bytes = 0;
+          if (cudaMalloc(&d.d_cen3, bytes) != cudaSuccess) { cudaGetLastError(); return fail(ctx, VSR_ENOMEM, "centre trajectories do not fit the device"); }
+          d.cen3_bytes = bytes;
+        }
+        x.d_cen3 = d.d_cen3;
+      }
     }
-    if (cnt > d.rt_robots) {
-      cudaFree(d.d_rbase); cudaFree(d.d_rplace); cudaFree(d.d_roff); d.d_rbase = d.d_rplace = nullptr; d.d_roff = nullptr; d.rt_robots = 0;
-      CK(cudaMalloc(&d.d_rbase, cnt * sizeof(double))); CK(cudaMalloc(&d.d_rplace, 2 * cnt * sizeof(double)));
-      CK(cudaMalloc(&d.d_roff, (cnt + 1) * sizeof(int32_t)));
-      d.rt_robots = cnt;
-    }
-    off.resize(cnt + 1);
-    for (size_t r = 0; r <= cnt; r++) off[r] = terrain_off[lo + r] - (int32_t)v0;
-    // small synchronous uploads (pageable sources); the genomes follow on the stream
-    CK(cudaMemcpy(d.d_rtx, terrain_x + v0, nv * sizeof(double), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(d.d_rty, terrain_y + v0, nv * sizeof(double), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(d.d_rbase, base.data() + lo, cnt * sizeof(double), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(d.d_rplace, place.data() + 2 * lo, 2 * cnt * sizeof(double), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(d.d_roff, off.data(), (cnt + 1) * sizeof(int32_t), cudaMemcpyHostToDevice));
     std::memcpy(d.h_genomes, genomes + lo * G, cnt * G * sizeof(double));
     CK(cudaMemcpyAsync(d.d_genomes, d.h_genomes, cnt * G * sizeof(double), cudaMemcpyHostToDevice, d.stream));
-    rc = enqueue(ctx, d, d.d_genomes, cnt, d.d_fitness, results_out ? d.d_results : nullptr, d.stream, nullptr, nullptr, nullptr, 0, i == 0, true, ymax);
+    rc = enqueue(ctx, d, d.d_genomes, cnt, d.d_fitness, results_out ? d.d_results : nullptr, d.stream, nullptr, nullptr, nullptr, 0, i == 0, &x);
     if (rc) return rc;
     CK(cudaMemcpyAsync(d.h_fitness, d.d_fitness, cnt * sizeof(double), cudaMemcpyDeviceToHost, d.stream));
     if (results_out) CK(cudaMemcpyAsync(d.h_results, d.d_results, cnt * sizeof(vsr_result), cudaMemcpyDeviceToHost, d.stream));
   }
+  std::vector<unsigned int> cnts;
   for (size_t i = 0; i < nd; i++) {
     DeviceState& d = ctx->devs[i];
     size_t lo = std::min((size_t)n, i * per), hi = std::min((size_t)n, lo + per), cnt = hi - lo;
@@ -898,9 +1063,45 @@ int vsr_eval_terrains(vsr_ctx* ctx, const double* genomes, int32_t n, const doub
     CK(cudaStreamSynchronize(d.stream));
     std::memcpy(fitness_out + lo, d.h_fitness, cnt * sizeof(double));
     if (results_out) std::memcpy(results_out + lo, d.h_results, cnt * sizeof(vsr_result));
+    if (o.posture_n > 0) { // average posture: cells set in MORE than half of the kept observations
+      cnts.resize(cnt * 64);
+      CK(cudaMemcpy(cnts.data(), d.d_post, cnt * 64 * sizeof(unsigned int), cudaMemcpyDeviceToHost));
+      for (size_t r = 0; r < cnt; r++)
+        for (size_t c = 0; c < P2; c++) o.posture_out[(lo + r) * P2 + c] = (uint8_t)(2 * (size_t)cnts[r * 64 + c] > K);
+    }
+    for (int q = 0; q < 2; q++)
+      if (o.footprint_n[q] > 0) CK(cudaMemcpy(o.footprints_out[q] + lo * K, d.d_fp[q], cnt * K, cudaMemcpyDeviceToHost));
+    if (o.centers_out) CK(cudaMemcpy(o.centers_out + lo * K * 3, d.d_cen3, cnt * K * 3 * sizeof(double), cudaMemcpyDeviceToHost));
   }
   return VSR_OK;
 }
+
+int vsr_stage_eval_opts(vsr_ctx* ctx, int32_t n, const vsr_eval_opts* opts) {
+  if (!ctx) return VSR_EINVAL;
+  if (!ctx->ready) return fail(ctx, VSR_ESTATE, "body and controller must be set before vsr_stage_eval_opts");
+  if (n < 0) return fail(ctx, VSR_EINVAL, "negative batch size");
+  if (n == 0 || !opts) { ctx->staged.clear(); return VSR_OK; }
+  if (opts->posture_n || opts->footprint_n[0] || opts->footprint_n[1] || opts->centers_out)
+    return fail(ctx, VSR_EUNSUPPORTED, "observation requests cannot be staged: use vsr_eval_ex");
+  HostExtras h;
+  int rc = build_host_extras(ctx, n, *opts, h);
+  if (rc) return rc;
+  // own the data: the caller's arrays may go away before the device-resident batch runs
+  if (h.frozen) { h.o_frozen.assign(h.frozen, h.frozen + n); }
+  if (h.tx) {
+    const size_t nv = (size_t)h.off[n];
+    h.o_tx.assign(h.tx, h.tx + nv); h.o_ty.assign(h.ty, h.ty + nv); h.o_off.assign(h.off, h.off + n + 1);
+  }
+  ctx->staged = std::move(h);
+  HostExtras& t = ctx->staged;
+  t.frozen = t.o_frozen.empty() ? nullptr : t.o_frozen.data();
+  t.tx = t.o_tx.empty() ? nullptr : t.o_tx.data(); t.ty = t.o_ty.empty() ? nullptr : t.o_ty.data();
+  t.off = t.o_off.empty() ? nullptr : t.o_off.data();
+  if (!t.frozen && !t.tx) t.clear();
+  return VSR_OK;
+}
+
+int vsr_central_voxel(const vsr_ctx* ctx) { return ctx && ctx->ready ? ctx->central_vox : VSR_ESTATE; }
 
 int vsr_eval_device(vsr_ctx* ctx, const double* d_genomes, int32_t n, double* d_fitness, vsr_result* d_results, void* stream) {
   if (!ctx) return VSR_EINVAL;
@@ -908,7 +1109,14 @@ int vsr_eval_device(vsr_ctx* ctx, const double* d_genomes, int32_t n, double* d_
   if (n < 0 || (n > 0 && (!d_genomes || !d_fitness))) return fail(ctx, VSR_EINVAL, "bad vsr_eval_device arguments");
   DeviceState& d = ctx->devs[0];
   CK(cudaSetDevice(d.dev));
-  return enqueue(ctx, d, d_genomes, (size_t)n, d_fitness, d_results, (cudaStream_t)stream, nullptr, nullptr, nullptr, 0, true);
+  LaunchExtras x;
+  if (ctx->staged.n > 0 && n > 0) {
+    if (n > ctx->staged.n) return fail(ctx, VSR_EINVAL, "the staged per-robot inputs cover fewer robots than the batch evaluates");
+    int rc = upload_extras(ctx, d, ctx->staged, 0, (size_t)n, x);
+    if (rc) return rc;
+  }
+  return enqueue(ctx, d, d_genomes, (size_t)n, d_fitness, d_results, (cudaStream_t)stream, nullptr, nullptr, nullptr, 0, true,
+                 ctx->staged.n > 0 ? &x : nullptr);
 }
 
 int vsr_trace(vsr_ctx* ctx, const double* genome, int32_t n_steps, double* vertices_out, double* bodies_out, double* ctrl_out,

@@ -27,4 +27,5 @@ VSR_HIDDEN const void* kernel_f32_s3(int ctrl, int full_scaff);
 VSR_HIDDEN const void* kernel_f32_s3_area(void);
 VSR_HIDDEN const void* kernel_f32_s2_area(void);
 VSR_HIDDEN const void* kernel_f64(int ctrl);
+VSR_HIDDEN const void* kernel_obs(int precision, int ctrl); // per-observation summaries (vsr_eval_observed)
 } // namespace vsr_internal

@@ -115,6 +115,15 @@ struct KParams {
   double* centers;       // optional [n_robots][k_last - k_first + 1][2]: robot centre (x, y) at every kept observation (vsr_eval_centers)
   void* energy;          // V4<R>[total lanes]: per-voxel energy accumulators (sum f^2 dt, sum |da|, sum |d(a^2)|, last a); used only with results
   int n_robots;
+  // robot transformation `broken-<ratio>-<seed>` (RobotUtils.buildRobotTransformation, Starter.java:126,428): bit v of frozen[robot] =
+  // the actuator of voxel v is frozen at 0 from the first step (BreakableVoxel, ACTUATOR FROZEN, trigger TIME >= 0); NULL = identity
+  const uint32_t* frozen;
+  // per-observation summaries (OBS builds only; vsr_eval_observed): average posture counters [n_robots][64], footprints
+  // [n_robots][K] bytes for up to two segment counts, centre trajectory [n_robots][K][3] = (x, y, angle of the central voxel)
+  int post_n, fp_n0, fp_n1, central_vox;
+  unsigned int* post_cnt;
+  uint8_t *footprints0, *footprints1;
+  double* centers3;
   // trace (robot 0 only)
   double *tr_vertices, *tr_bodies, *tr_ctrl;
   int trace_steps;
@@ -411,7 +420,8 @@ __device__ __forceinline__ int collide_box_top(R x1, R y1, R pnx, R pny, R bcx, 
 // ------------------------------------------------------------------------------------------------
 // SCAFF >= 0: the scaffolding mask is a compile-time constant (0xF, the Voxel default: no branch per spring); -1: read from P
 // SENS: 0 = generic sensor loop; 1 = exactly one soft-normalised, non-averaged AreaRatio sensor (optionally Noisy)
-template <class R, int CTRL, int WARPS, int MINB, int SCAFF = -1, int SENS = 0>
+// OBS: 1 = the build that also produces the per-observation summaries of vsr_eval_observed (posture, footprints, centre + angle)
+template <class R, int CTRL, int WARPS, int MINB, int SCAFF = -1, int SENS = 0, int OBS = 0>
 __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __grid_constant__ KParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -562,6 +572,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
   for (int i = 0; i < P.n_avg; i++) { savg[i * 32 + lane] = 0; savg_cnt[i * 32 + lane] = 0; }
   int sig_par = 0;
   R ctrl_f = 0;
+  const bool frozen = P.frozen != nullptr && valid && ((__ldg(&P.frozen[robot]) >> v) & 1u);
 
   auto ld4 = [](const R* q) -> V4<R> { return *reinterpret_cast<const V4<R>*>(q); };
   auto st4 = [](R* q, const V4<R>& v) { *reinterpret_cast<V4<R>*>(q) = v; };
@@ -1529,7 +1540,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
       }
     }
     PHASE_SYNC(1024)
-    // Voxel.applyForce(f), ForceMethod.DISTANCE
+    // Voxel.applyForce(f), ForceMethod.DISTANCE (a frozen actuator applies its last force before freezing: 0)
+    if (frozen) f = 0;
     if (M<R>::abs_(f) > R(1)) f = f > 0 ? R(1) : R(-1);
     ctrl_f = f;
 #pragma unroll
@@ -1595,6 +1607,85 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
             r.control_energy = en0; r.area_ratio_abs = en1; r.area_ratio_sq = en2; r.reserved = 0;
             P.results[robot] = r;
           }
+        }
+      }
+    }
+    // ---- per-observation summaries (OBS builds; BehaviorUtils of 2dhmsr [U], restated in oracle/vsr_oracle.c) ----------------
+    if (OBS && step >= P.k_first && step <= P.k_last) {
+      const unsigned robot_mask = lane_used ? (((L >= 32) ? FULL : ((1u << L) - 1u)) << base_lane) : (1u << lane);
+      // voxel polygon relative to the origin of the robot's first voxel (origins differ by integers: exact in FP32)
+      const R oxr = __shfl_sync(FULL, ox, base_lane & 31), oyr = __shfl_sync(FULL, oy, base_lane & 31);
+      R rx[4], ry[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) { rx[k] = qx[k] + (ox - oxr); ry[k] = qy[k] + (oy - oyr); }
+      const R vminx = M<R>::min_(M<R>::min_(rx[0], rx[1]), M<R>::min_(rx[2], rx[3])), vmaxx = M<R>::max_(M<R>::max_(rx[0], rx[1]), M<R>::max_(rx[2], rx[3]));
+      const R vminy = M<R>::min_(M<R>::min_(ry[0], ry[1]), M<R>::min_(ry[2], ry[3])), vmaxy = M<R>::max_(M<R>::max_(ry[0], ry[1]), M<R>::max_(ry[2], ry[3]));
+      R minx = vminx, maxx = vmaxx, miny = vminy, maxy = vmaxy;
+      for (int j = 0; j < L; j++) {
+        const int src = (base_lane + j) & 31;
+        minx = M<R>::min_(minx, __shfl_sync(FULL, vminx, src)); maxx = M<R>::max_(maxx, __shfl_sync(FULL, vmaxx, src));
+        miny = M<R>::min_(miny, __shfl_sync(FULL, vminy, src)); maxy = M<R>::max_(maxy, __shfl_sync(FULL, vmaxy, src));
+      }
+      const int ko = step - P.k_first, K = P.k_last - P.k_first + 1;
+      // BehaviorUtils.computeFootprint(polies, n): x-range of every touching voxel on n segments of the robot's x-extent
+#pragma unroll
+      for (int q = 0; q < 2; q++) {
+        const int n = q == 0 ? P.fp_n0 : P.fp_n1;
+        uint8_t* dst = q == 0 ? P.footprints0 : P.footprints1;
+        if (n <= 0 || dst == nullptr) continue;
+        unsigned bits = 0;
+        if (valid && touching) {
+          const R sc = R(n - 1) / (maxx - minx);
+          int i0 = (int)floor((double)((vminx - minx) * sc + R(0.5))), i1 = (int)floor((double)((vmaxx - minx) * sc + R(0.5)));
+          i0 = i0 < 0 ? 0 : i0; i1 = i1 > n - 1 ? n - 1 : i1;
+          for (int x = i0; x <= i1; x++) bits |= 1u << x;
+        }
+        bits = __reduce_or_sync(robot_mask, bits);
+        if (valid && v == 0) dst[(size_t)robot * K + ko] = (uint8_t)bits;
+      }
+      // BehaviorUtils.computePosture(polies, n): cells of the squared bounding box whose centre lies inside a voxel polygon
+      if (P.post_n > 0) {
+        const int n = P.post_n;
+        R bx0 = minx, bx1 = maxx, by0 = miny, by1 = maxy;
+        const R wdt = bx1 - bx0, hgt = by1 - by0;
+        if (hgt < wdt) { const R d = wdt - hgt; by0 -= d / 2; by1 += d / 2; }
+        else if (hgt > wdt) { const R d = hgt - wdt; bx0 -= d / 2; bx1 += d / 2; }
+        const R side = bx1 - bx0;
+        unsigned lo = 0, hi = 0;
+        if (valid) {
+          for (int iy = 0; iy < n; iy++) {
+            const R py = by0 + (R(iy) + R(0.5)) / R(n) * side;
+            if (py < vminy || py > vmaxy) continue;
+            for (int ix = 0; ix < n; ix++) {
+              const R px = bx0 + (R(ix) + R(0.5)) / R(n) * side;
+              if (px < vminx || px > vmaxx) continue;
+              bool in = false;
+#pragma unroll
+              for (int i = 0; i < 4; i++) {
+                const int j = (i + 3) & 3;
+                if (((ry[i] > py) != (ry[j] > py)) && (px < (rx[j] - rx[i]) * (py - ry[i]) / (ry[j] - ry[i]) + rx[i])) in = !in;
+              }
+              const int c = iy * n + ix;
+              if (in) { if (c < 32) lo |= 1u << c; else hi |= 1u << (c - 32); }
+            }
+          }
+        }
+        lo = __reduce_or_sync(robot_mask, lo); hi = __reduce_or_sync(robot_mask, hi);
+        if (valid)
+          for (int c = v; c < n * n; c += L)
+            if ((c < 32 ? (lo >> c) : (hi >> (c - 32))) & 1u) atomicAdd(&P.post_cnt[(size_t)robot * 64 + c], 1u);
+      }
+      if (P.centers3 != nullptr) {
+        const double cxv = (double)ox + (double)(R(0.25) * (qx[0] + qx[1] + qx[2] + qx[3]));
+        const double cyv = (double)oy + (double)(R(0.25) * (qy[0] + qy[1] + qy[2] + qy[3]));
+        // VoxelPoly.getAngle() of the central voxel: mean direction of the polygon's upper and lower sides
+        const double ang = (double)((M<R>::atan2_(qy[1] - qy[0], qx[1] - qx[0]) + M<R>::atan2_(qy[2] - qy[3], qx[2] - qx[3])) * R(0.5));
+        double sx = 0, sy = 0;
+        for (int j = 0; j < L; j++) { sx += __shfl_sync(FULL, cxv, (base_lane + j) & 31); sy += __shfl_sync(FULL, cyv, (base_lane + j) & 31); }
+        const double ca = __shfl_sync(FULL, ang, (base_lane + P.central_vox) & 31);
+        if (valid && v == 0) {
+          double* c = P.centers3 + ((size_t)robot * K + ko) * 3;
+          c[0] = sx / L; c[1] = sy / L; c[2] = ca;
         }
       }
     }

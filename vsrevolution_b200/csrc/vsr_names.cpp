@@ -98,6 +98,51 @@ int vsr_java_random_ints(int64_t seed, int32_t bound, int32_t* out, int32_t n) {
   return VSR_OK;
 }
 
+// RobotUtils.buildRobotTransformation(name, externalRandom) [U] (call sites Starter.java:126,428; CLI default `identity`, :153):
+//   identity | broken-<ratio>-<seed|rnd> | breakable-<time|area>-<mean>/<std>-<mean>/<std>-<seed|rnd>
+// kind: 0 identity, 1 broken; breakable (malfunctions triggered during the episode) is outside this build
+int vsr_robot_transformation(const char* name, int32_t* kind, double* ratio, int64_t* seed, int32_t* seed_is_rnd) {
+  if (!name || !kind) return VSR_EINVAL;
+  const std::string s(name);
+  if (s == "identity") { *kind = 0; return VSR_OK; }
+  auto p = split(s, '-');
+  if (p[0] == "broken") {
+    double r;
+    long sd = 0;
+    if (p.size() != 3 || !parse_double(p[1], &r) || r < 0) return VSR_EINVAL;
+    const bool rnd = p[2] == "rnd";
+    if (!rnd && (!parse_int(p[2], &sd) || sd < 0)) return VSR_EINVAL;
+    *kind = 1;
+    if (ratio) *ratio = r;
+    if (seed) *seed = sd;
+    if (seed_is_rnd) *seed_is_rnd = rnd ? 1 : 0;
+    return VSR_OK;
+  }
+  if (p[0] == "breakable") return VSR_EUNSUPPORTED;
+  return VSR_EINVAL;
+}
+
+int vsr_broken_masks(const vsr_ctx* ctx, double ratio, int64_t seed, int32_t n, uint32_t* masks_out) {
+  uint64_t state = ((uint64_t)seed ^ 0x5DEECE66DULL) & ((1ULL << 48) - 1);
+  return vsr_broken_masks_stream(ctx, ratio, &state, n, masks_out);
+}
+
+int vsr_broken_masks_stream(const vsr_ctx* ctx, double ratio, uint64_t* lcg_state, int32_t n, uint32_t* masks_out) {
+  const int nv = vsr_n_voxels(ctx);
+  if (nv < 0) return nv;
+  if (!lcg_state || n < 0 || (n > 0 && !masks_out) || !(ratio >= 0)) return VSR_EINVAL;
+  JavaRandom r(0);
+  r.seed = *lcg_state & ((1ULL << 48) - 1);
+  struct Save { JavaRandom& r; uint64_t* out; ~Save() { *out = r.seed; } } save{r, lcg_state};
+  for (int i = 0; i < n; i++) {
+    uint32_t m = 0;
+    for (int v = 0; v < nv; v++) // Grid.create(body, v -> v == null ? null : random.nextDouble() > ratio ? v : new BreakableVoxel(..., random.nextInt(), ...))
+      if (!(r.next_double() > ratio)) { m |= 1u << v; (void)r.next(32); }
+    masks_out[i] = m;
+  }
+  return VSR_OK;
+}
+
 int vsr_shape_mask(const char* name, int32_t* w, int32_t* h, uint8_t* mask, int32_t cap) {
   if (!name || !w || !h) return VSR_EINVAL;
   auto p = split(name, '-');

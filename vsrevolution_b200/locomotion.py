@@ -43,8 +43,10 @@ class Outcome:
     control_energy: float = 0.0      # sum over kept steps and voxels of f^2 dt                    [U]
     area_ratio_energy: float = 0.0   # sum over kept steps and voxels of |a_k - a_{k-1}|           [U]
     area_ratio_energy_sq: float = 0.0  # ... of |a_k^2 - a_{k-1}^2| (the other candidate formula)  [U]
-    centers: np.ndarray | None = None  # [K][2] robot centre (x, y) at the kept observations (apply_all_observed only)
+    centers: np.ndarray | None = None  # [K][2 or 3] robot centre (x, y[, angle of the central voxel]) at the kept observations (apply_all_observed only)
     dt: float = 1.0 / 60.0
+    posture: np.ndarray | None = None     # [n][n] bool, [y][x], y = 0 bottom: Outcome.getAveragePosture(n) (apply_all_observed only)
+    footprints: dict | None = None        # {n: uint8 [K]}: bit s = segment s touches the ground (apply_all_observed only)
 
     # centre spectra of detailedOutcomeFunctions (locomotion/NamedFunctions.java:139-162).  2dhmsr's BehaviorUtils is un-vendored:
     # the definition below is the documented one [U] -- magnitude of the FFT of the series zero-padded to a power of two
@@ -78,6 +80,27 @@ class Outcome:
 
     def get_center_y_velocity_spectrum(self, min_f: float, max_f: float, n_bins: int) -> np.ndarray:
         return self.quantized_spectrum(np.diff(self._need_centers()[:, 1]) / self.dt, self.dt, min_f, max_f, n_bins)
+
+    def get_center_angle_spectrum(self, min_f: float, max_f: float, n_bins: int) -> np.ndarray:
+        """Outcome.getCenterAngleSpectrum (locomotion/NamedFunctions.java:163-172): spectrum of the central voxel's angle [U]."""
+        c = self._need_centers()
+        if c.shape[1] < 3:
+            raise _ffi.VsrError(_ffi.VSR_ESTATE, "the central voxel's angle was not recorded: use Locomotion.apply_all_observed")
+        return self.quantized_spectrum(c[:, 2], self.dt, min_f, max_f, n_bins)
+
+    def get_average_posture(self, n: int) -> np.ndarray:
+        """Outcome.getAveragePosture(n) (Starter.java:180-190, NamedFunctions.java:356): [n][n] bool grid, [y][x]."""
+        if self.posture is None or self.posture.shape != (n, n):
+            raise _ffi.VsrError(_ffi.VSR_ESTATE, f"average posture of side {n} was not recorded: use Locomotion.apply_all_observed(posture_n={n})")
+        return self.posture
+
+    def get_footprints_spectra(self, n: int, min_f: float, max_f: float, n_bins: int) -> list[np.ndarray]:
+        """Outcome.getFootprintsSpectra(n, minF, maxF, nBins) (locomotion/NamedFunctions.java:179-180,392): one spectrum per footprint
+        segment, of the 0/1 series "segment touches the ground" over the kept observations [U]."""
+        if self.footprints is None or n not in self.footprints:
+            raise _ffi.VsrError(_ffi.VSR_ESTATE, f"footprints of {n} segments were not recorded: use Locomotion.apply_all_observed(footprint_ns=({n},))")
+        fp = self.footprints[n]
+        return [self.quantized_spectrum(((fp >> s) & 1).astype(np.float64), self.dt, min_f, max_f, n_bins) for s in range(n)]
 
     # detailedOutcomeFunctions (locomotion/NamedFunctions.java:135-137)
     def get_control_power(self) -> float:
@@ -227,28 +250,52 @@ class Locomotion:
             groups.setdefault(id(ctx), (ctx, []))[1].append(i)
         return list(groups.values())
 
+    @staticmethod
+    def _frozen(robots: Sequence[Robot], idx) -> np.ndarray | None:
+        """frozen-actuator masks of the robots a transformation broke (RobotUtils.build_robot_transformation), None if none is"""
+        masks = np.array([RobotUtils.frozen_mask(robots[i]) for i in idx], dtype=np.uint32)
+        return masks if masks.any() else None
+
+    def _terrains_for(self, n: int):
+        return None
+
     def apply_all(self, robots: Sequence[Robot]) -> list[Outcome]:
         if not robots:
             return []
+        terrains = self._terrains_for(len(robots))  # -rnd: seeds are drawn in robot order, before any grouping
         out: list = [None] * len(robots)
         for ctx, idx in self._groups(robots):
             genomes = np.stack([self.genome_of(robots[i]) for i in idx])
-            _, res = ctx.eval(genomes, want_results=True)
+            frozen = self._frozen(robots, idx)
+            if frozen is None and terrains is None:
+                _, res = ctx.eval(genomes, want_results=True)
+            else:
+                _, res, _ = ctx.eval_ex(genomes, frozen_masks=frozen, terrains=None if terrains is None else [terrains[i] for i in idx])
             for i, o in zip(idx, self._outcomes(res)):
                 out[i] = o
         return out
 
-    def apply_all_observed(self, robots: Sequence[Robot]) -> list[Outcome]:
-        """apply_all that also keeps every robot's centre trajectory over the kept observations (vsr_eval_centers): what
-        `detailedOutcomeFunctions` needs for the centre spectra, for the whole population in one launch per morphology."""
+    def apply_all_observed(self, robots: Sequence[Robot], posture_n: int = 8, footprint_ns: Sequence[int] = (4, 3)) -> list[Outcome]:
+        """apply_all that also keeps, for every robot, what the reference's listeners read from the observations (vsr_eval_ex): the
+        centre trajectory + central-voxel angle (centre spectra of `detailedOutcomeFunctions`, NamedFunctions.java:139-172), the
+        average posture (`numSpeciated` features Starter.java:180-190, minimap NamedFunctions.java:356) and the footprints
+        (NamedFunctions.java:179-180 n = 4, :392 n = 3) -- the whole population in one launch per morphology."""
         if not robots:
             return []
+        fns = tuple(footprint_ns) + (0, 0)
+        if len(footprint_ns) > 2:
+            raise _ffi.VsrError(_ffi.VSR_EUNSUPPORTED, "at most two footprint segment counts per call")
+        terrains = self._terrains_for(len(robots))
         out: list = [None] * len(robots)
         for ctx, idx in self._groups(robots):
             genomes = np.stack([self.genome_of(robots[i]) for i in idx])
-            _, res, cen = ctx.eval_centers(genomes)
+            _, res, ex = ctx.eval_ex(genomes, frozen_masks=self._frozen(robots, idx), posture_n=posture_n, footprint_n=fns[:2], centers=True,
+                                     terrains=None if terrains is None else [terrains[i] for i in idx])
             for j, (i, o) in enumerate(zip(idx, self._outcomes(res))):
-                o.centers, o.dt = cen[j], self.settings.step_frequency
+                o.centers, o.dt = ex["centers"][j], self.settings.step_frequency
+                if posture_n:
+                    o.posture = ex["posture"][j].reshape(posture_n, posture_n).astype(bool)
+                o.footprints = {n: ex["footprints"][q][j] for q, n in enumerate(fns[:2]) if n}
                 out[i] = o
         return out
 
@@ -283,17 +330,8 @@ class RandomTerrainLocomotion(Locomotion):
     def terrains_for(self, n: int):
         return [Locomotion.create_terrain(self.terrain_name.replace("-rnd", "-%d" % s)) for s in self.random.next_ints(10000, n)]
 
-    def apply_all(self, robots: Sequence[Robot]) -> list[Outcome]:
-        if not robots:
-            return []
-        terrains = self.terrains_for(len(robots))  # seeds are drawn in robot order, before any grouping
-        out: list = [None] * len(robots)
-        for ctx, idx in self._groups(robots):
-            genomes = np.stack([self.genome_of(robots[i]) for i in idx])
-            _, res = ctx.eval_terrains(genomes, [terrains[i] for i in idx], want_results=True)
-            for i, o in zip(idx, self._outcomes(res)):
-                out[i] = o
-        return out
+    def _terrains_for(self, n: int):
+        return self.terrains_for(n)
 
 
 def build_locomotion_task(terrain_name: str, episode_t: float, transient_t: float = 0.0, random: JavaRandomInts | None = None,
@@ -316,14 +354,18 @@ class ValidationOutcome:
 
 def validate(robots: Sequence[Robot], terrain_name: str, transformation_name: str, seed: int, episode_time: float,
              transient_time: float, **kw) -> list[ValidationOutcome]:
-    """Starter.validate (locomotion/Starter.java:122-135) for a batch of robots: re-evaluation on a validation terrain
-    (defaults `flat,downhill-30`, :171) with `new Random(seed)` feeding the `-rnd` terrain seeds.  Only the `identity`
-    transformation (the Starter default, :153) is built; robots of one call share body and controller structure."""
-    if transformation_name != "identity":
-        raise _ffi.VsrError(_ffi.VSR_EUNSUPPORTED, f"robot transformation {transformation_name!r} is outside the hot path")
-    task = build_locomotion_task(terrain_name, episode_time, transient_time, random=JavaRandomInts(seed), **kw)
+    """Starter.validate (locomotion/Starter.java:122-135) for a batch of robots: `RobotUtils.buildRobotTransformation(name, random)
+    .andThen(buildLocomotionTask(terrain, T, random, false))` with one `new Random(seed)`, re-evaluated on a validation terrain
+    (defaults `flat,downhill-30`, :171).  Transformations: `identity` (the Starter default, :153) and `broken-<ratio>-<seed|rnd>`.
+    The reference shares ONE Random between the transformation (`rnd` seed) and the `-rnd` terrain seeds and interleaves their draws
+    per robot in thread order; here the transformation draws for all robots first, then the terrain seeds (both in robot order)."""
+    rnd = _ffi.JavaRandomState(seed)
+    transformation = RobotUtils.build_robot_transformation(transformation_name, rnd)
+    transformed = [transformation(r) for r in robots]
+    terrain_random = JavaRandomInts(seed)
+    task = build_locomotion_task(terrain_name, episode_time, transient_time, random=terrain_random, **kw)
     return [ValidationOutcome(terrain_name, transformation_name, seed, o.sub_outcome(transient_time, episode_time))
-            for o in task.apply_all(robots)]
+            for o in task.apply_all(transformed)]
 
 
 class MicroBatchedLocomotion:
@@ -390,8 +432,13 @@ class PopulationEvaluator:
     robots go through `apply_all`, which groups them by morphology."""
 
     def __init__(self, shape: str, sensor_config: str, mapper: str, terrain: str, episode_t: float, transient_t: float,
-                 precision: int = 32, devices: Sequence[int] | None = None):
+                 precision: int = 32, devices: Sequence[int] | None = None, transformation: str = "identity", seed: int = 0):
         self.task = build_locomotion_task(terrain, episode_t, transient_t, precision=precision, devices=devices)
+        # `transformation.andThen(task)` of Problem.qualityFunction (Starter.java:427-429): one Random for the whole run
+        self.transformation_name = transformation
+        self._t_random = _ffi.JavaRandomState(seed)
+        self._t_spec = _ffi.robot_transformation(transformation)
+        self._transform = RobotUtils.build_robot_transformation(transformation, self._t_random)
         body = RobotUtils.build_sensorizing_function(sensor_config)(RobotUtils.build_shape(shape))
         self.target = Robot(None, body)
         self.mapper = build_mapper(mapper)
@@ -408,10 +455,35 @@ class PopulationEvaluator:
 
     def evaluate(self, genomes: np.ndarray) -> np.ndarray:
         if not self.direct:
-            return np.array([o.get_velocity() for o in self.task.apply_all([self._build(g) for g in np.asarray(genomes)])])
-        if isinstance(self.task, RandomTerrainLocomotion):
-            return self.ctx.eval_terrains(genomes, self.task.terrains_for(len(genomes)))
-        return self.ctx.eval(genomes)
+            return np.array([o.get_velocity() for o in
+                             self.task.apply_all([self._transform(self._build(g)) for g in np.asarray(genomes)])])
+        n = len(genomes)
+        frozen = None
+        if self._t_spec[0] == "broken":  # the library replays the transformation's draws on the run's stream, in robot order
+            frozen = self.ctx.broken_masks_stream(self._t_spec[1], self._transform_state(), n)
+        terrains = self.task.terrains_for(n) if isinstance(self.task, RandomTerrainLocomotion) else None
+        if frozen is None and terrains is None:
+            return self.ctx.eval(genomes)
+        return self.ctx.eval_ex(genomes, frozen_masks=frozen, terrains=terrains)[0]
+
+    @property
+    def has_per_evaluation_inputs(self) -> bool:
+        return self.direct and (self._t_spec[0] == "broken" or isinstance(self.task, RandomTerrainLocomotion))
+
+    def per_evaluation_inputs(self, n: int):
+        """(frozen masks or None, terrains or None) for the next n evaluations, drawn in evaluation order: what the device-resident
+        generation loop stages per batch (solver.GenerationLoop)."""
+        frozen = self.ctx.broken_masks_stream(self._t_spec[1], self._transform_state(), n) if self._t_spec[0] == "broken" else None
+        terrains = self.task.terrains_for(n) if isinstance(self.task, RandomTerrainLocomotion) else None
+        return frozen, terrains
+
+    def _transform_state(self) -> "_ffi.JavaRandomState":
+        """the Random the `broken` transformation draws from: its own `new Random(seed)` (created once, at build time), or the run's"""
+        if self._t_spec[2] is not None:
+            if not hasattr(self, "_own_random"):
+                self._own_random = _ffi.JavaRandomState(self._t_spec[2])
+            return self._own_random
+        return self._t_random
 
     def kernel_launches(self) -> int:
         return self.ctx.kernel_launches()

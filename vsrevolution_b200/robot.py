@@ -88,6 +88,14 @@ class Voxel:
                      for s in self.sensors)
 
 
+@dataclass
+class BreakableVoxel(Voxel):
+    """2dhmsr BreakableVoxel as `broken-<ratio>-<seed>` builds it [U]: ACTUATOR -> {FROZEN}, trigger TIME >= 0, restore time
+    infinite, i.e. the actuator applies its last force before freezing (none) for the whole episode; sensors keep working."""
+    seed: int = 0
+    actuator_frozen: bool = True
+
+
 # ---- functions ---------------------------------------------------------------------------------------
 class TimedRealFunction:
     def get_input_dimension(self) -> int:
@@ -267,7 +275,39 @@ class RobotUtils:
         return fn
 
     @staticmethod
-    def build_robot_transformation(name: str, _random=None) -> Callable[[Robot], Robot]:
-        if name != "identity":
-            raise _ffi.VsrError(_ffi.VSR_EUNSUPPORTED, f"transformation {name} is outside the hot path (SURVEY.md 8a-19)")
-        return lambda r: r
+    def build_robot_transformation(name: str, random: "_ffi.JavaRandomState | None" = None) -> Callable[[Robot], Robot]:
+        """RobotUtils.buildRobotTransformation(name, externalRandom) [U] (call sites Starter.java:126,428): `identity`, or
+        `broken-<ratio>-<seed|rnd>`: every voxel is replaced, with probability `ratio`, by a BreakableVoxel with a frozen actuator;
+        the Random is created ONCE here (seed) or is the caller's (`rnd`), so consecutive robots continue one stream.
+        `breakable-...` (malfunctions triggered during the episode) raises VSR_EUNSUPPORTED."""
+        t = _ffi.robot_transformation(name)
+        if t[0] == "identity":
+            return lambda r: r
+        _, ratio, seed = t
+        rnd = _ffi.JavaRandomState(seed) if seed is not None else random
+        if rnd is None:
+            raise _ffi.VsrIllegalArgument(_ffi.VSR_EINVAL, "transformation with seed `rnd` needs the run's Random")
+
+        def transform(robot: Robot) -> Robot:
+            def f(v):
+                if v is None:
+                    return None
+                if rnd.next_double() > ratio:
+                    return v
+                return BreakableVoxel(list(v.sensors), seed=rnd.next_int())
+            body = SerializationUtils.clone(robot.get_voxels())
+            return Robot(robot.get_controller(), Grid.create(body, f))
+
+        return transform
+
+    @staticmethod
+    def frozen_mask(robot: Robot) -> int:
+        """bit v (voxel order) = the actuator of voxel v is frozen: what vsr_eval_ex takes as frozen_masks."""
+        m, i = 0, 0
+        for v in robot.get_voxels().values():
+            if v is None:
+                continue
+            if getattr(v, "actuator_frozen", False):
+                m |= 1 << i
+            i += 1
+        return m

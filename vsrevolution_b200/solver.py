@@ -34,15 +34,14 @@ class GenerationLoop:
                  seed: int = 0, process_group=None, es: dict | None = None):
         self.evaluator = evaluator
         self.n_pop, self.n_eval = n_pop, n_eval
+        self.remap, self.es = remap, es
         if not getattr(evaluator, "direct", True):
             raise _ffi.VsrError(_ffi.VSR_EUNSUPPORTED, "the device-resident loop needs a mapper whose genome is the controller "
                                 "parameter vector; host-transforming mappers go through PopulationEvaluator.evaluate")
-        from .locomotion import RandomTerrainLocomotion
-        if isinstance(evaluator.task, RandomTerrainLocomotion):
-            # Starter.java:89-93 draws one terrain seed per evaluation; the device loop evaluates on the context's one terrain, so
-            # running it here would silently turn `-rnd` into `-0` for every individual of every generation
-            raise _ffi.VsrError(_ffi.VSR_EUNSUPPORTED, "per-evaluation (-rnd) terrains are not available inside the device-resident "
-                                "generation loop; evaluate with PopulationEvaluator.evaluate (vsr_eval_terrains) or use a fixed terrain")
+        # Per-evaluation inputs -- `-rnd` terrain seeds (Starter.java:89-93) and robot-transformation draws (Starter.java:427-429) --
+        # are drawn on the host for every batch the loop evaluates and staged with vsr_stage_eval_opts before the batch is enqueued
+        # (in batch order: with `remap` the re-evaluated parents come first).  Every rank of a multi-process run draws the same values.
+        self._per_eval = evaluator.per_evaluation_inputs if getattr(evaluator, "has_per_evaluation_inputs", False) else None
         if es is not None:  # SimpleEvolutionaryStrategy(..., nOfParents, nOfElites, sigma, remap)
             self.ga = _ffi.GeneticAlgorithm(evaluator.ctx, n_pop, seed=seed, remap=remap, solver=_ffi.SOLVER_ES,
                                             sigma_mut=es["sigma"], n_parents=es["n_parents"], n_elites=es["n_elites"])
@@ -70,12 +69,22 @@ class GenerationLoop:
         dist.all_gather_into_tensor(whole, mine, group=self.pg)
         torch.cuda.current_stream().synchronize()
 
+    def _stage(self, count: int):
+        if self._per_eval is not None:
+            frozen, terrains = self._per_eval(count)
+            self.evaluator.ctx.stage_eval_opts(count, frozen, terrains)
+
     def init(self):
+        self._stage(self.n_pop)
         self.ga.init_begin()
         self._exchange()
         self.ga.init_end()
 
     def step(self):
+        if self.es is None:   # numGA: offspring, preceded by the re-evaluated parents with remap
+            self._stage(2 * self.n_pop if self.remap else self.n_pop)
+        else:                 # ES: offspring only; the elites are re-evaluated too with remap
+            self._stage(self.n_pop if self.remap else self.n_pop - self.es["n_elites"])
         self.ga.step_begin()
         self._exchange()
         self.ga.step_end()
