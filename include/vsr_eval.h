@@ -191,7 +191,7 @@ typedef struct {
 } vsr_eval_opts;
 int vsr_eval_ex(vsr_ctx* ctx, const double* genomes, int32_t n, const vsr_eval_opts* opts, double* fitness_out, vsr_result* results_out);
 /*
- * Stage the per-robot inputs of vsr_eval_opts (frozen masks and / or per-robot terrains; no observation requests) for the
+ * Stage the per-robot inputs of a vsr_eval_opts record -- frozen masks and / or per-robot terrains, no observation requests -- for the
  * device-resident paths -- vsr_eval_device and the generation loop of vsr_ga.h: entry i applies to robot i of every following batch
  * (a batch may evaluate fewer than n robots, never more) until the next call; n = 0 or opts = NULL clears.  The data is copied.
  * This is how `-rnd` terrains (Starter.java:89-93) and robot transformations (Starter.java:427-429) reach the generation loop: the
