@@ -15,7 +15,7 @@ from vsrevolution_b200.locomotion import population_evaluator
 
 cmd = sys.argv[1]
 T = 30.0
-path = "gpurun_out/evolved_g.npy"
+path = "build_ab/evolved_g.npy"  # git-ignored, travels to the GPU box (gpurun_out/ does not)
 if cmd == "make":
     gens = int(sys.argv[2]) if len(sys.argv) > 2 else 20
     ev = population_evaluator("biped-4x3", "uniform-a-0", "brainCentralized<mlp;r=0.65;nIL=1", "flat", T, 1.0)
@@ -24,8 +24,10 @@ if cmd == "make":
     for _ in range(gens):
         ga.step()
     g, f = ga.population()
-    os.makedirs("gpurun_out", exist_ok=True)
+    os.makedirs("build_ab", exist_ok=True)
     np.save(path, g)
+    os.makedirs("gpurun_out", exist_ok=True)
+    np.save("gpurun_out/evolved_g.npy", g)
     print(json.dumps({"made": path, "gens": gens, "best": float(f[0]), "median": float(np.median(f)), "kernel_ms_last_gen": ev.ctx.last_kernel_ms()}))
 else:
     label = sys.argv[2] if len(sys.argv) > 2 else ""
@@ -49,6 +51,8 @@ else:
             ctx.eval(g)
             ms.append(ctx.last_kernel_ms())
         rec[k + "_ms"] = round(float(np.min(ms[1:])), 3)
+        import hashlib
+        rec[k + "_fit_sha"] = hashlib.sha1(ctx.eval(g).tobytes()).hexdigest()[:12]  # bit-identity across builds
     rec["info"] = ctx.kernel_info()
     ctx.close()
     print(json.dumps(rec))

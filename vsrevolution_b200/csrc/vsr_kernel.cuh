@@ -47,6 +47,9 @@ constexpr int kPoolStride = 36;
 #define VSR_SYNC_MASK_DEFAULT 115
 #endif
 constexpr int kSyncMaskDefault = VSR_SYNC_MASK_DEFAULT;
+#ifndef VSR_POS_V2
+#define VSR_POS_V2 1 // position iterations: branch-free rotations (deferred exact refresh), branch-free ropes, unrolled contact points
+#endif
 #ifndef VSR_SOFT_SYNC
 #define VSR_SOFT_SYNC 0 // > 0: bounded-skew phase alignment (warps may run this many boundaries ahead); 0: __syncthreads
 #endif
@@ -199,6 +202,18 @@ template <> struct M<float> {
       sincos_(a, &s, &c);
     }
   }
+  // branch-free variant for the position solver: always the small-angle update; `big` collects whether any step left the
+  // polynomial's range, in which case the caller re-evaluates sin / cos of the (exactly accumulated) angles once per iteration
+  static __device__ __forceinline__ void rotate_fast(float& a, float& c, float& s, float d, bool& big) {
+    a += d;
+    big |= !(fabsf(d) < 0.125f);
+    const float d2 = d * d;
+    const float sd = d * fmaf(d2, fmaf(d2, 8.33333333e-3f, -1.66666667e-1f), 1.0f);
+    const float cd = fmaf(d2, fmaf(d2, fmaf(d2, -1.38888889e-3f, 4.16666667e-2f), -0.5f), 1.0f);
+    const float c2 = c * cd - s * sd;
+    s = s * cd + c * sd;
+    c = c2;
+  }
   static __device__ __forceinline__ float tanh_(float x) {
 #ifdef VSR_LIBM_TANH
     return tanhf(x);
@@ -228,6 +243,7 @@ template <> struct M<double> {
   static __device__ __forceinline__ double rint_(double a) { return rint(a); }
   static __device__ __forceinline__ void sincos_(double a, double* s, double* c) { sincos(a, s, c); }
   static __device__ __forceinline__ void rotate(double& a, double& c, double& s, double d) { a += d; sincos(a, &s, &c); }
+  static __device__ __forceinline__ void rotate_fast(double& a, double& c, double& s, double d, bool&) { a += d; sincos(a, &s, &c); }
   static __device__ __forceinline__ double tanh_(double x) { return tanh(x); }
   static __device__ __forceinline__ double atan2_(double y, double x) { return atan2(y, x); }
   static __device__ __forceinline__ double phase_sin(double amp, double freq, double t, double phase) {
@@ -1217,6 +1233,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
       const R dox = __shfl_sync(FULL, ox, dn_s) - ox, doy = __shfl_sync(FULL, oy, dn_s) - oy;
       const unsigned robot_mask = lane_used ? (((L >= 32) ? FULL : ((1u << L) - 1u)) << base_lane) : (1u << lane);
       bool active = true;
+      bool bigrot = false; // FP32: some rotation step of this iteration left the small-angle polynomial's range (see M<float>::rotate_fast)
 #pragma unroll 1
       for (int it = 0; it < P.pos_iters; it++) {
         bool ok = true;
@@ -1249,6 +1266,26 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
               const R* sp = pool + s * kPoolStride;
               const V4<R> pa = ld4(sp), pb = ld4(sp + 4), pl = ld4(sp + kPS + 16);
               const R nx = pa.x, ny = pa.y;
+#if VSR_POS_V2
+              // the (at most two) points of a manifold, unrolled: the second one is masked by np instead of looped over
+#pragma unroll
+              for (int q = 0; q < 2; q++) {
+                const R lx = q == 0 ? pl.x : pl.z, ly = q == 0 ? pl.y : pl.w;
+                const R cpx = q == 0 ? pa.z : pb.y, cpy = q == 0 ? pa.w : pb.z, cdp = q == 0 ? pb.x : pb.w;
+                const bool on = q < np;
+                const R rx = ck * lx - sk * ly, ry = sk * lx + ck * ly;
+                const R sep = nx * (xk + rx - cpx) + ny * (yk + ry - cpy) - cdp;
+                if (on && sep < -R(3) * K_lin_tol) mybad |= 1u << ol;
+                R C = K_baum * (sep + K_lin_tol);
+                C = M<R>::min_(C, R(0));
+                C = M<R>::max_(C, -K_max_corr);
+                const R rn_ = rx * ny - ry * nx;
+                const R l_ = on ? -C * M<R>::rcp(K_im + K_ii * rn_ * rn_) : R(0);
+                xk += K_im * nx * l_; yk += K_im * ny * l_;
+                if (sizeof(R) == 4) M<R>::rotate_fast(ak, ck, sk, K_ii * rn_ * l_, bigrot);
+                else if (on) M<R>::rotate(ak, ck, sk, K_ii * rn_ * l_);
+              }
+#else
               for (int q = 0; q < np; q++) {
                 const R lx = q == 0 ? pl.x : pl.z, ly = q == 0 ? pl.y : pl.w;
                 const R cpx = q == 0 ? pa.z : pb.y, cpy = q == 0 ? pa.w : pb.z, cdp = q == 0 ? pb.x : pb.w;
@@ -1263,6 +1300,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
                 xk += K_im * nx * l_; yk += K_im * ny * l_;
                 M<R>::rotate(ak, ck, sk, K_ii * rn_ * l_);
               }
+#endif
             }
             stg[mi] = xk; stg[128 + mi] = yk; stg[256 + mi] = ak; pc[mi] = ck; pc[128 + mi] = sk;
           }
@@ -1279,6 +1317,30 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
           __syncwarp();
         }
         // ropes
+#if VSR_POS_V2
+        // branch-free: an inactive rope (or robot) applies a zero correction; ropes (0,1) / (2,3) and (1,2) / (3,0) touch disjoint masses,
+        // so the straight-line code gives the scheduler two independent chains
+        if (warp_rope) {
+#define ROPE_POS(i, a, b)                                                                  \
+  {                                                                                        \
+    const bool on_ = ract[i] && active;                                                    \
+    R nx = X[a] - X[b], ny = Y[a] - Y[b];                                                  \
+    const R l2 = nx * nx + ny * ny;                                                        \
+    const R il = M<R>::rsqrt_(l2);                                                         \
+    const R len = l2 * il;                                                                 \
+    if (!(len >= K_lin_tol)) { nx = 0; ny = 0; } else { nx *= il; ny *= il; }                \
+    R C = len - K_rope_lower;                                                                \
+    if (on_ && !(-C < K_lin_tol)) ok = false;                                                \
+    C = M<R>::min_(C, R(0));                                                               \
+    C = M<R>::max_(C, -K_max_corr);                                                          \
+    const R l_ = -K_rope_E * C;                                                              \
+    const R m_ = on_ ? l_ * K_im : R(0);                                                     \
+    X[a] += nx * m_; Y[a] += ny * m_; X[b] -= nx * m_; Y[b] -= ny * m_;                    \
+  }
+          VSR_ROPES(ROPE_POS)
+#undef ROPE_POS
+        }
+#else
         if (warp_rope) {
 #define ROPE_POS(i, a, b)                                                                  \
   if (ract[i] && active) {                                                                 \
@@ -1298,16 +1360,25 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
           VSR_ROPES(ROPE_POS)
 #undef ROPE_POS
         }
+#endif
         // weld position solve for owner weld (body1 = mine k1; partner pose + rotation pulled)
-#define WELD_POS(k1, px_, py_, pa_, pc_, ps_, ax_, ay_, dpx, dpy, dpa)                            \
+#if VSR_POS_V2
+#define POS_ROT(a_, c_, s_, d_) { if (sizeof(R) == 4) M<R>::rotate_fast(a_, c_, s_, d_, bigrot); else M<R>::rotate(a_, c_, s_, d_); }
+        // local anchor 2 is (m, 0) for a horizontal weld and (0, m) for a vertical one: r2 = R(partner) * anchor without the zero products
+#define WELD_R2(pc_, ps_, hz_) const R r2x = (hz_) ? (pc_) * K_wa : -(ps_) * K_wa, r2y = (hz_) ? (ps_) * K_wa : (pc_) * K_wa;
+#else
+#define POS_ROT(a_, c_, s_, d_) M<R>::rotate(a_, c_, s_, d_);
+#define WELD_R2(pc_, ps_, hz_) const R r2x = (pc_) * ((hz_) ? K_wa : R(0)) - (ps_) * ((hz_) ? R(0) : K_wa), r2y = (ps_) * ((hz_) ? K_wa : R(0)) + (pc_) * ((hz_) ? R(0) : K_wa);
+#endif
+#define WELD_POS(k1, px_, py_, pa_, pc_, ps_, hz_, dpx, dpy, dpa)                                 \
   {                                                                                             \
-    const R r2x = (pc_) * (ax_) - (ps_) * (ay_), r2y = (ps_) * (ax_) + (pc_) * (ay_);           \
+    WELD_R2(pc_, ps_, hz_)                                                                      \
     const R Cx = X[k1] - ((px_) + r2x), Cy = Y[k1] - ((py_) + r2y), Cz = A[k1] - (pa_);         \
     if (!(Cx * Cx + Cy * Cy <= K_lin_tol * K_lin_tol && M<R>::abs_(Cz) <= K_ang_tol)) ok = false;     \
     R lx_, ly_, lz_;                                                                            \
     WELD_SOLVE(r2x, r2y, Cx, Cy, Cz, lx_, ly_, lz_)                                             \
     X[k1] += K_im * lx_; Y[k1] += K_im * ly_;                                                       \
-    M<R>::rotate(A[k1], CS[k1], SN[k1], K_ii * lz_);                                              \
+    POS_ROT(A[k1], CS[k1], SN[k1], K_ii * lz_)                                                    \
     dpx = -K_im * lx_; dpy = -K_im * ly_; dpa = -K_ii * (r2x * ly_ - r2y * lx_ + lz_);                \
   }
         {
@@ -1317,14 +1388,14 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
           const R p1c = __shfl_sync(FULL, CS[2], ln_s), p1s = __shfl_sync(FULL, SN[2], ln_s);
           R d0x = 0, d0y = 0, d0a = 0, d1x = 0, d1y = 0, d1a = 0;
           if (ln >= 0 && active) {
-            WELD_POS(0, p0x, p0y, p0a, p0c, p0s, K_wa, R(0), d0x, d0y, d0a)
-            WELD_POS(3, p1x, p1y, p1a, p1c, p1s, K_wa, R(0), d1x, d1y, d1a)
+            WELD_POS(0, p0x, p0y, p0a, p0c, p0s, 1, d0x, d0y, d0a)
+            WELD_POS(3, p1x, p1y, p1a, p1c, p1s, 1, d1x, d1y, d1a)
           }
           const R a0 = __shfl_sync(FULL, d0x, rn_s), a1 = __shfl_sync(FULL, d0y, rn_s), a2 = __shfl_sync(FULL, d0a, rn_s);
           const R b0 = __shfl_sync(FULL, d1x, rn_s), b1 = __shfl_sync(FULL, d1y, rn_s), b2 = __shfl_sync(FULL, d1a, rn_s);
           if (rn >= 0 && active) {
-            X[1] += a0; Y[1] += a1; M<R>::rotate(A[1], CS[1], SN[1], a2);
-            X[2] += b0; Y[2] += b1; M<R>::rotate(A[2], CS[2], SN[2], b2);
+            X[1] += a0; Y[1] += a1; POS_ROT(A[1], CS[1], SN[1], a2)
+            X[2] += b0; Y[2] += b1; POS_ROT(A[2], CS[2], SN[2], b2)
           }
         }
         {
@@ -1334,17 +1405,28 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
           const R p1c = __shfl_sync(FULL, CS[1], dn_s), p1s = __shfl_sync(FULL, SN[1], dn_s);
           R d0x = 0, d0y = 0, d0a = 0, d1x = 0, d1y = 0, d1a = 0;
           if (dn >= 0 && active) {
-            WELD_POS(3, p0x, p0y, p0a, p0c, p0s, R(0), K_wa, d0x, d0y, d0a)
-            WELD_POS(2, p1x, p1y, p1a, p1c, p1s, R(0), K_wa, d1x, d1y, d1a)
+            WELD_POS(3, p0x, p0y, p0a, p0c, p0s, 0, d0x, d0y, d0a)
+            WELD_POS(2, p1x, p1y, p1a, p1c, p1s, 0, d1x, d1y, d1a)
           }
           const R e0 = __shfl_sync(FULL, d0x, un_s), e1 = __shfl_sync(FULL, d0y, un_s), e2 = __shfl_sync(FULL, d0a, un_s);
           const R f0 = __shfl_sync(FULL, d1x, un_s), f1 = __shfl_sync(FULL, d1y, un_s), f2 = __shfl_sync(FULL, d1a, un_s);
           if (un >= 0 && active) {
-            X[0] += e0; Y[0] += e1; M<R>::rotate(A[0], CS[0], SN[0], e2);
-            X[1] += f0; Y[1] += f1; M<R>::rotate(A[1], CS[1], SN[1], f2);
+            X[0] += e0; Y[0] += e1; POS_ROT(A[0], CS[0], SN[0], e2)
+            X[1] += f0; Y[1] += f1; POS_ROT(A[1], CS[1], SN[1], f2)
           }
         }
 #undef WELD_POS
+#undef WELD_R2
+#undef POS_ROT
+#if VSR_POS_V2
+        // a rotation step beyond the small-angle polynomial's range (never seen in a locomotion episode): refresh sin / cos of the
+        // exactly accumulated angles of the whole warp (the mass lanes rotate masses of other lanes) before the next iteration
+        if (sizeof(R) == 4 && __any_sync(FULL, bigrot)) {
+#pragma unroll
+          for (int k = 0; k < 4; k++) M<R>::sincos_(A[k], &SN[k], &CS[k]);
+          bigrot = false;
+        }
+#endif
         // robot-wide convergence
         const unsigned bad = __ballot_sync(FULL, active && !ok);
         if (!(bad & robot_mask)) active = false;
