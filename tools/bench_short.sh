@@ -1,6 +1,6 @@
 #!/bin/bash
 # usage: tools/bench_short.sh "<env assignments>" -> prints value and kernel info
-env $1 python bench.py --steps 2 --warmup 3 --no-cpu-baseline 2>&1 | python -c "
+env $1 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-parity --no-other-configs 2>&1 | python -c "
 import sys,json
 for l in sys.stdin:
     try: d=json.loads(l)

@@ -3,7 +3,7 @@
 for robots in 3 96 512 1024 2048; do
   for cfg in "X=1" "VSR_LAUNCH_SHAPE=2" "VSR_LAUNCH_SHAPE=2 VSR_WARPS=4" "VSR_LAUNCH_SHAPE=2 VSR_WARPS=2" "VSR_LAUNCH_SHAPE=2 VSR_WARPS=1" "VSR_LAUNCH_SHAPE=0 VSR_WARPS=2" "VSR_LAUNCH_SHAPE=0 VSR_WARPS=1"; do
     echo -n "robots $robots [$cfg]: "
-    env $cfg python bench.py --workload 2 --robots $robots --steps 2 --warmup 3 --no-cpu-baseline --ga-generations 0 2>&1 | python -c "
+    env $cfg python bench.py --workload 2 --robots $robots --steps 2 --warmup 3 --no-cpu-baseline --no-parity --no-other-configs --ga-generations 0 2>&1 | python -c "
 import sys,json
 for l in sys.stdin:
     try: d=json.loads(l)

@@ -6,7 +6,7 @@ for wl in 3 4; do
     for shape in auto 0 1 2 3; do
       if [ "$shape" = auto ]; then e="X=1"; else e="VSR_LAUNCH_SHAPE=$shape"; fi
       echo -n "workload $wl robots $robots shape $shape: "
-      env $e python bench.py --workload $wl --robots $robots --steps 2 --warmup 3 --no-cpu-baseline --ga-generations 0 2>&1 | python -c "
+      env $e python bench.py --workload $wl --robots $robots --steps 2 --warmup 3 --no-cpu-baseline --no-parity --no-other-configs --ga-generations 0 2>&1 | python -c "
 import sys,json
 for l in sys.stdin:
     try: d=json.loads(l)

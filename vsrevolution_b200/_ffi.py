@@ -588,8 +588,20 @@ class JavaRandomState:
     def next_double(self) -> float:
         return ((self._next(26) << 27) + self._next(27)) * (1.0 / (1 << 53))
 
-    def next_int(self) -> int:
-        return self._next(32)
+    def next_int(self, bound: int | None = None) -> int:
+        """java.util.Random.nextInt() / nextInt(bound)."""
+        if bound is None:
+            return self._next(32)
+        r = self._next(31)
+        m = bound - 1
+        if (bound & m) == 0:
+            return (bound * r) >> 31
+        u = r
+        while True:
+            r = u % bound
+            if u - r + m < (1 << 31):
+                return r
+            u = self._next(31)
 
 
 def robot_transformation(name: str):

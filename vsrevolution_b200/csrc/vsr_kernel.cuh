@@ -50,6 +50,9 @@ constexpr int kSyncMaskDefault = VSR_SYNC_MASK_DEFAULT;
 #ifndef VSR_POS_V2
 #define VSR_POS_V2 1 // position iterations: branch-free rotations (deferred exact refresh), branch-free ropes, unrolled contact points
 #endif
+#ifndef VSR_CACHE_MASS
+#define VSR_CACHE_MASS 1 // contact phases: the lane's touching mass and its manifold slots cached in a register per step
+#endif
 #ifndef VSR_SOFT_SYNC
 #define VSR_SOFT_SYNC 0 // > 0: bounded-skew phase alignment (warps may run this many boundaries ahead); 0: __syncthreads
 #endif
@@ -593,6 +596,14 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
   auto ld4 = [](const R* q) -> V4<R> { return *reinterpret_cast<const V4<R>*>(q); };
   auto st4 = [](R* q, const V4<R>& v) { *reinterpret_cast<V4<R>*>(q) = v; };
   int n_tm = 0; // warp-uniform: corner masses of this warp that have at least one manifold (length of tml)
+#if VSR_CACHE_MASS
+  unsigned cms = 0; // byte 0: the touching mass (owner lane * 4 + k) this lane serves, bytes 1..3: its manifold slots (massSlots entry)
+#define TM_MI(i) ((i) < 32 ? (int)(cms & 0xffu) : (int)tml[i])
+#define TM_SLOTS(i, mi) ((i) < 32 ? (cms >> 8) : massSlots[mi])
+#else
+#define TM_MI(i) ((int)tml[i])
+#define TM_SLOTS(i, mi) (massSlots[mi])
+#endif
   // per-lane cached ground polygon (the one under the voxel centre), in the lane's local frame
   int pk = 0;
   R px0 = 0, px1 = 0, py0 = 0, py1 = 0, pnx = 0, pny = 1;
@@ -814,6 +825,12 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
       n_tm = n;
     }
     __syncwarp();
+#if VSR_CACHE_MASS
+    // the touching mass this lane serves in every contact phase of the coming step (restitution / warm start, 10 velocity iterations,
+    // the position iterations) and its manifold slots, in ONE register: two dependent shared-memory loads less on each of those chains
+    cms = lane < n_tm ? (unsigned)tml[lane] : 0u;
+    cms |= lane < n_tm ? massSlots[cms] << 8 : 0u;
+#endif
   };
 
   detect(); // World.step's first-step detect()
@@ -866,8 +883,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
       __syncwarp();
 #pragma unroll 1
       for (int i = lane; i < n_tm; i += 32) {
-        const int mi = tml[i];
-        const unsigned slots = massSlots[mi];
+        const int mi = TM_MI(i);
+        const unsigned slots = TM_SLOTS(i, mi);
         const R vx0 = stg[mi], vy0 = stg[128 + mi], w0 = stg[256 + mi]; // pre-warm-start velocity of this mass
         R vxk = vx0, vyk = vy0, wk = w0;
 #pragma unroll 1
@@ -1122,8 +1139,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
         __syncwarp();
 #pragma unroll 1
         for (int i = lane; i < n_tm; i += 32) {
-          const int mi = tml[i]; // corner mass = owner lane * 4 + k
-          const unsigned slots = massSlots[mi];
+          const int mi = TM_MI(i); // corner mass = owner lane * 4 + k
+          const unsigned slots = TM_SLOTS(i, mi);
           R vxk = stg[mi], vyk = stg[128 + mi], wk = stg[256 + mi];
 #pragma unroll 1
           for (unsigned sl = slots; sl != 0; sl >>= 8) {
@@ -1253,11 +1270,12 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
           const unsigned actm = __ballot_sync(FULL, active);
           __syncwarp();
           unsigned mybad = 0;
+          unsigned bigm = 0; // owner lanes of the masses whose rotation step left the small-angle range (FP32, VSR_POS_V2)
 #pragma unroll 1
           for (int i = lane; i < n_tm; i += 32) {
-            const int mi = tml[i], ol = mi >> 2;
+            const int mi = TM_MI(i), ol = mi >> 2;
             if (!((actm >> ol) & 1u)) continue;
-            const unsigned slots = massSlots[mi];
+            const unsigned slots = TM_SLOTS(i, mi);
             R xk = stg[mi], yk = stg[128 + mi], ak = stg[256 + mi], ck = pc[mi], sk = pc[128 + mi];
 #pragma unroll 1
             for (unsigned sl = slots; sl != 0; sl >>= 8) {
@@ -1282,7 +1300,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
                 const R rn_ = rx * ny - ry * nx;
                 const R l_ = on ? -C * M<R>::rcp(K_im + K_ii * rn_ * rn_) : R(0);
                 xk += K_im * nx * l_; yk += K_im * ny * l_;
-                if (sizeof(R) == 4) M<R>::rotate_fast(ak, ck, sk, K_ii * rn_ * l_, bigrot);
+                if (sizeof(R) == 4) { bool big_ = false; M<R>::rotate_fast(ak, ck, sk, K_ii * rn_ * l_, big_); if (big_) bigm |= 1u << ol; }
                 else if (on) M<R>::rotate(ak, ck, sk, K_ii * rn_ * l_);
               }
 #else
@@ -1306,6 +1324,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
           }
           __syncwarp();
           if ((__reduce_or_sync(FULL, mybad) >> lane) & 1u) ok = false;
+#if VSR_POS_V2
+          if (sizeof(R) == 4 && __any_sync(FULL, bigm != 0) && ((__reduce_or_sync(FULL, bigm) >> lane) & 1u)) bigrot = true;
+#endif
           if (touching && active) {
             V4<R> t4;
             t4 = stage[0 * 32 + lane]; X[0] = t4.x; X[1] = t4.y; X[2] = t4.z; X[3] = t4.w;
@@ -1419,11 +1440,14 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
 #undef WELD_R2
 #undef POS_ROT
 #if VSR_POS_V2
-        // a rotation step beyond the small-angle polynomial's range (never seen in a locomotion episode): refresh sin / cos of the
-        // exactly accumulated angles of the whole warp (the mass lanes rotate masses of other lanes) before the next iteration
+        // a rotation step beyond the small-angle polynomial's range (rare: falls, hard landings): refresh sin / cos of the exactly
+        // accumulated angles of the voxel's masses before the next iteration (mass lanes report through `bigm` to the owner lane)
+        // (per lane: a robot's result must not depend on which robots share its warp)
         if (sizeof(R) == 4 && __any_sync(FULL, bigrot)) {
+          if (bigrot) {
 #pragma unroll
-          for (int k = 0; k < 4; k++) M<R>::sincos_(A[k], &SN[k], &CS[k]);
+            for (int k = 0; k < 4; k++) M<R>::sincos_(A[k], &SN[k], &CS[k]);
+          }
           bigrot = false;
         }
 #endif
@@ -1800,6 +1824,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
     if (P.results) P.results[robot].contact_overflow = ovf;
   }
   if (ovf && lane == 0 && P.overflow_count) atomicAdd(P.overflow_count, 1);
+#undef TM_MI
+#undef TM_SLOTS
 #undef WELD_APPLY
 #undef WELD_SOLVE
 #undef ln_s

@@ -259,10 +259,12 @@ class Locomotion:
     def _terrains_for(self, n: int):
         return None
 
-    def apply_all(self, robots: Sequence[Robot]) -> list[Outcome]:
+    def apply_all(self, robots: Sequence[Robot], terrains=None) -> list[Outcome]:
+        """`terrains`: optional per-robot (xs, ys) polylines (what a `-rnd` task draws itself)."""
         if not robots:
             return []
-        terrains = self._terrains_for(len(robots))  # -rnd: seeds are drawn in robot order, before any grouping
+        if terrains is None:
+            terrains = self._terrains_for(len(robots))  # -rnd: seeds are drawn in robot order, before any grouping
         out: list = [None] * len(robots)
         for ctx, idx in self._groups(robots):
             genomes = np.stack([self.genome_of(robots[i]) for i in idx])
@@ -354,18 +356,22 @@ class ValidationOutcome:
 
 def validate(robots: Sequence[Robot], terrain_name: str, transformation_name: str, seed: int, episode_time: float,
              transient_time: float, **kw) -> list[ValidationOutcome]:
-    """Starter.validate (locomotion/Starter.java:122-135) for a batch of robots: `RobotUtils.buildRobotTransformation(name, random)
-    .andThen(buildLocomotionTask(terrain, T, random, false))` with one `new Random(seed)`, re-evaluated on a validation terrain
-    (defaults `flat,downhill-30`, :171).  Transformations: `identity` (the Starter default, :153) and `broken-<ratio>-<seed|rnd>`.
-    The reference shares ONE Random between the transformation (`rnd` seed) and the `-rnd` terrain seeds and interleaves their draws
-    per robot in thread order; here the transformation draws for all robots first, then the terrain seeds (both in robot order)."""
-    rnd = _ffi.JavaRandomState(seed)
-    transformation = RobotUtils.build_robot_transformation(transformation_name, rnd)
-    transformed = [transformation(r) for r in robots]
-    terrain_random = JavaRandomInts(seed)
-    task = build_locomotion_task(terrain_name, episode_time, transient_time, random=terrain_random, **kw)
+    """Starter.validate (locomotion/Starter.java:122-135) for a batch of robots.  The reference validates ONE robot per call:
+    `random = new Random(seed)`, `robot = buildRobotTransformation(name, random).apply(robot)`, then
+    `buildLocomotionTask(terrain, T, random, false).apply(robot)` -- so every robot restarts the same stream: the transformation's draws
+    (only a `-rnd` seeded transformation takes them from `random`), then the `-rnd` terrain seed `random.nextInt(10000)`.  The batch
+    does exactly that per robot and evaluates all of them in one launch per morphology.  Transformations: `identity` (the Starter
+    default, :153) and `broken-<ratio>-<seed|rnd>`."""
+    transformed, terrains = [], [] if "-rnd" in terrain_name else None
+    for r in robots:
+        rnd = _ffi.JavaRandomState(seed)
+        transformed.append(RobotUtils.build_robot_transformation(transformation_name, rnd)(r))
+        if terrains is not None:
+            terrains.append(Locomotion.create_terrain(terrain_name.replace("-rnd", "-%d" % rnd.next_int(10000))))
+    base = terrain_name.replace("-rnd", "-0")
+    task = Locomotion(episode_time, Locomotion.create_terrain(base), Settings(), transient_time, **kw)
     return [ValidationOutcome(terrain_name, transformation_name, seed, o.sub_outcome(transient_time, episode_time))
-            for o in task.apply_all(transformed)]
+            for o in task.apply_all(transformed, terrains)]
 
 
 class MicroBatchedLocomotion:
