@@ -209,6 +209,8 @@ int vsr_broken_masks_stream(const vsr_ctx* ctx, double ratio, uint64_t* lcg_stat
 /* RobotUtils.buildRobotTransformation(name, random): parses `identity` (kind 0) and `broken-<ratio>-<seed|rnd>` (kind 1);
  * `breakable-...` (malfunctions triggered during the episode) returns VSR_EUNSUPPORTED, anything else VSR_EINVAL */
 int vsr_robot_transformation(const char* name, int32_t* kind, double* ratio, int64_t* seed, int32_t* seed_is_rnd);
+/* the episode of this context: simulated steps and the 1-based first / last kept observation (K = k_last - k_first + 1) */
+int vsr_ctx_episode(const vsr_ctx* ctx, int32_t* n_steps, int32_t* k_first, int32_t* k_last);
 /* index (voxel order) of BehaviorUtils.getCentralElement of the body: the voxel whose angle centers_out[..][2] records */
 int vsr_central_voxel(const vsr_ctx* ctx);
 

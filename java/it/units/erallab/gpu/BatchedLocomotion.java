@@ -4,6 +4,7 @@ import it.units.erallab.hmsrobots.core.controllers.CentralizedSensing;
 import it.units.erallab.hmsrobots.core.controllers.DistributedSensing;
 import it.units.erallab.hmsrobots.core.controllers.MultiLayerPerceptron;
 import it.units.erallab.hmsrobots.core.controllers.PhaseSin;
+import it.units.erallab.hmsrobots.core.objects.BreakableVoxel;
 import it.units.erallab.hmsrobots.core.objects.Robot;
 import it.units.erallab.hmsrobots.core.objects.Voxel;
 import it.units.erallab.hmsrobots.core.sensors.Angle;
@@ -15,6 +16,7 @@ import it.units.erallab.hmsrobots.core.sensors.Sensor;
 import it.units.erallab.hmsrobots.core.sensors.SoftNormalization;
 import it.units.erallab.hmsrobots.core.sensors.Touch;
 import it.units.erallab.hmsrobots.core.sensors.Velocity;
+import it.units.erallab.hmsrobots.tasks.locomotion.Outcome;
 import it.units.erallab.hmsrobots.util.Grid;
 
 import java.util.ArrayList;
@@ -22,132 +24,167 @@ import java.util.List;
 import java.util.function.Function;
 
 /**
- * Drop-in for the task built by Starter.buildLocomotionTask (locomotion/Starter.java:83-94):
- * {@code Function<Robot, GpuOutcome>} with the same constructor arguments as {@code new Locomotion(finalT, terrain, settings)}
- * plus the transient time that Starter applies afterwards through subOutcome (:430-433).
+ * Drop-in for the task built by Starter.buildLocomotionTask (locomotion/Starter.java:83-94): a {@code Function<Robot, Outcome>} -- the
+ * exact type of {@code Problem.qualityFunction} (Starter.java:75-77) -- with the constructor arguments of
+ * {@code new Locomotion(finalT, terrain, settings)} plus the transient time that Starter applies afterwards through subOutcome (:430-433).
  *
- * NOT COMPILED IN THE BUILD CONTAINER (no JDK, 2dhmsr/JGEA jars absent). Two ways to use it, both keep JGEA's API:
- *  (1) applyAll(List<Robot>) from a thin evolver subclass that maps the whole population at once (preferred);
- *  (2) apply(Robot) from JGEA's executor threads: calls are micro-batched (flush when `expectedBatch` robots are
- *      waiting, or by the first waiter whose `maxWaitMillis` expires), each caller blocks until its batch is evaluated.
+ * NOT COMPILED IN THE BUILD CONTAINER (no JDK, 2dhmsr/JGEA jars absent). Three ways to batch behind JGEA's one-robot-per-call contract,
+ * all keep JGEA's API and none needs a solver subclass (JGEA's AbstractPopulationBasedIterativeSolver.map is static [U], so a subclass
+ * could not replace `executor.invokeAll` (Starter.java:436) without re-implementing init() and update()):
+ *  (1) LAZY (default): apply(robot) only records the robot and returns a {@link GpuOutcome}; the first getter called on any outcome of
+ *      the batch -- JGEA sorting the new population -- evaluates the whole batch in ONE launch. One generation = one launch, no threads.
+ *  (2) applyAll(List<Robot>): the whole population in one call, for a host that already maps a population at once.
+ *  (3) BatchedExecutor (below): an ExecutorService whose invokeAll announces the batch size, for eager (non-lazy) semantics.
  */
-public class BatchedLocomotion implements Function<Robot, GpuOutcome>, AutoCloseable {
+public class BatchedLocomotion implements Function<Robot, Outcome>, AutoCloseable {
+
+  static final int POSTURE_N = 8;           // Starter.java:185, NamedFunctions.java:356
+  static final int[] FOOTPRINT_N = {4, 3};  // NamedFunctions.java:180, :392
 
   private final long ctx;
   private final double transientT, finalT;
-  private final int expectedBatch;
-  private final long maxWaitMillis;
+  private final boolean observe;
   private boolean configured = false;
+  private GpuOutcome.Pending open;
+  private volatile double lastBatchSeconds = 0;
 
-  public BatchedLocomotion(double finalT, double[][] groundProfile, double transientT, int expectedBatch, long maxWaitMillis) {
+  /**
+   * @param observe also record average posture, footprints and the centre trajectories (the detailed / visual outcome functions and the
+   *                numSpeciated features); false = fitness and the basic / energy getters only (fastest)
+   */
+  public BatchedLocomotion(double finalT, double[][] groundProfile, double transientT, boolean observe) {
     this.ctx = VsrEval.create(finalT, transientT, groundProfile[0], groundProfile[1], 32, new int[0]);
     this.finalT = finalT;
     this.transientT = transientT;
-    this.expectedBatch = expectedBatch;
-    this.maxWaitMillis = maxWaitMillis;
+    this.observe = observe;
+    this.open = new GpuOutcome.Pending(this);
   }
 
-  /** The whole population in one vsr_eval call. */
-  public synchronized List<GpuOutcome> applyAll(List<Robot> robots) {
-    if (robots.isEmpty()) {
-      return List.of();
+  /** (1) record the robot, return a lazy outcome. Thread-safe: JGEA calls this from its executor's threads. */
+  @Override
+  public synchronized Outcome apply(Robot robot) {
+    GpuOutcome.Pending batch = open;
+    batch.robots.add(robot);
+    return new GpuOutcome(batch, batch.robots.size() - 1, transientT, finalT);
+  }
+
+  /** (2) the whole population in one call. */
+  public List<Outcome> applyAll(List<Robot> robots) {
+    List<Outcome> outcomes = new ArrayList<>(robots.size());
+    GpuOutcome.Pending batch;
+    synchronized (this) { // a private batch: robots recorded by concurrent apply() calls stay in theirs
+      batch = new GpuOutcome.Pending(this);
+      batch.robots.addAll(robots);
     }
-    if (!configured) {
-      RobotFlattener.configure(ctx, robots.get(0)); // vsr_body_set + vsr_controller_set from the first robot
-      configured = true;
-    }
-    int g = VsrEval.genomeLength(ctx);
-    double[] genomes = new double[robots.size() * g];
     for (int i = 0; i < robots.size(); i++) {
-      System.arraycopy(RobotFlattener.parameters(robots.get(i)), 0, genomes, i * g, g);
+      outcomes.add(new GpuOutcome(batch, i, transientT, finalT));
     }
-    double[] r = VsrEval.eval(ctx, genomes, robots.size());
-    List<GpuOutcome> outcomes = new ArrayList<>(robots.size());
-    for (int i = 0; i < robots.size(); i++) {
-      outcomes.add(new GpuOutcome(r[i * 8], r[i * 8 + 1], r[i * 8 + 2], r[i * 8 + 5], r[i * 8 + 6], transientT, finalT));
+    if (!robots.isEmpty()) {
+      batch.resolve();
     }
     return outcomes;
   }
 
-  /** One open batch: callers append, the filler (or the first waiter whose wait expires) closes and evaluates it. */
-  private static final class Batch {
-    final List<Robot> robots = new ArrayList<>();
-    final long t0 = System.currentTimeMillis();
-    List<GpuOutcome> outcomes;
-    RuntimeException error;
-    boolean done;
+  double lastBatchSeconds() {
+    return lastBatchSeconds;
   }
 
-  private Batch open = new Batch();
-  private final Object queueLock = new Object();
-
-  private void flush(Batch batch) {
-    try {
-      batch.outcomes = applyAll(batch.robots); // synchronized: a vsr_ctx is not re-entrant
-    } catch (RuntimeException e) {
-      batch.error = e;
-    }
-    synchronized (batch) {
-      batch.done = true;
-      batch.notifyAll();
-    }
-  }
-
-  /** Same protocol as vsrevolution_b200/locomotion.py:MicroBatchedLocomotion (exercised there by tests/test_host_mirror_cpu.py). */
-  @Override
-  public GpuOutcome apply(Robot robot) {
-    Batch batch;
-    int slot;
-    boolean full;
-    synchronized (queueLock) {
-      batch = open;
-      slot = batch.robots.size();
-      batch.robots.add(robot);
-      full = batch.robots.size() >= expectedBatch;
-      if (full) {
-        open = new Batch();
+  /** Called by Pending.resolve(): close the batch, flatten the robots, one vsr_eval_ex launch, keep the raw arrays. */
+  void evaluate(GpuOutcome.Pending batch) {
+    List<Robot> robots;
+    synchronized (this) {
+      if (open == batch) {
+        open = new GpuOutcome.Pending(this); // robots applied from now on belong to the next batch
+      }
+      robots = batch.robots;
+      if (!configured && !robots.isEmpty()) {
+        RobotFlattener.configure(ctx, robots.get(0)); // vsr_body_set + vsr_controller_set from the first robot
+        configured = true;
       }
     }
-    if (full) {
-      flush(batch);
-    } else {
-      boolean leader = false;
-      synchronized (batch) {
-        while (!batch.done && !leader) {
-          long left = batch.t0 + maxWaitMillis - System.currentTimeMillis();
-          if (left > 0) {
-            try {
-              batch.wait(left);
-            } catch (InterruptedException e) {
-              Thread.currentThread().interrupt();
-              throw new RuntimeException(e);
-            }
-          } else {
-            synchronized (queueLock) { // timeout: the first waiter that still finds the batch open closes it
-              if (open == batch) {
-                open = new Batch();
-                leader = true;
-              }
-            }
-            if (!leader) {
-              try {
-                batch.wait();
-              } catch (InterruptedException e) {
-                Thread.currentThread().interrupt();
-                throw new RuntimeException(e);
-              }
-            }
-          }
+    int n = robots.size();
+    if (n == 0) {
+      batch.results = new double[0];
+      return;
+    }
+    synchronized (VsrEval.class) { // a vsr_ctx is not re-entrant
+      long t0 = System.nanoTime();
+      int g = VsrEval.genomeLength(ctx);
+      double[] genomes = new double[n * g];
+      int[] frozen = new int[n];
+      boolean anyFrozen = false;
+      for (int i = 0; i < n; i++) {
+        System.arraycopy(RobotFlattener.parameters(robots.get(i)), 0, genomes, i * g, g);
+        frozen[i] = RobotFlattener.frozenMask(robots.get(i));
+        anyFrozen |= frozen[i] != 0;
+      }
+      int[] ep = VsrEval.episode(ctx);
+      batch.kept = ep[2] - ep[1] + 1;
+      if (observe) {
+        batch.posture = new byte[n * POSTURE_N * POSTURE_N];
+        batch.footprints = new byte[][]{new byte[n * batch.kept], new byte[n * batch.kept]};
+        batch.centers = new double[n * batch.kept * 3];
+        batch.results = VsrEval.evalEx(ctx, genomes, n, anyFrozen ? frozen : null, POSTURE_N, FOOTPRINT_N[0], FOOTPRINT_N[1],
+            batch.posture, batch.footprints[0], batch.footprints[1], batch.centers, batch.kept);
+      } else {
+        batch.results = VsrEval.evalEx(ctx, genomes, n, anyFrozen ? frozen : null, 0, 0, 0, null, null, null, null, batch.kept);
+      }
+      lastBatchSeconds = (System.nanoTime() - t0) * 1e-9;
+    }
+  }
+
+  /**
+   * (3) Eager batching for hosts that must not hand out lazy outcomes: wraps the run's ExecutorService; invokeAll(tasks) -- what JGEA's
+   * map() calls once per generation (Starter.java:436) -- runs the callables (each records its robot through apply()) and then resolves
+   * the batch before returning the futures, so every Individual leaves invokeAll with an evaluated fitness.
+   */
+  public java.util.concurrent.ExecutorService eagerExecutor(java.util.concurrent.ExecutorService inner) {
+    BatchedLocomotion self = this;
+    return new java.util.concurrent.AbstractExecutorService() {
+      @Override
+      public <T> List<java.util.concurrent.Future<T>> invokeAll(java.util.Collection<? extends java.util.concurrent.Callable<T>> tasks)
+          throws InterruptedException {
+        List<java.util.concurrent.Future<T>> futures = inner.invokeAll(tasks);
+        GpuOutcome.Pending batch;
+        synchronized (self) {
+          batch = self.open;
         }
+        if (!batch.robots.isEmpty()) {
+          batch.resolve();
+        }
+        return futures;
       }
-      if (leader) {
-        flush(batch);
+
+      @Override
+      public void execute(Runnable command) {
+        inner.execute(command);
       }
-    }
-    if (batch.error != null) {
-      throw batch.error;
-    }
-    return batch.outcomes.get(slot);
+
+      @Override
+      public void shutdown() {
+        inner.shutdown();
+      }
+
+      @Override
+      public List<Runnable> shutdownNow() {
+        return inner.shutdownNow();
+      }
+
+      @Override
+      public boolean isShutdown() {
+        return inner.isShutdown();
+      }
+
+      @Override
+      public boolean isTerminated() {
+        return inner.isTerminated();
+      }
+
+      @Override
+      public boolean awaitTermination(long timeout, java.util.concurrent.TimeUnit unit) throws InterruptedException {
+        return inner.awaitTermination(timeout, unit);
+      }
+    };
   }
 
   @Override
@@ -239,19 +276,59 @@ public class BatchedLocomotion implements Function<Robot, GpuOutcome>, AutoClose
         return ((MultiLayerPerceptron) cs.getFunction()).getParams();
       }
       if (c instanceof PhaseSin ps) {
-        // the phases of the voxels in Grid iteration order (brainPhaseFun fills the non-voxel cells too: skip them by the body)
+        // the phases of the voxels in the kernel's voxel order: y outer, x inner, y = 0 the bottom row -- an EXPLICIT loop, so that the
+        // order does not depend on how Grid.stream() / Grid.iterator() walk the cells (brainPhaseFun fills the non-voxel cells too: they
+        // are skipped by the body, builder/robot/BrainPhaseFunction.java:36-43)
         Grid<Voxel> body = robot.getVoxels();
-        return body.stream().filter(e -> e.value() != null).mapToDouble(e -> ps.getPhases().get(e.key().x(), e.key().y())).toArray();
+        double[] phases = new double[(int) body.values().stream().filter(v -> v != null).count()];
+        int c = 0;
+        for (int y = 0; y < body.getH(); y++) {
+          for (int x = 0; x < body.getW(); x++) {
+            if (body.get(x, y) != null) {
+              phases[c++] = ps.getPhases().get(x, y);
+            }
+          }
+        }
+        return phases;
       }
       if (c instanceof DistributedSensing ds) {
         // kind 2 (brainHomoDist): the shared weights once; kind 3 (brainHeteroDist): every voxel's weights, Grid iteration order
         // (== FunctionsGrid's slicing order, builder/misc/FunctionsGrid.java:31-46)
-        List<double[]> ws = ds.getFunctions().values().stream().filter(f -> f != null)
-            .map(f -> ((MultiLayerPerceptron) f).getParams()).toList();
+        List<double[]> ws = new ArrayList<>();
+        for (int y = 0; y < ds.getFunctions().getH(); y++) { // explicit y-outer / x-inner order, as for the phases above
+          for (int x = 0; x < ds.getFunctions().getW(); x++) {
+            if (ds.getFunctions().get(x, y) != null) {
+              ws.add(((MultiLayerPerceptron) ds.getFunctions().get(x, y)).getParams());
+            }
+          }
+        }
         boolean homo = ws.stream().allMatch(w -> java.util.Arrays.equals(w, ws.get(0)));
         return homo ? ws.get(0) : ws.stream().flatMapToDouble(java.util.Arrays::stream).toArray();
       }
       throw new IllegalArgumentException("Unsupported controller " + c.getClass().getSimpleName());
+    }
+
+    /**
+     * bit v (voxel order: y outer, x inner) = voxel v is a BreakableVoxel, i.e. what `broken-<ratio>-<seed>` of
+     * RobotUtils.buildRobotTransformation put there (Starter.java:126,428): ACTUATOR FROZEN from t = 0 [U]. Other BreakableVoxel
+     * configurations (`breakable-...`: malfunctions triggered during the episode) are outside the device build and are rejected.
+     */
+    static int frozenMask(Robot robot) {
+      Grid<Voxel> body = robot.getVoxels();
+      int mask = 0, v = 0;
+      for (int y = 0; y < body.getH(); y++) {
+        for (int x = 0; x < body.getW(); x++) {
+          Voxel voxel = body.get(x, y);
+          if (voxel == null) {
+            continue;
+          }
+          if (voxel instanceof BreakableVoxel) {
+            mask |= 1 << v;
+          }
+          v++;
+        }
+      }
+      return mask;
     }
   }
 }

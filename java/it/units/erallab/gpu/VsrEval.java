@@ -27,6 +27,14 @@ public final class VsrEval {
   /** vsr_eval: genomes[n*G] row-major -> results[n*8] = {velocity, distance, time, firstX, lastX, controlEnergy, areaRatioAbs, areaRatioSq}. */
   public static native double[] eval(long ctx, double[] genomes, int n);
 
+  /** vsr_eval_ex: frozen-actuator masks (`broken-<ratio>-<seed>` robots) and the per-observation summaries; null / 0 = not requested.
+   *  Returns results[n*8] like eval; fills postureOut[n*pN*pN], footprints{0,1}Out[n*kept], centersOut[n*kept*3]. */
+  public static native double[] evalEx(long ctx, double[] genomes, int n, int[] frozenMasks, int postureN, int footprintN0, int footprintN1,
+                                       byte[] postureOut, byte[] footprints0Out, byte[] footprints1Out, double[] centersOut, int kept);
+
+  /** {nSteps, kFirst, kLast} of the context's episode: kept = kLast - kFirst + 1 observations. */
+  public static native int[] episode(long ctx);
+
   /** vsr_eval_terrains: robot i on the polyline xs/ys[off[i]..off[i+1]) -- the -rnd terrains of Starter.java:89-93. */
   public static native double[] evalTerrains(long ctx, double[] genomes, int n, double[] terrainXs, double[] terrainYs, int[] terrainOff);
 

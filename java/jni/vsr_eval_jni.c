@@ -160,6 +160,68 @@ JNIEXPORT jdoubleArray JNICALL Java_it_units_erallab_gpu_VsrEval_evalTerrains(JN
   return out;
 }
 
+/* vsr_eval_ex: the general batched call -- frozen-actuator masks of `broken-<ratio>-<seed>` robots (Starter.java:126,428), average
+ * posture (Starter.java:180-190), footprints (NamedFunctions.java:179-180,392), centre + central-voxel-angle trajectories
+ * (NamedFunctions.java:139-172).  Output arrays may be null (= not requested); lengths are checked against n and K. */
+JNIEXPORT jdoubleArray JNICALL Java_it_units_erallab_gpu_VsrEval_evalEx(JNIEnv* env, jclass c, jlong h, jdoubleArray genomes, jint n,
+                                                                        jintArray frozenMasks, jint postureN, jint fpN0, jint fpN1,
+                                                                        jbyteArray postureOut, jbyteArray fp0Out, jbyteArray fp1Out,
+                                                                        jdoubleArray centersOut, jint kept) {
+  (void)c;
+  vsr_ctx* ctx = (vsr_ctx*)(intptr_t)h;
+  if (bad_batch(env, ctx, genomes, n)) return NULL;
+  if (postureN < 0 || postureN > 8 || fpN0 < 0 || fpN0 > 8 || fpN1 < 0 || fpN1 > 8 || kept < 0) { throw_iae(env, "bad observation request"); return NULL; }
+  if (frozenMasks && (*env)->GetArrayLength(env, frozenMasks) < n) { throw_iae(env, "frozenMasks.length < n"); return NULL; }
+  if ((postureN > 0) != (postureOut != NULL) || (fpN0 > 0) != (fp0Out != NULL) || (fpN1 > 0) != (fp1Out != NULL)) {
+    throw_iae(env, "observation sizes and output arrays go together"); return NULL;
+  }
+  if (postureOut && (jlong)(*env)->GetArrayLength(env, postureOut) < (jlong)n * postureN * postureN) { throw_iae(env, "postureOut too short"); return NULL; }
+  if (fp0Out && (jlong)(*env)->GetArrayLength(env, fp0Out) < (jlong)n * kept) { throw_iae(env, "footprints0Out too short"); return NULL; }
+  if (fp1Out && (jlong)(*env)->GetArrayLength(env, fp1Out) < (jlong)n * kept) { throw_iae(env, "footprints1Out too short"); return NULL; }
+  if (centersOut && (jlong)(*env)->GetArrayLength(env, centersOut) < (jlong)n * kept * 3) { throw_iae(env, "centersOut too short"); return NULL; }
+  {
+    /* `kept` must be the library's own K, or the native writes would not match the Java arrays */
+    int32_t ns = 0, kf = 0, kl = 0;
+    if (vsr_ctx_episode(ctx, &ns, &kf, &kl) || kl - kf + 1 != kept) { throw_iae(env, "kept != k_last - k_first + 1 of this context"); return NULL; }
+  }
+  vsr_eval_opts o;
+  memset(&o, 0, sizeof(o));
+  jdouble* pg = (*env)->GetDoubleArrayElements(env, genomes, NULL);
+  jint* pf = frozenMasks ? (*env)->GetIntArrayElements(env, frozenMasks, NULL) : NULL;
+  jbyte* pp = postureOut ? (*env)->GetByteArrayElements(env, postureOut, NULL) : NULL;
+  jbyte* p0 = fp0Out ? (*env)->GetByteArrayElements(env, fp0Out, NULL) : NULL;
+  jbyte* p1 = fp1Out ? (*env)->GetByteArrayElements(env, fp1Out, NULL) : NULL;
+  jdouble* pc = centersOut ? (*env)->GetDoubleArrayElements(env, centersOut, NULL) : NULL;
+  o.frozen_masks = (const uint32_t*)pf;
+  o.posture_n = postureN; o.footprint_n[0] = fpN0; o.footprint_n[1] = fpN1;
+  o.posture_out = (uint8_t*)pp; o.footprints_out[0] = (uint8_t*)p0; o.footprints_out[1] = (uint8_t*)p1; o.centers_out = pc;
+  double* fit = (double*)malloc(sizeof(double) * (n ? n : 1));
+  vsr_result* res = (vsr_result*)malloc(sizeof(vsr_result) * (n ? n : 1));
+  int rc = vsr_eval_ex(ctx, pg, n, &o, fit, res);
+  if (pc) (*env)->ReleaseDoubleArrayElements(env, centersOut, pc, 0); /* mode 0: copy back */
+  if (p1) (*env)->ReleaseByteArrayElements(env, fp1Out, p1, 0);
+  if (p0) (*env)->ReleaseByteArrayElements(env, fp0Out, p0, 0);
+  if (pp) (*env)->ReleaseByteArrayElements(env, postureOut, pp, 0);
+  if (pf) (*env)->ReleaseIntArrayElements(env, frozenMasks, pf, JNI_ABORT);
+  (*env)->ReleaseDoubleArrayElements(env, genomes, pg, JNI_ABORT);
+  jdoubleArray out = NULL;
+  if (rc) throw_status(env, ctx, rc);
+  else out = pack_results(env, res, n);
+  free(fit); free(res);
+  return out;
+}
+
+/* {n_steps, k_first, k_last} of the context's episode (vsr_episode_steps on its own final_t / transient_t / dt) */
+JNIEXPORT jintArray JNICALL Java_it_units_erallab_gpu_VsrEval_episode(JNIEnv* env, jclass c, jlong h) {
+  (void)c;
+  int32_t v[3] = {0, 0, 0};
+  int rc = vsr_ctx_episode((vsr_ctx*)(intptr_t)h, &v[0], &v[1], &v[2]);
+  if (rc) { throw_status(env, (vsr_ctx*)(intptr_t)h, rc); return NULL; }
+  jintArray out = (*env)->NewIntArray(env, 3);
+  (*env)->SetIntArrayRegion(env, out, 0, 3, (const jint*)v);
+  return out;
+}
+
 /* ---- the device-resident numGA loop (include/vsr_ga.h; DoublesStandard.java:41-71) ---- */
 static void throw_ga(JNIEnv* env, vsr_ga* ga, int rc) {
   const char* cls = (rc == VSR_EINVAL || rc == VSR_EDIM) ? "java/lang/IllegalArgumentException" : "java/lang/RuntimeException";

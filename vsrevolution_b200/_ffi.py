@@ -97,6 +97,7 @@ _SIGS = {
     "vsr_broken_masks_stream": (C.c_int, [C.c_void_p, C.c_double, C.POINTER(C.c_uint64), C.c_int32, C.c_void_p]),
     "vsr_robot_transformation": (C.c_int, [C.c_char_p, C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     "vsr_central_voxel": (C.c_int, [C.c_void_p]),
+    "vsr_ctx_episode": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "vsr_trace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vsr_last_kernel_ms": (C.c_double, [C.c_void_p]),
     "vsr_kernel_launches": (C.c_int64, [C.c_void_p]),

@@ -1101,6 +1101,14 @@ int vsr_stage_eval_opts(vsr_ctx* ctx, int32_t n, const vsr_eval_opts* opts) {
   return VSR_OK;
 }
 
+int vsr_ctx_episode(const vsr_ctx* ctx, int32_t* n_steps, int32_t* k_first, int32_t* k_last) {
+  if (!ctx || !ctx->ready) return VSR_ESTATE;
+  if (n_steps) *n_steps = ctx->kp.n_steps;
+  if (k_first) *k_first = ctx->kp.k_first;
+  if (k_last) *k_last = ctx->kp.k_last;
+  return VSR_OK;
+}
+
 int vsr_central_voxel(const vsr_ctx* ctx) { return ctx && ctx->ready ? ctx->central_vox : VSR_ESTATE; }
 
 int vsr_eval_device(vsr_ctx* ctx, const double* d_genomes, int32_t n, double* d_fitness, vsr_result* d_results, void* stream) {

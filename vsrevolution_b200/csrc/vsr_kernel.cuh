@@ -51,7 +51,7 @@ constexpr int kSyncMaskDefault = VSR_SYNC_MASK_DEFAULT;
 #define VSR_POS_V2 1 // position iterations: branch-free rotations (deferred exact refresh), branch-free ropes, unrolled contact points
 #endif
 #ifndef VSR_CACHE_MASS
-#define VSR_CACHE_MASS 1 // contact phases: the lane's touching mass and its manifold slots cached in a register per step
+#define VSR_CACHE_MASS 0 // contact phases: the touching mass + its manifold slots cached in a register per step (A/B r2: -1.7 %: not kept)
 #endif
 #ifndef VSR_SOFT_SYNC
 #define VSR_SOFT_SYNC 0 // > 0: bounded-skew phase alignment (warps may run this many boundaries ahead); 0: __syncthreads
