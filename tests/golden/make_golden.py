@@ -58,7 +58,27 @@ def build(cfg) -> dict:
                 k_first=np.array([r.k_first for r in res]), k_last=np.array([r.k_last for r in res]), n_steps=np.array([r.n_steps for r in res]))
 
 
+# what java/harness/DumpLocomotion.java (the real 2dhmsr Locomotion, run by a maintainer with the jars or by `bench.py --impl reference`
+# when it finds a JVM) needs to replay the same robots: header `shape;sensorConfig;mapper;terrain;finalT`, one genome per line
+REF_SPECS = {1: ("biped-4x3", "uniform-a-0", "brainCentralized<mlp;r=0.65;nIL=1", "flat"),
+             3: ("worm-8x2", "uniform-a-0", "brainPhaseVals;f=1", "hilly-1-10-0"),
+             4: ("comb-7x2", "uniform-t+vxy+a-0", "brainHomoDist;s=1<mlp;r=0.65;nIL=1", "steppy-0.25-1-0")}
+
+
+def write_reference_inputs():
+    for cfg, (shape, sensors, mapper, terrain) in REF_SPECS.items():
+        g = np.load(os.path.join(HERE, f"config{cfg}.npz"))["genomes"]
+        with open(os.path.join(HERE, f"config{cfg}.genomes.csv"), "w") as f:
+            f.write(f"{shape};{sensors};{mapper};{terrain};{T}\n")
+            for row in g:
+                f.write(",".join(repr(float(x)) for x in row) + "\n")
+        print("wrote config%d.genomes.csv" % cfg)
+
+
 if __name__ == "__main__":
+    if sys.argv[1:] == ["--csv"]:
+        write_reference_inputs()
+        sys.exit(0)
     only = sys.argv[1:]
     for cfg in list(SEEDS) + ["hetero", "timesin"]:
         name = cfg if isinstance(cfg, str) else f"config{cfg}"

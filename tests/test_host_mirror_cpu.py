@@ -303,3 +303,40 @@ def test_outcome_quantized_spectrum(V):
     assert int(np.argmax(o.get_center_x_position_spectrum(0.0, 4.0, 8))) == 0             # the drift dominates the position spectrum
     with pytest.raises(F.VsrError):
         L.Outcome(0.5, 4.5, 9.0, 0.0, 4.5, 1.0, 10.0).get_center_x_velocity_spectrum(0, 4, 8)
+
+
+def test_lazy_batching_evaluates_a_generation_in_one_call(V):
+    """LazyBatchedLocomotion (the Java shim's default strategy): apply() records, the first getter on any outcome of the batch evaluates
+    the whole batch once; robots applied afterwards open the next batch; an evaluation error reaches every outcome of its batch."""
+    from concurrent.futures import ThreadPoolExecutor
+    from vsrevolution_b200.locomotion import LazyBatchedLocomotion, Outcome
+
+    class FakeTask:
+        transient_t, final_t = 1.0, 3.0
+
+        def __init__(self):
+            self.calls = []
+
+        def apply_all(self, robots):
+            self.calls.append(len(robots))
+            if any(r == "boom" for r in robots):
+                raise RuntimeError("device failure")
+            return [Outcome(float(r), float(r) * 2, 2.0, 0.0, 0.0, 1.0, 3.0) for r in robots]
+
+    task = FakeTask()
+    lazy = LazyBatchedLocomotion(task)
+    with ThreadPoolExecutor(8) as ex:                                 # JGEA's executor threads (Starter.java:436)
+        gen1 = list(ex.map(lambda r: lazy.apply(r).sub_outcome(1.0, 3.0), range(40)))
+    assert task.calls == []                                            # nothing evaluated while the Individuals are being built
+    ranked = sorted(gen1, key=lambda o: -o.get_velocity())             # the comparator reads the first fitness: one call for all 40
+    assert task.calls == [40] and ranked[0].get_velocity() == 39.0 and lazy.batches_flushed == 1
+    assert sorted(o.get_distance() for o in gen1) == [2.0 * i for i in range(40)]
+    gen2 = [lazy.apply(r) for r in (5, 6, 7)]
+    assert gen2[2].get_velocity() == 7.0 and task.calls == [40, 3]
+    bad = [lazy.apply(r) for r in (1, "boom", 2)]
+    for o in bad:
+        with pytest.raises(RuntimeError):
+            o.get_velocity()
+    assert task.calls == [40, 3, 3]
+    with pytest.raises(ValueError):
+        lazy.apply(1).sub_outcome(0.0, 3.0)

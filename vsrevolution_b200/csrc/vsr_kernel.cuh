@@ -50,6 +50,9 @@ constexpr int kSyncMaskDefault = VSR_SYNC_MASK_DEFAULT;
 #ifndef VSR_POS_V2
 #define VSR_POS_V2 1 // position iterations: branch-free rotations (deferred exact refresh), branch-free ropes, unrolled contact points
 #endif
+#ifndef VSR_REFRESH_CS
+#define VSR_REFRESH_CS 1 // FP32: exact sin / cos from the accumulated angles after the position iterations
+#endif
 #ifndef VSR_CACHE_MASS
 #define VSR_CACHE_MASS 0 // contact phases: the touching mass + its manifold slots cached in a register per step (A/B r2: -1.7 %: not kept)
 #endif
@@ -149,9 +152,10 @@ struct KParams {
 template <class R> struct M;
 // A/B switches for the FP32 approximations (profiles/r2_fp32_approx_ab.md: which one ends step-wise tracking of the oracle first):
 //   -DVSR_IEEE_DIV      correctly rounded reciprocal / reciprocal square root instead of the MUFU approximations
-//   -DVSR_LIBM_SINCOS   CUDA libm sincosf instead of the Cody-Waite polynomials
+//   -DVSR_FAST_SINCOS   the Cody-Waite sincos polynomials instead of CUDA libm sincosf (the round-1 form)
 //   -DVSR_NO_SMALL_ROTATE  every position-solver rotation re-evaluates sin / cos of the angle (no small-angle update)
-//   -DVSR_LIBM_TANH     tanhf instead of ex2.approx + rcp.approx
+//   -DVSR_FAST_TANH     ex2.approx + rcp.approx tanh instead of tanhf (the round-1 form)
+//   -DVSR_REFRESH_CS=0  no exact sin / cos refresh after the position iterations (the round-1 behaviour)
 template <> struct M<float> {
 #ifdef VSR_IEEE_DIV
   static __device__ __forceinline__ float rcp(float x) { return __frcp_rn(x); }
@@ -166,7 +170,9 @@ template <> struct M<float> {
   static __device__ __forceinline__ float rint_(float a) { return rintf(a); }
   // Cody-Waite reduction by pi/2 + minimax polynomials on [-pi/4, pi/4]; |a| < ~1e5
   static __device__ __forceinline__ void sincos_(float a, float* sn, float* cs) {
-#ifdef VSR_LIBM_SINCOS
+#ifndef VSR_FAST_SINCOS
+    // CUDA libm sincosf (<= 2 ulp over the whole range): +0.6 % kernel time on config 2, and the step count over which the FP32 kernel
+    // tracks the oracle grows 1.4-3.3x (profiles/r2_fp32_approx_ab.md); -DVSR_FAST_SINCOS restores the Cody-Waite polynomials below
     sincosf(a, sn, cs);
     return;
 #endif
@@ -218,7 +224,10 @@ template <> struct M<float> {
     c = c2;
   }
   static __device__ __forceinline__ float tanh_(float x) {
-#ifdef VSR_LIBM_TANH
+#ifndef VSR_FAST_TANH
+    // CUDA libm tanhf (<= 2 ulp): the controller's 27 tanh per robot-step cost nothing measurable, while the 2e-7 absolute error of the
+    // ex2.approx / rcp.approx form below cut the number of steps the FP32 kernel tracks the oracle by 2.6x on the MLP robots
+    // (profiles/r2_fp32_approx_ab.md); -DVSR_FAST_TANH restores it
     return tanhf(x);
 #endif
     // 1 - 2/(e^{2x}+1); ex2.approx + rcp.approx, abs error ~2e-7
@@ -1456,6 +1465,15 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
         if (!(bad & robot_mask)) active = false;
         if (!__any_sync(FULL, active)) break;
       }
+#if VSR_REFRESH_CS
+      // (cos, sin) were rotated incrementally through the iterations (FP32: each update rounds): re-evaluate them once from the exactly
+      // accumulated angles, so that detect, sensing and the next step's spring initialisation start from sin / cos accurate to 2 ulp
+      // (profiles/r2_fp32_approx_ab.md: this is what ended step-wise tracking of the oracle first)
+      if (sizeof(R) == 4) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) M<R>::sincos_(A[k], &SN[k], &CS[k]);
+      }
+#endif
     }
 
     // ---- re-centre the lane origin (integer shifts; keeps |local| small) -------------------------------

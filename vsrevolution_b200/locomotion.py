@@ -430,6 +430,75 @@ class MicroBatchedLocomotion:
         return batch.outcomes[slot]
 
 
+class LazyOutcome:
+    """What `LazyBatchedLocomotion.apply` returns: an Outcome whose getters are answered after the whole batch it belongs to has been
+    evaluated in ONE launch; the first getter called on any outcome of the batch triggers that evaluation
+    (java/it/units/erallab/gpu/GpuOutcome.java is the Java form)."""
+
+    def __init__(self, batch: "LazyBatchedLocomotion._Batch", slot: int):
+        self._batch, self._slot = batch, slot
+
+    def _resolved(self) -> Outcome:
+        return self._batch.resolve()[self._slot]
+
+    def sub_outcome(self, start_t: float, end_t: float) -> "LazyOutcome":
+        task = self._batch.task
+        if start_t != task.transient_t or end_t != task.final_t:
+            raise _ffi.VsrIllegalArgument(_ffi.VSR_EINVAL, "the device only keeps the window given to Locomotion(transient_t=...)")
+        return self  # still lazy: Starter.java:430-433 calls it on every outcome before anybody reads a value
+
+    def __getattr__(self, name):  # every other getter / field of Outcome: resolve, then delegate
+        if name.startswith("_"):
+            raise AttributeError(name)
+        return getattr(self._resolved(), name)
+
+
+class LazyBatchedLocomotion:
+    """Host strategy (3) of SURVEY.md 8b, the one the Java shim uses by default: keep JGEA's one-robot-per-call contract
+    (`qualityFunction.apply(robot)`, Starter.java:427-436) with NO extra threads and NO time-outs.  `apply(robot)` only records the
+    robot and returns a LazyOutcome; JGEA builds its Individuals without reading the fitness object and reads it when it orders the new
+    population -- at that moment the whole generation goes to the device in one `apply_all` call."""
+
+    class _Batch:
+        def __init__(self, task):
+            self.task, self.robots, self.outcomes, self.error = task, [], None, None
+            self.lock = threading.Lock()
+
+        def resolve(self):
+            with self.lock:
+                if self.outcomes is None and self.error is None:
+                    self.task._close(self)
+                    try:
+                        self.outcomes = self.task._evaluate(self.robots)
+                    except Exception as e:  # every outcome of the batch reports the failure, like Locomotion.apply throwing
+                        self.error = e
+            if self.error is not None:
+                raise self.error
+            return self.outcomes
+
+    def __init__(self, task: "Locomotion", observed: bool = False):
+        self.task, self.observed = task, observed
+        self.transient_t, self.final_t = task.transient_t, task.final_t
+        self._lock = threading.Lock()
+        self._open = self._Batch(self)
+        self.batches_flushed = 0
+
+    def apply(self, robot: Robot) -> LazyOutcome:
+        with self._lock:
+            batch = self._open
+            batch.robots.append(robot)
+            return LazyOutcome(batch, len(batch.robots) - 1)
+
+    def _close(self, batch):
+        with self._lock:
+            if self._open is batch:
+                self._open = self._Batch(self)  # robots applied from now on belong to the next batch
+
+    def _evaluate(self, robots):
+        self.batches_flushed += 1
+        return self.task.apply_all_observed(robots) if self.observed else self.task.apply_all(robots)
+
+
 class PopulationEvaluator:
     """genome matrix -> fitness vector for one (shape, sensors, mapper, terrain): what a batching JGEA evolver calls
     once per generation.  For the mappers whose genome IS the controller parameter vector (brainCentralized<mlp,
