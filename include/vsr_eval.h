@@ -65,15 +65,22 @@ typedef struct {
 
 /* ---- sensors: one entry of the uniform per-voxel list built by
  *      RobotUtils.buildSensorizingFunction("uniform-<s1+s2..>-<sigma>") (Starter.java:404-405) - */
-enum { VSR_SENSOR_AREA_RATIO = 0, VSR_SENSOR_TOUCH = 1, VSR_SENSOR_VELOCITY = 2, VSR_SENSOR_ANGLE = 3 };
+/* CONSTANT: Constant(value) -- the `px` / `py` predefined sensors (the voxel's relative grid position); TIME_SIN:
+ * TimeFunction(t -> sin(2 pi param t), -1, 1) -- `cpg` (param = -1); LIDAR: Lidar(rayLength = param, {side: n_rays}) -- `l1`, `l5`, `lf5`:
+ * distance to the ground along n_rays rays of one side's sector, rotating with the voxel (the rays see the ground only) [U] */
+enum { VSR_SENSOR_AREA_RATIO = 0, VSR_SENSOR_TOUCH = 1, VSR_SENSOR_VELOCITY = 2, VSR_SENSOR_ANGLE = 3, VSR_SENSOR_CONSTANT = 4,
+       VSR_SENSOR_TIME_SIN = 5, VSR_SENSOR_LIDAR = 6 };
 typedef struct {
   int32_t kind;
   int32_t axes;       /* VELOCITY: bit0 X, bit1 Y */
   int32_t rotated;    /* VELOCITY: voxel frame */
-  int32_t soft_norm;  /* SoftNormalization wrapper */
+  int32_t soft_norm;  /* 1: SoftNormalization wrapper; 2: Normalization wrapper ((x - min) / (max - min), clipped to [0, 1]) */
   double dom_min, dom_max;
   double avg_window;  /* Average wrapper window [s], 0 = none */
   double noise_sigma; /* Noisy(sensor, sigma, seed 0) wrapper: + nextGaussian()*sigma*|domain| (java.util.Random replayed on the host) */
+  double param;       /* CONSTANT: the value; TIME_SIN: frequency; LIDAR: ray length */
+  int32_t n_rays;     /* LIDAR: number of rays = readings (1..8) */
+  int32_t side;       /* LIDAR: 0 N, 1 E, 2 S, 3 W */
 } vsr_sensor_desc;
 
 /* ---- controllers: CentralizedSensing (builder/robot/BrainCentralized.java:42-45), PhaseSin
@@ -122,6 +129,13 @@ const char* vsr_last_error(const vsr_ctx* ctx); /* ctx may be NULL: error of the
 /* body grid: mask[y*w+x] != 0 where a voxel exists, y = 0 is the bottom row; same sensors on every voxel.
  * Replaces RobotUtils.buildSensorizingFunction(cfg).apply(RobotUtils.buildShape(shape)) (Starter.java:402-406). */
 int vsr_body_set(vsr_ctx* ctx, int32_t w, int32_t h, const uint8_t* mask, const vsr_sensor_desc* sensors, int32_t n_sensors);
+
+/* The same with one sensor list PER VOXEL: what RobotUtils.buildSensorizingFunction returns for names other than `uniform-...`
+ * (`spinedTouch-<cpg>-<malfunction>-<sigma>`, `spinedTouchSighted-...`) and for the position-dependent predefined sensors (`px`, `py`,
+ * `l1`, `l5`).  Voxel v (grid order: y outer, x inner, y = 0 bottom) carries sensors[sensor_off[v] .. sensor_off[v + 1]); at most 8
+ * readings per voxel.  CentralizedSensing concatenates the voxels' readings in grid order (vsr_input_map); DistributedSensing needs the
+ * same number of readings on every voxel (one MLP input size), as in the reference (builder/robot/BrainHomoDistributed.java:52-58). */
+int vsr_body_set_voxels(vsr_ctx* ctx, int32_t w, int32_t h, const uint8_t* mask, const vsr_sensor_desc* sensors, const int32_t* sensor_off);
 
 /* controller: layers[] = MLP neurons per layer incl. input and output (ignored for PHASE_SIN / TIME_SIN) */
 int vsr_controller_set(vsr_ctx* ctx, vsr_ctrl_kind kind, const int32_t* layers, int32_t n_layers, int32_t signals,
@@ -242,6 +256,11 @@ int vsr_shape_mask(const char* name, int32_t* w, int32_t* h, uint8_t* mask, int3
 int vsr_terrain(const char* name, double* xs, double* ys, int32_t cap);
 /* RobotUtils.buildSensorizingFunction("uniform-a+t-0"): returns number of sensors per voxel */
 int vsr_sensor_config(const char* name, vsr_sensor_desc* out, int32_t cap);
+/* RobotUtils.buildSensorizingFunction(name).apply(body) with per-voxel lists [U]: `uniform-<s1+s2..>-<sigma>` over the predefined
+ * sensors a, t, r, vx, vy, vxy, px, py, cpg, l1, l5, lf5; `spinedTouch-<t|f>-<t|f>-<sigma>`; `spinedTouchSighted-<t|f>-<t|f>-<sigma>`;
+ * `empty`.  Writes the concatenated lists (voxels in grid order) and off_out[n_voxels + 1]; returns the total number of sensors.
+ * The predefined sensors ax / ay / axy (Trend) and m (Malfunction) are outside this build: VSR_EUNSUPPORTED. */
+int vsr_sensor_config_voxels(const char* name, int32_t w, int32_t h, const uint8_t* mask, vsr_sensor_desc* out, int32_t cap, int32_t* off_out);
 /* builder/function/MLP.java:28-42 innerNeurons */
 int vsr_mlp_inner_neurons(int32_t n_in, int32_t n_out, double ratio, int32_t n_inner, int32_t* out);
 /* MultiLayerPerceptron.countWeights(neurons) */

@@ -187,6 +187,19 @@ public class BatchedLocomotion implements Function<Robot, Outcome>, AutoCloseabl
     };
   }
 
+  /** Lidar.Side of a one-sided Lidar from its first ray direction [U]: N (pi/4, 3pi/4) = 0, E (-pi/4, pi/4) = 1, S = 2, W = 3. */
+  static int lidarSide(double[] rayDirections) {
+    double a = rayDirections[rayDirections.length / 2];
+    a = Math.atan2(Math.sin(a), Math.cos(a));
+    if (a > Math.PI / 4 && a <= 3 * Math.PI / 4) {
+      return 0;
+    }
+    if (a > -Math.PI / 4 && a <= Math.PI / 4) {
+      return 1;
+    }
+    return a < 0 ? 2 : 3;
+  }
+
   @Override
   public void close() {
     VsrEval.destroy(ctx);
@@ -218,19 +231,32 @@ public class BatchedLocomotion implements Function<Robot, Outcome>, AutoCloseabl
       if (first == null) {
         throw new IllegalArgumentException("Target robot has no voxels");
       }
-      // the uniform per-voxel sensor list (buildSensorizingFunction("uniform-...")), wrappers peeled from the outside in
-      List<Sensor> sensors = first.getSensors();
-      int[] si = new int[4 * sensors.size()];
-      double[] sd = new double[4 * sensors.size()];
+      // every voxel's own sensor list (RobotUtils.buildSensorizingFunction: uniform, spinedTouch, px / py / l5 ...), voxels in the
+      // kernel's order (y outer, x inner), wrappers peeled from the outside in
+      List<Sensor> sensors = new ArrayList<>();
+      List<Integer> offsets = new ArrayList<>(List.of(0));
+      for (int y = 0; y < h; y++) {
+        for (int x = 0; x < w; x++) {
+          if (body.get(x, y) != null) {
+            sensors.addAll(body.get(x, y).getSensors());
+            offsets.add(sensors.size());
+          }
+        }
+      }
+      int[] sensorOff = offsets.stream().mapToInt(Integer::intValue).toArray();
+      int[] si = new int[6 * sensors.size()];
+      double[] sd = new double[5 * sensors.size()];
       for (int i = 0; i < sensors.size(); i++) {
         Sensor s = sensors.get(i);
         double window = 0, sigma = 0;
-        boolean softNorm = false;
+        int norm = 0;
         while (s instanceof CompositeSensor cs) {
           if (s instanceof Noisy n) {
             sigma = n.getSigma();
           } else if (s instanceof SoftNormalization) {
-            softNorm = true;
+            norm = 1;
+          } else if (s instanceof it.units.erallab.hmsrobots.core.sensors.Normalization) {
+            norm = 2;
           } else if (s instanceof Average a) {
             window = a.getInterval();
           } else {
@@ -238,7 +264,8 @@ public class BatchedLocomotion implements Function<Robot, Outcome>, AutoCloseabl
           }
           s = cs.getSensor();
         }
-        int kind, axes = 0, rotated = 0;
+        int kind, axes = 0, rotated = 0, nRays = 0, side = 0;
+        double param = 0;
         if (s instanceof AreaRatio) {
           kind = 0;
         } else if (s instanceof Touch) {
@@ -249,13 +276,23 @@ public class BatchedLocomotion implements Function<Robot, Outcome>, AutoCloseabl
           rotated = vel.isRotated() ? 1 : 0;
         } else if (s instanceof Angle) {
           kind = 3;
+        } else if (s instanceof it.units.erallab.hmsrobots.core.sensors.Constant k) {
+          kind = 4;
+          param = k.getValues()[0]; // [U]
+        } else if (s instanceof it.units.erallab.hmsrobots.core.sensors.Lidar l) {
+          kind = 6;
+          param = l.getRayLength(); // [U]
+          nRays = l.getRayDirections().length; // [U]; one side per Lidar, as RobotUtils builds them
+          side = BatchedLocomotion.lidarSide(l.getRayDirections());
         } else {
+          // TimeFunction sensors hold an opaque lambda: only RobotUtils' `cpg` (sin(-2 pi t)) is known to the device (kind 5, param -1)
           throw new IllegalArgumentException("Unsupported sensor " + s.getClass().getSimpleName());
         }
-        si[4 * i] = kind; si[4 * i + 1] = axes; si[4 * i + 2] = rotated; si[4 * i + 3] = softNorm ? 1 : 0;
-        sd[4 * i] = s.getDomains()[0].min(); sd[4 * i + 1] = s.getDomains()[0].max(); sd[4 * i + 2] = window; sd[4 * i + 3] = sigma;
+        si[6 * i] = kind; si[6 * i + 1] = axes; si[6 * i + 2] = rotated; si[6 * i + 3] = norm; si[6 * i + 4] = nRays; si[6 * i + 5] = side;
+        sd[5 * i] = s.getDomains()[0].min(); sd[5 * i + 1] = s.getDomains()[0].max(); sd[5 * i + 2] = window; sd[5 * i + 3] = sigma;
+        sd[5 * i + 4] = param;
       }
-      VsrEval.setBody(ctx, w, h, mask, si, sd);
+      VsrEval.setBody(ctx, w, h, mask, si, sd, sensorOff);
       Object c = robot.getController();
       if (c instanceof PhaseSin ps) {
         VsrEval.setController(ctx, 0, new int[0], 0, ps.getFrequency(), ps.getAmplitude(), true);

@@ -14,8 +14,9 @@ public final class VsrEval {
   /** vsr_env_default + vsr_ctx_create; terrain = Locomotion.createTerrain(name) ({xs, ys}). Returns the vsr_ctx handle. */
   public static native long create(double finalT, double transientT, double[] terrainXs, double[] terrainYs, int precision, int[] devices);
 
-  /** vsr_body_set: mask[y*w+x], y = 0 bottom row; sensors flattened as {kind, axes, rotated, softNorm} ints + {min, max, window, sigma} doubles. */
-  public static native void setBody(long ctx, int w, int h, byte[] mask, int[] sensorInts, double[] sensorDoubles);
+  /** vsr_body_set_voxels: mask[y*w+x], y = 0 bottom row; sensors flattened as {kind, axes, rotated, norm, nRays, side} ints +
+   *  {min, max, window, sigma, param} doubles; sensorOff[nVoxels + 1] = every voxel's slice of them (voxels in grid order). */
+  public static native void setBody(long ctx, int w, int h, byte[] mask, int[] sensorInts, double[] sensorDoubles, int[] sensorOff);
 
   /** vsr_controller_set: kind 0 PhaseSin, 1 CentralizedSensing MLP, 2 homogeneous DistributedSensing MLP, 3 heterogeneous
    *  DistributedSensing (one MLP per voxel, weights concatenated in Grid order), 4 TimeFunctions of per-voxel sinusoids

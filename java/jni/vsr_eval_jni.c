@@ -56,29 +56,41 @@ JNIEXPORT jlong JNICALL Java_it_units_erallab_gpu_VsrEval_create(JNIEnv* env, jc
   return (jlong)(intptr_t)ctx;
 }
 
+/* vsr_body_set_voxels: sensors flattened as 6 ints {kind, axes, rotated, norm, nRays, side} + 5 doubles {min, max, window, sigma, param}
+ * each; sensorOff[nVoxels + 1] gives every voxel's slice (voxels in grid order: y outer, x inner) */
 JNIEXPORT void JNICALL Java_it_units_erallab_gpu_VsrEval_setBody(JNIEnv* env, jclass c, jlong h, jint w, jint hh, jbyteArray mask,
-                                                                 jintArray si, jdoubleArray sd) {
+                                                                 jintArray si, jdoubleArray sd, jintArray sensorOff) {
   vsr_ctx* ctx = (vsr_ctx*)(intptr_t)h;
-  if (!ctx || !mask || !si || !sd) { throw_iae(env, "null argument"); return; }
+  if (!ctx || !mask || !si || !sd || !sensorOff) { throw_iae(env, "null argument"); return; }
   if (w <= 0 || hh <= 0 || (jlong)(*env)->GetArrayLength(env, mask) < (jlong)w * hh) { throw_iae(env, "mask.length < w * h"); return; }
-  if ((*env)->GetArrayLength(env, si) % 4 || (*env)->GetArrayLength(env, sd) != (*env)->GetArrayLength(env, si)) {
-    throw_iae(env, "sensor arrays must hold 4 ints and 4 doubles per sensor"); return;
+  if ((*env)->GetArrayLength(env, si) % 6 || (*env)->GetArrayLength(env, sd) % 5 ||
+      (*env)->GetArrayLength(env, sd) / 5 != (*env)->GetArrayLength(env, si) / 6) {
+    throw_iae(env, "sensor arrays must hold 6 ints and 5 doubles per sensor"); return;
   }
-  jsize ns = (*env)->GetArrayLength(env, si) / 4;
+  jsize ns = (*env)->GetArrayLength(env, si) / 6;
   jbyte* pm = (*env)->GetByteArrayElements(env, mask, NULL);
   jint* pi = (*env)->GetIntArrayElements(env, si, NULL);
   jdouble* pd = (*env)->GetDoubleArrayElements(env, sd, NULL);
+  jint* po = (*env)->GetIntArrayElements(env, sensorOff, NULL);
+  int nv = 0, bad = 0;
+  for (int i = 0; i < w * hh; i++) nv += pm[i] ? 1 : 0;
+  if ((*env)->GetArrayLength(env, sensorOff) < nv + 1) bad = 1;
+  for (int v = 0; !bad && v <= nv; v++) if (po[v] < 0 || po[v] > ns || (v > 0 && po[v] < po[v - 1])) bad = 1;
   vsr_sensor_desc* s = (vsr_sensor_desc*)calloc(ns ? ns : 1, sizeof(*s));
   for (int i = 0; i < ns; i++) {
-    s[i].kind = pi[4 * i]; s[i].axes = pi[4 * i + 1]; s[i].rotated = pi[4 * i + 2]; s[i].soft_norm = pi[4 * i + 3];
-    s[i].dom_min = pd[4 * i]; s[i].dom_max = pd[4 * i + 1]; s[i].avg_window = pd[4 * i + 2]; s[i].noise_sigma = pd[4 * i + 3];
+    s[i].kind = pi[6 * i]; s[i].axes = pi[6 * i + 1]; s[i].rotated = pi[6 * i + 2]; s[i].soft_norm = pi[6 * i + 3];
+    s[i].n_rays = pi[6 * i + 4]; s[i].side = pi[6 * i + 5];
+    s[i].dom_min = pd[5 * i]; s[i].dom_max = pd[5 * i + 1]; s[i].avg_window = pd[5 * i + 2]; s[i].noise_sigma = pd[5 * i + 3];
+    s[i].param = pd[5 * i + 4];
   }
-  int rc = vsr_body_set(ctx, w, hh, (const uint8_t*)pm, s, ns);
+  int rc = bad ? VSR_EINVAL : vsr_body_set_voxels(ctx, w, hh, (const uint8_t*)pm, s, (const int32_t*)po);
   free(s);
+  (*env)->ReleaseIntArrayElements(env, sensorOff, po, JNI_ABORT);
   (*env)->ReleaseDoubleArrayElements(env, sd, pd, JNI_ABORT);
   (*env)->ReleaseIntArrayElements(env, si, pi, JNI_ABORT);
   (*env)->ReleaseByteArrayElements(env, mask, pm, JNI_ABORT);
-  if (rc) throw_status(env, ctx, rc);
+  if (bad) throw_iae(env, "sensorOff must hold nVoxels + 1 non-decreasing offsets into the sensor arrays");
+  else if (rc) throw_status(env, ctx, rc);
 }
 
 JNIEXPORT void JNICALL Java_it_units_erallab_gpu_VsrEval_setController(JNIEnv* env, jclass c, jlong h, jint kind, jintArray layers,

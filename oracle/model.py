@@ -146,14 +146,17 @@ def create_terrain(name: str) -> tuple[np.ndarray, np.ndarray]:
 SENSOR_AREA_RATIO, SENSOR_TOUCH, SENSOR_VELOCITY, SENSOR_ANGLE = 0, 1, 2, 3
 
 
+SENSOR_CONSTANT, SENSOR_TIME_SIN, SENSOR_LIDAR = 4, 5, 6
+
+
 class VoSensor(C.Structure):
     _fields_ = [("kind", C.c_int), ("axes", C.c_int), ("rotated", C.c_int), ("soft_norm", C.c_int),
                 ("dom_min", C.c_double), ("dom_max", C.c_double), ("avg_window", C.c_double),
-                ("noise_sigma", C.c_double)]
+                ("noise_sigma", C.c_double), ("param", C.c_double), ("n_rays", C.c_int), ("side", C.c_int)]
 
 
-def _sensor(kind, axes=0, rotated=0, soft_norm=0, dom=(0.0, 1.0), avg=0.0, noise=0.0):
-    return VoSensor(kind, axes, rotated, soft_norm, dom[0], dom[1], avg, noise)
+def _sensor(kind, axes=0, rotated=0, soft_norm=0, dom=(0.0, 1.0), avg=0.0, noise=0.0, param=0.0, n_rays=0, side=0):
+    return VoSensor(kind, axes, rotated, soft_norm, dom[0], dom[1], avg, noise, param, n_rays, side)
 
 
 def sensor_config(name: str) -> list[VoSensor]:
@@ -179,7 +182,81 @@ def sensor_config(name: str) -> list[VoSensor]:
 
 
 def sensor_dim(s: VoSensor) -> int:
+    if s.kind == SENSOR_LIDAR:
+        return s.n_rays
     return bin(s.axes & 3).count("1") if s.kind == SENSOR_VELOCITY else 1
+
+
+def _lidar_side(x: float, y: float) -> int:
+    """RobotUtils.lidarSide [U]: 0 N, 1 E, 2 S, 3 W."""
+    if y > x and y > 1 - x:
+        return 2
+    if y >= x and y <= 1 - x:
+        return 3
+    if y < x and y < 1 - x:
+        return 0
+    return 1
+
+
+def predefined_sensor(name: str, x: int, y: int, w: int, h: int, sigma: float) -> VoSensor:
+    """One entry of RobotUtils' PREDEFINED_SENSORS for the voxel at (x, y) of a w x h grid [U]."""
+    rx = x / (w - 1) if w > 1 else float("nan")
+    ry = y / (h - 1) if h > 1 else float("nan")
+    if name == "a":
+        return _sensor(SENSOR_AREA_RATIO, soft_norm=1, dom=(0.5, 1.5), noise=sigma)
+    if name == "t":
+        return _sensor(SENSOR_TOUCH, avg=0.25, noise=sigma)
+    if name == "r":
+        return _sensor(SENSOR_ANGLE, soft_norm=1, dom=(-math.pi, math.pi), noise=sigma)
+    if name in ("vx", "vy", "vxy"):
+        return _sensor(SENSOR_VELOCITY, axes={"vx": 1, "vy": 2, "vxy": 3}[name], rotated=1, soft_norm=1, dom=(-8.0, 8.0), avg=0.5, noise=sigma)
+    if name == "px":
+        return _sensor(SENSOR_CONSTANT, noise=sigma, param=rx)
+    if name == "py":
+        return _sensor(SENSOR_CONSTANT, noise=sigma, param=ry)
+    if name == "cpg":
+        return _sensor(SENSOR_TIME_SIN, soft_norm=2, dom=(-1.0, 1.0), noise=sigma, param=-1.0)
+    if name in ("l1", "l5", "lf5"):
+        return _sensor(SENSOR_LIDAR, soft_norm=2, dom=(0.0, 10.0), noise=sigma, param=10.0, n_rays=1 if name == "l1" else 5,
+                       side=1 if name == "lf5" else _lidar_side(rx, ry))
+    raise ValueError(f"unsupported sensor {name}")
+
+
+def sensor_config_voxels(name: str, mask: np.ndarray) -> tuple[list[VoSensor], list[int]]:
+    """RobotUtils.buildSensorizingFunction(name).apply(body) [U]: (the voxels' sensor lists concatenated in grid order, offsets)."""
+    h, w = mask.shape
+    p = name.split("-")
+    sensors, off = [], [0]
+    for y in range(h):
+        for x in range(w):
+            if not mask[y, x]:
+                continue
+            if name == "empty":
+                pass
+            elif p[0] == "uniform":
+                sigma = float(p[2])
+                sensors += [predefined_sensor(s, x, y, w, h, sigma) for s in p[1].split("+")]
+            elif p[0] in ("spinedTouch", "spinedTouchSighted"):
+                cpg, malfunction, sigma = p[1] == "t", p[2] == "t", float(p[3])
+                if malfunction:
+                    raise ValueError("the Malfunction sensor is not built")
+                if y == 0:
+                    sensors.append(predefined_sensor("t", x, y, w, h, sigma))
+                if y == h - 1:
+                    v = predefined_sensor("vxy", x, y, w, h, sigma)
+                    v.soft_norm, v.avg_window = 2, 0.0
+                    sensors.append(v)
+                a = predefined_sensor("a", x, y, w, h, sigma)
+                a.soft_norm = 2
+                sensors.append(a)
+                if cpg and x == w - 1 and y == h - 1:
+                    sensors.append(predefined_sensor("cpg", x, y, w, h, sigma))
+                if p[0] == "spinedTouchSighted" and x == w - 1:
+                    sensors.append(predefined_sensor("lf5", x, y, w, h, sigma))
+            else:
+                raise ValueError(f"unsupported sensor config {name}")
+            off.append(len(sensors))
+    return sensors, off
 
 
 def java_round(x: float) -> int:
@@ -251,7 +328,8 @@ class VoResult(C.Structure):
 
 class VoExtras(C.Structure):
     _fields_ = [("frozen_mask", C.c_uint32), ("posture_n", C.c_int), ("posture_out", C.c_void_p), ("posture_counts", C.c_void_p),
-                ("footprint_n", C.c_int * 2), ("footprints_out", C.c_void_p * 2), ("centers_out", C.c_void_p)]
+                ("footprint_n", C.c_int * 2), ("footprints_out", C.c_void_p * 2), ("centers_out", C.c_void_p),
+                ("vox_sensors", C.c_void_p), ("vox_sensor_off", C.c_void_p)]
 
 
 CTRL_PHASE_SIN, CTRL_MLP_CENTRALIZED, CTRL_MLP_DISTRIBUTED_HOMO, CTRL_MLP_DISTRIBUTED_HETERO, CTRL_TIME_SIN = 0, 1, 2, 3, 4
@@ -276,6 +354,8 @@ def lib():
         _lib.vo_genome_len.restype = C.c_int
         _lib.vo_run.restype = C.c_int
         _lib.vo_run_ex.restype = C.c_int
+        _lib.vo_eval_batch_vox.restype = C.c_int
+        _lib.vo_genome_len_vox.restype = C.c_int
         _lib.vo_central_voxel.restype = C.c_int
         _lib.vo_eval_batch.restype = C.c_int
     return _lib
@@ -312,16 +392,22 @@ class Model:
     def __post_init__(self):
         self.mask = np.ascontiguousarray(build_shape(self.shape))
         self.tx, self.ty = create_terrain(self.terrain)
-        self.sensors = sensor_config(self.sensors_name) if self.sensors_name else []
         nv = int(self.mask.sum())
-        dim = sum(sensor_dim(s) for s in self.sensors)
+        # every voxel's own sensor list; `sensors` stays the common list when all voxels agree (the uniform C entry points take it)
+        self.vox_sensors, self.vox_off = sensor_config_voxels(self.sensors_name, self.mask) if self.sensors_name else ([], [0] * (nv + 1))
+        key = lambda s: (s.kind, s.axes, s.rotated, s.soft_norm, s.dom_min, s.dom_max, s.avg_window, s.noise_sigma, s.param, s.n_rays, s.side)
+        lists = [[key(s) for s in self.vox_sensors[self.vox_off[v]:self.vox_off[v + 1]]] for v in range(nv)]
+        self.uniform = all(l == lists[0] for l in lists)
+        self.sensors = self.vox_sensors[:self.vox_off[1]] if self.uniform else None
+        dims = [sum(sensor_dim(s) for s in self.vox_sensors[self.vox_off[v]:self.vox_off[v + 1]]) for v in range(nv)]
+        dim, total_dim = dims[0], sum(dims)
         c = VoCtrl()
         c.kind = self.ctrl_kind
         c.freq, c.amp = self.freq, self.amp
         c.signals = self.signals
         c.input_activation = self.input_activation
         if self.ctrl_kind == CTRL_MLP_CENTRALIZED:
-            n_in, n_out = nv * dim, nv
+            n_in, n_out = total_dim, nv
         elif self.ctrl_kind in (CTRL_MLP_DISTRIBUTED_HOMO, CTRL_MLP_DISTRIBUTED_HETERO):
             n_in, n_out = dim + 4 * self.signals, 1 + 4 * self.signals
         else:
@@ -346,14 +432,28 @@ class Model:
         return self.mask.shape[1]
 
     def _sensor_array(self):
-        arr = (VoSensor * max(1, len(self.sensors)))()
-        for i, s in enumerate(self.sensors):
+        src = self.sensors or []
+        arr = (VoSensor * max(1, len(src)))()
+        for i, s in enumerate(src):
             arr[i] = s
         return arr
 
+    def _n_uniform(self) -> int:
+        return len(self.sensors) if self.sensors is not None else 0
+
+    def _vox_arrays(self):
+        arr = (VoSensor * max(1, len(self.vox_sensors)))()
+        for i, s in enumerate(self.vox_sensors):
+            arr[i] = s
+        off = (C.c_int * len(self.vox_off))(*self.vox_off)
+        return arr, off
+
     def genome_len(self) -> int:
+        if not self.uniform:
+            arr, off = self._vox_arrays()
+            return lib().vo_genome_len_vox(self.w, self.h, self.mask.ctypes.data_as(C.c_void_p), arr, off, C.byref(self.ctrl))
         return lib().vo_genome_len(self.w, self.h, self.mask.ctypes.data_as(C.c_void_p), self._sensor_array(),
-                                   len(self.sensors), C.byref(self.ctrl))
+                                   self._n_uniform(), C.byref(self.ctrl))
 
     def run(self, genome: np.ndarray, trace_steps: int = 0):
         g = np.ascontiguousarray(genome, dtype=np.float64)
@@ -363,9 +463,13 @@ class Model:
         tc = np.zeros((trace_steps, nv)) if trace_steps else None
         res = VoResult()
         ptr = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
-        rc = lib().vo_run(C.byref(self.params), self.w, self.h, ptr(self.mask), self._sensor_array(), len(self.sensors),
-                          C.byref(self.ctrl), ptr(self.tx), ptr(self.ty), len(self.tx), ptr(g), len(g),
-                          trace_steps, ptr(tv), ptr(tb), ptr(tc), C.byref(res))
+        ex = VoExtras()
+        keep = self._vox_arrays()
+        if not self.uniform:
+            ex.vox_sensors, ex.vox_sensor_off = C.addressof(keep[0]), C.addressof(keep[1])
+        rc = lib().vo_run_ex(C.byref(self.params), self.w, self.h, ptr(self.mask), self._sensor_array(), self._n_uniform(),
+                             C.byref(self.ctrl), ptr(self.tx), ptr(self.ty), len(self.tx), ptr(g), len(g),
+                             trace_steps, ptr(tv), ptr(tb), ptr(tc), C.byref(ex), C.byref(res))
         if rc:
             raise RuntimeError(f"vo_run failed: {rc}")
         return res, tv, tb, tc
@@ -377,6 +481,9 @@ class Model:
         _, kf, kl = episode_steps(self.params.final_t, self.params.transient_t, self.params.dt)
         K = kl - kf + 1
         ex = VoExtras()
+        keep = self._vox_arrays()
+        if not self.uniform:
+            ex.vox_sensors, ex.vox_sensor_off = C.addressof(keep[0]), C.addressof(keep[1])
         ex.frozen_mask, ex.posture_n = frozen_mask, posture_n
         post = np.zeros(max(1, posture_n * posture_n), dtype=np.uint8)
         cnt = np.zeros(max(1, posture_n * posture_n), dtype=np.int32)
@@ -392,7 +499,7 @@ class Model:
             ex.centers_out = cen.ctypes.data
         res = VoResult()
         ptr = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
-        rc = lib().vo_run_ex(C.byref(self.params), self.w, self.h, ptr(self.mask), self._sensor_array(), len(self.sensors),
+        rc = lib().vo_run_ex(C.byref(self.params), self.w, self.h, ptr(self.mask), self._sensor_array(), self._n_uniform(),
                              C.byref(self.ctrl), ptr(self.tx), ptr(self.ty), len(self.tx), ptr(g), len(g),
                              0, None, None, None, C.byref(ex), C.byref(res))
         if rc:
@@ -409,9 +516,14 @@ class Model:
         fit = np.zeros(n)
         results = (VoResult * n)() if want_results else None
         ptr = lambda a: a.ctypes.data_as(C.c_void_p)
-        rc = lib().vo_eval_batch(C.byref(self.params), self.w, self.h, ptr(self.mask), self._sensor_array(),
-                                 len(self.sensors), C.byref(self.ctrl), ptr(self.tx), ptr(self.ty), len(self.tx),
-                                 ptr(g), g.shape[1], n, n_threads, ptr(fit), results)
+        if self.uniform:
+            rc = lib().vo_eval_batch(C.byref(self.params), self.w, self.h, ptr(self.mask), self._sensor_array(),
+                                     self._n_uniform(), C.byref(self.ctrl), ptr(self.tx), ptr(self.ty), len(self.tx),
+                                     ptr(g), g.shape[1], n, n_threads, ptr(fit), results)
+        else:
+            arr, off = self._vox_arrays()
+            rc = lib().vo_eval_batch_vox(C.byref(self.params), self.w, self.h, ptr(self.mask), arr, off, C.byref(self.ctrl),
+                                         ptr(self.tx), ptr(self.ty), len(self.tx), ptr(g), g.shape[1], n, n_threads, ptr(fit), results)
         if rc:
             raise RuntimeError(f"vo_eval_batch failed: {rc}")
         return (fit, results) if want_results else fit

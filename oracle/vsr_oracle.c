@@ -928,20 +928,24 @@ static double jr_gaussian(JRandom* r) {
 }
 
 typedef struct {
-  int n_sensors, dim; /* per voxel */
-  JRandom rng[8];     /* Noisy: one stream per sensor */
-  const vo_sensor* sensors;
-  int* off;           /* [n_sensors] offset of each sensor's readings in the voxel's reading vector */
-  double* readings;   /* [n_vox][dim] */
-  /* Average windows: ring of (t, value) per voxel per reading */
+  int n_vox, n_inst;       /* sensor instances over all voxels */
+  vo_sensor* list;         /* [n_inst] the voxels' sensor lists, concatenated in voxel (grid) order */
+  int* voff;               /* [n_vox + 1] first instance of each voxel */
+  int* roff;               /* [n_inst + 1] first reading of each instance */
+  int* vroff;              /* [n_vox + 1] first reading of each voxel */
+  int total;               /* readings of the whole robot */
+  JRandom* rng;            /* Noisy: every wrapper owns `new Random(0)` [U]: one stream per instance */
+  double* readings;        /* [total] */
+  /* Average windows: ring of (t, value) per reading */
   int hist_cap;
-  double* hist_t;     /* [hist_cap] */
-  double* hist_v;     /* [hist_cap][n_vox][dim] raw readings */
-  int hist_n;         /* number of steps stored so far */
+  double* hist_t;          /* [hist_cap] */
+  double* hist_v;          /* [hist_cap][total] raw readings */
+  int hist_n;              /* number of steps stored so far */
 } Sensing;
 
 static int sensor_dim(const vo_sensor* s) {
   if (s->kind == VO_SENSOR_VELOCITY) return ((s->axes & 1) ? 1 : 0) + ((s->axes & 2) ? 1 : 0);
+  if (s->kind == VO_SENSOR_LIDAR) return s->n_rays;
   return 1;
 }
 
@@ -950,16 +954,45 @@ static double soft_norm(double r, double lo, double hi) {
   return tanh(((v * 2.0) - 1.0) * 2.0) / 2.0 + 0.5;
 }
 
+/* Lidar [U]: Side sectors N (pi/4, 3pi/4), E (-pi/4, pi/4), S (5pi/4, 7pi/4), W (3pi/4, 5pi/4); one ray sits at (end - start) / 2
+ * (the upstream sampleRangeWithRays quirk), n > 1 rays are spread from start to end inclusive */
+static double lidar_direction(int side, int n, int i) {
+  static const double START[4] = {M_PI * 1.0 / 4.0, M_PI * -1.0 / 4.0, M_PI * 5.0 / 4.0, M_PI * 3.0 / 4.0};
+  static const double END[4] = {M_PI * 3.0 / 4.0, M_PI * 1.0 / 4.0, M_PI * 7.0 / 4.0, M_PI * 5.0 / 4.0};
+  if (n == 1) return (END[side] - START[side]) / 2.0;
+  return START[side] + (END[side] - START[side]) / (double)(n - 1) * (double)i;
+}
+
+/* distance along the ray (ox, oy) + t (dx, dy), |d| = 1, to the ground's surface (the polyline, closed by the two outer walls), or
+ * max_len when nothing is hit within max_len.  The rays see the ground only (the robot's own voxels are filtered out [U]). */
+static double raycast_ground(const World* W, double ox, double oy, double dx, double dy, double max_len) {
+  double best = max_len;
+  for (int k = 1; k < W->n_t; k++) {
+    const double x0 = W->tx[k - 1], y0 = W->ty[k - 1], ex = W->tx[k] - x0, ey = W->ty[k] - y0;
+    if (fmax(x0, x0 + ex) < fmin(ox, ox + dx * max_len) || fmin(x0, x0 + ex) > fmax(ox, ox + dx * max_len)) continue;
+    const double den = dx * ey - dy * ex;
+    if (den == 0.0) continue;
+    const double t = ((x0 - ox) * ey - (y0 - oy) * ex) / den, u = ((x0 - ox) * dy - (y0 - oy) * dx) / den;
+    if (t >= 0.0 && t < best && u >= 0.0 && u <= 1.0) best = t;
+  }
+  for (int side = 0; side < 2; side++) { /* outer walls of the first / last ground polygon, from the surface down to the base */
+    const double xw = side == 0 ? W->tx[0] : W->tx[W->n_t - 1], yt = side == 0 ? W->ty[0] : W->ty[W->n_t - 1];
+    if (dx == 0.0) continue;
+    const double t = (xw - ox) / dx, y = oy + t * dy;
+    if (t >= 0.0 && t < best && y <= yt && y >= W->base_y) best = t;
+  }
+  return best;
+}
+
 static void sense(World* W, Sensing* S, double t) {
-  int D = S->dim;
   /* raw readings of this step go in the ring */
   int slot = S->hist_n % S->hist_cap;
   S->hist_t[slot] = t;
-  double* raw = &S->hist_v[(size_t)slot * W->n_vox * D];
+  double* raw = &S->hist_v[(size_t)slot * S->total];
   for (int v = 0; v < W->n_vox; v++)
-    for (int si = 0; si < S->n_sensors; si++) {
-      const vo_sensor* s = &S->sensors[si];
-      double* r = &raw[v * D + S->off[si]];
+    for (int si = S->voff[v]; si < S->voff[v + 1]; si++) {
+      const vo_sensor* s = &S->list[si];
+      double* r = &raw[S->roff[si]];
       switch (s->kind) {
         case VO_SENSOR_AREA_RATIO: r[0] = voxel_area_ratio(W, v); break;
         case VO_SENSOR_TOUCH: {
@@ -981,39 +1014,46 @@ static void sense(World* W, Sensing* S, double t) {
           if (s->axes & 1) r[o++] = vx;
           if (s->axes & 2) r[o++] = vy;
         } break;
+        case VO_SENSOR_CONSTANT: r[0] = s->param; break;
+        case VO_SENSOR_TIME_SIN: r[0] = sin(2.0 * M_PI * s->param * t); break;
+        case VO_SENSOR_LIDAR: {
+          double cx = 0, cy = 0;
+          for (int k = 0; k < 4; k++) { cx += W->bodies[v * 4 + k].x; cy += W->bodies[v * 4 + k].y; }
+          cx /= 4.0; cy /= 4.0;
+          const double va = voxel_angle(W, v);
+          for (int i = 0; i < s->n_rays; i++) {
+            const double dir = lidar_direction(s->side, s->n_rays, i) + va;
+            r[i] = raycast_ground(W, cx, cy, cos(dir), sin(dir), s->param);
+          }
+        } break;
       }
     }
   S->hist_n++;
-  double noise[8][2] = {{0}};
-  for (int si = 0; si < S->n_sensors; si++) {
-    const vo_sensor* s = &S->sensors[si];
-    if (s->noise_sigma > 0)
-      for (int d = 0; d < sensor_dim(s); d++) /* Noisy.sense: value + nextGaussian() * sigma * |domain| of the wrapped sensor */
-        noise[si][d] = jr_gaussian(&S->rng[si]) * s->noise_sigma * (s->soft_norm ? 1.0 : fabs(s->dom_max - s->dom_min));
-  }
-  for (int v = 0; v < W->n_vox; v++)
-    for (int si = 0; si < S->n_sensors; si++) {
-      const vo_sensor* s = &S->sensors[si];
-      int dim = sensor_dim(s);
-      for (int d = 0; d < dim; d++) {
-        int idx = v * D + S->off[si] + d;
-        double val = raw[idx];
-        if (s->avg_window > 0) {
-          /* Average: mean of stored readings with t_j >= t - window */
-          double sum = 0; int n = 0;
-          int have = S->hist_n < S->hist_cap ? S->hist_n : S->hist_cap;
-          for (int back = 0; back < have; back++) {
-            int sl = (S->hist_n - 1 - back) % S->hist_cap;
-            if (S->hist_t[sl] < t - s->avg_window) break;
-            sum += S->hist_v[(size_t)sl * W->n_vox * D + idx];
-            n++;
-          }
-          val = sum / n;
+  for (int si = 0; si < S->n_inst; si++) {
+    const vo_sensor* s = &S->list[si];
+    const int dim = sensor_dim(s);
+    for (int d = 0; d < dim; d++) {
+      const int idx = S->roff[si] + d;
+      double val = raw[idx];
+      if (s->avg_window > 0) {
+        /* Average: mean of stored readings with t_j >= t - window */
+        double sum = 0; int n = 0;
+        int have = S->hist_n < S->hist_cap ? S->hist_n : S->hist_cap;
+        for (int back = 0; back < have; back++) {
+          int sl = (S->hist_n - 1 - back) % S->hist_cap;
+          if (S->hist_t[sl] < t - s->avg_window) break;
+          sum += S->hist_v[(size_t)sl * S->total + idx];
+          n++;
         }
-        if (s->soft_norm) val = soft_norm(val, s->dom_min, s->dom_max);
-        S->readings[idx] = val + noise[si][d];
+        val = sum / n;
       }
+      if (s->soft_norm == 1) val = soft_norm(val, s->dom_min, s->dom_max);
+      else if (s->soft_norm == 2) val = fmin(fmax((val - s->dom_min) / (s->dom_max - s->dom_min), 0.0), 1.0);
+      /* Noisy.sense: value + nextGaussian() * sigma * |domain| of the wrapped sensor */
+      if (s->noise_sigma > 0) val += jr_gaussian(&S->rng[si]) * s->noise_sigma * (s->soft_norm ? 1.0 : fabs(s->dom_max - s->dom_min));
+      S->readings[idx] = val;
     }
+  }
 }
 
 static void mlp_apply(const vo_ctrl* c, const double* wts, const double* in, double* out) {
@@ -1039,15 +1079,37 @@ static int mlp_n_weights(const vo_ctrl* c) {
   return n;
 }
 
+static int genome_len_dims(int nv, int total_dim, int dim, const vo_ctrl* ctrl);
+
 int vo_genome_len(int w, int h, const uint8_t* mask, const vo_sensor* sensors, int n_sensors, const vo_ctrl* ctrl) {
   int nv = 0;
   for (int i = 0; i < w * h; i++) nv += mask[i] ? 1 : 0;
   int dim = 0;
   for (int i = 0; i < n_sensors; i++) dim += sensor_dim(&sensors[i]);
+  return genome_len_dims(nv, nv * dim, dim, ctrl);
+}
+
+int vo_genome_len_vox(int w, int h, const uint8_t* mask, const vo_sensor* vox_sensors, const int* vox_sensor_off, const vo_ctrl* ctrl) {
+  int nv = 0;
+  for (int i = 0; i < w * h; i++) nv += mask[i] ? 1 : 0;
+  int total = 0, dim0 = -1, uniform = 1;
+  for (int v = 0; v < nv; v++) {
+    int d = 0;
+    for (int i = vox_sensor_off[v]; i < vox_sensor_off[v + 1]; i++) d += sensor_dim(&vox_sensors[i]);
+    if (dim0 < 0) dim0 = d;
+    if (d != dim0) uniform = 0;
+    total += d;
+  }
+  return genome_len_dims(nv, total, uniform ? dim0 : -1, ctrl);
+}
+
+/* dim = readings per voxel, or -1 when the voxels differ (distributed controllers then have no single MLP input size) */
+static int genome_len_dims(int nv, int total_dim, int dim, const vo_ctrl* ctrl) {
+  if ((ctrl->kind == VO_CTRL_MLP_DISTRIBUTED_HOMO || ctrl->kind == VO_CTRL_MLP_DISTRIBUTED_HETERO) && dim < 0) return -2;
   switch (ctrl->kind) {
     case VO_CTRL_PHASE_SIN: return nv;
     case VO_CTRL_MLP_CENTRALIZED:
-      if (ctrl->layers[0] != nv * dim || ctrl->layers[ctrl->n_layers - 1] != nv) return -2;
+      if (ctrl->layers[0] != total_dim || ctrl->layers[ctrl->n_layers - 1] != nv) return -2;
       return mlp_n_weights(ctrl);
     case VO_CTRL_MLP_DISTRIBUTED_HOMO:
       if (ctrl->layers[0] != dim + 4 * ctrl->signals || ctrl->layers[ctrl->n_layers - 1] != 1 + 4 * ctrl->signals) return -2;
@@ -1232,9 +1294,11 @@ int vo_run_ex(const vo_params* p, int w, int h, const uint8_t* mask,
               const vo_extras* ex, vo_result* out) {
   if (!p || !mask || !ctrl || !out || w <= 0 || h <= 0 || n_terrain < 2) return -1;
   if (n_sensors > 8) return -3;
+  const int per_voxel = ex && ex->vox_sensor_off && ex->vox_sensors;
   if (ex && (ex->posture_n < 0 || ex->posture_n > 8 || ex->footprint_n[0] < 0 || ex->footprint_n[0] > 8 || ex->footprint_n[1] < 0 ||
              ex->footprint_n[1] > 8)) return -6;
-  int glen = vo_genome_len(w, h, mask, sensors, n_sensors, ctrl);
+  int glen = per_voxel ? vo_genome_len_vox(w, h, mask, ex->vox_sensors, ex->vox_sensor_off, ctrl)
+                       : vo_genome_len(w, h, mask, sensors, n_sensors, ctrl);
   if (glen < 0) return glen;
   if (glen != genome_len) return -4;
   memset(out, 0, sizeof(*out));
@@ -1269,24 +1333,35 @@ int vo_run_ex(const vo_params* p, int w, int h, const uint8_t* mask,
   place_robot(W);
   detect(W); /* World.step's first-step detect() */
 
-  /* sensing state */
+  /* sensing state: the voxels' sensor lists (the uniform list repeated for every voxel, or the per-voxel lists of vo_extras) */
   Sensing S;
   memset(&S, 0, sizeof(S));
-  S.n_sensors = n_sensors;
-  S.sensors = sensors;
-  for (int i = 0; i < 8; i++) jr_init(&S.rng[i], 0);
-  S.off = (int*)malloc(sizeof(int) * (n_sensors > 0 ? n_sensors : 1));
+  S.n_vox = W->n_vox;
+  S.voff = (int*)malloc(sizeof(int) * (W->n_vox + 1));
+  S.vroff = (int*)malloc(sizeof(int) * (W->n_vox + 1));
+  for (int v = 0; v <= W->n_vox; v++) S.voff[v] = per_voxel ? ex->vox_sensor_off[v] - ex->vox_sensor_off[0] : v * n_sensors;
+  S.n_inst = S.voff[W->n_vox];
+  S.list = (vo_sensor*)malloc(sizeof(vo_sensor) * (S.n_inst > 0 ? S.n_inst : 1));
+  for (int v = 0; v < W->n_vox; v++)
+    for (int i = S.voff[v]; i < S.voff[v + 1]; i++)
+      S.list[i] = per_voxel ? ex->vox_sensors[ex->vox_sensor_off[0] + i] : sensors[i - S.voff[v]];
+  S.roff = (int*)malloc(sizeof(int) * (S.n_inst + 1));
+  S.rng = (JRandom*)malloc(sizeof(JRandom) * (S.n_inst > 0 ? S.n_inst : 1));
   double max_window = 0;
-  for (int i = 0; i < n_sensors; i++) {
-    S.off[i] = S.dim;
-    S.dim += sensor_dim(&sensors[i]);
-    if (sensors[i].avg_window > max_window) max_window = sensors[i].avg_window;
+  S.total = 0;
+  for (int i = 0; i < S.n_inst; i++) {
+    S.roff[i] = S.total;
+    S.total += sensor_dim(&S.list[i]);
+    jr_init(&S.rng[i], 0);
+    if (S.list[i].avg_window > max_window) max_window = S.list[i].avg_window;
   }
+  S.roff[S.n_inst] = S.total;
+  for (int v = 0; v <= W->n_vox; v++) S.vroff[v] = S.roff[S.voff[v]];
   S.hist_cap = (int)ceil(max_window / p->dt) + 4;
-  int D = S.dim > 0 ? S.dim : 1;
-  S.readings = (double*)calloc((size_t)W->n_vox * D, sizeof(double));
+  int D = S.total > 0 ? S.total : 1;
+  S.readings = (double*)calloc((size_t)D, sizeof(double));
   S.hist_t = (double*)calloc(S.hist_cap, sizeof(double));
-  S.hist_v = (double*)calloc((size_t)S.hist_cap * W->n_vox * D, sizeof(double));
+  S.hist_v = (double*)calloc((size_t)S.hist_cap * D, sizeof(double));
   /* distributed controller signal buffers */
   int sig = (ctrl->kind == VO_CTRL_MLP_DISTRIBUTED_HOMO || ctrl->kind == VO_CTRL_MLP_DISTRIBUTED_HETERO) ? ctrl->signals : 0;
   const int w_stride = ctrl->kind == VO_CTRL_MLP_DISTRIBUTED_HETERO ? mlp_n_weights(ctrl) : 0; /* per-voxel weight block */
@@ -1313,7 +1388,7 @@ int vo_run_ex(const vo_params* p, int w, int h, const uint8_t* mask,
           apply_control(W, v, ctrl->amp * sin(2.0 * M_PI * ctrl->freq * t + genome[v]));
         break;
       case VO_CTRL_MLP_CENTRALIZED: {
-        for (int i = 0; i < W->n_vox * S.dim; i++) in[i] = S.readings[i];
+        for (int i = 0; i < S.total; i++) in[i] = S.readings[i];
         mlp_apply(ctrl, genome, in, o);
         for (int v = 0; v < W->n_vox; v++) apply_control(W, v, o[v]);
       } break;
@@ -1327,7 +1402,7 @@ int vo_run_ex(const vo_params* p, int w, int h, const uint8_t* mask,
         static const int DX[4] = {0, 1, 0, -1}, DY[4] = {-1, 0, 1, 0}, OPP[4] = {2, 3, 0, 1};
         for (int v = 0; v < W->n_vox; v++) {
           int ni = 0;
-          for (int i = 0; i < S.dim; i++) in[ni++] = S.readings[v * S.dim + i];
+          for (int i = S.vroff[v]; i < S.vroff[v + 1]; i++) in[ni++] = S.readings[i];
           for (int d = 0; d < 4; d++) {
             int ax = W->cell_x[v] + DX[d], ay = W->cell_y[v] + DY[d];
             int nb = (ax >= 0 && ax < w && ay >= 0 && ay < h) ? W->vox_of_cell[ay * w + ax] : -1;
@@ -1398,7 +1473,8 @@ int vo_run_ex(const vo_params* p, int w, int h, const uint8_t* mask,
       if (ex->posture_out) ex->posture_out[c] = (uint8_t)(2 * post_cnt[c] > n_kept); /* average over the observations > 0.5 */
       if (ex->posture_counts) ex->posture_counts[c] = post_cnt[c];
     }
-  free(S.off); free(S.readings); free(S.hist_t); free(S.hist_v); free(last_sig); free(cur_sig); free(last_area);
+  free(S.list); free(S.voff); free(S.vroff); free(S.roff); free(S.rng);
+  free(S.readings); free(S.hist_t); free(S.hist_v); free(last_sig); free(cur_sig); free(last_area);
   world_free(W);
   return 0;
 }
@@ -1410,6 +1486,7 @@ typedef struct {
   const vo_params* p; int w, h; const uint8_t* mask; const vo_sensor* sensors; int n_sensors; const vo_ctrl* ctrl;
   const double *tx, *ty; int nt; const double* genomes; int glen, n; double* fit; vo_result* res;
   int* next; pthread_mutex_t* mu; int err;
+  const vo_sensor* vox_sensors; const int* vox_sensor_off; /* per-voxel sensor lists (vo_eval_batch_vox) or NULL */
 } BatchJob;
 
 static void* batch_worker(void* arg) {
@@ -1420,8 +1497,11 @@ static void* batch_worker(void* arg) {
     pthread_mutex_unlock(J->mu);
     if (i >= J->n) break;
     vo_result r;
-    int rc = vo_run(J->p, J->w, J->h, J->mask, J->sensors, J->n_sensors, J->ctrl, J->tx, J->ty, J->nt,
-                    J->genomes + (size_t)i * J->glen, J->glen, 0, NULL, NULL, NULL, &r);
+    vo_extras ex;
+    memset(&ex, 0, sizeof(ex));
+    ex.vox_sensors = J->vox_sensors; ex.vox_sensor_off = J->vox_sensor_off;
+    int rc = vo_run_ex(J->p, J->w, J->h, J->mask, J->sensors, J->n_sensors, J->ctrl, J->tx, J->ty, J->nt,
+                       J->genomes + (size_t)i * J->glen, J->glen, 0, NULL, NULL, NULL, J->vox_sensor_off ? &ex : NULL, &r);
     if (rc) { J->err = rc; J->fit[i] = NAN; continue; }
     J->fit[i] = r.velocity;
     if (J->res) J->res[i] = r;
@@ -1429,11 +1509,33 @@ static void* batch_worker(void* arg) {
   return NULL;
 }
 
+static int eval_batch_impl(const vo_params* p, int w, int h, const uint8_t* mask,
+                           const vo_sensor* sensors, int n_sensors, const vo_sensor* vox_sensors, const int* vox_sensor_off,
+                           const vo_ctrl* ctrl, const double* terrain_x, const double* terrain_y, int n_terrain,
+                           const double* genomes, int genome_len, int n, int n_threads, double* fitness_out, vo_result* results_out);
+
 int vo_eval_batch(const vo_params* p, int w, int h, const uint8_t* mask,
                   const vo_sensor* sensors, int n_sensors, const vo_ctrl* ctrl,
                   const double* terrain_x, const double* terrain_y, int n_terrain,
                   const double* genomes, int genome_len, int n, int n_threads,
                   double* fitness_out, vo_result* results_out) {
+  return eval_batch_impl(p, w, h, mask, sensors, n_sensors, NULL, NULL, ctrl, terrain_x, terrain_y, n_terrain, genomes, genome_len, n,
+                         n_threads, fitness_out, results_out);
+}
+
+int vo_eval_batch_vox(const vo_params* p, int w, int h, const uint8_t* mask,
+                      const vo_sensor* vox_sensors, const int* vox_sensor_off, const vo_ctrl* ctrl,
+                      const double* terrain_x, const double* terrain_y, int n_terrain,
+                      const double* genomes, int genome_len, int n, int n_threads,
+                      double* fitness_out, vo_result* results_out) {
+  return eval_batch_impl(p, w, h, mask, NULL, 0, vox_sensors, vox_sensor_off, ctrl, terrain_x, terrain_y, n_terrain, genomes, genome_len, n,
+                         n_threads, fitness_out, results_out);
+}
+
+static int eval_batch_impl(const vo_params* p, int w, int h, const uint8_t* mask,
+                           const vo_sensor* sensors, int n_sensors, const vo_sensor* vox_sensors, const int* vox_sensor_off,
+                           const vo_ctrl* ctrl, const double* terrain_x, const double* terrain_y, int n_terrain,
+                           const double* genomes, int genome_len, int n, int n_threads, double* fitness_out, vo_result* results_out) {
   if (n_threads < 1) n_threads = 1;
   if (n_threads > 256) n_threads = 256;
   pthread_t th[256];
@@ -1442,7 +1544,7 @@ int vo_eval_batch(const vo_params* p, int w, int h, const uint8_t* mask,
   pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER;
   for (int i = 0; i < n_threads; i++) {
     BatchJob j = {p, w, h, mask, sensors, n_sensors, ctrl, terrain_x, terrain_y, n_terrain, genomes, genome_len, n,
-                  fitness_out, results_out, &next, &mu, 0};
+                  fitness_out, results_out, &next, &mu, 0, vox_sensors, vox_sensor_off};
     jobs[i] = j;
     pthread_create(&th[i], NULL, batch_worker, &jobs[i]);
   }

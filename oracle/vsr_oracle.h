@@ -62,18 +62,24 @@ typedef struct {
   double transient_t;          /* Starter.java:143 episodeTransientTime                    */
 } vo_params;
 
-enum { VO_SENSOR_AREA_RATIO = 0, VO_SENSOR_TOUCH = 1, VO_SENSOR_VELOCITY = 2, VO_SENSOR_ANGLE = 3 };
+/* CONSTANT: Constant(value) (the `px` / `py` entries of RobotUtils' predefined sensors: the voxel's relative grid position);
+ * TIME_SIN: TimeFunction(t -> sin(2 pi param t), -1, 1) (the `cpg` entry, param = -1); LIDAR: Lidar(rayLength = param, {side: n_rays})
+ * (the `l1` / `l5` / `lf5` entries): distance to the ground along n_rays rays of one side's sector, rotated with the voxel [U] */
+enum { VO_SENSOR_AREA_RATIO = 0, VO_SENSOR_TOUCH = 1, VO_SENSOR_VELOCITY = 2, VO_SENSOR_ANGLE = 3, VO_SENSOR_CONSTANT = 4,
+       VO_SENSOR_TIME_SIN = 5, VO_SENSOR_LIDAR = 6 };
 
-/* One sensor of the uniform per-voxel sensor list: Noisy(SoftNormalization(Average(base))) with each
- * wrapper optional. */
+/* One sensor of a voxel's sensor list: Noisy(SoftNormalization | Normalization(Average(base))) with each wrapper optional. */
 typedef struct {
   int    kind;
   int    axes;        /* VELOCITY: bit0 = X, bit1 = Y (readings emitted in that order) */
   int    rotated;     /* VELOCITY: express in the voxel frame */
-  int    soft_norm;   /* wrap in SoftNormalization */
+  int    soft_norm;   /* 1: wrap in SoftNormalization; 2: wrap in Normalization ((x - min) / (max - min) clipped to [0, 1]) */
   double dom_min, dom_max;
   double avg_window;  /* >0: wrap in Average(window seconds) */
   double noise_sigma; /* >0: Noisy(sensor, sigma, seed 0): + nextGaussian()*sigma*|domain| per reading per step */
+  double param;       /* CONSTANT: the value; TIME_SIN: frequency; LIDAR: ray length */
+  int    n_rays;      /* LIDAR: rays (= readings) */
+  int    side;        /* LIDAR: 0 N, 1 E, 2 S, 3 W */
 } vo_sensor;
 
 /* DISTRIBUTED_HETERO: one MLP per voxel, genome = the voxels' weight vectors concatenated in grid order
@@ -130,6 +136,11 @@ typedef struct {
   int      footprint_n[2];   /* 0 = off, else 1..8 */
   uint8_t* footprints_out[2]; /* [kept observations] each */
   double*  centers_out;      /* optional [kept observations][3] */
+  /* per-voxel sensor lists (RobotUtils.buildSensorizingFunction names other than `uniform-...`, e.g. `spinedTouch-...`): when
+   * vox_sensor_off is non-NULL the sensors of voxel v (grid order) are vox_sensors[vox_sensor_off[v] .. vox_sensor_off[v + 1]) and the
+   * uniform list passed to vo_run_ex is ignored; CentralizedSensing concatenates the voxels' readings in grid order */
+  const vo_sensor* vox_sensors;
+  const int*       vox_sensor_off;
 } vo_extras;
 
 void vo_default_params(vo_params* p);
@@ -139,6 +150,8 @@ int vo_counts(const vo_params* p, int w, int h, const uint8_t* mask, int* n_vox,
 
 /* Genome length for the given body/sensors/controller (or <0 on error). */
 int vo_genome_len(int w, int h, const uint8_t* mask, const vo_sensor* sensors, int n_sensors, const vo_ctrl* ctrl);
+/* ... with per-voxel sensor lists (distributed controllers need the same reading count on every voxel) */
+int vo_genome_len_vox(int w, int h, const uint8_t* mask, const vo_sensor* vox_sensors, const int* vox_sensor_off, const vo_ctrl* ctrl);
 
 /*
  * Run one episode.
@@ -170,6 +183,13 @@ int vo_eval_batch(const vo_params* p, int w, int h, const uint8_t* mask,
                   const double* terrain_x, const double* terrain_y, int n_terrain,
                   const double* genomes, int genome_len, int n, int n_threads,
                   double* fitness_out, vo_result* results_out);
+
+/* ... with per-voxel sensor lists (see vo_extras) */
+int vo_eval_batch_vox(const vo_params* p, int w, int h, const uint8_t* mask,
+                      const vo_sensor* vox_sensors, const int* vox_sensor_off, const vo_ctrl* ctrl,
+                      const double* terrain_x, const double* terrain_y, int n_terrain,
+                      const double* genomes, int genome_len, int n, int n_threads,
+                      double* fitness_out, vo_result* results_out);
 
 /* Low-level test hooks for known-answer tests (single bodies / single joints, no robot). */
 int vo_test_free_fall(const vo_params* p, int n_steps, double* y_out, double* vy_out);

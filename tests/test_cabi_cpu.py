@@ -114,3 +114,30 @@ def test_jni_glue_type_checks_against_the_headers():
     natives = set(re.findall(r"public static native [\w\[\]]+ (\w+)\(", java))
     glue = set(re.findall(r"Java_it_units_erallab_gpu_VsrEval_(\w+)\(", open(src).read()))
     assert natives == glue and len(natives) >= 14
+
+
+def test_sensor_config_voxels_matches_the_oracle_name_layer(F):
+    """vsr_sensor_config_voxels (C++) against oracle/model.py sensor_config_voxels (Python): two independent restatements of
+    RobotUtils.buildSensorizingFunction + PREDEFINED_SENSORS [U], compared field by field; unsupported vocabulary is loud."""
+    import numpy as np
+    from oracle import model as O
+    for shape in ("biped-4x3", "worm-8x2", "comb-7x2", "box-1x1"):
+        mask = O.build_shape(shape)
+        for name in ("uniform-a-0", "uniform-t+vxy+a-0.01", "uniform-px+py+a-0", "uniform-l5+l1+lf5+cpg+r-0.02", "spinedTouch-f-f-0",
+                     "spinedTouch-t-f-0.01", "spinedTouchSighted-t-f-0", "empty"):
+            ls, off = F.sensor_config_voxels(name, mask)
+            os_, ooff = O.sensor_config_voxels(name, mask)
+            assert off.tolist() == ooff and len(ls) == len(os_), (shape, name)
+            for a, b in zip(ls, os_):
+                kb = (b.kind, b.axes, b.rotated, b.soft_norm, b.dom_min, b.dom_max, b.avg_window, b.noise_sigma, b.param, b.n_rays, b.side)
+                ka = a.key()
+                assert all((x == y) or (x != x and y != y) for x, y in zip(ka, kb)), (shape, name, ka, kb)  # NaN == NaN (px on a 1-wide grid)
+    mask = O.build_shape("biped-4x3")
+    for bad, code in (("uniform-m-0", F.VSR_EUNSUPPORTED), ("uniform-ax-0", F.VSR_EUNSUPPORTED), ("spinedTouch-t-t-0", F.VSR_EUNSUPPORTED),
+                      ("spined-t-f-0", F.VSR_EINVAL), ("uniform-a", F.VSR_EINVAL)):
+        with pytest.raises(F.VsrError) as ei:
+            F.sensor_config_voxels(bad, mask)
+        assert ei.value.code == code, (bad, ei.value.code)
+    # the uniform entry point refuses the position-dependent sensors instead of returning one voxel's values for all
+    with pytest.raises(F.VsrError):
+        F.sensor_config("uniform-px+a-0")

@@ -38,8 +38,11 @@ def make_ctx(F, m, precision=32, devices=None, gravity=None):
         for i, d in enumerate(devices):
             e.devices[i] = d
     ctx = F.Context(e, m.tx, m.ty)
-    sens = [F.SensorDesc(s.kind, s.axes, s.rotated, s.soft_norm, s.dom_min, s.dom_max, s.avg_window, s.noise_sigma) for s in m.sensors]
-    ctx.body_set(m.mask, sens)
+    conv = lambda s: F.SensorDesc(s.kind, s.axes, s.rotated, s.soft_norm, s.dom_min, s.dom_max, s.avg_window, s.noise_sigma, s.param, s.n_rays, s.side)
+    if m.uniform:
+        ctx.body_set(m.mask, [conv(s) for s in m.sensors])
+    else:  # every voxel its own sensor list (spinedTouch, px / py / l5 ...)
+        ctx.body_set_voxels(m.mask, [conv(s) for s in m.vox_sensors], m.vox_off)
     layers = [m.ctrl.layers[i] for i in range(m.ctrl.n_layers)]
     ctx.controller_set(m.ctrl_kind, layers, m.signals if m.ctrl_kind in (2, 3) else 0, m.freq, m.amp, m.input_activation)
     return ctx
@@ -867,3 +870,49 @@ def test_broken_robots_population_parity(F, oracle, bounds):
     d = np.abs(fit - ref)
     bounds.check("broken2.fp32.spearman", spearman(fit, ref), 0.9, kind="spearman")
     bounds.check("broken2.fp32.median_abs", np.median(d), 1e-3)
+
+
+@pytest.mark.parametrize("shape,sensors,terrain,ctrl", [
+    ("biped-4x3", "spinedTouchSighted-t-f-0", "hilly-1-10-0", "central"),
+    ("biped-4x3", "uniform-px+py+l5+a-0", "flat", "central"),
+    ("worm-6x2", "spinedTouch-t-f-0.01", "steppy-0.25-1-0", "central"),
+    ("comb-7x2", "uniform-py+lf5+t-0", "hilly-1-10-0", "dist"),
+])
+def test_per_voxel_sensor_lists_and_the_extra_sensor_vocabulary(F, oracle, bounds, shape, sensors, terrain, ctrl):
+    """RobotUtils.buildSensorizingFunction names whose lists differ between voxels (`spinedTouch[Sighted]`, and `uniform-` over the
+    position-dependent predefined sensors px / py / l5) with the Constant, TimeFunction (cpg), Lidar and hard-Normalization sensors:
+    the library's own name layer against the oracle's (bit-exact), FP64 kernel == oracle over 40 steps, FP32 kernel tracks for 10."""
+    kind = oracle.CTRL_MLP_CENTRALIZED if ctrl == "central" else oracle.CTRL_MLP_DISTRIBUTED_HOMO
+    m = oracle.Model(shape, terrain, sensors, kind, oracle.default_params(2.0, 0.5), signals=1)
+    # name layer: vsr_sensor_config_voxels == oracle/model.py sensor_config_voxels
+    lib_s, lib_off = F.sensor_config_voxels(sensors, m.mask)
+    assert lib_off.tolist() == m.vox_off and len(lib_s) == len(m.vox_sensors)
+    for a, b in zip(lib_s, m.vox_sensors):
+        ka = a.key()
+        kb = (b.kind, b.axes, b.rotated, b.soft_norm, b.dom_min, b.dom_max, b.avg_window, b.noise_sigma, b.param, b.n_rays, b.side)
+        assert ka == kb, (ka, kb)
+    g = np.random.default_rng(12).uniform(-1, 1, (3, m.genome_len()))
+    c64 = make_ctx(F, m, 64)
+    assert c64.genome_len == m.genome_len()
+    cell, sensor, reading = c64.input_map()
+    if ctrl == "central":
+        assert len(cell) == m.ctrl.layers[0]
+    for r in range(3):
+        _, otv, otb, otc = m.run(g[r], trace_steps=40)
+        _, tv, tb, tc = c64.trace(g[r], 40)
+        assert np.abs(tb - otb).max() < 1e-9 and np.abs(tc - otc).max() < 1e-9, (r, np.abs(tb - otb).max(), np.abs(tc - otc).max())
+    c64.close()
+    c32 = make_ctx(F, m, 32)
+    for r in range(3):
+        _, otv, _, otc = m.run(g[r], trace_steps=10)
+        _, tv, _, tc = c32.trace(g[r], 10)
+        bounds.check(f"voxsens.{shape}.{sensors}.fp32.vertex_err_first10", np.abs(tv - otv).max() / 3.0, 1e-4)
+        bounds.check(f"voxsens.{shape}.{sensors}.fp32.ctrl_err_first10", np.abs(tc - otc).max(), 1e-3)
+    whole = c32.eval(g)
+    assert np.isfinite(whole).all() and c32.eval(g[1:2])[0] == whole[1]
+    c32.close()
+    # host mirror: the same robot through RobotUtils.build_sensorizing_function + the mapper
+    from vsrevolution_b200.locomotion import population_evaluator
+    mapper = "brainCentralized<mlp;r=0.65;nIL=1" if ctrl == "central" else "brainHomoDist;s=1<mlp;r=0.65;nIL=1"
+    ev = population_evaluator(shape, sensors, mapper, terrain, 2.0, 0.5)
+    assert ev.genome_len == m.genome_len() and np.array_equal(ev.evaluate(g), whole)

@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("VSR_LIB") or os.path.join(_HERE, "libvsr_eval.so")  #
 
 VSR_OK, VSR_EINVAL, VSR_ECUDA, VSR_ENOMEM, VSR_EDIM, VSR_EUNSUPPORTED, VSR_ESTATE = 0, -1, -2, -3, -4, -5, -6
 CTRL_PHASE_SIN, CTRL_MLP_CENTRALIZED, CTRL_MLP_DISTRIBUTED_HOMO, CTRL_MLP_DISTRIBUTED_HETERO, CTRL_TIME_SIN = 0, 1, 2, 3, 4
-SENSOR_AREA_RATIO, SENSOR_TOUCH, SENSOR_VELOCITY, SENSOR_ANGLE = 0, 1, 2, 3
+SENSOR_AREA_RATIO, SENSOR_TOUCH, SENSOR_VELOCITY, SENSOR_ANGLE, SENSOR_CONSTANT, SENSOR_TIME_SIN, SENSOR_LIDAR = 0, 1, 2, 3, 4, 5, 6
 
 
 class EnvDesc(C.Structure):
@@ -33,7 +33,11 @@ class EnvDesc(C.Structure):
 class SensorDesc(C.Structure):
     _fields_ = [("kind", C.c_int32), ("axes", C.c_int32), ("rotated", C.c_int32), ("soft_norm", C.c_int32),
                 ("dom_min", C.c_double), ("dom_max", C.c_double), ("avg_window", C.c_double),
-                ("noise_sigma", C.c_double)]
+                ("noise_sigma", C.c_double), ("param", C.c_double), ("n_rays", C.c_int32), ("side", C.c_int32)]
+
+    def key(self) -> tuple:
+        return (self.kind, self.axes, self.rotated, self.soft_norm, self.dom_min, self.dom_max, self.avg_window, self.noise_sigma,
+                self.param, self.n_rays, self.side)
 
 
 class Result(C.Structure):
@@ -83,6 +87,8 @@ _SIGS = {
     "vsr_ctx_destroy": (None, [C.c_void_p]),
     "vsr_last_error": (C.c_char_p, [C.c_void_p]),
     "vsr_body_set": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(SensorDesc), C.c_int32]),
+    "vsr_body_set_voxels": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(SensorDesc), C.c_void_p]),
+    "vsr_sensor_config_voxels": (C.c_int, [C.c_char_p, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(SensorDesc), C.c_int32, C.c_void_p]),
     "vsr_controller_set": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_double,
                                      C.c_double, C.c_int32]),
     "vsr_genome_len": (C.c_int, [C.c_void_p]),
@@ -216,6 +222,15 @@ class Context:
         m = np.ascontiguousarray(mask, dtype=np.uint8)
         arr = (SensorDesc * max(1, len(sensors)))(*sensors)
         check(lib().vsr_body_set(self._h, m.shape[1], m.shape[0], _ptr(m), arr, len(sensors)), self._h)
+
+    def body_set_voxels(self, mask: np.ndarray, sensors: list[SensorDesc], offsets):
+        """vsr_body_set_voxels: voxel v (grid order) carries sensors[offsets[v]:offsets[v + 1]]."""
+        m = np.ascontiguousarray(mask, dtype=np.uint8)
+        arr = (SensorDesc * max(1, len(sensors)))()
+        for i, sd in enumerate(sensors):
+            arr[i] = sd
+        off = np.ascontiguousarray(offsets, dtype=np.int32)
+        check(lib().vsr_body_set_voxels(self._h, m.shape[1], m.shape[0], _ptr(m), arr, _ptr(off)), self._h)
 
     def controller_set(self, kind: int, layers=(), signals=0, freq=1.0, amp=1.0, input_activation=1):
         arr = (C.c_int32 * max(1, len(layers)))(*layers)
@@ -551,6 +566,17 @@ def sensor_config(name: str) -> list[SensorDesc]:
     arr = (SensorDesc * max(1, n))()
     check(lib().vsr_sensor_config(name.encode(), arr, n))
     return [arr[i] for i in range(n)]
+
+
+def sensor_config_voxels(name: str, mask: np.ndarray):
+    """RobotUtils.buildSensorizingFunction(name).apply(body): (per-voxel sensor lists concatenated in grid order, offsets [n_vox + 1])."""
+    m = np.ascontiguousarray(mask, dtype=np.uint8)
+    nv = int(m.sum())
+    n = check(lib().vsr_sensor_config_voxels(name.encode(), m.shape[1], m.shape[0], _ptr(m), None, 0, None))
+    arr = (SensorDesc * max(1, n))()
+    off = np.zeros(nv + 1, dtype=np.int32)
+    check(lib().vsr_sensor_config_voxels(name.encode(), m.shape[1], m.shape[0], _ptr(m), arr, n, _ptr(off)))
+    return [arr[i] for i in range(n)], off
 
 
 def mlp_inner_neurons(n_in: int, n_out: int, ratio: float, n_inner: int) -> list[int]:

@@ -100,7 +100,11 @@ struct vsr_ctx {
   int w = 0, h = 0, n_vox = 0;
   std::vector<uint8_t> mask;
   std::vector<int> cell_of_vox, vox_of_cell;
-  std::vector<vsr_sensor_desc> sensors;
+  std::vector<vsr_sensor_desc> sensors;      // the distinct sensors of the body (position-dependent fields zeroed)
+  std::vector<vsr_sensor_desc> vsens;        // every voxel's own list, concatenated in voxel (grid) order
+  std::vector<int> vsens_off;                // [n_vox + 1]
+  std::vector<int> vsens_u;                  // [vsens.size()] index into `sensors`
+  bool uniform_sensors = true;               // every voxel carries the same list
   // controller
   vsr_ctrl_kind kind = VSR_CTRL_PHASE_SIN;
   std::vector<int> layers;
@@ -176,20 +180,29 @@ bool placement(const vsr_ctx* ctx, const double* tx, const double* ty, int nt, d
 
 int sensor_dim(const vsr_sensor_desc& s) {
   if (s.kind == VSR_SENSOR_VELOCITY) return ((s.axes & 1) ? 1 : 0) + ((s.axes & 2) ? 1 : 0);
+  if (s.kind == VSR_SENSOR_LIDAR) return s.n_rays;
   return 1;
+}
+
+int voxel_dim(const vsr_ctx* c, int v) {
+  int dim = 0;
+  for (int i = c->vsens_off[v]; i < c->vsens_off[v + 1]; i++) dim += sensor_dim(c->vsens[i]);
+  return dim;
 }
 
 int genome_len_of(const vsr_ctx* c) {
   if (!c->has_body || !c->has_ctrl) return VSR_ESTATE;
-  int dim = 0;
-  for (auto& s : c->sensors) dim += sensor_dim(s);
+  int total = 0, dim = voxel_dim(c, 0);
+  bool same = true;
+  for (int v = 0; v < c->n_vox; v++) { const int d = voxel_dim(c, v); total += d; same &= d == dim; }
   if (c->kind == VSR_CTRL_PHASE_SIN) return c->n_vox;
   if (c->kind == VSR_CTRL_TIME_SIN) return 3 * c->n_vox;
   int n_in = c->layers.front(), n_out = c->layers.back();
   if (c->kind == VSR_CTRL_MLP_CENTRALIZED) {
-    if (n_in != c->n_vox * dim || n_out != c->n_vox) return VSR_EDIM;
+    if (n_in != total || n_out != c->n_vox) return VSR_EDIM;
   } else {
-    if (n_in != dim + 4 * c->signals || n_out != 1 + 4 * c->signals) return VSR_EDIM;
+    // DistributedSensing: one MLP input size, so every voxel must produce the same number of readings
+    if (!same || n_in != dim + 4 * c->signals || n_out != 1 + 4 * c->signals) return VSR_EDIM;
   }
   const int nw = vsr_mlp_count_weights(c->layers.data(), (int)c->layers.size());
   return c->kind == VSR_CTRL_MLP_DISTRIBUTED_HETERO ? c->n_vox * nw : nw;
@@ -316,26 +329,50 @@ int finalize(vsr_ctx* ctx) {
     volatile double t = 0.0;
     for (int s = 1; s <= ns; s++) { t = t + e.dt; if (s == kf) k.t_first = t; if (s == kl) k.t_last = t; }
   }
-  // sensors
+  // sensors: the distinct sensors (k.sensors) and every voxel's list of them (k.vs_*)
   k.n_sensors = (int)ctx->sensors.size();
-  int off = 0, navg = 0;
+  int navg = 0, nrows = 0;
   std::vector<double> windows;
+  std::vector<int> row_of_dim(16, -1); // Noisy rows depend on the sensor's dimension only (every wrapper replays `new Random(0)`)
   for (int i = 0; i < k.n_sensors; i++) {
     const vsr_sensor_desc& s = ctx->sensors[i];
     vsr::SensorK& sk = k.sensors[i];
     sk.kind = s.kind; sk.axes = s.axes; sk.rotated = s.rotated; sk.soft_norm = s.soft_norm;
     sk.dom_min = s.dom_min; sk.dom_inv = s.soft_norm ? 1.0 / (s.dom_max - s.dom_min) : 1.0;
-    sk.off = off; sk.dim = sensor_dim(s);
+    sk.dim = sensor_dim(s); sk.off = 0;
+    sk.n_rays = s.n_rays; sk.param = s.param;
     sk.avg = -1;
     if (s.avg_window > 0) {
       sk.avg = navg;
       for (int d = 0; d < sk.dim; d++) windows.push_back(s.avg_window);
       navg += sk.dim;
     }
-    off += sk.dim;
+    sk.noise_row = 0;
+    if (s.noise_sigma > 0) {
+      if (row_of_dim[sk.dim] < 0) { row_of_dim[sk.dim] = nrows; nrows += sk.dim; }
+      sk.noise_row = row_of_dim[sk.dim];
+    }
   }
-  if (off > 8 || navg > vsr::kMaxAvg) return fail(ctx, VSR_EUNSUPPORTED, "more than 8 readings / 6 averaged readings per voxel");
-  k.sens_dim = off; k.n_avg = navg;
+  if (navg > vsr::kMaxAvg) return fail(ctx, VSR_EUNSUPPORTED, "more than 6 averaged readings over the body's distinct sensors");
+  k.vs_max = 0;
+  int total_dim = 0;
+  for (int v = 0; v < ctx->n_vox; v++) {
+    const int n = ctx->vsens_off[v + 1] - ctx->vsens_off[v], dim = voxel_dim(ctx, v);
+    if (n > vsr::kMaxVoxSensors || dim > 8) return fail(ctx, VSR_EUNSUPPORTED, "more than 8 sensors / readings on one voxel");
+    k.vs_n[v] = (uint8_t)n; k.vs_max = std::max(k.vs_max, n);
+    k.vox_dim[v] = (uint8_t)dim; k.vox_in_off[v] = (uint16_t)total_dim;
+    total_dim += dim;
+    for (int j = 0; j < n; j++) {
+      const vsr_sensor_desc& s = ctx->vsens[ctx->vsens_off[v] + j];
+      k.vs_idx[v][j] = (uint8_t)ctx->vsens_u[ctx->vsens_off[v] + j];
+      k.vs_param[v][j] = s.kind == VSR_SENSOR_CONSTANT ? (float)s.param : (s.kind == VSR_SENSOR_LIDAR ? (float)s.side : 0.0f);
+    }
+  }
+  if (ctx->uniform_sensors) { // offsets inside the (common) reading vector, for the specialised builds
+    int off = 0;
+    for (int j = 0; j < (int)k.vs_n[0]; j++) { k.sensors[k.vs_idx[0][j]].off = off; off += k.sensors[k.vs_idx[0][j]].dim; }
+  }
+  k.sens_dim = voxel_dim(ctx, 0); k.n_avg = navg;
   // Average windows: count of stored readings with t_j >= t_k - window, emulated in double
   ctx->win_tab.assign((size_t)std::max(navg, 1) * (ns + 1), 1);
   int max_win = 1;
@@ -353,24 +390,28 @@ int finalize(vsr_ctx* ctx) {
       }
   }
   k.hist_cap = max_win + 2;
-  // Noisy wrappers: `new Noisy(sensor, sigma, 0)` on every voxel [U] -> one java.util.Random(0) stream per sensor, one
-  // Gaussian per reading per step, scaled by sigma * |domain of the wrapped sensor| ([0,1] after SoftNormalization)
+  // Noisy wrappers: `new Noisy(sensor, sigma, 0)` on every voxel [U] -> every wrapper replays java.util.Random(0): one Gaussian per
+  // reading per step, scaled by sigma * |domain| of the wrapped sensor ([0,1] after a normalisation).  The table holds, per distinct
+  // (dimension, sigma scale) ... rows are per dimension; the scale is folded in per sensor below, so sensors of one dimension must
+  // share sigma * |domain| (true for every configuration RobotUtils builds: one sigma for the whole body)
   ctx->noise_tab.clear();
-  {
-    bool any = false;
-    for (auto& sd : ctx->sensors) any |= sd.noise_sigma > 0;
-    if (any) {
-      ctx->noise_tab.assign((size_t)k.sens_dim * (ns + 1), 0.0);
-      for (int i = 0; i < k.n_sensors; i++) {
-        const vsr_sensor_desc& sd = ctx->sensors[i];
-        if (!(sd.noise_sigma > 0)) continue;
-        const int dim = k.sensors[i].dim;
-        std::vector<double> g((size_t)dim * ns);
-        vsr_java_random_gaussians(0, g.data(), dim * ns);
-        const double scale = sd.noise_sigma * (sd.soft_norm ? 1.0 : std::fabs(sd.dom_max - sd.dom_min));
-        for (int st = 1; st <= ns; st++)
-          for (int d = 0; d < dim; d++) ctx->noise_tab[(size_t)(k.sensors[i].off + d) * (ns + 1) + st] = g[(size_t)(st - 1) * dim + d] * scale;
+  if (nrows > 0) {
+    ctx->noise_tab.assign((size_t)nrows * (ns + 1), 0.0);
+    std::vector<double> scale_of_dim(16, -1.0);
+    for (int i = 0; i < k.n_sensors; i++) {
+      const vsr_sensor_desc& sd = ctx->sensors[i];
+      if (!(sd.noise_sigma > 0)) continue;
+      const int dim = k.sensors[i].dim;
+      const double scale = sd.noise_sigma * (sd.soft_norm ? 1.0 : std::fabs(sd.dom_max - sd.dom_min));
+      if (scale_of_dim[dim] >= 0) {
+        if (scale_of_dim[dim] != scale) return fail(ctx, VSR_EUNSUPPORTED, "Noisy sensors of the same dimension with different sigma * |domain|");
+        continue;
       }
+      scale_of_dim[dim] = scale;
+      std::vector<double> g((size_t)dim * ns);
+      vsr_java_random_gaussians(0, g.data(), dim * ns);
+      for (int st = 1; st <= ns; st++)
+        for (int d = 0; d < dim; d++) ctx->noise_tab[(size_t)(k.sensors[i].noise_row + d) * (ns + 1) + st] = g[(size_t)(st - 1) * dim + d] * scale;
     }
   }
   // controller
@@ -454,7 +495,7 @@ int finalize(vsr_ctx* ctx) {
   ctx->kernel = kernel_ptr(e.precision, kernel_ctrl(ctx->kind), ctx->shape, full_scaff);
   // the reference's default robot: one soft-normalised, non-averaged AreaRatio reading per voxel into a centralized MLP
   if (e.precision == 32 && ctx->shape == 3 && ctx->warps == 10 && full_scaff && ctx->kind == VSR_CTRL_MLP_CENTRALIZED &&
-      ctx->sensors.size() == 1 && ctx->sensors[0].kind == VSR_SENSOR_AREA_RATIO && ctx->sensors[0].soft_norm &&
+      ctx->uniform_sensors && ctx->sensors.size() == 1 && ctx->sensors[0].kind == VSR_SENSOR_AREA_RATIO && ctx->sensors[0].soft_norm == 1 &&
       !(ctx->sensors[0].avg_window > 0) && !std::getenv("VSR_GENERIC_SENSORS"))
     ctx->kernel = vsr_internal::kernel_f32_s3_area();
   ctx->smem_bytes = o * ctx->warps + 128; // + the CTA's phase counters (bounded-skew alignment)
@@ -834,16 +875,68 @@ const char* vsr_last_error(const vsr_ctx* c) { return c ? c->err.c_str() : g_cre
 int vsr_body_set(vsr_ctx* ctx, int32_t w, int32_t h, const uint8_t* mask, const vsr_sensor_desc* sensors, int32_t n_sensors) {
   if (!ctx) return VSR_EINVAL;
   if (w <= 0 || h <= 0 || !mask || n_sensors < 0 || (n_sensors > 0 && !sensors)) return fail(ctx, VSR_EINVAL, "bad body arguments");
-  if (n_sensors > vsr::kMaxSensors) return fail(ctx, VSR_EUNSUPPORTED, "too many sensors per voxel");
+  int nv = 0;
+  for (int i = 0; i < w * h; i++) nv += mask[i] ? 1 : 0;
+  if (nv == 0) return fail(ctx, VSR_EINVAL, "Target robot has no voxels");
+  // the same list on every voxel
+  std::vector<vsr_sensor_desc> all;
+  std::vector<int32_t> off(nv + 1);
+  for (int v = 0; v < nv; v++) {
+    off[v] = (int32_t)all.size();
+    all.insert(all.end(), sensors, sensors + n_sensors);
+  }
+  off[nv] = (int32_t)all.size();
+  return vsr_body_set_voxels(ctx, w, h, mask, all.data(), off.data());
+}
+
+int vsr_body_set_voxels(vsr_ctx* ctx, int32_t w, int32_t h, const uint8_t* mask, const vsr_sensor_desc* sensors, const int32_t* sensor_off) {
+  if (!ctx) return VSR_EINVAL;
+  if (w <= 0 || h <= 0 || !mask || !sensor_off) return fail(ctx, VSR_EINVAL, "bad body arguments");
   int nv = 0;
   for (int i = 0; i < w * h; i++) nv += mask[i] ? 1 : 0;
   if (nv == 0) return fail(ctx, VSR_EINVAL, "Target robot has no voxels");
   if (nv > vsr::kMaxVox) return fail(ctx, VSR_EUNSUPPORTED, "bodies with more than 32 voxels are not supported by this build");
-  for (int i = 0; i < n_sensors; i++) {
-    if (sensors[i].noise_sigma < 0) return fail(ctx, VSR_EINVAL, "negative noise sigma");
-    if (sensors[i].kind < 0 || sensors[i].kind > VSR_SENSOR_ANGLE) return fail(ctx, VSR_EINVAL, "unknown sensor kind");
-    if (sensors[i].kind == VSR_SENSOR_VELOCITY && !(sensors[i].axes & 3)) return fail(ctx, VSR_EINVAL, "velocity sensor without axes");
-    if (sensors[i].soft_norm && !(sensors[i].dom_max > sensors[i].dom_min)) return fail(ctx, VSR_EINVAL, "empty sensor domain");
+  if (sensor_off[0] != 0) return fail(ctx, VSR_EINVAL, "sensor_off[0] must be 0");
+  for (int v = 0; v < nv; v++)
+    if (sensor_off[v + 1] < sensor_off[v]) return fail(ctx, VSR_EINVAL, "sensor_off must be non-decreasing");
+  const int total = sensor_off[nv];
+  if (total > 0 && !sensors) return fail(ctx, VSR_EINVAL, "bad body arguments");
+  for (int v = 0; v < nv; v++)
+    if (sensor_off[v + 1] - sensor_off[v] > vsr::kMaxVoxSensors) return fail(ctx, VSR_EUNSUPPORTED, "too many sensors per voxel");
+  for (int i = 0; i < total; i++) {
+    const vsr_sensor_desc& d = sensors[i];
+    if (d.noise_sigma < 0) return fail(ctx, VSR_EINVAL, "negative noise sigma");
+    if (d.kind < 0 || d.kind > VSR_SENSOR_LIDAR) return fail(ctx, VSR_EINVAL, "unknown sensor kind");
+    if (d.kind == VSR_SENSOR_VELOCITY && !(d.axes & 3)) return fail(ctx, VSR_EINVAL, "velocity sensor without axes");
+    if (d.soft_norm < 0 || d.soft_norm > 2) return fail(ctx, VSR_EINVAL, "soft_norm must be 0 (none), 1 (SoftNormalization) or 2 (Normalization)");
+    if (d.soft_norm && !(d.dom_max > d.dom_min)) return fail(ctx, VSR_EINVAL, "empty sensor domain");
+    if (d.kind == VSR_SENSOR_LIDAR && (d.n_rays < 1 || d.n_rays > 8 || d.side < 0 || d.side > 3 || !(d.param > 0)))
+      return fail(ctx, VSR_EINVAL, "lidar needs 1..8 rays, a side in 0..3 and a positive ray length");
+    if (d.kind == VSR_SENSOR_LIDAR && d.avg_window > 0) return fail(ctx, VSR_EUNSUPPORTED, "averaged lidar readings are not built");
+  }
+  // the distinct sensors of the body: position-dependent fields (CONSTANT value, LIDAR side) are kept per voxel, not per sensor
+  std::vector<vsr_sensor_desc> uniq;
+  std::vector<int> which((size_t)total);
+  for (int i = 0; i < total; i++) {
+    vsr_sensor_desc d = sensors[i];
+    if (d.kind == VSR_SENSOR_CONSTANT) d.param = 0;
+    if (d.kind == VSR_SENSOR_LIDAR) d.side = 0;
+    int u = -1;
+    for (size_t j = 0; j < uniq.size() && u < 0; j++)
+      if (uniq[j].kind == d.kind && uniq[j].axes == d.axes && uniq[j].rotated == d.rotated && uniq[j].soft_norm == d.soft_norm &&
+          uniq[j].dom_min == d.dom_min && uniq[j].dom_max == d.dom_max && uniq[j].avg_window == d.avg_window &&
+          uniq[j].noise_sigma == d.noise_sigma && uniq[j].param == d.param && uniq[j].n_rays == d.n_rays) u = (int)j;
+    if (u < 0) { u = (int)uniq.size(); uniq.push_back(d); }
+    which[i] = u;
+  }
+  if ((int)uniq.size() > vsr::kMaxSensors) return fail(ctx, VSR_EUNSUPPORTED, "more than 8 distinct sensors on one body");
+  bool uniform = true;
+  for (int v = 1; v < nv && uniform; v++) {
+    const int n = sensor_off[v + 1] - sensor_off[v];
+    if (n != sensor_off[1] - sensor_off[0]) { uniform = false; break; }
+    for (int j = 0; j < n; j++)
+      if (which[sensor_off[v] + j] != which[sensor_off[0] + j] || sensors[sensor_off[v] + j].param != sensors[sensor_off[0] + j].param ||
+          sensors[sensor_off[v] + j].side != sensors[sensor_off[0] + j].side) uniform = false;
   }
   ctx->w = w; ctx->h = h; ctx->n_vox = nv;
   ctx->mask.assign(mask, mask + w * h);
@@ -851,7 +944,11 @@ int vsr_body_set(vsr_ctx* ctx, int32_t w, int32_t h, const uint8_t* mask, const 
   ctx->cell_of_vox.clear();
   for (int i = 0; i < w * h; i++)
     if (mask[i]) { ctx->vox_of_cell[i] = (int)ctx->cell_of_vox.size(); ctx->cell_of_vox.push_back(i); }
-  ctx->sensors.assign(sensors, sensors + n_sensors);
+  ctx->sensors = uniq;
+  ctx->vsens.assign(sensors, sensors + total);
+  ctx->vsens_off.assign(sensor_off, sensor_off + nv + 1);
+  ctx->vsens_u = which;
+  ctx->uniform_sensors = uniform;
   ctx->has_body = true;
   return finalize(ctx);
 }
@@ -1208,12 +1305,13 @@ int vsr_input_map(const vsr_ctx* ctx, int32_t* cell, int32_t* sensor, int32_t* r
   if (!ctx || !ctx->has_body) return VSR_ESTATE;
   int n = 0;
   // CentralizedSensing: voxels in Grid.values() order (row-major y*w+x, nulls skipped), sensors in list order
+  // (`sensor` = position in the voxel's own list)
   for (int v = 0; v < ctx->n_vox; v++)
-    for (size_t s = 0; s < ctx->sensors.size(); s++)
-      for (int r = 0; r < sensor_dim(ctx->sensors[s]); r++) {
+    for (int s = ctx->vsens_off[v]; s < ctx->vsens_off[v + 1]; s++)
+      for (int r = 0; r < sensor_dim(ctx->vsens[s]); r++) {
         if (n < cap) {
           if (cell) cell[n] = ctx->cell_of_vox[v];
-          if (sensor) sensor[n] = (int)s;
+          if (sensor) sensor[n] = s - ctx->vsens_off[v];
           if (reading) reading[n] = r;
         }
         n++;

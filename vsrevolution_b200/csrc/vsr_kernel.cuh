@@ -27,7 +27,8 @@
 namespace vsr {
 
 constexpr int kMaxVox = 32;
-constexpr int kMaxSensors = 6;
+constexpr int kMaxSensors = 8;   // distinct sensors over all voxels (position-dependent values are per voxel: vs_param)
+constexpr int kMaxVoxSensors = 8; // sensors (and readings) per voxel
 constexpr int kMaxLayers = 8;
 constexpr int kMaxMan = 3;       // manifolds per corner mass (ground polygons it can touch at once)
 constexpr int kMaxAvg = 6;       // averaged readings per voxel
@@ -64,7 +65,10 @@ struct SensorK {
   int kind, axes, rotated, soft_norm;
   double dom_min, dom_inv; // soft norm: (x - dom_min) * dom_inv
   int avg;                 // index into the averaged-reading table or -1
-  int off, dim;            // offset / size inside the voxel's reading vector
+  int off, dim;            // offset inside a uniform voxel's reading vector (unused with per-voxel lists) / number of readings
+  int noise_row;           // first row of the Noisy table for this sensor (rows depend on the sensor's dimension only)
+  int n_rays;              // LIDAR
+  double param;            // TIME_SIN: frequency; LIDAR: ray length (CONSTANT values and LIDAR sides are per voxel: KParams::vs_param)
 };
 
 // FP32 copies of the scalar constants: the FP32 kernel reads them straight from the constant bank
@@ -102,9 +106,16 @@ struct KParams {
   const int* toff;
   const double* tbase;
   const double* tplace;
-  // sensors
+  // sensors: the distinct sensors of the body, and every voxel's own list (RobotUtils.buildSensorizingFunction: `uniform-...` gives the
+  // same list everywhere, `spinedTouch-...` / px / py / l5 depend on the voxel's grid position)
   int n_sensors, sens_dim, n_avg, hist_cap;
   SensorK sensors[kMaxSensors];
+  int vs_max;                                   // longest per-voxel list
+  uint8_t vs_n[kMaxVox];                        // sensors of voxel v
+  uint8_t vs_idx[kMaxVox][kMaxVoxSensors];      // ... and which (index into sensors[])
+  float vs_param[kMaxVox][kMaxVoxSensors];      // CONSTANT: the value; LIDAR: the side (0 N, 1 E, 2 S, 3 W)
+  uint8_t vox_dim[kMaxVox];                     // readings of voxel v
+  uint16_t vox_in_off[kMaxVox];                 // CentralizedSensing: first MLP input of voxel v
   const uint8_t* win_tab; // [n_avg][n_steps+1] window length (in readings) at step k
   const double* noise;    // Noisy sensors: [sens_dim][n_steps+1] additive noise of reading r at step k (NULL = none)
   void* hist;             // R[hist_cap][n_avg][total_lanes] ring of raw readings
@@ -1535,10 +1546,14 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
         if (P.noise) val += (R)__ldg(&P.noise[step]);
         rd[0] = val;
       } else {
+      const int nsv = valid ? (int)P.vs_n[vi] : 0;
+      int ri = 0; // next reading of this voxel
 #pragma unroll 1
-      for (int si = 0; si < P.n_sensors; si++) {
-        const SensorK& sk = P.sensors[si];
+      for (int sj = 0; sj < P.vs_max; sj++) { // warp-uniform trip count; voxels with shorter lists idle
+        if (sj >= nsv) continue;
+        const SensorK& sk = P.sensors[P.vs_idx[vi][sj]];
         R raw0 = 0, raw1 = 0;
+        R rays[kMaxVoxSensors];
         if (sk.kind == VSR_SENSOR_AREA_RATIO) {
           R a2 = 0;
 #pragma unroll
@@ -1546,13 +1561,64 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
           raw0 = M<R>::abs_(a2) * K_inv_area2;
         } else if (sk.kind == VSR_SENSOR_TOUCH) {
           raw0 = touching ? R(1) : R(0);
+        } else if (sk.kind == VSR_SENSOR_CONSTANT) {
+          raw0 = (R)P.vs_param[vi][sj];
+        } else if (sk.kind == VSR_SENSOR_TIME_SIN) {
+          raw0 = M<R>::phase_sin(1.0, sk.param, t, R(0));
         } else {
           if (!have_ang) {
             vang = (M<R>::atan2_(Y[1] - Y[0], X[1] - X[0]) + M<R>::atan2_(Y[2] - Y[3], X[2] - X[3])) * R(0.5);
             have_ang = true;
           }
           if (sk.kind == VSR_SENSOR_ANGLE) raw0 = vang;
-          else {
+          else if (sk.kind == VSR_SENSOR_LIDAR) {
+            // Lidar [U]: rays from the voxel centre, directions of one side's sector rotated by the voxel angle, first hit on the
+            // ground's surface (the polyline + the two outer walls) within the ray length; restated in oracle raycast_ground
+            const double oxd = (double)ox, oyd = (double)oy;
+            const R cx = R(0.25) * (X[0] + X[1] + X[2] + X[3]), cy = R(0.25) * (Y[0] + Y[1] + Y[2] + Y[3]);
+            const R len = (R)sk.param;
+            const int side = (int)P.vs_param[vi][sj];
+            const int t0 = P.toff ? __ldg(&P.toff[robot]) : 0, tn = P.toff ? __ldg(&P.toff[robot + 1]) - t0 : P.n_t;
+            const double* tx = P.tx + t0;
+            const double* ty = P.ty + t0;
+            const double basey = P.toff ? __ldg(&P.tbase[robot]) : P.base_y;
+            // first segment that can matter: the one whose right end is not left of cx - len
+            int k0 = kh;
+            const double xl = oxd + (double)(cx - len), xr = oxd + (double)(cx + len);
+            while (k0 > 1 && __ldg(&tx[k0 - 1]) > xl) k0--;
+            while (k0 < tn - 1 && __ldg(&tx[k0]) < xl) k0++;
+            const double startA = side == 0 ? 0.25 : (side == 1 ? -0.25 : (side == 2 ? 1.25 : 0.75)); // in units of pi
+            const double endA = side == 0 ? 0.75 : (side == 1 ? 0.25 : (side == 2 ? 1.75 : 1.25));
+#pragma unroll 1
+            for (int i = 0; i < sk.n_rays; i++) {
+              const double rel = sk.n_rays == 1 ? (endA - startA) / 2.0 * 3.14159265358979323846
+                                                : (startA * 3.14159265358979323846 + (endA - startA) * 3.14159265358979323846 / (double)(sk.n_rays - 1) * (double)i);
+              R dx, dy;
+              M<R>::sincos_((R)rel + vang, &dy, &dx);
+              R best = len;
+#pragma unroll 1
+              for (int k = k0; k < tn; k++) {
+                const double x0d = __ldg(&tx[k - 1]);
+                if (x0d > xr) break;
+                const R x0 = (R)(x0d - oxd), y0 = (R)(__ldg(&ty[k - 1]) - oyd);
+                const R ex = (R)(__ldg(&tx[k]) - oxd) - x0, ey = (R)(__ldg(&ty[k]) - oyd) - y0;
+                const R den = dx * ey - dy * ex;
+                if (den == R(0)) continue;
+                const R tt = ((x0 - cx) * ey - (y0 - cy) * ex) / den, uu = ((x0 - cx) * dy - (y0 - cy) * dx) / den;
+                if (tt >= R(0) && tt < best && uu >= R(0) && uu <= R(1)) best = tt;
+              }
+#pragma unroll
+              for (int wside = 0; wside < 2; wside++) { // outer walls of the first / last ground polygon
+                const int kw = wside == 0 ? 0 : tn - 1;
+                const R xw = (R)(__ldg(&tx[kw]) - oxd), yt = (R)(__ldg(&ty[kw]) - oyd);
+                if (dx == R(0)) continue;
+                const R tt = (xw - cx) / dx, yy = cy + tt * dy;
+                if (tt >= R(0) && tt < best && yy <= yt && yy >= (R)(basey - oyd)) best = tt;
+              }
+#pragma unroll
+              for (int z = 0; z < kMaxVoxSensors; z++) if (z == i) rays[z] = best;
+            }
+          } else {
             R vx = R(0.25) * (VX[0] + VX[1] + VX[2] + VX[3]), vy = R(0.25) * (VY[0] + VY[1] + VY[2] + VY[3]);
             if (sk.rotated) {
               R sn_, cs_;
@@ -1566,6 +1632,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
         }
         for (int d = 0; d < sk.dim; d++) {
           R val = d == 0 ? raw0 : raw1;
+          if (sk.kind == VSR_SENSOR_LIDAR) {
+#pragma unroll
+            for (int z = 0; z < kMaxVoxSensors; z++) if (z == d) val = rays[z];
+          }
           if (sk.avg >= 0) {
             // Average: mean of the last win readings (window table emulates the t_j >= t - w test in double)
             const int ai = sk.avg + d;
@@ -1583,14 +1653,16 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
             savg[ai * 32 + lane] = sum; savg_cnt[ai * 32 + lane] = cnt;
             val = (R)(sum / cnt);
           }
-          if (sk.soft_norm) {
+          if (sk.soft_norm == 1) {
             const R vv = (val - (R)sk.dom_min) * (R)sk.dom_inv;
             val = M<R>::tanh_((vv * R(2) - R(1)) * R(2)) * R(0.5) + R(0.5);
+          } else if (sk.soft_norm == 2) { // Normalization: linear map of the domain on [0, 1], clipped
+            val = M<R>::min_(M<R>::max_((val - (R)sk.dom_min) * (R)sk.dom_inv, R(0)), R(1));
           }
-          const int ri = sk.off + d;
-          if (P.noise) val += (R)__ldg(&P.noise[(size_t)ri * (P.n_steps + 1) + step]); // Noisy wrapper (host-replayed java.util.Random)
+          if (P.noise) val += (R)__ldg(&P.noise[(size_t)(sk.noise_row + d) * (P.n_steps + 1) + step]); // Noisy wrapper (host-replayed java.util.Random)
 #pragma unroll
           for (int z = 0; z < 8; z++) if (z == ri) rd[z] = val;
+          ri++;
         }
       }
       }
@@ -1600,7 +1672,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
         const R* w_ = wts + (size_t)(lane_used ? rw : 0) * P.genome_len;
         if (valid) {
 #pragma unroll
-          for (int d = 0; d < 8; d++) if (d < D) a0[v * D + d] = P.in_act ? M<R>::tanh_(rd[d]) : rd[d];
+          for (int d = 0; d < 8; d++) if (d < (int)P.vox_dim[vi]) a0[P.vox_in_off[vi] + d] = P.in_act ? M<R>::tanh_(rd[d]) : rd[d];
         }
         __syncwarp();
         int cur = 0, o = 0;

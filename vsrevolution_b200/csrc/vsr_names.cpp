@@ -212,6 +212,41 @@ int vsr_terrain(const char* name, double* xs_out, double* ys_out, int32_t cap) {
   return n;
 }
 
+namespace {
+// Lidar.Side of a voxel at relative grid position (x, y) in [0, 1]^2 [U] (RobotUtils.lidarSide): the side that faces outwards
+int lidar_side(double x, double y) {
+  if (y > x && y > 1 - x) return 2;   // S
+  if (y >= x && y <= 1 - x) return 3; // W
+  if (y < x && y < 1 - x) return 0;   // N
+  return 1;                           // E
+}
+
+// one entry of RobotUtils' PREDEFINED_SENSORS [U] for the voxel at (x, y) of a w x h grid; false = not built here
+bool predefined_sensor(const std::string& s, int x, int y, int w, int h, double sigma, vsr_sensor_desc* d) {
+  std::memset(d, 0, sizeof(*d));
+  d->dom_min = 0; d->dom_max = 1; d->noise_sigma = sigma;
+  const double rx = w > 1 ? (double)x / ((double)w - 1.0) : 0.0 / 0.0, ry = h > 1 ? (double)y / ((double)h - 1.0) : 0.0 / 0.0; // Java: 0d / 0d = NaN
+  if (s == "a") { d->kind = VSR_SENSOR_AREA_RATIO; d->soft_norm = 1; d->dom_min = 0.5; d->dom_max = 1.5; }
+  else if (s == "t") { d->kind = VSR_SENSOR_TOUCH; d->avg_window = 0.25; }
+  else if (s == "r") { d->kind = VSR_SENSOR_ANGLE; d->soft_norm = 1; d->dom_min = -M_PI; d->dom_max = M_PI; }
+  else if (s == "vx" || s == "vy" || s == "vxy") {
+    d->kind = VSR_SENSOR_VELOCITY;
+    d->axes = s == "vx" ? 1 : (s == "vy" ? 2 : 3);
+    d->rotated = 1; d->soft_norm = 1; d->dom_min = -8; d->dom_max = 8; d->avg_window = 0.5;
+  }
+  else if (s == "px") { d->kind = VSR_SENSOR_CONSTANT; d->param = rx; }
+  else if (s == "py") { d->kind = VSR_SENSOR_CONSTANT; d->param = ry; }
+  else if (s == "cpg") { d->kind = VSR_SENSOR_TIME_SIN; d->param = -1.0; d->soft_norm = 2; d->dom_min = -1; d->dom_max = 1; }
+  else if (s == "l1" || s == "l5" || s == "lf5") {
+    d->kind = VSR_SENSOR_LIDAR; d->param = 10.0; d->soft_norm = 2; d->dom_min = 0; d->dom_max = 10.0;
+    d->n_rays = s == "l1" ? 1 : 5;
+    d->side = s == "lf5" ? 1 : lidar_side(rx, ry);
+  }
+  else return false;
+  return true;
+}
+} // namespace
+
 int vsr_sensor_config(const char* name, vsr_sensor_desc* out, int32_t cap) {
   if (!name) return VSR_EINVAL;
   auto p = split(name, '-');
@@ -221,24 +256,71 @@ int vsr_sensor_config(const char* name, vsr_sensor_desc* out, int32_t cap) {
   int n = 0;
   for (auto& s : names) {
     vsr_sensor_desc d;
-    std::memset(&d, 0, sizeof(d));
-    d.dom_min = 0;
-    d.dom_max = 1;
-    d.noise_sigma = sigma;
-    if (s == "a") { d.kind = VSR_SENSOR_AREA_RATIO; d.soft_norm = 1; d.dom_min = 0.5; d.dom_max = 1.5; }
-    else if (s == "t") { d.kind = VSR_SENSOR_TOUCH; d.avg_window = 0.25; }
-    else if (s == "r") { d.kind = VSR_SENSOR_ANGLE; d.soft_norm = 1; d.dom_min = -M_PI; d.dom_max = M_PI; }
-    else if (s == "vx" || s == "vy" || s == "vxy") {
-      d.kind = VSR_SENSOR_VELOCITY;
-      d.axes = s == "vx" ? 1 : (s == "vy" ? 2 : 3);
-      d.rotated = 1; d.soft_norm = 1; d.dom_min = -8; d.dom_max = 8; d.avg_window = 0.5;
-    } else return VSR_EUNSUPPORTED;
+    // the position-dependent entries (px, py, l1, l5) differ between voxels: they need vsr_sensor_config_voxels
+    if (s == "px" || s == "py" || s == "l1" || s == "l5" || !predefined_sensor(s, 0, 0, 2, 2, sigma, &d)) return VSR_EUNSUPPORTED;
     if (out) {
       if (n >= cap) return VSR_EINVAL;
       out[n] = d;
     }
     n++;
   }
+  return n;
+}
+
+int vsr_sensor_config_voxels(const char* name, int32_t w, int32_t h, const uint8_t* mask, vsr_sensor_desc* out, int32_t cap, int32_t* off_out) {
+  if (!name || !mask || w <= 0 || h <= 0) return VSR_EINVAL;
+  const std::string nm(name);
+  auto p = split(nm, '-');
+  enum { UNIFORM, SPINED, SPINED_SIGHTED, EMPTY } form;
+  double sigma = 0;
+  bool cpg = false;
+  std::vector<std::string> names;
+  if (nm == "empty") form = EMPTY;
+  else if (p[0] == "uniform" && p.size() == 3 && parse_double(p[2], &sigma)) { form = UNIFORM; names = split(p[1], '+'); }
+  else if ((p[0] == "spinedTouch" || p[0] == "spinedTouchSighted") && p.size() == 4 && (p[1] == "t" || p[1] == "f") &&
+           (p[2] == "t" || p[2] == "f") && parse_double(p[3], &sigma)) {
+    form = p[0] == "spinedTouch" ? SPINED : SPINED_SIGHTED;
+    cpg = p[1] == "t";
+    if (p[2] == "t") return VSR_EUNSUPPORTED; // the Malfunction sensor
+  } else return VSR_EINVAL;
+  if (sigma < 0) return VSR_EINVAL;
+  int n = 0, v = 0;
+  auto emit = [&](const vsr_sensor_desc& d) -> bool {
+    if (out) {
+      if (n >= cap) return false;
+      out[n] = d;
+    }
+    n++;
+    return true;
+  };
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w; x++) {
+      if (!mask[y * w + x]) continue;
+      if (off_out) off_out[v] = n;
+      v++;
+      vsr_sensor_desc d;
+      if (form == UNIFORM) {
+        for (auto& s : names) {
+          if (!predefined_sensor(s, x, y, w, h, sigma, &d)) return VSR_EUNSUPPORTED;
+          if (!emit(d)) return VSR_EINVAL;
+        }
+      } else if (form == SPINED || form == SPINED_SIGHTED) {
+        // [U] spinedTouch: touch on the bottom row, (hard-normalised, un-averaged) velocity on the top row, area ratio everywhere,
+        // the central pattern generator on the top-right voxel; Sighted: a 5-ray front lidar on the right column
+        if (y == 0) { predefined_sensor("t", x, y, w, h, sigma, &d); if (!emit(d)) return VSR_EINVAL; }
+        if (y == h - 1) {
+          predefined_sensor("vxy", x, y, w, h, sigma, &d);
+          d.soft_norm = 2; d.avg_window = 0;
+          if (!emit(d)) return VSR_EINVAL;
+        }
+        predefined_sensor("a", x, y, w, h, sigma, &d);
+        d.soft_norm = 2;
+        if (!emit(d)) return VSR_EINVAL;
+        if (cpg && x == w - 1 && y == h - 1) { predefined_sensor("cpg", x, y, w, h, sigma, &d); if (!emit(d)) return VSR_EINVAL; }
+        if (form == SPINED_SIGHTED && x == w - 1) { predefined_sensor("lf5", x, y, w, h, sigma, &d); if (!emit(d)) return VSR_EINVAL; }
+      }
+    }
+  if (off_out) off_out[v] = n;
   return n;
 }
 

@@ -159,9 +159,7 @@ class Locomotion:
         voxels = [v for v in body.values() if v is not None]
         if not voxels:
             raise _ffi.VsrIllegalArgument(_ffi.VSR_EINVAL, "Target robot has no voxels")
-        skey = voxels[0].sensor_key()
-        if any(v.sensor_key() != skey for v in voxels):
-            raise _ffi.VsrError(_ffi.VSR_EUNSUPPORTED, "per-voxel sensor lists must be uniform in this build")
+        skey = tuple(v.sensor_key() for v in voxels)  # every voxel's own sensor list (they may differ: spinedTouch, px, py, l5)
         c = robot.get_controller()
         if isinstance(c, PhaseSin):
             ckey = ("phase", c.frequency, c.amplitude)
@@ -191,7 +189,8 @@ class Locomotion:
             for i, d in enumerate(self.devices):
                 e.devices[i] = d
             ctx = _ffi.Context(e, self.xs, self.ys)
-            ctx.body_set(mask, voxels[0].sensors)
+            off = np.concatenate([[0], np.cumsum([len(v.sensors) for v in voxels])]).astype(np.int32)
+            ctx.body_set_voxels(mask, [sd for v in voxels for sd in v.sensors], off)
             if ckey[0] == "phase":
                 ctx.controller_set(_ffi.CTRL_PHASE_SIN, (), 0, c.frequency, c.amplitude)
             elif ckey[0] == "central":

@@ -81,11 +81,11 @@ class Voxel:
     sensors: list = field(default_factory=list)  # list[_ffi.SensorDesc]
 
     def sensor_dim(self) -> int:
-        return sum(bin(s.axes & 3).count("1") if s.kind == _ffi.SENSOR_VELOCITY else 1 for s in self.sensors)
+        return sum(s.n_rays if s.kind == _ffi.SENSOR_LIDAR else (bin(s.axes & 3).count("1") if s.kind == _ffi.SENSOR_VELOCITY else 1)
+                   for s in self.sensors)
 
     def sensor_key(self) -> tuple:
-        return tuple((s.kind, s.axes, s.rotated, s.soft_norm, s.dom_min, s.dom_max, s.avg_window, s.noise_sigma)
-                     for s in self.sensors)
+        return tuple(s.key() for s in self.sensors)
 
 
 @dataclass
@@ -267,10 +267,21 @@ class RobotUtils:
 
     @staticmethod
     def build_sensorizing_function(name: str) -> Callable[[Grid], Grid]:
-        sensors = _ffi.sensor_config(name) if name else []
-
+        """RobotUtils.buildSensorizingFunction(name) (Starter.java:404-405): `uniform-<s1+s2..>-<sigma>`, `spinedTouch-<t|f>-<t|f>-<sigma>`,
+        `spinedTouchSighted-...`, `empty`; the lists may differ between voxels (px, py, l1, l5, the spined configurations)."""
         def fn(body: Grid) -> Grid:
-            return Grid(body.w, body.h, lambda x, y: Voxel(list(sensors)) if body.get(x, y) else None)
+            if not name:
+                return Grid(body.w, body.h, lambda x, y: Voxel([]) if body.get(x, y) else None)
+            sensors, off = _ffi.sensor_config_voxels(name, body.mask())
+            vox = iter(range(len(off) - 1))
+
+            def make(x, y):
+                if not body.get(x, y):
+                    return None
+                v = next(vox)
+                return Voxel(list(sensors[off[v]:off[v + 1]]))
+
+            return Grid(body.w, body.h, make)  # Grid's filler runs in grid order (y outer, x inner): the order of `off`
 
         return fn
 
