@@ -133,7 +133,7 @@ int vsr_body_set(vsr_ctx* ctx, int32_t w, int32_t h, const uint8_t* mask, const 
 /* The same with one sensor list PER VOXEL: what RobotUtils.buildSensorizingFunction returns for names other than `uniform-...`
  * (`spinedTouch-<cpg>-<malfunction>-<sigma>`, `spinedTouchSighted-...`) and for the position-dependent predefined sensors (`px`, `py`,
  * `l1`, `l5`).  Voxel v (grid order: y outer, x inner, y = 0 bottom) carries sensors[sensor_off[v] .. sensor_off[v + 1]); at most 8
- * readings per voxel.  CentralizedSensing concatenates the voxels' readings in grid order (vsr_input_map); DistributedSensing needs the
+ * sensors and 12 readings per voxel.  CentralizedSensing concatenates the voxels' readings in grid order (vsr_input_map); DistributedSensing needs the
  * same number of readings on every voxel (one MLP input size), as in the reference (builder/robot/BrainHomoDistributed.java:52-58). */
 int vsr_body_set_voxels(vsr_ctx* ctx, int32_t w, int32_t h, const uint8_t* mask, const vsr_sensor_desc* sensors, const int32_t* sensor_off);
 

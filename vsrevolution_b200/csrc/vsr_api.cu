@@ -358,14 +358,14 @@ int finalize(vsr_ctx* ctx) {
   int total_dim = 0;
   for (int v = 0; v < ctx->n_vox; v++) {
     const int n = ctx->vsens_off[v + 1] - ctx->vsens_off[v], dim = voxel_dim(ctx, v);
-    if (n > vsr::kMaxVoxSensors || dim > 8) return fail(ctx, VSR_EUNSUPPORTED, "more than 8 sensors / readings on one voxel");
+    if (n > vsr::kMaxVoxSensors || dim > vsr::kMaxReadings) return fail(ctx, VSR_EUNSUPPORTED, "more than 8 sensors / 12 readings on one voxel");
     k.vs_n[v] = (uint8_t)n; k.vs_max = std::max(k.vs_max, n);
     k.vox_dim[v] = (uint8_t)dim; k.vox_in_off[v] = (uint16_t)total_dim;
     total_dim += dim;
     for (int j = 0; j < n; j++) {
       const vsr_sensor_desc& s = ctx->vsens[ctx->vsens_off[v] + j];
       k.vs_idx[v][j] = (uint8_t)ctx->vsens_u[ctx->vsens_off[v] + j];
-      k.vs_param[v][j] = s.kind == VSR_SENSOR_CONSTANT ? (float)s.param : (s.kind == VSR_SENSOR_LIDAR ? (float)s.side : 0.0f);
+      k.vs_param[v][j] = s.kind == VSR_SENSOR_CONSTANT ? s.param : (s.kind == VSR_SENSOR_LIDAR ? (double)s.side : 0.0);
     }
   }
   if (ctx->uniform_sensors) { // offsets inside the (common) reading vector, for the specialised builds

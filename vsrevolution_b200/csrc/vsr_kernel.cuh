@@ -28,7 +28,8 @@ namespace vsr {
 
 constexpr int kMaxVox = 32;
 constexpr int kMaxSensors = 8;   // distinct sensors over all voxels (position-dependent values are per voxel: vs_param)
-constexpr int kMaxVoxSensors = 8; // sensors (and readings) per voxel
+constexpr int kMaxVoxSensors = 8; // sensors per voxel
+constexpr int kMaxReadings = 12;  // readings per voxel (spinedTouchSighted's top-right voxel: vxy + a + cpg + 5 lidar rays = 9)
 constexpr int kMaxLayers = 8;
 constexpr int kMaxMan = 3;       // manifolds per corner mass (ground polygons it can touch at once)
 constexpr int kMaxAvg = 6;       // averaged readings per voxel
@@ -113,7 +114,7 @@ struct KParams {
   int vs_max;                                   // longest per-voxel list
   uint8_t vs_n[kMaxVox];                        // sensors of voxel v
   uint8_t vs_idx[kMaxVox][kMaxVoxSensors];      // ... and which (index into sensors[])
-  float vs_param[kMaxVox][kMaxVoxSensors];      // CONSTANT: the value; LIDAR: the side (0 N, 1 E, 2 S, 3 W)
+  double vs_param[kMaxVox][kMaxVoxSensors];     // CONSTANT: the value; LIDAR: the side (0 N, 1 E, 2 S, 3 W)
   uint8_t vox_dim[kMaxVox];                     // readings of voxel v
   uint16_t vox_in_off[kMaxVox];                 // CentralizedSensing: first MLP input of voxel v
   const uint8_t* win_tab; // [n_avg][n_steps+1] window length (in readings) at step k
@@ -155,6 +156,8 @@ struct KParams {
                  // iteration, bit3 before position phase, bit4 before detect, bit5 before sensing, bit6 before spring
                  // init, bit7 before weld init, bit8 after the velocity loop, bit9 after the position phase, bit10 after control)
 };
+
+static_assert(sizeof(KParams) <= 8192, "KParams is passed by value as a __grid_constant__ kernel parameter");
 
 // ------------------------------------------------------------------------------------------------
 // math: the FP32 build uses single-instruction MUFU reciprocals / rsqrt and short polynomial
@@ -1528,9 +1531,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
         f = M<R>::phase_sin(P.amp, P.freq, t, phase);
     } else {
       // sensor readings of this voxel
-      R rd[8];
+      R rd[kMaxReadings];
 #pragma unroll
-      for (int i = 0; i < 8; i++) rd[i] = 0;
+      for (int i = 0; i < kMaxReadings; i++) rd[i] = 0;
       R vang = 0;
       bool have_ang = false;
       if (SENS == 1) {
@@ -1661,7 +1664,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
           }
           if (P.noise) val += (R)__ldg(&P.noise[(size_t)(sk.noise_row + d) * (P.n_steps + 1) + step]); // Noisy wrapper (host-replayed java.util.Random)
 #pragma unroll
-          for (int z = 0; z < 8; z++) if (z == ri) rd[z] = val;
+          for (int z = 0; z < kMaxReadings; z++) if (z == ri) rd[z] = val;
           ri++;
         }
       }
@@ -1672,7 +1675,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
         const R* w_ = wts + (size_t)(lane_used ? rw : 0) * P.genome_len;
         if (valid) {
 #pragma unroll
-          for (int d = 0; d < 8; d++) if (d < (int)P.vox_dim[vi]) a0[P.vox_in_off[vi] + d] = P.in_act ? M<R>::tanh_(rd[d]) : rd[d];
+          for (int d = 0; d < (SENS == 1 ? 1 : kMaxReadings); d++) if (d < (int)P.vox_dim[vi]) a0[P.vox_in_off[vi] + d] = P.in_act ? M<R>::tanh_(rd[d]) : rd[d];
         }
         __syncwarp();
         int cur = 0, o = 0;
@@ -1702,7 +1705,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
         R* sout = sig + (size_t)(sig_par ^ 1) * 32 * 4 * sg;
         int ni = 0;
 #pragma unroll
-        for (int d = 0; d < 8; d++) if (d < D) a0[(ni++) * 32 + lane] = P.in_act ? M<R>::tanh_(rd[d]) : rd[d];
+        for (int d = 0; d < kMaxReadings; d++) if (d < D) a0[(ni++) * 32 + lane] = P.in_act ? M<R>::tanh_(rd[d]) : rd[d];
         // Dir N(0,-1) E(1,0) S(0,1) W(-1,0); read the neighbour's signal emitted towards me (opposite side)
 #pragma unroll
         for (int d = 0; d < 4; d++) {
