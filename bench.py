@@ -40,9 +40,9 @@ sys.path.insert(0, ROOT)
 FLOPS = dict(spring_vel=38, spring_init=71, rope_vel=40, rope_init=30, weld_vel=78, weld_init=54, weld_pos=115,
              contact_pt_vel=47, contact_pt_pos=33, contact_init=43, detect_pair=280, body_step=48, voxel_act=140)
 
-# DRAM bytes per launch from the committed ncu capture (profiles/r1_prof_l.csv: dram__bytes_read.sum + dram__bytes_write.sum;
+# DRAM bytes per launch from the committed ncu capture (profiles/r2_prof_a.csv: dram__bytes_read.sum + dram__bytes_write.sum;
 # the 32 KB of fitness values stay in L2 within the capture): {(workload, robots): bytes}
-NCU_DRAM_BYTES = {(2, 4096): 5781504 + 0}
+NCU_DRAM_BYTES = {(2, 4096): 5306880 + 0}
 
 WORKLOADS = {
     2: dict(name="config2: biped-4x3, brainCentralized<mlp;r=0.65;nIL=1 (10-7-10), uniform-a-0, flat, 30 s",
@@ -472,7 +472,7 @@ def main():
             sust = (clocks or {}).get("sm_mhz") or None
             line["roofline"] = {"bound": "fp32", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                                 "traffic": NCU_DRAM_BYTES.get((args.workload, n)), "kernel": "vsr_episode_kernel<float, ctrl, %d warps/CTA, %d CTA/SM>" % (kinfo["threads_per_cta"] // 32, kinfo["ctas_per_sm"]), "kernel_ms": kms,
-                                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture profiles/r1_prof_l.csv; algorithmic bytes = genomes in + fitness out = %d" % (n * G * 8 + n * 8),
+                                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture profiles/r2_prof_a.csv; algorithmic bytes = genomes in + fitness out = %d" % (n * G * 8 + n * 8),
                                 "units": {"flops": "algorithmic FP32 flop counted on the oracle (DESIGN.md 5)"},
                                 "algorithmic_flops_per_voxel_step": flops_per_robot / (nv * n_steps),
                                 "peak_source": f"148 SM x 128 lanes x 2 x sm_max_mhz ({src} MEASURED_PEAKS.json)",
