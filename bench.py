@@ -428,13 +428,21 @@ def main():
     kinfo = ev.ctx.kernel_info()  # launch shape of the timed launches (before the extra blocks below launch anything else)
     # ---- outside the timed region: parity sample, the other configs (N=1), the in-process multi-device path (N>1) -------
     parity = others = multi = None
+
+    def guarded(fn, *a):
+        """The extra blocks must never cost the bench line itself: a failure is reported in place of the block."""
+        try:
+            return fn(*a)
+        except Exception as e:  # noqa: BLE001
+            return {"error": f"{type(e).__name__}: {e}"[:300]}
+
     if rank == 0:
         if not args.no_parity:
-            parity = parity_block(ev, w)
+            parity = guarded(parity_block, ev, w)
         if world > 1:
-            multi = multi_device_check(w, world)
+            multi = guarded(multi_device_check, w, world)
         elif not args.no_other_configs:
-            others = [other_config(3, 65536, dev, torch), other_config(4, 16384, dev, torch)]
+            others = [guarded(other_config, 3, 65536, dev, torch), guarded(other_config, 4, 16384, dev, torch)]
     if rank == 0:
         units = world * n * nv * n_steps * args.steps  # voxel-steps over all ranks and steps
         value = units / (dev_ms * 1e-3)
