@@ -921,3 +921,23 @@ def test_per_voxel_sensor_lists_and_the_extra_sensor_vocabulary(F, oracle, bound
     mapper = "brainCentralized<mlp;r=0.65;nIL=1" if ctrl == "central" else "brainHomoDist;s=1<mlp;r=0.65;nIL=1"
     ev = population_evaluator(shape, sensors, mapper, terrain, 2.0, 0.5)
     assert ev.genome_len == m.genome_len() and np.array_equal(ev.evaluate(g), whole)
+
+
+def test_observation_build_is_launch_shape_independent(F, oracle):
+    """vsr_eval_ex runs the default robot on the flexible 8-warp observation build for batches of up to 8 robot-warps per SM and on the
+    10-warp / 168-register one above (4000 bipeds = 9 warps per SM stay one wave).  Both carry the specialisations of the plain
+    kernels, so fitness, posture, footprints and centres of a robot are bit-identical in either shape, and the fitness is the one
+    vsr_eval returns."""
+    m = oracle.config_model(2, final_t=1.5)
+    g = np.random.default_rng(21).uniform(-1, 1, (4000, m.genome_len()))
+    ctx = make_ctx(F, m, 32)
+    fit, res, ex = ctx.eval_ex(g, posture_n=8, footprint_n=(4, 3), centers=True)
+    assert ctx.kernel_info()["threads_per_cta"] == 320 and ctx.kernel_info()["ctas_per_sm"] == 1
+    f2, r2, e2 = ctx.eval_ex(g[:300], posture_n=8, footprint_n=(4, 3), centers=True)
+    assert ctx.kernel_info()["threads_per_cta"] < 320
+    assert np.isfinite(fit).all() and ctx.contact_overflows() == 0
+    assert np.array_equal(fit[:300], f2) and np.array_equal(ex["posture"][:300], e2["posture"])
+    assert np.array_equal(ex["footprints"][0][:300], e2["footprints"][0]) and np.array_equal(ex["centers"][:300], e2["centers"])
+    assert ex["posture"].any(axis=1).all()
+    assert np.array_equal(ctx.eval(g), fit)
+    ctx.close()

@@ -105,6 +105,8 @@ struct vsr_ctx {
   std::vector<int> vsens_off;                // [n_vox + 1]
   std::vector<int> vsens_u;                  // [vsens.size()] index into `sensors`
   bool uniform_sensors = true;               // every voxel carries the same list
+  bool full_scaff = false;                   // all four scaffoldings enabled: builds with the mask folded at compile time
+  bool area_robot = false;                   // FP32, the reference default: one soft-normalised AreaRatio reading per voxel into a centralized MLP
   // controller
   vsr_ctrl_kind kind = VSR_CTRL_PHASE_SIN;
   std::vector<int> layers;
@@ -494,10 +496,11 @@ int finalize(vsr_ctx* ctx) {
   const bool full_scaff = e.scaffolding_mask == 0xF && !std::getenv("VSR_GENERIC_SCAFF");
   ctx->kernel = kernel_ptr(e.precision, kernel_ctrl(ctx->kind), ctx->shape, full_scaff);
   // the reference's default robot: one soft-normalised, non-averaged AreaRatio reading per voxel into a centralized MLP
-  if (e.precision == 32 && ctx->shape == 3 && ctx->warps == 10 && full_scaff && ctx->kind == VSR_CTRL_MLP_CENTRALIZED &&
-      ctx->uniform_sensors && ctx->sensors.size() == 1 && ctx->sensors[0].kind == VSR_SENSOR_AREA_RATIO && ctx->sensors[0].soft_norm == 1 &&
-      !(ctx->sensors[0].avg_window > 0) && !std::getenv("VSR_GENERIC_SENSORS"))
-    ctx->kernel = vsr_internal::kernel_f32_s3_area();
+  ctx->full_scaff = full_scaff;
+  ctx->area_robot = e.precision == 32 && full_scaff && ctx->kind == VSR_CTRL_MLP_CENTRALIZED && ctx->uniform_sensors && ctx->sensors.size() == 1 &&
+                    ctx->sensors[0].kind == VSR_SENSOR_AREA_RATIO && ctx->sensors[0].soft_norm == 1 && !(ctx->sensors[0].avg_window > 0) &&
+                    !std::getenv("VSR_GENERIC_SENSORS");
+  if (ctx->area_robot && ctx->shape == 3 && ctx->warps == 10) ctx->kernel = vsr_internal::kernel_f32_s3_area();
   ctx->smem_bytes = o * ctx->warps + 128; // + the CTA's phase counters (bounded-skew alignment)
   ctx->smem_warp = o;
   ctx->kernel_lat = nullptr; ctx->warps_lat = 0; ctx->last_kernel = nullptr;
@@ -605,16 +608,31 @@ int enqueue(vsr_ctx* ctx, DeviceState& d, const double* d_genomes, size_t n, dou
   LaunchPlan lp = trace_steps > 0 ? LaunchPlan{ctx->kernel, ctx->warps, (int)((((n + k.robots_per_warp - 1) / k.robots_per_warp) + ctx->warps - 1) / ctx->warps), ctx->smem_bytes}
                                   : plan_for(ctx, n);
   if (x && x->obs) {
-    // the observation build: FP32 = the flexible 8-warp shape at 255 registers, FP64 = the parity build's shape; spread over the SMs
+    // the observation build, spread over the SMs: FP64 = the parity build's shape; FP32 = the flexible 8-warp shape at 255 registers, with
+    // the same specialisations as the plain kernels (default scaffolding; the default robot's sensor), and for the default robot the
+    // 10-warp / 168-register shape when the batch needs more than 8 robot-warps per SM
     const size_t robot_warps = (n + k.robots_per_warp - 1) / k.robots_per_warp;
-    int maxw = ctx->env.precision == 64 ? kWarps64 : 8;
+    const bool f32 = ctx->env.precision != 64;
+    int maxw = f32 ? 8 : kWarps64;
     while (maxw > 1 && (size_t)maxw * ctx->smem_warp + 1024 > 227 * 1024) maxw--;
-    lp.kernel = vsr_internal::kernel_obs(ctx->env.precision, kernel_ctrl(ctx->kind));
-    lp.warps = (int)std::min<size_t>((size_t)maxw, std::max<size_t>(1, (robot_warps + ctx->n_sm - 1) / ctx->n_sm));
+    lp.kernel = !f32 || !ctx->full_scaff ? vsr_internal::kernel_obs(ctx->env.precision, kernel_ctrl(ctx->kind))
+                : (ctx->area_robot ? vsr_internal::kernel_obs_area(8) : vsr_internal::kernel_obs_scaff(kernel_ctrl(ctx->kind)));
+    // several waves: equal ones (two waves of 5-warp CTAs, not one of 8-warp CTAs and a nearly empty one)
+    const size_t waves = std::max<size_t>(1, (robot_warps + (size_t)maxw * ctx->n_sm - 1) / ((size_t)maxw * ctx->n_sm));
+    lp.warps = (int)std::min<size_t>((size_t)maxw, std::max<size_t>(1, (robot_warps + waves * ctx->n_sm - 1) / (waves * ctx->n_sm)));
+    if (f32 && ctx->area_robot && maxw == 8 && robot_warps > (size_t)8 * ctx->n_sm && (size_t)10 * ctx->smem_warp + 1024 <= 227 * 1024 &&
+        !std::getenv("VSR_NO_OBS_WAVE")) {
+      lp.kernel = vsr_internal::kernel_obs_area(10); // folds its warp count at compile time: always launched full
+      lp.warps = 10;
+    }
     lp.grid = (int)((robot_warps + lp.warps - 1) / lp.warps);
     lp.smem = ctx->smem_warp * lp.warps + 128;
     if (!d.obs_attr) {
-      CK(cudaFuncSetAttribute(lp.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      const void* ks[] = {vsr_internal::kernel_obs(ctx->env.precision, VSR_CTRL_PHASE_SIN), vsr_internal::kernel_obs(ctx->env.precision, VSR_CTRL_MLP_CENTRALIZED),
+                          vsr_internal::kernel_obs(ctx->env.precision, VSR_CTRL_MLP_DISTRIBUTED_HOMO), vsr_internal::kernel_obs_scaff(VSR_CTRL_PHASE_SIN),
+                          vsr_internal::kernel_obs_scaff(VSR_CTRL_MLP_CENTRALIZED), vsr_internal::kernel_obs_scaff(VSR_CTRL_MLP_DISTRIBUTED_HOMO),
+                          vsr_internal::kernel_obs_area(8), vsr_internal::kernel_obs_area(10)};
+      for (const void* kf : ks) CK(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       d.obs_attr = true;
     }
   }

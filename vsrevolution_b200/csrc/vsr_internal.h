@@ -27,5 +27,7 @@ VSR_HIDDEN const void* kernel_f32_s3(int ctrl, int full_scaff);
 VSR_HIDDEN const void* kernel_f32_s3_area(void);
 VSR_HIDDEN const void* kernel_f32_s2_area(void);
 VSR_HIDDEN const void* kernel_f64(int ctrl);
-VSR_HIDDEN const void* kernel_obs(int precision, int ctrl); // per-observation summaries (vsr_eval_observed)
+VSR_HIDDEN const void* kernel_obs(int precision, int ctrl); // per-observation summaries (vsr_eval_ex): generic scaffolding / sensors, 8 warps (FP64: 4)
+VSR_HIDDEN const void* kernel_obs_scaff(int ctrl);          // ... default scaffolding folded in, generic sensors, 8 warps
+VSR_HIDDEN const void* kernel_obs_area(int warps);          // ... the default robot (one AreaRatio reading into a centralized MLP), 8 or 10 warps
 } // namespace vsr_internal

@@ -613,6 +613,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
   int* savg_cnt = reinterpret_cast<int*>(savg + P.n_avg * 32);          // [n_avg][32]
   for (int i = 0; i < P.n_avg; i++) { savg[i * 32 + lane] = 0; savg_cnt[i * 32 + lane] = 0; }
   int sig_par = 0;
+  unsigned pcnt[4] = {0u, 0u, 0u, 0u}; // OBS builds: on-chip average-posture counters (16 bits each) of the cells this lane counts
   R ctrl_f = 0;
   const bool frozen = P.frozen != nullptr && valid && ((__ldg(&P.frozen[robot]) >> v) & 1u);
 
@@ -1850,14 +1851,24 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
         if (hgt < wdt) { const R d = wdt - hgt; by0 -= d / 2; by1 += d / 2; }
         else if (hgt > wdt) { const R d = hgt - wdt; bx0 -= d / 2; bx1 += d / 2; }
         const R side = bx1 - bx0;
-        unsigned lo = 0, hi = 0;
+        unsigned lo = 0, hi = 0, colm = 0, rowm = 0;
         if (valid) {
-          for (int iy = 0; iy < n; iy++) {
-            const R py = by0 + (R(iy) + R(0.5)) / R(n) * side;
-            if (py < vminy || py > vmaxy) continue;
-            for (int ix = 0; ix < n; ix++) {
-              const R px = bx0 + (R(ix) + R(0.5)) / R(n) * side;
-              if (px < vminx || px > vmaxx) continue;
+          // rows / columns whose cell centre lies inside the voxel's bounding box (a cell outside it cannot be inside the polygon)
+          for (int i = 0; i < n; i++) {
+            const R px = bx0 + (R(i) + R(0.5)) / R(n) * side, py = by0 + (R(i) + R(0.5)) / R(n) * side;
+            if (!(px < vminx || px > vmaxx)) colm |= 1u << i;
+            if (!(py < vminy || py > vmaxy)) rowm |= 1u << i;
+          }
+        }
+        // every lane walks ITS OWN candidate cells (rows x columns, typically 9-16 of the 64), one per trip: the trip count is the
+        // largest candidate count of the warp, not the union of everybody's rows times the widest column set
+        {
+          unsigned rm = rowm, cm = colm;
+          bool more = rm != 0 && cm != 0;
+          while (__any_sync(FULL, more)) {
+            if (more) {
+              const int iy = __ffs(rm) - 1, ix = __ffs(cm) - 1;
+              const R px = bx0 + (R(ix) + R(0.5)) / R(n) * side, py = by0 + (R(iy) + R(0.5)) / R(n) * side;
               bool in = false;
 #pragma unroll
               for (int i = 0; i < 4; i++) {
@@ -1866,13 +1877,36 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
               }
               const int c = iy * n + ix;
               if (in) { if (c < 32) lo |= 1u << c; else hi |= 1u << (c - 32); }
+              cm &= cm - 1;
+              if (cm == 0) { cm = colm; rm &= rm - 1; more = rm != 0; }
             }
           }
         }
         lo = __reduce_or_sync(robot_mask, lo); hi = __reduce_or_sync(robot_mask, hi);
-        if (valid)
-          for (int c = v; c < n * n; c += L)
-            if ((c < 32 ? (lo >> c) : (hi >> (c - 32))) & 1u) atomicAdd(&P.post_cnt[(size_t)robot * 64 + c], 1u);
+        // cell c of a robot is counted by its lane c mod L.  Bodies of 8 voxels or more (at most 8 cells per lane) keep the counters
+        // on chip, two 16-bit counters per register, and store them once at the last kept observation; smaller bodies (or more than
+        // 65535 observations) count in L2
+        const bool reg_cnt = L >= 8 && K <= 65535;
+        if (valid) {
+          if (reg_cnt) {
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+              const int c = v + q * L;
+              const unsigned bit = c < 32 ? (lo >> c) & 1u : (c < 64 ? (hi >> (c - 32)) & 1u : 0u);
+              pcnt[q >> 1] += bit << (16 * (q & 1));
+            }
+            if (step == P.k_last) {
+#pragma unroll
+              for (int q = 0; q < 8; q++) {
+                const int c = v + q * L;
+                if (c < n * n) P.post_cnt[(size_t)robot * 64 + c] = (pcnt[q >> 1] >> (16 * (q & 1))) & 0xffffu;
+              }
+            }
+          } else {
+            for (int c = v; c < n * n; c += L)
+              if ((c < 32 ? (lo >> c) : (hi >> (c - 32))) & 1u) atomicAdd(&P.post_cnt[(size_t)robot * 64 + c], 1u);
+          }
+        }
       }
       if (P.centers3 != nullptr) {
         const double cxv = (double)ox + (double)(R(0.25) * (qx[0] + qx[1] + qx[2] + qx[3]));
