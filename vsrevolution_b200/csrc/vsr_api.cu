@@ -13,6 +13,7 @@
 #include "vsr_internal.h"
 #include "vsr_kernel.cuh"
 
+constexpr float kHeightBucket = 4.0f; // width of a bucket of the terrain height map (corner masses are under 1 unit wide)
 namespace {
 
 // launch shapes (warps per CTA, min CTAs per SM -> register cap): 0/2 = 255 registers, 8 warps/SM (3552 bipeds per wave);
@@ -33,6 +34,7 @@ struct DeviceState {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t ev_join = nullptr; // eval_range: this device's slice is back on the primary device
   double *d_tx = nullptr, *d_ty = nullptr;
+  float* d_thmax = nullptr; // coarse height map of the terrain (contact broadphase)
   uint8_t* d_win = nullptr;
   double* d_noise = nullptr;
   void* d_hist = nullptr;
@@ -95,6 +97,7 @@ struct HostExtras {
 struct vsr_ctx {
   vsr_env_desc env;
   std::vector<double> tx, ty;
+  std::vector<float> thmax; float thx0 = 0; // coarse height map (build_height_map)
   // body
   bool has_body = false, has_ctrl = false;
   int w = 0, h = 0, n_vox = 0;
@@ -319,6 +322,7 @@ int finalize(vsr_ctx* ctx) {
   k.n_t = (int)ctx->tx.size();
   k.base_y = *std::min_element(ctx->ty.begin(), ctx->ty.end()) - e.ground_thickness;
   k.ty_max = *std::max_element(ctx->ty.begin(), ctx->ty.end());
+  k.thx0 = ctx->thx0; k.thinv = 1.0f / kHeightBucket; k.thn = (int)ctx->thmax.size(); k.thmax = nullptr; // device pointer set per launch
   // episode
   int ns, kf, kl;
   int rc = vsr_episode_steps(e.final_t, e.transient_t, e.dt, &ns, &kf, &kl);
@@ -644,11 +648,11 @@ int enqueue(vsr_ctx* ctx, DeviceState& d, const double* d_genomes, size_t n, dou
     if (rc) return rc;
   }
   k.energy = d.d_energy;
-  k.tx = d.d_tx; k.ty = d.d_ty; k.win_tab = d.d_win; k.hist = d.d_hist; k.noise = d.d_noise;
+  k.tx = d.d_tx; k.ty = d.d_ty; k.thmax = d.d_thmax; k.win_tab = d.d_win; k.hist = d.d_hist; k.noise = d.d_noise;
   k.genomes = d_genomes; k.fitness = d_fitness; k.results = d_results; k.n_robots = (int)n;
   k.centers = d.cur_centers;
   k.overflow_count = d.d_ovf;
-  if (x && x->robot_terrains) { k.tx = d.d_rtx; k.ty = d.d_rty; k.toff = d.d_roff; k.tbase = d.d_rbase; k.tplace = d.d_rplace; k.ty_max = x->rt_ymax; }
+  if (x && x->robot_terrains) { k.tx = d.d_rtx; k.ty = d.d_rty; k.toff = d.d_roff; k.tbase = d.d_rbase; k.tplace = d.d_rplace; k.ty_max = x->rt_ymax; k.thmax = nullptr; }
   if (x) {
     k.frozen = x->d_frozen;
     if (x->obs) {
@@ -738,6 +742,28 @@ int upload_extras(vsr_ctx* ctx, DeviceState& d, const HostExtras& h, size_t lo, 
   return VSR_OK;
 }
 
+// Coarse height map for the contact broadphase: bucket b holds an upper bound of the terrain height over the bucket and its two
+// neighbours ([x0 + (b - 1) B, x0 + (b + 2) B]), so a corner mass (extent < 1) anywhere inside bucket b that floats above
+// thmax[b] cannot touch the ground.  The bound of a polygon's top edge is the larger of its two vertices; the float value is
+// rounded up and padded, the test is a filter only (the narrowphase decides), so results do not depend on it.
+void build_height_map(vsr_ctx* c) {
+  const size_t nt = c->tx.size();
+  c->thmax.clear();
+  c->thx0 = nt ? (float)std::floor(c->tx.front()) : 0.0f;
+  if (nt < 2) { c->thmax.assign(1, 3.0e38f); return; }
+  const double x0 = c->thx0, B = kHeightBucket;
+  const int nb = std::max(1, (int)std::ceil((c->tx.back() - x0) / B) + 1);
+  std::vector<double> h(nb, -1.0e300);
+  for (size_t i = 1; i < nt; i++) {
+    const double top = std::fmax(c->ty[i - 1], c->ty[i]);
+    // buckets whose widened range intersects [tx[i-1], tx[i]]: (b - 1) B <= tx[i] - x0  and  (b + 2) B >= tx[i-1] - x0
+    const int b0 = std::max(0, (int)std::floor((c->tx[i - 1] - x0) / B) - 2), b1 = std::min(nb - 1, (int)std::floor((c->tx[i] - x0) / B) + 1);
+    for (int b = b0; b <= b1; b++) h[b] = std::fmax(h[b], top);
+  }
+  c->thmax.resize(nb);
+  for (int b = 0; b < nb; b++) c->thmax[b] = h[b] < -1.0e299 ? -3.0e38f : std::nextafter((float)h[b], 3.0e38f) + 1.0e-3f;
+}
+
 } // namespace
 
 // ---- internal surface for vsr_ga.cu (vsr_internal.h) ---------------------------------------------------
@@ -811,6 +837,7 @@ int vsr_env_default(vsr_env_desc* e) {
   return VSR_OK;
 }
 
+
 int vsr_ctx_create(const vsr_env_desc* env, vsr_ctx** out) {
   vsr_ctx* ctx = nullptr; // for CK/fail before the context exists
   if (!env || !out) return fail(nullptr, VSR_EINVAL, "null argument");
@@ -832,6 +859,7 @@ int vsr_ctx_create(const vsr_env_desc* env, vsr_ctx** out) {
   c->tx.assign(env->terrain_x, env->terrain_x + env->n_terrain);
   c->ty.assign(env->terrain_y, env->terrain_y + env->n_terrain);
   c->env.terrain_x = nullptr; c->env.terrain_y = nullptr;
+  build_height_map(c);
   std::vector<int> ids;
   if (env->n_devices == 0) {
     int cur = 0;
@@ -861,7 +889,9 @@ int vsr_ctx_create(const vsr_env_desc* env, vsr_ctx** out) {
               ck(cudaMalloc(&d.d_tx, sizeof(double) * c->tx.size()), "cudaMalloc") && ck(cudaMalloc(&d.d_ty, sizeof(double) * c->ty.size()), "cudaMalloc") &&
               ck(cudaMemcpy(d.d_tx, c->tx.data(), sizeof(double) * c->tx.size(), cudaMemcpyHostToDevice), "cudaMemcpy") &&
               ck(cudaMemcpy(d.d_ty, c->ty.data(), sizeof(double) * c->ty.size(), cudaMemcpyHostToDevice), "cudaMemcpy") &&
-              ck(cudaMalloc(&d.d_ovf, sizeof(int)), "cudaMalloc") && ck(cudaMemset(d.d_ovf, 0, sizeof(int)), "cudaMemset");
+              ck(cudaMalloc(&d.d_ovf, sizeof(int)), "cudaMalloc") && ck(cudaMemset(d.d_ovf, 0, sizeof(int)), "cudaMemset") &&
+              ck(cudaMalloc(&d.d_thmax, sizeof(float) * c->thmax.size()), "cudaMalloc") &&
+              ck(cudaMemcpy(d.d_thmax, c->thmax.data(), sizeof(float) * c->thmax.size(), cudaMemcpyHostToDevice), "cudaMemcpy");
     if (!ok) { vsr_ctx_destroy(c); return VSR_ECUDA; }
   }
   *out = c;
@@ -873,7 +903,7 @@ void vsr_ctx_destroy(vsr_ctx* c) {
   for (auto& d : c->devs) {
     cudaSetDevice(d.dev);
     if (d.stream) cudaStreamSynchronize(d.stream);
-    cudaFree(d.d_tx); cudaFree(d.d_ty); cudaFree(d.d_win); cudaFree(d.d_hist); cudaFree(d.d_noise); cudaFree(d.d_energy);
+    cudaFree(d.d_tx); cudaFree(d.d_ty); cudaFree(d.d_thmax); cudaFree(d.d_win); cudaFree(d.d_hist); cudaFree(d.d_noise); cudaFree(d.d_energy);
     cudaFree(d.d_rtx); cudaFree(d.d_rty); cudaFree(d.d_rbase); cudaFree(d.d_rplace); cudaFree(d.d_roff);
     cudaFree(d.d_genomes); cudaFree(d.d_fitness); cudaFree(d.d_results); cudaFree(d.d_centers); cudaFree(d.d_ovf);
     cudaFree(d.d_frozen); cudaFree(d.d_post); cudaFree(d.d_fp[0]); cudaFree(d.d_fp[1]); cudaFree(d.d_cen3);

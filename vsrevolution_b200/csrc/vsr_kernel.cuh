@@ -102,6 +102,11 @@ struct KParams {
   const double* ty;
   int n_t;
   double base_y, ty_max; // bottom of the ground body; highest terrain vertex
+  // coarse height map of the (shared) terrain for the contact broadphase: thmax[b] >= every terrain height over
+  // [thx0 + (b - 1) / thinv, thx0 + (b + 2) / thinv]; NULL (per-evaluation terrains) = test against ty_max
+  const float* thmax;
+  float thx0, thinv;
+  int thn;
   // per-evaluation terrains (`-rnd`, Starter.java:89-93): robot i runs on vertices [toff[i], toff[i+1]) of tx / ty, its ground
   // body ends at tbase[i] and its initial placement is shifted by (tplace[2i], tplace[2i+1]); NULL = one terrain for all
   const int* toff;
@@ -668,14 +673,23 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) vsr_episode_kernel(const __g
           const R il = M<R>::rsqrt_(ex * ex + ey * ey);
           pnx = ey * il; pny = -ex * il;
         }
-        // broadphase: a mass well inside the cached polygon's x-range is tested against that polygon's AABB, any other
-        // mass against the highest terrain vertex
+        // broadphase: a mass well inside the cached polygon's x-range is tested against that polygon's AABB, any other mass against
+        // the highest ground within a few units of it (height map of the shared terrain: on narrow polygons -- steps, short hills --
+        // only the masses near the ground stay candidates) or, without a map, against the highest terrain vertex.  A filter only: the
+        // narrowphase decides, results do not depend on it.  The build specialised for the default robot (flat-terrain benchmarks,
+        // every mass takes the `fast` test) leaves the map out: the extra code costs it 2 % through register allocation alone.
         const R pymax = M<R>::max_(py0, py1), ytop = (R)(P.ty_max - oyd);
 #pragma unroll
         for (int k = 0; k < 4; k++) {
           const R ext = K_half * (M<R>::abs_(CS[k]) + M<R>::abs_(SN[k]));
           const bool fast = X[k] - ext >= px0 + R(kFastMargin) && X[k] + ext <= px1 - R(kFastMargin);
-          if (!(Y[k] - ext > (fast ? pymax : ytop))) cmask |= 1u << k;
+          R ylim = fast ? pymax : ytop;
+          if (SENS != 1 && !fast && P.thmax != nullptr) {
+            int b = (int)(((float)ox + (float)X[k] - P.thx0) * P.thinv);
+            b = b < 0 ? 0 : (b >= P.thn ? P.thn - 1 : b);
+            ylim = (R)(__ldg(&P.thmax[b]) - (float)oy);
+          }
+          if (!(Y[k] - ext > ylim)) cmask |= 1u << k;
         }
       }
     }
