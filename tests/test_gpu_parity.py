@@ -941,3 +941,20 @@ def test_observation_build_is_launch_shape_independent(F, oracle):
     assert ex["posture"].any(axis=1).all()
     assert np.array_equal(ctx.eval(g), fit)
     ctx.close()
+
+
+@pytest.mark.parametrize("cfg", [3, 4])
+def test_height_map_broadphase_is_a_filter_only(F, oracle, cfg, monkeypatch):
+    """The coarse height map of the terrain only thins out the narrowphase candidates: fitness and vsr_result of every
+    robot are bit-identical with the map and with the old test against the highest terrain vertex (VSR_NO_HEIGHT_MAP)."""
+    m = oracle.config_model(cfg, final_t=4.0)
+    g = np.random.default_rng(40 + cfg).uniform(-1, 1, (600, m.genome_len()))
+    ctx = make_ctx(F, m)
+    fit, res = ctx.eval(g, want_results=True)
+    ctx.close()
+    monkeypatch.setenv("VSR_NO_HEIGHT_MAP", "1")
+    ref = make_ctx(F, m)
+    monkeypatch.delenv("VSR_NO_HEIGHT_MAP")
+    fit0, res0 = ref.eval(g, want_results=True)
+    ref.close()
+    assert np.isfinite(fit).all() and np.array_equal(fit, fit0) and res.tobytes() == res0.tobytes()

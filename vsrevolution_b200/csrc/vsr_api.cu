@@ -98,6 +98,7 @@ struct vsr_ctx {
   vsr_env_desc env;
   std::vector<double> tx, ty;
   std::vector<float> thmax; float thx0 = 0; // coarse height map (build_height_map)
+  bool use_height_map = true;
   // body
   bool has_body = false, has_ctrl = false;
   int w = 0, h = 0, n_vox = 0;
@@ -648,7 +649,7 @@ int enqueue(vsr_ctx* ctx, DeviceState& d, const double* d_genomes, size_t n, dou
     if (rc) return rc;
   }
   k.energy = d.d_energy;
-  k.tx = d.d_tx; k.ty = d.d_ty; k.thmax = d.d_thmax; k.win_tab = d.d_win; k.hist = d.d_hist; k.noise = d.d_noise;
+  k.tx = d.d_tx; k.ty = d.d_ty; k.thmax = ctx->use_height_map ? d.d_thmax : nullptr; k.win_tab = d.d_win; k.hist = d.d_hist; k.noise = d.d_noise;
   k.genomes = d_genomes; k.fitness = d_fitness; k.results = d_results; k.n_robots = (int)n;
   k.centers = d.cur_centers;
   k.overflow_count = d.d_ovf;
@@ -860,6 +861,7 @@ int vsr_ctx_create(const vsr_env_desc* env, vsr_ctx** out) {
   c->ty.assign(env->terrain_y, env->terrain_y + env->n_terrain);
   c->env.terrain_x = nullptr; c->env.terrain_y = nullptr;
   build_height_map(c);
+  c->use_height_map = !std::getenv("VSR_NO_HEIGHT_MAP"); // test switch: the broadphase then tests against the highest terrain vertex
   std::vector<int> ids;
   if (env->n_devices == 0) {
     int cur = 0;
