@@ -1,0 +1,61 @@
+"""include/vsr_host.hpp, the C++ host side above the C ABI (the reference's mapper / task interface: buildShape, buildSensorizingFunction,
+getMapper(...).buildFor(target), Locomotion.apply -> Outcome; locomotion/Starter.java:402-436), driven by tests/cabi/host_mirror.cpp.
+CPU: dimensions, genotype sizes and the Java error messages; no CPU fallback for the task itself.  GPU: the velocities of a population
+mapped and evaluated through the C++ host side are bit-identical to the Python mirror's on the same genotypes."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _build(tmp_path):
+    import __graft_entry__ as g
+    from vsrevolution_b200 import _ffi
+    if not os.path.exists(_ffi.LIB_PATH):
+        g.build()
+    exe = str(tmp_path / "host_mirror")
+    libdir = os.path.dirname(_ffi.LIB_PATH)
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cabi", "host_mirror.cpp"), "-L" + libdir, "-lvsr_eval",
+                           "-Wl,-rpath," + libdir, "-o", exe])
+    return exe
+
+
+def _lcg_uniform(seed: int, count: int) -> np.ndarray:
+    out, s = np.empty(count), seed & 0xFFFFFFFFFFFFFFFF
+    for i in range(count):
+        s = (s * 6364136223846793005 + 1442695040888963407) & 0xFFFFFFFFFFFFFFFF
+        out[i] = (s >> 11) * (1.0 / 9007199254740992.0)
+    return out
+
+
+def test_cpp_host_side_checks(tmp_path):
+    exe = _build(tmp_path)
+    import torch
+    r = subprocess.run([exe, "check"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert "host mirror checks ok" in r.stdout
+    assert ("gpu: velocity" in r.stdout) if torch.cuda.is_available() else ("no gpu:" in r.stdout and "no CPU fallback" in r.stdout)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,sensors,mapper,terrain", [("biped-4x3", "uniform-a-0", "brainCentralized<mlp;r=0.65;nIL=1", "flat"),
+                                                          ("worm-8x2", "", "brainPhaseVals;f=1", "hilly-1-10-0"),
+                                                          ("comb-7x2", "uniform-t+vxy+a-0", "brainHomoDist;s=1<mlp;r=0.65;nIL=1", "steppy-0.25-1-0")])
+def test_cpp_host_side_matches_the_python_mirror(tmp_path, shape, sensors, mapper, terrain):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from vsrevolution_b200.locomotion import population_evaluator
+    exe = _build(tmp_path)
+    out = str(tmp_path / "vel.bin")
+    n, seed = 40, 2024
+    r = subprocess.run([exe, "eval", shape, sensors, mapper, terrain, "3", "0.5", str(n), str(seed), out], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    ev = population_evaluator(shape, sensors, mapper, terrain, 3.0, 0.5)
+    assert f"genotype {ev.genome_len} robots {n}" in r.stdout
+    g = (2.0 * _lcg_uniform(seed, n * ev.genome_len) - 1.0).reshape(n, ev.genome_len)
+    assert np.array_equal(np.fromfile(out, dtype=np.float64), ev.evaluate(g))
