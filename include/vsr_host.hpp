@@ -22,7 +22,10 @@
 #include <cstring>
 #include <functional>
 #include <map>
+#include <atomic>
+#include <exception>
 #include <memory>
+#include <mutex>
 #include <optional>
 #include <sstream>
 #include <stdexcept>
@@ -504,6 +507,66 @@ class Locomotion {
   int precision_;
   std::vector<double> xs_, ys_;
   std::map<std::string, vsr_ctx*> ctxs_;
+};
+
+// Batching behind JGEA's one-robot-per-call contract (`qualityFunction.apply(robot)` once per individual from a thread pool,
+// locomotion/Starter.java:427-436; SURVEY 8b "granularity mismatch"), with no extra threads and no time-outs: apply(robot) only records
+// the robot and returns a LazyOutcome; JGEA builds its individuals without reading the fitness object and reads it when it orders the
+// new population -- the first getter called on any outcome of the batch sends the whole generation to the device in one applyAll.
+// The Java form is java/it/units/erallab/gpu/{BatchedLocomotion,GpuOutcome}.java.  Thread-safe like the Java one.
+class LazyBatchedLocomotion {
+  struct Batch {
+    Locomotion* task;
+    std::mutex lock;
+    std::vector<Robot> robots;
+    std::vector<Outcome> outcomes;
+    std::exception_ptr error;
+    bool done = false;
+  };
+ public:
+  class LazyOutcome {
+   public:
+    double getVelocity() const { return resolved().getVelocity(); }
+    double getDistance() const { return resolved().getDistance(); }
+    double getTime() const { return resolved().getTime(); }
+    double getControlPower() const { return resolved().getControlPower(); }
+    double getAreaRatioPower() const { return resolved().getAreaRatioPower(); }
+    double getCorrectedEfficiency() const { return resolved().getCorrectedEfficiency(); }
+   private:
+    friend class LazyBatchedLocomotion;
+    LazyOutcome(LazyBatchedLocomotion* owner, std::shared_ptr<Batch> batch, size_t slot) : owner_(owner), batch_(std::move(batch)), slot_(slot) {}
+    const Outcome& resolved() const {
+      owner_->close(batch_); // robots applied from now on belong to the next batch
+      std::lock_guard<std::mutex> g(batch_->lock);
+      if (!batch_->done) {
+        try { batch_->outcomes = batch_->task->applyAll(batch_->robots); owner_->flushed_++; }
+        catch (...) { batch_->error = std::current_exception(); } // every outcome of the batch reports it, like Locomotion.apply throwing
+        batch_->done = true;
+      }
+      if (batch_->error) std::rethrow_exception(batch_->error);
+      return batch_->outcomes[slot_];
+    }
+    LazyBatchedLocomotion* owner_;
+    std::shared_ptr<Batch> batch_;
+    size_t slot_;
+  };
+  explicit LazyBatchedLocomotion(Locomotion& task) : task_(&task) { open_ = newBatch(); }
+  LazyOutcome apply(const Robot& robot) {
+    std::lock_guard<std::mutex> g(lock_);
+    open_->robots.push_back(robot);
+    return LazyOutcome(this, open_, open_->robots.size() - 1);
+  }
+  int batchesFlushed() const { return flushed_; }
+ private:
+  std::shared_ptr<Batch> newBatch() { auto b = std::make_shared<Batch>(); b->task = task_; return b; }
+  void close(const std::shared_ptr<Batch>& batch) {
+    std::lock_guard<std::mutex> g(lock_);
+    if (open_ == batch) open_ = newBatch();
+  }
+  Locomotion* task_;
+  std::mutex lock_;
+  std::shared_ptr<Batch> open_;
+  std::atomic<int> flushed_{0};
 };
 
 // Starter.buildLocomotionTask(terrainName, episodeT, random, cacheOutcome) for a fixed terrain (Starter.java:83-88), with the

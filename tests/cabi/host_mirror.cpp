@@ -5,7 +5,7 @@
 //   host_mirror check                                                       host-side checks only (dimensions, error messages); no GPU needed
 //   host_mirror eval <shape> <sensors> <mapper> <terrain> <T> <transient> <n> <seed> <out.bin>
 //
-//   g++ -std=c++17 -O2 -Iinclude tests/cabi/host_mirror.cpp -Lvsrevolution_b200 -lvsr_eval -Wl,-rpath,$PWD/vsrevolution_b200 -o host_mirror
+//   g++ -std=c++17 -O2 -pthread -Iinclude tests/cabi/host_mirror.cpp -Lvsrevolution_b200 -lvsr_eval -Wl,-rpath,$PWD/vsrevolution_b200 -o host_mirror
 #include <cstdio>
 #include <cstdlib>
 #include <string>
@@ -63,6 +63,21 @@ static int check() {
     const Outcome o = task.apply(r);
     std::printf("gpu: velocity %.17g distance %.17g time %.17g\n", o.getVelocity(), o.getDistance(), o.getTime());
     EXPECT(o.getTime() > 1.4 && o.getTime() < 1.6 && o.getVelocity() == o.getDistance() / o.getTime());
+    // JGEA's contract, one apply(robot) per individual: a generation is ONE launch, started by the first fitness that is read
+    LazyBatchedLocomotion lazy(task);
+    std::vector<LazyBatchedLocomotion::LazyOutcome> generation;
+    std::vector<Robot> robots;
+    for (int i = 0; i < 12; i++) {
+      robots.push_back(central.buildFor(biped)(std::vector<double>(157, 0.05 * i - 0.3)));
+      generation.push_back(lazy.apply(robots.back()));
+    }
+    EXPECT(lazy.batchesFlushed() == 0);
+    const std::vector<Outcome> direct = task.applyAll(robots);
+    for (int i = 11; i >= 0; i--) EXPECT(generation[i].getVelocity() == direct[i].getVelocity());
+    EXPECT(lazy.batchesFlushed() == 1);
+    const auto next = lazy.apply(robots[3]); // the next generation opens a new batch
+    EXPECT(next.getVelocity() == direct[3].getVelocity() && lazy.batchesFlushed() == 2);
+    std::printf("lazy batching ok\n");
   } catch (const VsrException& e) {
     EXPECT(e.status == VSR_ECUDA);
     std::printf("no gpu: %s\n", e.what());
