@@ -16,7 +16,9 @@ GPU gets its own R robots); timing is max over ranks.
 `--impl reference`: times that CPU port alone on the SAME config (one full population batch per step when the host cores
            finish K of them within ~4.5 minutes, else the largest sample that does); it first probes for a JVM and the
            reference jars (`java_reference` key) -- the Java reference cannot run in the build image (no JVM, deps un-vendored).
-`parity`  : a 64-robot sample of the workload evaluated by the CUDA path and by the oracle, outside the timed region.
+`parity`  : a 64-robot sample of the workload evaluated by the CUDA path and by the oracle, outside the timed region; its
+           `evolved_population` key repeats that on 64 robots of the population 20 `numGA` generations leave behind (robots that move),
+           FP32 kernel and FP64 kernel against the oracle.
 `other_configs`: one timed launch each of BASELINE configs 3 and 4 at full size (N=1 only).
 `multi_device_exact` (N>1): rank 0 also drives ONE context over all N devices (in-process sharding with peer copies) and checks
            it bit for bit against a single-device context.
@@ -261,6 +263,34 @@ def parity_block(ev, w, n=64):
             "fitness statistically (the model has knife-edge discontinuities, DESIGN.md 6)"}
 
 
+def parity_evolved_block(ev, w, n=64, generations=20, n_pop=4096):
+    """Parity on robots that actually locomote: `n` robots spread over the population that `generations`
+    generations of the device `numGA` loop leave behind, evaluated by the FP32 kernel, by the FP64 kernel (the chaotic floor: two
+    roundings of one algorithm) and by the oracle (checker only).  Outside the timed region."""
+    from oracle import model as O
+    from vsrevolution_b200 import _ffi
+    from vsrevolution_b200.locomotion import population_evaluator
+    ga = _ffi.GeneticAlgorithm(ev.ctx, n_pop, seed=0)
+    ga.init()
+    for _ in range(generations):
+        ga.step()
+    pop, _ = ga.population()
+    ga.close()
+    g = np.ascontiguousarray(pop[np.linspace(0, n_pop - 1, n).astype(int)])
+    m = O.config_model(w["oracle_cfg"], final_t=w["T"])
+    ref = m.eval_batch(g, n_threads=os.cpu_count() or 1)
+    fit = ev.evaluate(g)
+    ev64 = population_evaluator(w["shape"], w["sensors"], w["mapper"], w["terrain"], w["T"], 1.0, precision=64)
+    fit64 = ev64.evaluate(g)
+    ev64.ctx.close()
+    rel = lambda a: float(np.median(np.abs(a - ref) / np.maximum(np.abs(ref), 1e-9)))
+    return {"robots": n, "generations": generations, "n_pop": n_pop, "mean_abs_velocity": float(np.abs(ref).mean()),
+            "fp32_vs_oracle": {"spearman": spearman(fit, ref), "median_rel_dfitness": rel(fit)},
+            "fp64_kernel_vs_oracle": {"spearman": spearman(fit64, ref), "median_rel_dfitness": rel(fit64)},
+            "note": "robots moving at several voxel sides per second diverge chaotically within the 30 s episode in any two roundings of "
+                    "the algorithm; the FP64 kernel against the oracle is that floor, the FP32 kernel sits on it (DESIGN.md 13.4)"}
+
+
 def other_config(wk, robots, dev, torch):
     """One warm-up and ONE timed launch of another BASELINE config at full size (device-resident genomes, CUDA events)."""
     from vsrevolution_b200.locomotion import population_evaluator
@@ -439,6 +469,8 @@ def main():
     if rank == 0:
         if not args.no_parity:
             parity = guarded(parity_block, ev, w)
+            if isinstance(parity, dict) and "error" not in parity and args.workload == 2:
+                parity["evolved_population"] = guarded(parity_evolved_block, ev, w)
         if world > 1:
             multi = guarded(multi_device_check, w, world)
         elif not args.no_other_configs:
