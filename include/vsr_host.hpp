@@ -92,7 +92,34 @@ inline int sensorDim(const vsr_sensor_desc& s) {
 // 2dhmsr Voxel: here the list of its sensors (RobotUtils.buildSensorizingFunction)
 struct Voxel {
   std::vector<vsr_sensor_desc> sensors;
+  // 2dhmsr BreakableVoxel as `broken-<ratio>-<seed>` builds it [U]: the actuator is frozen from t = 0 (it applies no force, sensors work)
+  bool actuatorFrozen = false;
   int sensorDim() const { int d = 0; for (const auto& s : sensors) d += vsr_host::sensorDim(s); return d; }
+};
+
+// java.util.Random (the 48-bit LCG of the Java class library): the run's shared Random of locomotion/Starter.java:89-93,126,428
+class JavaRandom {
+ public:
+  explicit JavaRandom(int64_t seed) : state_(((uint64_t)seed ^ 0x5DEECE66DULL) & kMask) {}
+  double nextDouble() { return (double)(((int64_t)next(26) << 27) + next(27)) * (1.0 / (double)(1LL << 53)); }
+  int32_t nextInt() { return next(32); }
+  int32_t nextInt(int32_t bound) {
+    if (bound <= 0) throw IllegalArgumentException("bound must be positive");
+    int32_t r = next(31);
+    const int32_t m = bound - 1;
+    if ((bound & m) == 0) return (int32_t)(((int64_t)bound * (int64_t)r) >> 31);
+    for (int32_t u = r;; u = next(31)) { // Java: `u - (r = u % bound) + m < 0` on wrapping ints = the sum exceeds 2^31 - 1
+      r = u % bound;
+      if ((int64_t)u - r + m < (1LL << 31)) return r;
+    }
+  }
+ private:
+  static constexpr uint64_t kMask = (1ULL << 48) - 1;
+  int32_t next(int bits) {
+    state_ = (state_ * 0x5DEECE66DULL + 0xBULL) & kMask;
+    return (int32_t)((int64_t)state_ >> (48 - bits)); // bits == 32: the truncation to int is Java's
+  }
+  uint64_t state_;
 };
 
 // ---- functions (2dhmsr core/controllers) -------------------------------------------------------------------------------------------
@@ -209,6 +236,30 @@ struct RobotUtils {
     };
   }
 };
+
+// RobotUtils.buildRobotTransformation(name, externalRandom) [U] (locomotion/Starter.java:126,428): `identity`, or
+// `broken-<ratio>-<seed|rnd>`: every voxel becomes, with probability `ratio`, a voxel with a frozen actuator; the Random is created once
+// here (seed) or is the caller's (`rnd`), so consecutive robots continue one stream.  `breakable-...` is outside this build.
+inline std::function<Robot(const Robot&)> buildRobotTransformation(const std::string& name, std::shared_ptr<JavaRandom> externalRandom = nullptr) {
+  int32_t kind = 0, seedIsRnd = 0;
+  double ratio = 0;
+  int64_t seed = 0;
+  detail::check(vsr_robot_transformation(name.c_str(), &kind, &ratio, &seed, &seedIsRnd), nullptr, "RobotUtils.buildRobotTransformation");
+  if (kind == 0) return [](const Robot& r) { return r; };
+  std::shared_ptr<JavaRandom> random = seedIsRnd ? externalRandom : std::make_shared<JavaRandom>(seed);
+  if (!random) throw IllegalArgumentException("transformation with seed `rnd` needs the run's Random");
+  return [ratio, random](const Robot& robot) {
+    Grid<Voxel> body = robot.getVoxels();
+    robot.getVoxels().forEach([&](auto e) {
+      if (!e.value || random->nextDouble() > ratio) return;
+      Voxel broken = *e.value;
+      broken.actuatorFrozen = true;
+      random->nextInt(); // the BreakableVoxel's own seed
+      body.set(e.x, e.y, broken);
+    });
+    return Robot(robot.getController(), body);
+  };
+}
 
 // ---- builders (builder/*.java) ------------------------------------------------------------------------------------------------------------
 using Params = std::map<std::string, std::string>;
@@ -381,7 +432,6 @@ class Locomotion {
   }
   Locomotion(const Locomotion&) = delete;
   Locomotion& operator=(const Locomotion&) = delete;
-  ~Locomotion() { for (auto& kv : ctxs_) vsr_ctx_destroy(kv.second); }
 
   static void createTerrain(const std::string& name, std::vector<double>& xs, std::vector<double>& ys) {
     const int n = detail::check(vsr_terrain(name.c_str(), nullptr, nullptr, 0), nullptr, "Locomotion.createTerrain");
@@ -389,10 +439,26 @@ class Locomotion {
     detail::check(vsr_terrain(name.c_str(), xs.data(), ys.data(), n), nullptr, "Locomotion.createTerrain");
   }
 
+  virtual ~Locomotion() { for (auto& kv : ctxs_) vsr_ctx_destroy(kv.second); }
+
+  struct Terrain { std::vector<double> xs, ys; };
+  // per-evaluation terrains of a `-rnd` task (RandomTerrainLocomotion), none for a shared terrain
+  virtual std::vector<Terrain> terrainsFor(size_t) { return {}; }
+  // bit v (voxel order) = the actuator of voxel v is frozen (what a `broken-...` transformation left behind)
+  static uint32_t frozenMask(const Robot& robot) {
+    uint32_t m = 0;
+    int v = 0;
+    robot.getVoxels().forEach([&](auto e) { if (e.value) { if (e.value->actuatorFrozen) m |= 1u << v; v++; } });
+    return m;
+  }
+
   Outcome apply(const Robot& robot) { return applyAll({robot}).front(); }
 
-  // one launch per distinct (body, sensors, controller structure); the outcomes come back in the order of `robots`
-  std::vector<Outcome> applyAll(const std::vector<Robot>& robots) {
+  // one launch per distinct (body, sensors, controller structure); the outcomes come back in the order of `robots`.
+  // `terrains`: one polyline per robot (what a `-rnd` task draws itself, in robot order, before any grouping)
+  std::vector<Outcome> applyAll(const std::vector<Robot>& robots, std::vector<Terrain> terrains = {}) {
+    if (terrains.empty()) terrains = terrainsFor(robots.size());
+    if (!terrains.empty() && terrains.size() != robots.size()) throw IllegalArgumentException("one terrain per robot expected");
     std::vector<Outcome> out(robots.size());
     std::vector<vsr_ctx*> order;
     std::map<vsr_ctx*, std::vector<size_t>> groups;
@@ -411,7 +477,27 @@ class Locomotion {
         if ((int)g.size() != G) throw IllegalArgumentException(detail::format("Wrong number of controller parameters: %d expected, %d found", G, (int)g.size()));
         std::memcpy(&genomes[k * (size_t)G], g.data(), sizeof(double) * G);
       }
-      detail::check(vsr_eval(ctx, genomes.data(), (int32_t)idx.size(), fitness.data(), results.data()), ctx, "vsr_eval");
+      std::vector<uint32_t> frozen(idx.size());
+      bool anyFrozen = false;
+      for (size_t k = 0; k < idx.size(); k++) anyFrozen |= (frozen[k] = frozenMask(robots[idx[k]])) != 0;
+      if (!anyFrozen && terrains.empty()) {
+        detail::check(vsr_eval(ctx, genomes.data(), (int32_t)idx.size(), fitness.data(), results.data()), ctx, "vsr_eval");
+      } else { // per-evaluation inputs: transformation masks and / or terrains
+        vsr_eval_opts opts;
+        std::memset(&opts, 0, sizeof opts);
+        std::vector<double> tx, ty;
+        std::vector<int32_t> toff{0};
+        if (anyFrozen) opts.frozen_masks = frozen.data();
+        if (!terrains.empty()) {
+          for (size_t i : idx) {
+            tx.insert(tx.end(), terrains[i].xs.begin(), terrains[i].xs.end());
+            ty.insert(ty.end(), terrains[i].ys.begin(), terrains[i].ys.end());
+            toff.push_back((int32_t)tx.size());
+          }
+          opts.terrain_x = tx.data(); opts.terrain_y = ty.data(); opts.terrain_off = toff.data();
+        }
+        detail::check(vsr_eval_ex(ctx, genomes.data(), (int32_t)idx.size(), &opts, fitness.data(), results.data()), ctx, "vsr_eval_ex");
+      }
       for (size_t k = 0; k < idx.size(); k++) {
         const vsr_result& r = results[k];
         out[idx[k]] = Outcome{fitness[k], r.distance, r.time, r.control_energy, r.area_ratio_abs}; // velocity: NaN if the contact pool overflowed
@@ -569,12 +655,64 @@ class LazyBatchedLocomotion {
   std::atomic<int> flushed_{0};
 };
 
-// Starter.buildLocomotionTask(terrainName, episodeT, random, cacheOutcome) for a fixed terrain (Starter.java:83-88), with the
-// subOutcome(transientT, episodeT) of the quality function (:430-433) folded in; the fitness is Outcome::getVelocity, maximised (:174)
-inline std::unique_ptr<Locomotion> buildLocomotionTask(const std::string& terrainName, double episodeT, double transientT = 0.0) {
-  if (terrainName.size() >= 4 && terrainName.compare(terrainName.size() - 4, 4, "-rnd") == 0)
-    throw VsrException(VSR_EUNSUPPORTED, "per-evaluation terrains: use vsr_eval_terrains of the C ABI (Starter.java:89-93)");
+// r -> new Locomotion(T, createTerrain(name.replace("-rnd", "-" + random.nextInt(10000))), settings).apply(r) (Starter.java:89-93):
+// every evaluation gets its own terrain, the batch still goes to the device in one call.  Seeds are drawn in robot order (the
+// reference draws them in thread-completion order, which is not reproducible).
+inline std::string replaceRnd(const std::string& terrainName, int seed) {
+  const size_t at = terrainName.find("-rnd");
+  if (at == std::string::npos) throw IllegalArgumentException("terrain name without -rnd");
+  return terrainName.substr(0, at) + "-" + std::to_string(seed) + terrainName.substr(at + 4);
+}
+class RandomTerrainLocomotion : public Locomotion {
+ public:
+  RandomTerrainLocomotion(double finalT, const std::string& terrainName, std::shared_ptr<JavaRandom> random, double transientT = 0.0)
+      : Locomotion(finalT, replaceRnd(terrainName, 0), transientT), terrainName_(terrainName), random_(std::move(random)) {}
+  std::vector<Terrain> terrainsFor(size_t n) override {
+    std::vector<Terrain> ts(n);
+    for (auto& t : ts) createTerrain(replaceRnd(terrainName_, random_->nextInt(10000)), t.xs, t.ys);
+    return ts;
+  }
+ private:
+  std::string terrainName_;
+  std::shared_ptr<JavaRandom> random_;
+};
+
+// Starter.buildLocomotionTask(terrainName, episodeT, random, cacheOutcome) (Starter.java:83-94): one shared Locomotion for a fixed
+// terrain, a per-evaluation terrain for `-rnd` names; the subOutcome(transientT, episodeT) of the quality function (:430-433) is
+// folded in; the fitness is Outcome::getVelocity, maximised (:174)
+inline std::unique_ptr<Locomotion> buildLocomotionTask(const std::string& terrainName, double episodeT, double transientT = 0.0,
+                                                       std::shared_ptr<JavaRandom> random = nullptr) {
+  if (terrainName.find("-rnd") != std::string::npos)
+    return std::make_unique<RandomTerrainLocomotion>(episodeT, terrainName, random ? random : std::make_shared<JavaRandom>(0), transientT);
   return std::make_unique<Locomotion>(episodeT, terrainName, transientT);
+}
+
+// Starter.validate (locomotion/Starter.java:122-135) for a batch of robots.  The reference validates ONE robot per call: random = new
+// Random(seed); robot = buildRobotTransformation(name, random).apply(robot); buildLocomotionTask(terrain, T, random, false).apply(robot)
+// -- every robot restarts the same stream: the transformation's draws (only a `-rnd` seeded one takes them from `random`), then the
+// `-rnd` terrain seed.  The batch does exactly that per robot and evaluates all of them in one launch per morphology.
+struct ValidationOutcome {
+  std::string terrainName, transformationName;
+  int64_t seed;
+  Outcome outcome;
+};
+inline std::vector<ValidationOutcome> validate(const std::vector<Robot>& robots, const std::string& terrainName, const std::string& transformationName,
+                                               int64_t seed, double episodeTime, double transientTime) {
+  const bool rnd = terrainName.find("-rnd") != std::string::npos;
+  std::vector<Robot> transformed;
+  std::vector<Locomotion::Terrain> terrains;
+  for (const Robot& r : robots) {
+    auto random = std::make_shared<JavaRandom>(seed);
+    transformed.push_back(buildRobotTransformation(transformationName, random)(r));
+    if (rnd) {
+      terrains.emplace_back();
+      Locomotion::createTerrain(replaceRnd(terrainName, random->nextInt(10000)), terrains.back().xs, terrains.back().ys);
+    }
+  }
+  Locomotion task(episodeTime, rnd ? replaceRnd(terrainName, 0) : terrainName, transientTime);
+  std::vector<ValidationOutcome> out;
+  for (const Outcome& o : task.applyAll(transformed, terrains)) out.push_back({terrainName, transformationName, seed, o});
+  return out;
 }
 
 } // namespace vsr_host

@@ -4,6 +4,7 @@
 //
 //   host_mirror check                                                       host-side checks only (dimensions, error messages); no GPU needed
 //   host_mirror eval <shape> <sensors> <mapper> <terrain> <T> <transient> <n> <seed> <out.bin>
+//   host_mirror validate <shape> <sensors> <mapper> <terrain> <T> <transient> <n> <seed> <out.bin> <transformation> <validation seed>
 //
 //   g++ -std=c++17 -O2 -pthread -Iinclude tests/cabi/host_mirror.cpp -Lvsrevolution_b200 -lvsr_eval -Wl,-rpath,$PWD/vsrevolution_b200 -o host_mirror
 #include <cstdio>
@@ -57,6 +58,24 @@ static int check() {
   EXPECT(messageOf([&] { BrainHomoDistributed::build({{"s", "2"}}).buildFor(comb)(RealFunction::build(12, 8)); }) == "Wrong number of function output args: 9 expected, 8 found");
   EXPECT(!messageOf([&] { RobotUtils::buildShape("hexapod-4x3"); }).empty() && !messageOf([&] { buildMapper("brainQuantum<mlp"); }).empty());
   EXPECT(!messageOf([&] { Locomotion(10.0, "lunar-3"); }).empty());
+  // java.util.Random: the known first double of new Random(0), and nextInt(bound) against the library's own replay
+  EXPECT(JavaRandom(0).nextDouble() == 0.730967787376657);
+  {
+    JavaRandom jr(42);
+    int32_t lib[50];
+    EXPECT(vsr_java_random_ints(42, 10000, lib, 50) >= 0);
+    for (int i = 0; i < 50; i++) EXPECT(jr.nextInt(10000) == lib[i]);
+    JavaRandom p2(7);
+    EXPECT(vsr_java_random_ints(7, 1024, lib, 10) >= 0); // power-of-two bound: the other branch of nextInt(bound)
+    for (int i = 0; i < 10; i++) EXPECT(p2.nextInt(1024) == lib[i]);
+  }
+  // robot transformations: identity keeps the robot, broken-<ratio>-<seed> freezes actuators reproducibly, ratio 0 / 1 are the extremes
+  EXPECT(Locomotion::frozenMask(buildRobotTransformation("identity")(r)) == 0);
+  EXPECT(Locomotion::frozenMask(buildRobotTransformation("broken-0-1")(r)) == 0 && Locomotion::frozenMask(buildRobotTransformation("broken-1-1")(r)) == 0x3ffu);
+  const uint32_t m1 = Locomotion::frozenMask(buildRobotTransformation("broken-0.5-7")(r)), m2 = Locomotion::frozenMask(buildRobotTransformation("broken-0.5-7")(r));
+  EXPECT(m1 == m2 && m1 != 0 && m1 != 0x3ffu);
+  EXPECT(!messageOf([&] { buildRobotTransformation("broken-0.5-rnd"); }).empty() && !messageOf([&] { buildRobotTransformation("melted-0.5-1"); }).empty());
+  EXPECT(replaceRnd("hilly-1-10-rnd", 123) == "hilly-1-10-123");
   // the task itself needs a GPU: without one the library refuses (no CPU fallback)
   try {
     Locomotion task(2.0, "flat", 0.5);
@@ -88,14 +107,17 @@ static int check() {
 
 int main(int argc, char** argv) {
   if (argc >= 2 && std::string(argv[1]) == "check") return check();
-  if (argc < 11 || std::string(argv[1]) != "eval") {
-    std::fprintf(stderr, "usage: %s check | eval shape sensors mapper terrain T transient n seed out.bin\n", argv[0]);
+  const std::string mode = argc >= 2 ? argv[1] : "";
+  if (argc < 11 || (mode != "eval" && mode != "validate") || (mode == "validate" && argc < 13)) {
+    std::fprintf(stderr, "usage: %s check | eval shape sensors mapper terrain T transient n seed out.bin\n"
+                         "       %s validate shape sensors mapper terrain T transient n seed out.bin transformation validationSeed\n", argv[0], argv[0]);
     return 2;
   }
   try {
     const Robot target = targetRobot(argv[2], argv[3]);
     const auto mapper = buildMapper(argv[4]);
-    auto task = buildLocomotionTask(argv[5], std::atof(argv[6]), std::atof(argv[7]));
+    // eval: the run's shared Random(1) draws the `-rnd` terrain seeds (Starter.java:89-93)
+    auto task = buildLocomotionTask(argv[5], std::atof(argv[6]), std::atof(argv[7]), std::make_shared<JavaRandom>(1));
     const int n = std::atoi(argv[8]);
     unsigned long long s = std::strtoull(argv[9], nullptr, 10);
     const size_t G = mapper.exampleFor(target).size();
@@ -109,9 +131,12 @@ int main(int argc, char** argv) {
       }
       robots.push_back(build(genotype));
     }
-    const std::vector<Outcome> outcomes = task->applyAll(robots);
     std::vector<double> v;
-    for (const Outcome& o : outcomes) v.push_back(o.getVelocity());
+    if (mode == "validate") { // Starter.validate (Starter.java:122-135) on every robot of the population
+      for (const ValidationOutcome& vo : validate(robots, argv[5], argv[11], std::atoll(argv[12]), std::atof(argv[6]), std::atof(argv[7]))) v.push_back(vo.outcome.getVelocity());
+    } else {
+      for (const Outcome& o : task->applyAll(robots)) v.push_back(o.getVelocity());
+    }
     std::FILE* f = std::fopen(argv[10], "wb");
     if (!f || std::fwrite(v.data(), sizeof(double), v.size(), f) != v.size()) { std::fprintf(stderr, "cannot write %s\n", argv[10]); return 1; }
     std::fclose(f);

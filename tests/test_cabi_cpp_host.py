@@ -62,3 +62,32 @@ def test_cpp_host_side_matches_the_python_mirror(tmp_path, shape, sensors, mappe
     assert f"genotype {ev.genome_len} robots {n}" in r.stdout
     g = (2.0 * _lcg_uniform(seed, n * ev.genome_len) - 1.0).reshape(n, ev.genome_len)
     assert np.array_equal(np.fromfile(out, dtype=np.float64), ev.evaluate(g))
+
+
+@pytest.mark.gpu
+def test_cpp_host_side_random_terrains_and_validation_match_the_python_mirror(tmp_path):
+    """`-rnd` terrains drawn from the run's java.util.Random (Starter.java:89-93) and Starter.validate with a `broken-...` robot
+    transformation (Starter.java:122-135), through the C++ host side and through the Python mirror: bit-identical velocities."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from vsrevolution_b200.locomotion import JavaRandomInts, build_locomotion_task, population_evaluator, validate
+    exe = _build(tmp_path)
+    out = str(tmp_path / "vel.bin")
+    shape, sensors, mapper, n, seed = "biped-4x3", "uniform-a-0", "brainCentralized<mlp;r=0.65;nIL=1", 24, 77
+    ev = population_evaluator(shape, sensors, mapper, "flat", 3.0, 0.5)
+    g = (2.0 * _lcg_uniform(seed, n * ev.genome_len) - 1.0).reshape(n, ev.genome_len)
+    robots = [ev._build(row) for row in g]
+    # eval on hilly-1-10-rnd: the harness hands new Random(1) to buildLocomotionTask
+    r = subprocess.run([exe, "eval", shape, sensors, mapper, "hilly-1-10-rnd", "3", "0.5", str(n), str(seed), out], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    task = build_locomotion_task("hilly-1-10-rnd", 3.0, 0.5, random=JavaRandomInts(1))
+    want = np.array([o.get_velocity() for o in task.apply_all(robots)])
+    assert np.array_equal(np.fromfile(out, dtype=np.float64), want) and len(set(want)) > 1
+    # validate: broken-0.4-rnd draws from new Random(5) of every validation, then the terrain seed
+    for terrain, transformation in (("hilly-1-10-rnd", "broken-0.4-rnd"), ("flat", "broken-0.3-11"), ("downhill-20", "identity")):
+        r = subprocess.run([exe, "validate", shape, sensors, mapper, terrain, "3", "0.5", str(n), str(seed), out, transformation, "5"],
+                           capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        want = np.array([vo.outcome.get_velocity() for vo in validate(robots, terrain, transformation, 5, 3.0, 0.5)])
+        assert np.array_equal(np.fromfile(out, dtype=np.float64), want), (terrain, transformation)
