@@ -420,6 +420,14 @@ struct Outcome {
   double getControlPower() const { return controlEnergy / time; }
   double getAreaRatioPower() const { return areaRatioEnergy / time; }
   double getCorrectedEfficiency() const { return distance / (1.0 + controlEnergy); }
+  // Outcome.getAveragePosture(n) (Starter.java:180-190 numSpeciated features, NamedFunctions.java:356): [y * n + x], y = 0 the bottom row;
+  // recorded by Locomotion::applyAllObserved(robots, n)
+  std::vector<bool> averagePosture;
+  int postureN = 0;
+  const std::vector<bool>& getAveragePosture(int n) const {
+    if (n != postureN) throw VsrException(VSR_ESTATE, "average posture of side " + std::to_string(n) + " was not recorded: use Locomotion::applyAllObserved");
+    return averagePosture;
+  }
 };
 
 // new Locomotion(finalT, Locomotion.createTerrain(name), new Settings()) followed by .subOutcome(transientT, finalT)
@@ -456,7 +464,12 @@ class Locomotion {
 
   // one launch per distinct (body, sensors, controller structure); the outcomes come back in the order of `robots`.
   // `terrains`: one polyline per robot (what a `-rnd` task draws itself, in robot order, before any grouping)
-  std::vector<Outcome> applyAll(const std::vector<Robot>& robots, std::vector<Terrain> terrains = {}) {
+  std::vector<Outcome> applyAll(const std::vector<Robot>& robots, std::vector<Terrain> terrains = {}) { return evaluate(robots, std::move(terrains), 0); }
+  // ... that also keeps every robot's average posture on the postureN x postureN grid (the `numSpeciated` features), same launch
+  std::vector<Outcome> applyAllObserved(const std::vector<Robot>& robots, int postureN = 8) { return evaluate(robots, {}, postureN); }
+
+ private:
+  std::vector<Outcome> evaluate(const std::vector<Robot>& robots, std::vector<Terrain> terrains, int postureN) {
     if (terrains.empty()) terrains = terrainsFor(robots.size());
     if (!terrains.empty() && terrains.size() != robots.size()) throw IllegalArgumentException("one terrain per robot expected");
     std::vector<Outcome> out(robots.size());
@@ -480,11 +493,13 @@ class Locomotion {
       std::vector<uint32_t> frozen(idx.size());
       bool anyFrozen = false;
       for (size_t k = 0; k < idx.size(); k++) anyFrozen |= (frozen[k] = frozenMask(robots[idx[k]])) != 0;
-      if (!anyFrozen && terrains.empty()) {
+      std::vector<uint8_t> posture(postureN > 0 ? idx.size() * (size_t)postureN * postureN : 0);
+      if (!anyFrozen && terrains.empty() && postureN <= 0) {
         detail::check(vsr_eval(ctx, genomes.data(), (int32_t)idx.size(), fitness.data(), results.data()), ctx, "vsr_eval");
-      } else { // per-evaluation inputs: transformation masks and / or terrains
+      } else { // per-evaluation inputs (transformation masks, terrains) and / or observation summaries
         vsr_eval_opts opts;
         std::memset(&opts, 0, sizeof opts);
+        if (postureN > 0) { opts.posture_n = postureN; opts.posture_out = posture.data(); }
         std::vector<double> tx, ty;
         std::vector<int32_t> toff{0};
         if (anyFrozen) opts.frozen_masks = frozen.data();
@@ -500,12 +515,20 @@ class Locomotion {
       }
       for (size_t k = 0; k < idx.size(); k++) {
         const vsr_result& r = results[k];
-        out[idx[k]] = Outcome{fitness[k], r.distance, r.time, r.control_energy, r.area_ratio_abs}; // velocity: NaN if the contact pool overflowed
+        Outcome& o = out[idx[k]];
+        o.velocity = fitness[k]; // NaN if the contact pool overflowed
+        o.distance = r.distance; o.time = r.time; o.controlEnergy = r.control_energy; o.areaRatioEnergy = r.area_ratio_abs;
+        if (postureN > 0) {
+          o.postureN = postureN;
+          o.averagePosture.assign(posture.begin() + k * (size_t)postureN * postureN, posture.begin() + (k + 1) * (size_t)postureN * postureN);
+        }
       }
     }
     return out;
   }
 
+
+ public:
   // the controller parameters in the order the kernel reads them (== the mappers' genome order)
   static std::vector<double> genomeOf(const Robot& robot) {
     const Controller* c = robot.getController().get();

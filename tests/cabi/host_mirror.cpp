@@ -97,6 +97,18 @@ static int check() {
     const auto next = lazy.apply(robots[3]); // the next generation opens a new batch
     EXPECT(next.getVelocity() == direct[3].getVelocity() && lazy.batchesFlushed() == 2);
     std::printf("lazy batching ok\n");
+    // Outcome.getAveragePosture(8) of a population in the same launch; the velocity does not depend on what else is recorded
+    const std::vector<Outcome> observed = task.applyAllObserved(robots, 8);
+    for (int i = 0; i < 12; i++) {
+      EXPECT(observed[i].getVelocity() == direct[i].getVelocity() && observed[i].getAveragePosture(8).size() == 64);
+      int cells = 0;
+      for (bool b : observed[i].getAveragePosture(8)) cells += b;
+      EXPECT(cells >= 20 && cells <= 50); // 10 of the 12 cells of the 4 x 3 bounding box, squared to 4 x 4: about 40 of 64 cells
+    }
+    bool threw = false;
+    try { direct[0].getAveragePosture(8); } catch (const VsrException& e) { threw = e.status == VSR_ESTATE; }
+    EXPECT(threw);
+    std::printf("average posture ok\n");
   } catch (const VsrException& e) {
     EXPECT(e.status == VSR_ECUDA);
     std::printf("no gpu: %s\n", e.what());

@@ -39,7 +39,7 @@ def test_cpp_host_side_checks(tmp_path):
     assert r.returncode == 0, r.stderr
     assert "host mirror checks ok" in r.stdout
     if torch.cuda.is_available():  # the task ran: one robot, then a generation behind the one-robot-per-call contract in one launch
-        assert "gpu: velocity" in r.stdout and "lazy batching ok" in r.stdout
+        assert "gpu: velocity" in r.stdout and "lazy batching ok" in r.stdout and "average posture ok" in r.stdout
     else:
         assert "no gpu:" in r.stdout and "no CPU fallback" in r.stdout
 
