@@ -9,7 +9,10 @@
 //   g++ -std=c++17 -O2 -pthread -Iinclude tests/cabi/host_mirror.cpp -Lvsrevolution_b200 -lvsr_eval -Wl,-rpath,$PWD/vsrevolution_b200 -o host_mirror
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
+#include <optional>
 #include <string>
+#include <thread>
 
 #include "vsr_host.hpp"
 
@@ -96,6 +99,18 @@ static int check() {
     EXPECT(lazy.batchesFlushed() == 1);
     const auto next = lazy.apply(robots[3]); // the next generation opens a new batch
     EXPECT(next.getVelocity() == direct[3].getVelocity() && lazy.batchesFlushed() == 2);
+    { // JGEA applies the quality function from a thread pool (Starter.java:424-436): concurrent apply(), then concurrent reads
+      std::vector<std::optional<LazyBatchedLocomotion::LazyOutcome>> slots(12);
+      std::vector<std::thread> pool;
+      for (int t = 0; t < 4; t++) pool.emplace_back([&, t] { for (int i = t; i < 12; i += 4) slots[i] = lazy.apply(robots[i]); });
+      for (auto& th : pool) th.join();
+      pool.clear();
+      std::vector<double> got(12);
+      for (int t = 0; t < 4; t++) pool.emplace_back([&, t] { for (int i = t; i < 12; i += 4) got[i] = slots[i]->getVelocity(); });
+      for (auto& th : pool) th.join();
+      for (int i = 0; i < 12; i++) EXPECT(got[i] == direct[i].getVelocity());
+      EXPECT(lazy.batchesFlushed() == 3);
+    }
     std::printf("lazy batching ok\n");
     // Outcome.getAveragePosture(8) of a population in the same launch; the velocity does not depend on what else is recorded
     const std::vector<Outcome> observed = task.applyAllObserved(robots, 8);
